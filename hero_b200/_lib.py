@@ -1,0 +1,101 @@
+"""ctypes binding of the C-ABI in include/hero_b200.h.
+
+The product path has no CPU fallback: if `libhero_b200.so` is missing, `lib()` raises with the
+build command instead of silently routing around the CUDA kernels.
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libhero_b200.so")
+
+_lib = None
+
+
+class HeroError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    """Mirror of `hero_gemm_args` (include/hero_b200.h)."""
+    _fields_ = [
+        ("a", C.c_void_p), ("b", C.c_void_p),
+        ("lda", C.c_int64), ("ldb", C.c_int64),
+        ("a_mn_major", C.c_int32), ("b_mn_major", C.c_int32),
+        ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+        ("bias", C.c_void_p),
+        ("resid", C.c_void_p), ("ld_resid", C.c_int64),
+        ("aux_in", C.c_void_p), ("ld_aux_in", C.c_int64),
+        ("aux_out", C.c_void_p), ("ld_aux_out", C.c_int64),
+        ("out", C.c_void_p), ("ld_out", C.c_int64),
+        ("act", C.c_int32), ("out_f32_accumulate", C.c_int32),
+        ("drop_threshold", C.c_uint32), ("drop_key", C.c_uint32),
+        ("drop_scale", C.c_float),
+        ("block_n", C.c_int32), ("k_splits", C.c_int32),
+    ]
+
+
+class LnArgs(C.Structure):
+    """Mirror of `hero_ln_args` (include/hero_b200.h)."""
+    _fields_ = [
+        ("x", C.c_void_p), ("x_is_f32", C.c_int32),
+        ("x_rows", C.c_void_p), ("add_tab", C.c_void_p), ("add_idx", C.c_void_p),
+        ("add_vec", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("eps", C.c_float), ("n_rows", C.c_int32), ("h", C.c_int32),
+        ("y", C.c_void_p), ("y_rows", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
+        ("drop_threshold", C.c_uint32), ("drop_key", C.c_uint32), ("drop_scale", C.c_float),
+        ("dy", C.c_void_p), ("dx", C.c_void_p), ("dx_drop", C.c_void_p),
+        ("drop2_threshold", C.c_uint32), ("drop2_key", C.c_uint32), ("drop2_scale", C.c_float),
+        ("d_x_tab", C.c_void_p), ("x_pad_idx", C.c_int32),
+        ("d_add_tab", C.c_void_p), ("add_pad_idx", C.c_int32),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+    ]
+
+
+def _declare(lib):
+    vp, i32, i64, f32, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint32
+    lib.hero_last_error.restype = C.c_char_p
+    lib.hero_last_error.argtypes = []
+    lib.hero_version.restype = C.c_int
+    lib.hero_sm_count.restype = C.c_int
+    lib.hero_gemm_bf16.restype = C.c_int
+    lib.hero_gemm_bf16.argtypes = [C.POINTER(GemmArgs), vp]
+
+    def sig(name, *argtypes):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = list(argtypes)
+
+    sig("hero_ln_fwd", C.POINTER(LnArgs), vp)
+    sig("hero_ln_bwd", C.POINTER(LnArgs), vp)
+    sig("hero_attn_fwd", vp, vp, vp, i32, i32, i32, i32, f32, u32, u32, f32, vp)
+    sig("hero_attn_bwd", vp, vp, vp, vp, i32, i32, i32, i32, f32, u32, u32, f32, vp)
+    sig("hero_cast_f32_to_bf16", vp, vp, i64, vp)
+    sig("hero_gather_rows_bf16", vp, vp, vp, i32, i32, vp)
+    sig("hero_gather_sum_rows_bf16", vp, vp, vp, vp, i32, i32, vp)
+    sig("hero_gather_sum_rows_f32", vp, vp, vp, vp, i32, i32, vp)
+    sig("hero_colsum_bf16", vp, i64, i32, i32, vp, vp)
+    sig("hero_relu_bwd_bf16", vp, vp, vp, i64, vp)
+    sig("hero_adamw_step", vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp)
+    sig("hero_sumsq_f32", vp, i64, vp, vp)
+
+
+def lib():
+    """Load (once) and return the shared library; raise if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HeroError(
+                f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+                "Build it with `python -m hero_b200.build` (needs nvcc).")
+        l = C.CDLL(LIB_PATH)
+        _declare(l)
+        _lib = l
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        msg = lib().hero_last_error()
+        raise HeroError(f"hero_b200 call failed (status {status}): "
+                        f"{msg.decode() if msg else 'unknown error'}")

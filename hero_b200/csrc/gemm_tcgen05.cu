@@ -1,0 +1,463 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring ->
+// tcgen05.mma (fp32 accumulators in TMEM, double buffered) -> fused epilogue.
+//
+// One CTA per SM, 6 warps:
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      TMEM allocator + MMA issuer (one lane issues tcgen05.mma / tcgen05.commit)
+//   warps 2..5  epilogue: tcgen05.ld their 32-lane TMEM quadrant, bias/act/dropout/residual,
+//               bf16 store or fp32 atomic accumulate (split-K wgrad)
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty x2 (MMA <-> epilogue), so the
+// epilogue of tile i overlaps the mainloop of tile i+1.
+//
+// Replaces the cuBLAS calls behind nn.Linear in model/layers.py:125-127,176,237,251,
+// model/embed.py:112 and model/layers.py:82-90 (reference), forward and backward.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace hero {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle span
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_GELU_GRAD = 3 };
+
+struct GemmShape {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, k_splits, k_blocks;
+};
+
+struct GemmEpilogue {
+  const float* bias;
+  const __nv_bfloat16* resid;
+  long long ld_resid;
+  const __nv_bfloat16* aux_in;
+  long long ld_aux_in;
+  __nv_bfloat16* aux_out;
+  long long ld_aux_out;
+  void* out;
+  long long ld_out;
+  uint32_t drop_threshold;
+  uint32_t drop_key;
+  float drop_scale;
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// Epilogue on 8 consecutive columns of one row.
+template <int ACT, int OUT_F32>
+__device__ __forceinline__ void epilogue8(float (&v)[8], int row, int col, const GemmShape& s,
+                                          const GemmEpilogue& e) {
+  if (e.bias != nullptr) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (e.aux_out != nullptr) {
+    uint4 p;
+    p.x = pack_bf16x2(v[0], v[1]); p.y = pack_bf16x2(v[2], v[3]);
+    p.z = pack_bf16x2(v[4], v[5]); p.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(e.aux_out + (long long)row * e.ld_aux_out + col) = p;
+  }
+  if (ACT == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+  } else if (ACT == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (ACT == ACT_GELU_GRAD) {
+    const uint4 p = *reinterpret_cast<const uint4*>(e.aux_in + (long long)row * e.ld_aux_in + col);
+    const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = unpack_bf16x2(pw[j]);
+      v[2 * j] *= gelu_erf_grad(x.x);
+      v[2 * j + 1] *= gelu_erf_grad(x.y);
+    }
+  }
+  if (e.drop_threshold != 0u) {
+    const uint32_t base = (uint32_t)row * (uint32_t)s.N + (uint32_t)col;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = dropout_keep(e.drop_key, base + j, e.drop_threshold) ? v[j] * e.drop_scale : 0.0f;
+  }
+  if (e.resid != nullptr) {
+    const uint4 p = *reinterpret_cast<const uint4*>(e.resid + (long long)row * e.ld_resid + col);
+    const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = unpack_bf16x2(pw[j]);
+      v[2 * j] += x.x;
+      v[2 * j + 1] += x.y;
+    }
+  }
+  if (OUT_F32) {
+    float* o = reinterpret_cast<float*>(e.out) + (long long)row * e.ld_out + col;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]), "f"(v[1]),
+                 "f"(v[2]), "f"(v[3])
+                 : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(v[4]),
+                 "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+  } else {
+    uint4 p;
+    p.x = pack_bf16x2(v[0], v[1]); p.y = pack_bf16x2(v[2], v[3]);
+    p.z = pack_bf16x2(v[4], v[5]); p.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + (long long)row * e.ld_out +
+                              col) = p;
+  }
+}
+
+template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT_F32>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmShape s,
+                    const GemmEpilogue e) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;
+  uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = s.num_m_blocks * s.num_n_blocks * s.k_splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ks = tile % s.k_splits;
+        const int t2 = tile / s.k_splits;
+        const int n_blk = t2 % s.num_n_blocks;
+        const int m_blk = t2 / s.num_n_blocks;
+        const int kb0 = (int)(((long long)ks * s.k_blocks) / s.k_splits);
+        const int kb1 = (int)(((long long)(ks + 1) * s.k_blocks) / s.k_splits);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t stage = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(&empty_bar[stage], ph ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (A_MN)
+            tma_load_3d(sa, &tmap_a, &full_bar[stage], 0, kb * BLOCK_K, m_blk * (BLOCK_M / 64));
+          else
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          if (B_MN)
+            tma_load_3d(sb, &tmap_b, &full_bar[stage], 0, kb * BLOCK_K, n_blk * (BLOCK_N / 64));
+          else
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      // K-major: 8-row groups 1024 B apart (SBO), LBO unused (encoded 1 like CUTLASS).
+      // MN-major: 64-element MN chunks BLOCK_K*128 B apart (LBO), 8-k groups 1024 B apart (SBO).
+      constexpr uint32_t A_LBO = A_MN ? BLOCK_K * 128 : 16;
+      constexpr uint32_t B_LBO = B_MN ? BLOCK_K * 128 : 16;
+      constexpr uint32_t A_KSTEP = A_MN ? UMMA_K * 128 : UMMA_K * 2;
+      constexpr uint32_t B_KSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+      uint32_t it = 0;
+      uint32_t local_tile = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
+        const int ks = tile % s.k_splits;
+        const int kb0 = (int)(((long long)ks * s.k_blocks) / s.k_splits);
+        const int kb1 = (int)(((long long)(ks + 1) * s.k_blocks) / s.k_splits);
+        const uint32_t acc = local_tile & 1u;
+        const uint32_t acc_ph = (local_tile >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t stage = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(&full_bar[stage], ph);
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = make_sw128_desc(sa + k * A_KSTEP, A_LBO, 1024);
+            const uint64_t bdesc = make_sw128_desc(sb + k * B_KSTEP, B_LBO, 1024);
+            umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------- epilogue warps
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    uint32_t local_tile = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
+      const int t2 = tile / s.k_splits;
+      const int n_blk = t2 % s.num_n_blocks;
+      const int m_blk = t2 / s.num_n_blocks;
+      const uint32_t acc = local_tile & 1u;
+      const uint32_t acc_ph = (local_tile >> 1) & 1u;
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after_sync();
+      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c * 32, r);
+        tmem_ld_wait();
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (row < s.M) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            if (col < s.N) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+              epilogue8<ACT, OUT_F32>(v, row, col, s, e);
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  return fn;
+}
+
+// K-major operand: global [rows, k] row-major (ld elements); box = 64 k x box_rows rows.
+static int encode_kmajor(CUtensorMap* map, const void* ptr, int rows, int k, long long ld,
+                         int box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled(K-major %dx%d ld %lld) failed: %d", rows,
+                     k, ld, (int)r);
+  return HERO_OK;
+}
+
+// MN-major operand: global [k, mn] row-major (ld elements), viewed as (64, k, mn/64) so one box
+// (64, BLOCK_K, box_mn/64) lands in smem as consecutive [BLOCK_K x 128 B] swizzle-128B chunks.
+static int encode_mnmajor(CUtensorMap* map, const void* ptr, int k, int mn, long long ld,
+                          int box_mn) {
+  auto fn = get_encode_fn();
+  if (!fn) return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {64, (cuuint64_t)k, (cuuint64_t)(mn / 64)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, 128};
+  cuuint32_t box[3] = {64, (cuuint32_t)BLOCK_K, (cuuint32_t)(box_mn / 64)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled(MN-major %dx%d ld %lld) failed: %d", k,
+                     mn, ld, (int)r);
+  return HERO_OK;
+}
+
+template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT_F32>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& s,
+                  const GemmEpilogue& e, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, ACT, OUT_F32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HERO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = s.num_m_blocks * s.num_n_blocks * s.k_splits;
+  const int sms = sm_count();
+  if (sms <= 0) return set_error(HERO_ERR_NO_DEVICE, "no CUDA device");
+  const int grid = total < sms ? total : sms;
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, s, e);
+  HERO_LAUNCH_CHECK();
+  return HERO_OK;
+}
+
+template <int BLOCK_N>
+static int dispatch(const hero_gemm_args* g, const CUtensorMap& ta, const CUtensorMap& tb,
+                    const GemmShape& s, const GemmEpilogue& e, cudaStream_t st) {
+  const int layout = g->a_mn_major * 2 + g->b_mn_major;
+  if (g->out_f32_accumulate) {
+    HERO_REQUIRE(g->act == ACT_NONE, "fp32-accumulate output supports act=0 only");
+    if (layout == 3) return launch<BLOCK_N, 1, 1, ACT_NONE, 1>(ta, tb, s, e, st);
+    if (layout == 0) return launch<BLOCK_N, 0, 0, ACT_NONE, 1>(ta, tb, s, e, st);
+    return set_error(HERO_ERR_INVALID, "fp32-accumulate supports layouts (0,0) and (1,1)");
+  }
+  if (layout == 0) {
+    switch (g->act) {
+      case ACT_NONE: return launch<BLOCK_N, 0, 0, ACT_NONE, 0>(ta, tb, s, e, st);
+      case ACT_GELU: return launch<BLOCK_N, 0, 0, ACT_GELU, 0>(ta, tb, s, e, st);
+      case ACT_RELU: return launch<BLOCK_N, 0, 0, ACT_RELU, 0>(ta, tb, s, e, st);
+      default: break;
+    }
+  } else if (layout == 1) {
+    switch (g->act) {
+      case ACT_NONE: return launch<BLOCK_N, 0, 1, ACT_NONE, 0>(ta, tb, s, e, st);
+      case ACT_GELU_GRAD: return launch<BLOCK_N, 0, 1, ACT_GELU_GRAD, 0>(ta, tb, s, e, st);
+      default: break;
+    }
+  }
+  return set_error(HERO_ERR_INVALID, "unsupported gemm variant: a_mn=%d b_mn=%d act=%d f32=%d",
+                   g->a_mn_major, g->b_mn_major, g->act, g->out_f32_accumulate);
+}
+
+}  // namespace hero
+
+extern "C" int hero_gemm_bf16(const hero_gemm_args* g, void* stream) {
+  using namespace hero;
+  HERO_REQUIRE(g != nullptr, "null args");
+  HERO_REQUIRE(g->a && g->b && g->out, "null operand pointer");
+  HERO_REQUIRE(g->m > 0 && g->n > 0 && g->k > 0, "empty gemm %dx%dx%d", g->m, g->n, g->k);
+  HERO_REQUIRE(g->k % 8 == 0 && g->n % 8 == 0, "n and k must be multiples of 8 (n=%d k=%d)", g->n,
+               g->k);
+  HERO_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0 && g->ld_out % 4 == 0, "unaligned leading dim");
+  HERO_REQUIRE(g->act != ACT_GELU_GRAD || g->aux_in != nullptr, "act=3 needs aux_in");
+  if (g->a_mn_major) HERO_REQUIRE(g->m % 64 == 0, "MN-major A needs m %% 64 == 0 (m=%d)", g->m);
+  if (g->b_mn_major) HERO_REQUIRE(g->n % 64 == 0, "MN-major B needs n %% 64 == 0 (n=%d)", g->n);
+
+  int block_n = g->block_n;
+  const int sms = sm_count();
+  if (sms <= 0) return set_error(HERO_ERR_NO_DEVICE, "no CUDA device");
+  const int m_blocks = ceil_div(g->m, BLOCK_M);
+  if (block_n == 0) {
+    // Prefer 256-wide tiles (less smem traffic per MAC) unless that leaves most SMs idle.
+    const int t256 = m_blocks * ceil_div(g->n, 256);
+    block_n = (g->n % 256 == 0 || g->n > 1024) ? 256 : 128;
+    if (block_n == 256 && t256 < 2 * sms && !g->out_f32_accumulate) {
+      const int t128 = m_blocks * ceil_div(g->n, 128);
+      const double eff256 = (double)t256 / (ceil_div(t256, sms) * (double)sms);
+      const double eff128 = (double)t128 / (ceil_div(t128, sms) * (double)sms);
+      if (eff128 > eff256 * 1.15) block_n = 128;
+    }
+  }
+  HERO_REQUIRE(block_n == 128 || block_n == 256, "block_n must be 128 or 256");
+
+  GemmShape s;
+  s.M = g->m; s.N = g->n; s.K = g->k;
+  s.num_m_blocks = m_blocks;
+  s.num_n_blocks = ceil_div(g->n, block_n);
+  s.k_blocks = ceil_div(g->k, BLOCK_K);
+  int k_splits = g->k_splits;
+  if (!g->out_f32_accumulate) {
+    k_splits = 1;
+  } else if (k_splits <= 0) {
+    const int tiles = s.num_m_blocks * s.num_n_blocks;
+    k_splits = 1;
+    if (tiles < sms) k_splits = ceil_div(sms, tiles);
+    // keep at least 4 k-blocks per split so the pipeline has something to overlap
+    if (k_splits > s.k_blocks / 4) k_splits = s.k_blocks / 4;
+    if (k_splits < 1) k_splits = 1;
+  }
+  if (k_splits > s.k_blocks) k_splits = s.k_blocks;
+  s.k_splits = k_splits;
+
+  GemmEpilogue e;
+  e.bias = g->bias;
+  e.resid = reinterpret_cast<const __nv_bfloat16*>(g->resid);
+  e.ld_resid = g->ld_resid;
+  e.aux_in = reinterpret_cast<const __nv_bfloat16*>(g->aux_in);
+  e.ld_aux_in = g->ld_aux_in;
+  e.aux_out = reinterpret_cast<__nv_bfloat16*>(g->aux_out);
+  e.ld_aux_out = g->ld_aux_out;
+  e.out = g->out;
+  e.ld_out = g->ld_out;
+  e.drop_threshold = g->drop_threshold;
+  e.drop_key = g->drop_key;
+  e.drop_scale = g->drop_scale;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (g->a_mn_major)
+    rc = encode_mnmajor(&ta, g->a, g->k, g->m, g->lda, BLOCK_M);
+  else
+    rc = encode_kmajor(&ta, g->a, g->m, g->k, g->lda, BLOCK_M);
+  if (rc) return rc;
+  if (g->b_mn_major)
+    rc = encode_mnmajor(&tb, g->b, g->k, g->n, g->ldb, block_n);
+  else
+    rc = encode_kmajor(&tb, g->b, g->n, g->k, g->ldb, block_n);
+  if (rc) return rc;
+
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (block_n == 256) return dispatch<256>(g, ta, tb, s, e, st);
+  return dispatch<128>(g, ta, tb, s, e, st);
+}

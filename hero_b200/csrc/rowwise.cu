@@ -1,0 +1,519 @@
+// HBM-bound row kernels: fused gather+add+LayerNorm(+dropout)+scatter forward/backward, row
+// gathers (pack / unpack / frame merge), column sums (bias grads), casts.
+// One warp owns one row; 16-byte vector accesses; fp32 statistics via a true two-pass over
+// registers (mean, then centred sum of squares) like apex FusedLayerNorm / torch.nn.LayerNorm.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace hero {
+
+constexpr int LN_WARPS = 4;
+
+struct LnParams {
+  hero_ln_args a;
+};
+
+// Load 8 consecutive elements of the (gathered, summed) pre-LN row into v[8].
+__device__ __forceinline__ void ln_load8(const hero_ln_args& a, long long xrow, int add_row, int e0,
+                                         float (&v)[8]) {
+  if (a.x_is_f32) {
+    const float* p = reinterpret_cast<const float*>(a.x) + xrow * a.h + e0;
+    const float4 u0 = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 u1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w;
+    v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+  } else {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(a.x) + xrow * a.h + e0;
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      v[2 * j] = f.x;
+      v[2 * j + 1] = f.y;
+    }
+  }
+  if (a.add_tab != nullptr) {
+    const float* p = a.add_tab + (long long)add_row * a.h + e0;
+    const float4 u0 = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 u1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] += u0.x; v[1] += u0.y; v[2] += u0.z; v[3] += u0.w;
+    v[4] += u1.x; v[5] += u1.y; v[6] += u1.z; v[7] += u1.w;
+  }
+  if (a.add_vec != nullptr) {
+    const float* p = a.add_vec + e0;
+    const float4 u0 = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 u1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+    v[0] += u0.x; v[1] += u0.y; v[2] += u0.z; v[3] += u0.w;
+    v[4] += u1.x; v[5] += u1.y; v[6] += u1.z; v[7] += u1.w;
+  }
+}
+
+__device__ __forceinline__ void load_f32x8(const float* p, float (&v)[8]) {
+  const float4 u0 = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 u1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w;
+  v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+}
+
+__device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2(w[j]);
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ------------------------------------------------------------------ LN forward
+template <int MAXJ>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_fwd_kernel(const hero_ln_args a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * LN_WARPS + warp;
+  if (i >= a.n_rows) return;
+  const long long xrow = a.x_rows ? a.x_rows[i] : i;
+  const int add_row = a.add_tab ? a.add_idx[i] : 0;
+  const long long yrow = a.y_rows ? a.y_rows[i] : i;
+
+  float v[MAXJ][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXJ; ++c) {
+    const int e0 = (c * 32 + lane) * 8;
+    if (e0 < a.h) {
+      ln_load8(a, xrow, add_row, e0, v[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[c][j];
+    }
+  }
+  const float inv_h = 1.0f / (float)a.h;
+  const float mean = warp_sum(sum) * inv_h;
+  float sq = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXJ; ++c) {
+    const int e0 = (c * 32 + lane) * 8;
+    if (e0 < a.h) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[c][j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float var = warp_sum(sq) * inv_h;
+  const float rstd = rsqrtf(var + a.eps);
+  if (lane == 0) {
+    if (a.mean) a.mean[i] = mean;
+    if (a.rstd) a.rstd[i] = rstd;
+  }
+  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.y) + yrow * a.h;
+#pragma unroll
+  for (int c = 0; c < MAXJ; ++c) {
+    const int e0 = (c * 32 + lane) * 8;
+    if (e0 < a.h) {
+      float g[8], b[8], o[8];
+      load_f32x8(a.gamma + e0, g);
+      load_f32x8(a.beta + e0, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * g[j] + b[j];
+      if (a.drop_threshold != 0u) {
+        const uint32_t base = (uint32_t)i * (uint32_t)a.h + (uint32_t)e0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = dropout_keep(a.drop_key, base + j, a.drop_threshold) ? o[j] * a.drop_scale : 0.f;
+      }
+      store_bf16x8(y + e0, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LN backward
+// Persistent blocks: each warp walks rows i = gwarp, gwarp + total_warps, ...; with PARAM_GRADS the
+// per-lane column partials of dgamma/dbeta stay in registers and are reduced once per block.
+template <int MAXJ, bool PARAM_GRADS>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_bwd_kernel(const hero_ln_args a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_warps = gridDim.x * LN_WARPS;
+  float dg[PARAM_GRADS ? MAXJ : 1][8], db[PARAM_GRADS ? MAXJ : 1][8];
+  if (PARAM_GRADS) {
+#pragma unroll
+    for (int c = 0; c < MAXJ; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dg[c][j] = db[c][j] = 0.f;
+  }
+  const float inv_h = 1.0f / (float)a.h;
+
+  for (int i = blockIdx.x * LN_WARPS + warp; i < a.n_rows; i += total_warps) {
+    const long long xrow = a.x_rows ? a.x_rows[i] : i;
+    const int add_row = a.add_tab ? a.add_idx[i] : 0;
+    const long long yrow = a.y_rows ? a.y_rows[i] : i;
+    const float mean = a.mean[i], rstd = a.rstd[i];
+    const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(a.dy) + yrow * a.h;
+
+    float xh[MAXJ][8], gy[MAXJ][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXJ; ++c) {
+      const int e0 = (c * 32 + lane) * 8;
+      if (e0 < a.h) {
+        ln_load8(a, xrow, add_row, e0, xh[c]);
+        float d[8], g[8];
+        load_bf16x8(dy + e0, d);
+        load_f32x8(a.gamma + e0, g);
+        if (a.drop_threshold != 0u) {
+          const uint32_t base = (uint32_t)i * (uint32_t)a.h + (uint32_t)e0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            d[j] = dropout_keep(a.drop_key, base + j, a.drop_threshold) ? d[j] * a.drop_scale : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[c][j] = (xh[c][j] - mean) * rstd;
+          if (PARAM_GRADS) {
+            dg[c][j] += d[j] * xh[c][j];
+            db[c][j] += d[j];
+          }
+          gy[c][j] = d[j] * g[j];
+          s1 += gy[c][j];
+          s2 += gy[c][j] * xh[c][j];
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_h;
+    const float c2 = warp_sum(s2) * inv_h;
+#pragma unroll
+    for (int c = 0; c < MAXJ; ++c) {
+      const int e0 = (c * 32 + lane) * 8;
+      if (e0 < a.h) {
+        float dx[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dx[j] = rstd * (gy[c][j] - c1 - xh[c][j] * c2);
+        if (a.dx) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(a.dx) + (long long)i * a.h + e0, dx);
+        if (a.dx_drop) {
+          float dd[8];
+          const uint32_t base = (uint32_t)i * (uint32_t)a.h + (uint32_t)e0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dd[j] = (a.drop2_threshold == 0u ||
+                     dropout_keep(a.drop2_key, base + j, a.drop2_threshold))
+                        ? dx[j] * (a.drop2_threshold == 0u ? 1.0f : a.drop2_scale)
+                        : 0.f;
+          store_bf16x8(reinterpret_cast<__nv_bfloat16*>(a.dx_drop) + (long long)i * a.h + e0, dd);
+        }
+        if (a.d_x_tab && (int)xrow != a.x_pad_idx) {
+          float* t = a.d_x_tab + xrow * a.h + e0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(t + j, dx[j]);
+        }
+        if (a.d_add_tab && a.add_tab && add_row != a.add_pad_idx) {
+          float* t = a.d_add_tab + (long long)add_row * a.h + e0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(t + j, dx[j]);
+        }
+      }
+    }
+  }
+
+  if (PARAM_GRADS) {
+    // block reduce over the LN_WARPS warps through smem, then one atomic per column per block
+    __shared__ float red[LN_WARPS][32 * 8 + 1];
+    for (int pass = 0; pass < 2; ++pass) {
+      float* out = pass == 0 ? a.dgamma : a.dbeta;
+      if (out == nullptr) continue;
+#pragma unroll
+      for (int c = 0; c < MAXJ; ++c) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? dg[c][j] : db[c][j];
+        __syncthreads();
+        for (int t = threadIdx.x; t < 256; t += LN_WARPS * 32) {
+          const int e = c * 256 + t;
+          if (e < a.h) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < LN_WARPS; ++w) s += red[w][t];
+            atomicAdd(out + e, s);
+          }
+        }
+      }
+    }
+  }
+}
+
+// Column-parallel dgamma/dbeta for wide rows (H = 4352): block = 32 columns x 8 row lanes.
+__global__ void __launch_bounds__(256)
+ln_param_grad_kernel(const hero_ln_args a, int rows_per_block) {
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(a.n_rows, r0 + rows_per_block);
+  float dg = 0.f, db = 0.f;
+  if (col < a.h) {
+    for (int i = r0 + rl; i < r1; i += 8) {
+      const long long xrow = a.x_rows ? a.x_rows[i] : i;
+      const long long yrow = a.y_rows ? a.y_rows[i] : i;
+      float x = a.x_is_f32 ? __ldg(reinterpret_cast<const float*>(a.x) + xrow * a.h + col)
+                           : __bfloat162float(
+                                 reinterpret_cast<const __nv_bfloat16*>(a.x)[xrow * a.h + col]);
+      if (a.add_tab) x += __ldg(a.add_tab + (long long)a.add_idx[i] * a.h + col);
+      if (a.add_vec) x += __ldg(a.add_vec + col);
+      float d = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.dy)[yrow * a.h + col]);
+      if (a.drop_threshold != 0u)
+        d = dropout_keep(a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)col, a.drop_threshold)
+                ? d * a.drop_scale
+                : 0.f;
+      dg += d * (x - a.mean[i]) * a.rstd[i];
+      db += d;
+    }
+  }
+  __shared__ float sg[8][33], sb[8][33];
+  sg[rl][threadIdx.x & 31] = dg;
+  sb[rl][threadIdx.x & 31] = db;
+  __syncthreads();
+  if (rl == 0 && col < a.h) {
+    float g = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      g += sg[w][threadIdx.x];
+      b += sb[w][threadIdx.x];
+    }
+    if (a.dgamma) atomicAdd(a.dgamma + col, g);
+    if (a.dbeta) atomicAdd(a.dbeta + col, b);
+  }
+}
+
+// ------------------------------------------------------------------ row gathers
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src,
+                                   const int32_t* __restrict__ idx, __nv_bfloat16* __restrict__ dst,
+                                   int n, int h8) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * h8) return;
+  const int i = (int)(t / h8), c = (int)(t % h8);
+  const int s = idx[i];
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (s >= 0) v = reinterpret_cast<const uint4*>(src)[(long long)s * h8 + c];
+  reinterpret_cast<uint4*>(dst)[(long long)i * h8 + c] = v;
+}
+
+template <bool OUT_F32>
+__global__ void gather_sum_rows_kernel(const __nv_bfloat16* __restrict__ src,
+                                       const int32_t* __restrict__ off,
+                                       const int32_t* __restrict__ idx, void* __restrict__ dst, int n,
+                                       int h8) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * h8) return;
+  const int i = (int)(t / h8), c = (int)(t % h8);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int e0 = off[i], e1 = off[i + 1];
+  for (int e = e0; e < e1; ++e) {
+    float v[8];
+    load_bf16x8(src + ((long long)idx[e] * h8 + c) * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+  if (OUT_F32) {
+    if (e1 > e0) {
+      float* o = reinterpret_cast<float*>(dst) + ((long long)i * h8 + c) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += acc[j];
+    }
+  } else {
+    store_bf16x8(reinterpret_cast<__nv_bfloat16*>(dst) + ((long long)i * h8 + c) * 8, acc);
+  }
+}
+
+// out[n] += sum_m x[m, n]: block = 32 columns x 8 row lanes, grid.y splits the rows.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int m, int n,
+              float* __restrict__ out, int rows_per_block) {
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(m, r0 + rows_per_block);
+  float s = 0.f;
+  if (col < n)
+    for (int r = r0 + rl; r < r1; r += 8) s += __bfloat162float(x[(long long)r * ld + col]);
+  __shared__ float sm[8][33];
+  sm[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && col < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
+    atomicAdd(out + col, t);
+  }
+}
+
+__global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                const __nv_bfloat16* __restrict__ pre,
+                                __nv_bfloat16* __restrict__ out, long long n8) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n8) return;
+  float d[8], p[8];
+  load_bf16x8(dy + t * 8, d);
+  load_bf16x8(pre + t * 8, p);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) d[j] = p[j] > 0.f ? d[j] : 0.f;
+  store_bf16x8(out + t * 8, d);
+}
+
+__global__ void cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                            long long n) {
+  const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (t + 8 <= n) {
+    float v[8];
+    load_f32x8(src + t, v);
+    store_bf16x8(dst + t, v);
+  } else {
+    for (long long j = t; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+  }
+}
+
+static int check_ln(const hero_ln_args* a) {
+  HERO_REQUIRE(a != nullptr, "null ln args");
+  HERO_REQUIRE(a->x && a->gamma, "ln: null x/gamma");
+  HERO_REQUIRE(a->h > 0 && a->h % 8 == 0 && a->h <= 4352, "ln: unsupported row length %d", a->h);
+  HERO_REQUIRE(a->add_tab == nullptr || a->add_idx != nullptr, "ln: add_tab needs add_idx");
+  return HERO_OK;
+}
+
+}  // namespace hero
+
+using namespace hero;
+
+extern "C" int hero_ln_fwd(const hero_ln_args* a, void* stream) {
+  if (int rc = check_ln(a)) return rc;
+  HERO_REQUIRE(a->y && a->beta, "ln_fwd: null y/beta");
+  if (a->n_rows <= 0) return HERO_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = ceil_div(a->n_rows, LN_WARPS);
+  if (a->h <= 768)
+    ln_fwd_kernel<3><<<grid, LN_WARPS * 32, 0, st>>>(*a);
+  else
+    ln_fwd_kernel<17><<<grid, LN_WARPS * 32, 0, st>>>(*a);
+  HERO_LAUNCH_CHECK();
+  return HERO_OK;
+}
+
+extern "C" int hero_ln_bwd(const hero_ln_args* a, void* stream) {
+  if (int rc = check_ln(a)) return rc;
+  HERO_REQUIRE(a->dy && a->mean && a->rstd, "ln_bwd: null dy/mean/rstd");
+  if (a->n_rows <= 0) return HERO_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int sms = sm_count();
+  if (sms <= 0) return set_error(HERO_ERR_NO_DEVICE, "no CUDA device");
+  int grid = ceil_div(a->n_rows, LN_WARPS);
+  if (grid > sms * 4) grid = sms * 4;
+  const bool want_param = a->dgamma != nullptr || a->dbeta != nullptr;
+  if (a->h <= 768) {
+    if (want_param)
+      ln_bwd_kernel<3, true><<<grid, LN_WARPS * 32, 0, st>>>(*a);
+    else
+      ln_bwd_kernel<3, false><<<grid, LN_WARPS * 32, 0, st>>>(*a);
+    HERO_LAUNCH_CHECK();
+  } else {
+    if (a->dx || a->dx_drop || a->d_x_tab || a->d_add_tab) {
+      ln_bwd_kernel<17, false><<<grid, LN_WARPS * 32, 0, st>>>(*a);
+      HERO_LAUNCH_CHECK();
+    }
+    if (want_param) {
+      const int col_blocks = ceil_div(a->h, 32);
+      int row_splits = ceil_div(sms * 8, col_blocks);
+      if (row_splits > ceil_div(a->n_rows, 8)) row_splits = ceil_div(a->n_rows, 8);
+      if (row_splits < 1) row_splits = 1;
+      const int rpb = ceil_div(a->n_rows, row_splits);
+      dim3 g(col_blocks, ceil_div(a->n_rows, rpb));
+      ln_param_grad_kernel<<<g, 256, 0, st>>>(*a, rpb);
+      HERO_LAUNCH_CHECK();
+    }
+  }
+  return HERO_OK;
+}
+
+extern "C" int hero_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  HERO_REQUIRE(src && dst && n >= 0, "cast: bad args");
+  if (n == 0) return HERO_OK;
+  const long long groups = (n + 7) / 8;
+  cast_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  HERO_LAUNCH_CHECK();
+  return HERO_OK;
+}
+
+extern "C" int hero_gather_rows_bf16(const void* src, const int32_t* idx, void* dst, int32_t n,
+                                     int32_t h, void* stream) {
+  HERO_REQUIRE(src && idx && dst && h % 8 == 0, "gather_rows: bad args");
+  if (n <= 0) return HERO_OK;
+  const long long total = (long long)n * (h / 8);
+  gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0,
+                       reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), idx, reinterpret_cast<__nv_bfloat16*>(dst), n,
+      h / 8);
+  HERO_LAUNCH_CHECK();
+  return HERO_OK;
+}
+
+extern "C" int hero_gather_sum_rows_bf16(const void* src, const int32_t* off, const int32_t* idx,
+                                         void* dst, int32_t n, int32_t h, void* stream) {
+  HERO_REQUIRE(src && off && dst && h % 8 == 0, "gather_sum_rows: bad args");
+  if (n <= 0) return HERO_OK;
+  const long long total = (long long)n * (h / 8);
+  gather_sum_rows_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0,
+                                  reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), off, idx, dst, n, h / 8);
+  HERO_LAUNCH_CHECK();
+  return HERO_OK;
+}
+
+extern "C" int hero_gather_sum_rows_f32(const void* src, const int32_t* off, const int32_t* idx,
+                                        float* dst, int32_t n, int32_t h, void* stream) {
+  HERO_REQUIRE(src && off && dst && h % 8 == 0, "gather_sum_rows_f32: bad args");
+  if (n <= 0) return HERO_OK;
+  const long long total = (long long)n * (h / 8);
+  gather_sum_rows_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0,
+                                 reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), off, idx, dst, n, h / 8);
+  HERO_LAUNCH_CHECK();
+  return HERO_OK;
+}
+
+extern "C" int hero_colsum_bf16(const void* x, int64_t ld, int32_t m, int32_t n, float* out,
+                                void* stream) {
+  HERO_REQUIRE(x && out, "colsum: bad args");
+  if (m <= 0 || n <= 0) return HERO_OK;
+  const int sms = sm_count();
+  if (sms <= 0) return set_error(HERO_ERR_NO_DEVICE, "no CUDA device");
+  const int col_blocks = ceil_div(n, 32);
+  int row_splits = ceil_div(sms * 8, col_blocks);
+  if (row_splits > ceil_div(m, 8)) row_splits = ceil_div(m, 8);
+  if (row_splits < 1) row_splits = 1;
+  const int rpb = ceil_div(m, row_splits);
+  dim3 g(col_blocks, ceil_div(m, rpb));
+  colsum_kernel<<<g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), ld, m, n, out, rpb);
+  HERO_LAUNCH_CHECK();
+  return HERO_OK;
+}
+
+extern "C" int hero_relu_bwd_bf16(const void* dy, const void* pre, void* out, int64_t n,
+                                  void* stream) {
+  HERO_REQUIRE(dy && pre && out && n % 8 == 0, "relu_bwd: bad args");
+  if (n == 0) return HERO_OK;
+  const long long n8 = n / 8;
+  relu_bwd_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(pre),
+      reinterpret_cast<__nv_bfloat16*>(out), n8);
+  HERO_LAUNCH_CHECK();
+  return HERO_OK;
+}

@@ -1,0 +1,205 @@
+"""Tensor-level wrappers over the C-ABI: torch supplies device memory and the current stream,
+the arithmetic runs in `libhero_b200.so`. No autograd here (see `functional.py`).
+
+Every wrapper enqueues on torch's current CUDA stream, which is what the reference's
+PrefetchLoader has already synchronised the inputs against (data/loader.py:135-138).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_GELU_GRAD = 0, 1, 2, 3
+
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.HeroError("hero_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def drop_params(p, key):
+    """(threshold, key, scale) for dropout probability p; p == 0 disables."""
+    if p <= 0.0:
+        return 0, 0, 1.0
+    thr = min(int(p * 4294967296.0), 4294967295)
+    return thr, int(key) & 0xFFFFFFFF, 1.0 / (1.0 - p)
+
+
+def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None, resid=None,
+         aux_in=None, aux_out=None, act=ACT_NONE, accumulate_f32=False, drop=(0, 0, 1.0),
+         block_n=0, k_splits=0):
+    """out = epilogue(A·B) with the operand conventions of `hero_gemm_args`.
+
+    a: [M,K] (a_mn=False) or [K,M] (a_mn=True) bf16; b: [N,K] (b_mn=False) or [K,N] (b_mn=True).
+    """
+    _require_cuda(a, b, out)
+    assert a.dtype == BF16 and b.dtype == BF16
+    if m is None:
+        m = a.shape[1] if a_mn else a.shape[0]
+    if k is None:
+        k = a.shape[0] if a_mn else a.shape[1]
+    if n is None:
+        n = b.shape[1] if b_mn else b.shape[0]
+    g = _lib.GemmArgs()
+    g.a, g.b = _ptr(a), _ptr(b)
+    g.lda, g.ldb = a.stride(0), b.stride(0)
+    g.a_mn_major, g.b_mn_major = int(a_mn), int(b_mn)
+    g.m, g.n, g.k = m, n, k
+    g.bias = _ptr(bias)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == n
+    g.resid = _ptr(resid)
+    g.ld_resid = resid.stride(0) if resid is not None else 0
+    g.aux_in = _ptr(aux_in)
+    g.ld_aux_in = aux_in.stride(0) if aux_in is not None else 0
+    g.aux_out = _ptr(aux_out)
+    g.ld_aux_out = aux_out.stride(0) if aux_out is not None else 0
+    g.out = _ptr(out)
+    g.ld_out = out.stride(0)
+    g.act = act
+    g.out_f32_accumulate = int(accumulate_f32)
+    assert out.dtype == (torch.float32 if accumulate_f32 else BF16)
+    g.drop_threshold, g.drop_key, g.drop_scale = drop
+    g.block_n, g.k_splits = block_n, k_splits
+    _lib.check(_lib.lib().hero_gemm_bf16(C.byref(g), _stream()))
+    return out
+
+
+def _ln_args(x, gamma, beta, eps, n_rows, h, x_rows=None, add_tab=None, add_idx=None,
+             add_vec=None):
+    a = _lib.LnArgs()
+    a.x = _ptr(x)
+    a.x_is_f32 = int(x.dtype == torch.float32)
+    assert x.dtype in (torch.float32, BF16)
+    a.x_rows = _ptr(x_rows)
+    a.add_tab, a.add_idx, a.add_vec = _ptr(add_tab), _ptr(add_idx), _ptr(add_vec)
+    a.gamma, a.beta = _ptr(gamma), _ptr(beta)
+    a.eps = eps
+    a.n_rows, a.h = n_rows, h
+    a.x_pad_idx = -1
+    a.add_pad_idx = -1
+    for t in (x_rows, add_idx):
+        assert t is None or t.dtype == torch.int32
+    for t in (add_tab, add_vec, gamma, beta):
+        assert t is None or t.dtype == torch.float32
+    return a
+
+
+def ln_fwd(x, gamma, beta, eps, y, *, n_rows, x_rows=None, add_tab=None, add_idx=None,
+           add_vec=None, y_rows=None, mean=None, rstd=None, drop=(0, 0, 1.0)):
+    """Fused gather + add + LayerNorm (+dropout) + scatter; see `hero_ln_args`."""
+    _require_cuda(x, y)
+    h = gamma.numel()
+    a = _ln_args(x, gamma, beta, eps, n_rows, h, x_rows, add_tab, add_idx, add_vec)
+    a.y, a.y_rows = _ptr(y), _ptr(y_rows)
+    a.mean, a.rstd = _ptr(mean), _ptr(rstd)
+    a.drop_threshold, a.drop_key, a.drop_scale = drop
+    _lib.check(_lib.lib().hero_ln_fwd(C.byref(a), _stream()))
+    return y
+
+
+def ln_bwd(dy, x, gamma, mean, rstd, *, n_rows, x_rows=None, add_tab=None, add_idx=None,
+           add_vec=None, y_rows=None, drop=(0, 0, 1.0), dx=None, dx_drop=None,
+           drop2=(0, 0, 1.0), d_x_tab=None, x_pad_idx=-1, d_add_tab=None, add_pad_idx=-1,
+           dgamma=None, dbeta=None):
+    _require_cuda(dy, x)
+    h = gamma.numel()
+    a = _ln_args(x, gamma, None, 0.0, n_rows, h, x_rows, add_tab, add_idx, add_vec)
+    a.y_rows = _ptr(y_rows)
+    a.mean, a.rstd = _ptr(mean), _ptr(rstd)
+    a.drop_threshold, a.drop_key, a.drop_scale = drop
+    a.dy, a.dx, a.dx_drop = _ptr(dy), _ptr(dx), _ptr(dx_drop)
+    a.drop2_threshold, a.drop2_key, a.drop2_scale = drop2
+    a.d_x_tab, a.x_pad_idx = _ptr(d_x_tab), x_pad_idx
+    a.d_add_tab, a.add_pad_idx = _ptr(d_add_tab), add_pad_idx
+    a.dgamma, a.dbeta = _ptr(dgamma), _ptr(dbeta)
+    _lib.check(_lib.lib().hero_ln_bwd(C.byref(a), _stream()))
+
+
+def attn_fwd(qkv, cu_seqlens, ctx, *, n_seq, max_len, heads, head_dim=64, drop=(0, 0, 1.0)):
+    _require_cuda(qkv, cu_seqlens, ctx)
+    assert qkv.dtype == BF16 and cu_seqlens.dtype == torch.int32 and qkv.is_contiguous()
+    _lib.check(_lib.lib().hero_attn_fwd(
+        _ptr(qkv), _ptr(cu_seqlens), _ptr(ctx), n_seq, max_len, heads, head_dim,
+        1.0 / (head_dim ** 0.5), drop[0], drop[1], drop[2], _stream()))
+    return ctx
+
+
+def attn_bwd(qkv, cu_seqlens, dctx, dqkv, *, n_seq, max_len, heads, head_dim=64,
+             drop=(0, 0, 1.0)):
+    _require_cuda(qkv, cu_seqlens, dctx, dqkv)
+    assert dctx.is_contiguous() and dqkv.is_contiguous()
+    _lib.check(_lib.lib().hero_attn_bwd(
+        _ptr(qkv), _ptr(cu_seqlens), _ptr(dctx), _ptr(dqkv), n_seq, max_len, heads, head_dim,
+        1.0 / (head_dim ** 0.5), drop[0], drop[1], drop[2], _stream()))
+    return dqkv
+
+
+def cast_bf16(src, dst):
+    """dst (bf16, same numel) = src (fp32)."""
+    _require_cuda(src, dst)
+    assert src.dtype == torch.float32 and dst.dtype == BF16 and src.is_contiguous()
+    assert dst.is_contiguous() and src.numel() == dst.numel()
+    _lib.check(_lib.lib().hero_cast_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()))
+    return dst
+
+
+def gather_rows(src, idx, dst):
+    _require_cuda(src, idx, dst)
+    assert src.dtype == BF16 and dst.dtype == BF16 and idx.dtype == torch.int32
+    h = src.shape[-1]
+    _lib.check(_lib.lib().hero_gather_rows_bf16(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), h,
+                                                _stream()))
+    return dst
+
+
+def gather_sum_rows(src, off, idx, dst):
+    """dst[i] = sum_{e in off[i]:off[i+1]} src[idx[e]]; dst bf16 (overwrite) or f32 (accumulate)."""
+    _require_cuda(src, off, idx, dst)
+    assert src.dtype == BF16 and off.dtype == torch.int32 and idx.dtype == torch.int32
+    n, h = off.numel() - 1, src.shape[-1]
+    fn = (_lib.lib().hero_gather_sum_rows_f32 if dst.dtype == torch.float32
+          else _lib.lib().hero_gather_sum_rows_bf16)
+    _lib.check(fn(_ptr(src), _ptr(off), _ptr(idx), _ptr(dst), n, h, _stream()))
+    return dst
+
+
+def colsum(x, out):
+    """out[n] += sum_m x[m, n]  (x bf16 2-D, out fp32)."""
+    _require_cuda(x, out)
+    assert x.dtype == BF16 and out.dtype == torch.float32 and x.dim() == 2
+    _lib.check(_lib.lib().hero_colsum_bf16(_ptr(x), x.stride(0), x.shape[0], x.shape[1],
+                                           _ptr(out), _stream()))
+    return out
+
+
+def relu_bwd(dy, pre, out):
+    _require_cuda(dy, pre, out)
+    _lib.check(_lib.lib().hero_relu_bwd_bf16(_ptr(dy), _ptr(pre), _ptr(out), dy.numel(),
+                                             _stream()))
+    return out
+
+
+def adamw_step(p, g, m, v, p_bf16, *, step_size, beta1, beta2, eps, lr_wd, grad_scale=1.0):
+    _require_cuda(p, g, m, v)
+    _lib.check(_lib.lib().hero_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16),
+                                          p.numel(), step_size, beta1, beta2, eps, lr_wd,
+                                          grad_scale, _stream()))
+
+
+def sumsq(x, out):
+    _require_cuda(x, out)
+    _lib.check(_lib.lib().hero_sumsq_f32(_ptr(x), x.numel(), _ptr(out), _stream()))
+    return out

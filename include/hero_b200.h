@@ -1,0 +1,215 @@
+/*
+ * hero_b200 C-ABI — the drop-in boundary of the B200-native HERO encoder hot path.
+ *
+ * The reference (linjieli222/HERO) has no FFI layer: its boundary is the Python nn.Module
+ * surface of model/{layers,embed,encoder,model}.py. Each entry point below replaces the device
+ * arithmetic of one reference call site (cited per function, file:line relative to the reference
+ * repo). They are what a ctypes binding on the reference side binds.
+ *
+ * Conventions
+ *   - plain C types only: device pointers, sizes, strides in ELEMENTS unless a name says bytes.
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns 0 on
+ *     success or a non-zero hero_status; hero_last_error() describes the last failure of the
+ *     calling thread. No hidden allocation, no global mutable state besides cached device
+ *     attributes and TMA descriptor encode entry points.
+ *   - "bf16" buffers are raw uint16 bfloat16; "f32" are float.
+ *   - token-major packed layout: activations are [n_tokens, hidden] with only VALID (unmasked)
+ *     tokens present; sequences are described by cu_seqlens[n_seq + 1] (int32 prefix sums).
+ */
+#ifndef HERO_B200_H_
+#define HERO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum hero_status {
+  HERO_OK = 0,
+  HERO_ERR_INVALID = 1, /* bad argument / unsupported shape */
+  HERO_ERR_CUDA = 2,    /* CUDA runtime / driver error */
+  HERO_ERR_NO_DEVICE = 3
+} hero_status;
+
+/* Library / device info. */
+const char* hero_last_error(void);
+int hero_version(void);
+/* Returns SM count of the current device (148 on B200) or a negative hero_status. */
+int hero_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * GEMM family (tcgen05 / TMEM / TMA).   D[M,N] = epilogue( A · B^T-like contraction )
+ *
+ * Replaces every nn.Linear on the path — model/layers.py:125-127 (Q,K,V), :176 (attn out),
+ * :237 (FFN up + gelu :16-25), :251 (FFN down), model/embed.py:112 (img_linear),
+ * model/layers.py:82,90 (frame_transform Linear) — and their autograd backward
+ * (dgrad: dX = dY·W, wgrad: dW = dYᵀ·X).
+ *
+ * Operand addressing (bf16):
+ *   a_mn_major = 0 : A is [M, K] row-major, leading dim lda      (K contiguous)
+ *   a_mn_major = 1 : A is stored as [K, M] row-major, lda        (M contiguous; "transposed")
+ *   b_mn_major = 0 : B is [N, K] row-major, ldb                  (K contiguous; nn.Linear.weight)
+ *   b_mn_major = 1 : B is stored as [K, N] row-major, ldb        (N contiguous)
+ *   forward  Y = X·Wᵀ      : A = X  (0), B = W  (0)
+ *   dgrad    dX = dY·W     : A = dY (0), B = W  (1)   [W is [N_out, K_in] = [K', N']]
+ *   wgrad    dW = dYᵀ·X    : A = dY (1), B = X  (1), out_f32_accumulate = 1
+ * Epilogue, applied in this order on v = acc:
+ *   v += bias[n]                                  (bias != NULL; fp32)
+ *   if aux_out: aux_out[m,n] = bf16(v)            (pre-activation copy for backward)
+ *   act: 0 none | 1 gelu_erf(v) | 2 relu(v) | 3 v * gelu_erf'(aux_in[m,n])
+ *   dropout: v = keep(m*N+n) ? v * drop_scale : 0 (drop_threshold != 0; keep iff hash>=threshold)
+ *   v += resid[m,n]                               (resid != NULL; bf16)
+ *   out: bf16 store, or fp32 atomic accumulate (out_f32_accumulate; split-K allowed)
+ * Constraints: K % 8 == 0, N % 8 == 0, lds % 8 == 0, 16-byte aligned pointers; MN-major operands
+ * need their contiguous extent to be a multiple of 64.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct hero_gemm_args {
+  const void* a; /* bf16 */
+  const void* b; /* bf16 */
+  int64_t lda, ldb;
+  int32_t a_mn_major, b_mn_major;
+  int32_t m, n, k;
+  const float* bias;     /* [n] or NULL */
+  const void* resid;     /* bf16 [m, ld_resid] or NULL */
+  int64_t ld_resid;
+  const void* aux_in;    /* bf16 [m, ld_aux_in], required for act == 3 */
+  int64_t ld_aux_in;
+  void* aux_out;         /* bf16 [m, ld_aux_out] or NULL */
+  int64_t ld_aux_out;
+  void* out;             /* bf16 [m, ld_out] or f32 [m, ld_out] */
+  int64_t ld_out;
+  int32_t act;
+  int32_t out_f32_accumulate;
+  uint32_t drop_threshold; /* 0 = no dropout; else p * 2^32 */
+  uint32_t drop_key;
+  float drop_scale;        /* 1 / (1 - p) */
+  int32_t block_n;         /* 0 = auto, else 128 or 256 */
+  int32_t k_splits;        /* 0 = auto (only > 1 when out_f32_accumulate) */
+} hero_gemm_args;
+
+int hero_gemm_bf16(const hero_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused row kernels: gather + add + LayerNorm (+ dropout) + scatter, one warp per row.
+ *
+ * Replaces apex FusedLayerNorm and the embedding sums around it:
+ *   model/layers.py:178,253      LN(dropout(dense(x)) + residual), eps 1e-12 (post-GEMM form:
+ *                                x = pre-LN sum written by the GEMM epilogue)
+ *   model/embed.py:44-58         LN(word[ids] + pos[pos_ids] + type[1]); dropout
+ *                                (x = word table f32, x_rows = ids, add_tab = pos table,
+ *                                 add_vec = type row)
+ *   model/embed.py:108-116       img: x (+ mask_emb[mask]) -> LN_4352 ; then after img_linear
+ *                                LN(proj + pos_img[k] + type[1]); dropout
+ *   model/embed.py:156-160       LN(frame_feat + pos[t]); dropout
+ *   model/layers.py:88-89        LinearLayer.LayerNorm over the 4352-d frame feature
+ * Forward, for output row i in [0, n_rows):
+ *   s = X[x_rows ? x_rows[i] : i]  (bf16 or f32, row length H)
+ *       + (add_tab ? add_tab[add_idx[i]] : 0) + (add_vec ? add_vec : 0)
+ *   y = (s - mean(s)) * rsqrt(var_biased(s) + eps) * gamma + beta      (fp32 statistics)
+ *   y = dropout(y)  (element index i*H + j)  -> bf16 -> Y[y_rows ? y_rows[i] : i]
+ *   mean[i], rstd[i] saved when non-NULL.
+ * Backward recomputes s from the same gather description and returns
+ *   dx[i] (bf16, grad wrt s), optional dx_drop[i] = dx[i] * mask2 * scale2 (the gradient that
+ *   flows into the dropout'ed GEMM branch of a post-GEMM LN), fp32 atomic scatter-adds of dx into
+ *   d_x_tab[x_rows[i]] / d_add_tab[add_idx[i]], and dgamma/dbeta (atomic accumulate per block).
+ *   Rows whose x_rows / add_idx equal *_pad_idx get no table gradient (nn.Embedding padding_idx).
+ *   Heavily shared tables (position / type rows) are better reduced with
+ *   hero_gather_sum_rows_f32 / hero_colsum_bf16 over dx than with the atomic path.
+ * Constraints: H % 8 == 0, H <= 4352.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct hero_ln_args {
+  /* gather description (shared by fwd and bwd) */
+  const void* x;
+  int32_t x_is_f32;
+  const int32_t* x_rows;   /* NULL = identity */
+  const float* add_tab;    /* NULL = none */
+  const int32_t* add_idx;
+  const float* add_vec;    /* NULL = none */
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int32_t n_rows, h;
+  /* forward outputs / backward saved stats */
+  void* y;                 /* bf16 */
+  const int32_t* y_rows;   /* NULL = identity; also indexes dy in bwd */
+  float* mean;
+  float* rstd;
+  /* dropout applied to the LN output */
+  uint32_t drop_threshold, drop_key;
+  float drop_scale;
+  /* backward only */
+  const void* dy;          /* bf16, indexed like y */
+  void* dx;                /* bf16 [n_rows, h] or NULL */
+  void* dx_drop;           /* bf16 [n_rows, h] or NULL */
+  uint32_t drop2_threshold, drop2_key;
+  float drop2_scale;
+  float* d_x_tab;          /* f32 table grad (scatter by x_rows) or NULL */
+  int32_t x_pad_idx;       /* -1 = none */
+  float* d_add_tab;        /* f32 or NULL */
+  int32_t add_pad_idx;     /* -1 = none */
+  float* dgamma;           /* f32 [h] or NULL */
+  float* dbeta;            /* f32 [h] or NULL */
+} hero_ln_args;
+
+int hero_ln_fwd(const hero_ln_args* args, void* stream);
+int hero_ln_bwd(const hero_ln_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Variable-length multi-head self-attention over packed sequences.
+ *
+ * Replaces model/layers.py:129-160 (transpose_for_scores, QK^T/sqrt(d) + additive -10000 key
+ * mask, softmax, dropout on probabilities, P·V, head merge). Only valid tokens exist in the packed
+ * layout, so the key-padding mask of model/layers.py:299-302 is expressed by cu_seqlens.
+ *   qkv  bf16 [n_tokens, 3*heads*head_dim]  (Q | K | V, each head-major inside)
+ *   ctx  bf16 [n_tokens, heads*head_dim]
+ * Constraints: head_dim == 64, max_len <= 128.
+ * ---------------------------------------------------------------------------------------- */
+int hero_attn_fwd(const void* qkv, const int32_t* cu_seqlens, void* ctx, int32_t n_seq,
+                  int32_t max_len, int32_t heads, int32_t head_dim, float scale,
+                  uint32_t drop_threshold, uint32_t drop_key, float drop_scale, void* stream);
+int hero_attn_bwd(const void* qkv, const int32_t* cu_seqlens, const void* dctx, void* dqkv,
+                  int32_t n_seq, int32_t max_len, int32_t heads, int32_t head_dim, float scale,
+                  uint32_t drop_threshold, uint32_t drop_key, float drop_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Row utilities (HBM-bound).
+ * ---------------------------------------------------------------------------------------- */
+/* dst[i] = bf16(src[i]); keeps bf16 working copies of the fp32 master weights. */
+int hero_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* dst[i, :] = idx[i] >= 0 ? src[idx[i], :] : 0   (bf16 rows of length h, h % 8 == 0).
+ * Packs/unpacks padded <-> packed token layouts (replaces torch.gather at
+ * model/encoder.py:271-279) and is the backward of hero_gather_sum_rows_bf16. */
+int hero_gather_rows_bf16(const void* src, const int32_t* idx, void* dst, int32_t n, int32_t h,
+                          void* stream);
+/* dst[i, :] = sum_{e in [off[i], off[i+1])} src[idx[e], :]   (CSR gather-sum, fp32 accumulate).
+ * Deterministic replacement of collect_frame_outputs (model/model.py:156-187). */
+int hero_gather_sum_rows_bf16(const void* src, const int32_t* off, const int32_t* idx, void* dst,
+                              int32_t n, int32_t h, void* stream);
+/* Same CSR gather-sum over bf16 rows but accumulating into fp32 rows: dst[i, :] += sum(...).
+ * Deterministic embedding-table gradients (position tables) from the LN backward's dx. */
+int hero_gather_sum_rows_f32(const void* src, const int32_t* off, const int32_t* idx, float* dst,
+                             int32_t n, int32_t h, void* stream);
+/* out[n] += sum_m x[m, n]  (bias gradients). */
+int hero_colsum_bf16(const void* x, int64_t ld, int32_t m, int32_t n, float* out, void* stream);
+/* out = dy * (pre > 0)   (ReLU backward of model/layers.py:92). */
+int hero_relu_bwd_bf16(const void* dy, const void* pre, void* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer (flat buffers). Follows optim/adamw.py:80-104 exactly:
+ *   g' = g * grad_scale
+ *   m = b1*m + (1-b1)*g' ; v = b2*v + (1-b2)*g'^2
+ *   p -= step_size * m / (sqrt(v) + eps)      step_size = lr*sqrt(1-b2^t)/(1-b1^t) (host-computed)
+ *   p -= lr_wd * p                            lr_wd = lr * weight_decay (0 for bias/LayerNorm)
+ * and optionally refreshes the bf16 working copy.
+ * ---------------------------------------------------------------------------------------- */
+int hero_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n,
+                    float step_size, float beta1, float beta2, float eps, float lr_wd,
+                    float grad_scale, void* stream);
+/* out[0] += sum x^2 (global-norm clipping, train_vcmr.py:258-259). */
+int hero_sumsq_f32(const float* x, int64_t n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HERO_B200_H_ */

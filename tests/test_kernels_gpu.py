@@ -1,0 +1,314 @@
+"""Per-kernel numerics on the GPU: every C-ABI entry point against a plain torch fp32
+restatement of the same op on the same (bf16-rounded) inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rand(shape, scale=1.0, seed=0, dtype=BF16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).to(_dev())
+
+
+def _close(got, ref, atol, rtol, what=""):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = (err > tol).sum().item()
+    assert bad == 0, (f"{what}: {bad}/{err.numel()} elements out of tolerance; "
+                      f"max abs err {err.max().item():.4g}, ref max {ref.abs().max().item():.4g}")
+
+
+# ------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (300, 768, 768), (16000, 768, 768),
+                                   (1000, 2304, 768), (515, 3072, 768), (640, 768, 3072),
+                                   (777, 768, 4352), (8, 128, 64)])
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_gemm_forward_kmajor(m, n, k, block_n):
+    from hero_b200 import ops
+    a, w = _rand((m, k), seed=1), _rand((n, k), 0.05, seed=2)
+    bias = _rand((n,), 0.5, seed=3, dtype=torch.float32)
+    out = torch.empty(m, n, dtype=BF16, device=_dev())
+    ops.gemm(a, w, out, bias=bias, block_n=block_n)
+    ref = a.float() @ w.float().t() + bias
+    _close(out, ref, 2e-2, 1.6e-2, f"gemm fwd {m}x{n}x{k} bn{block_n}")
+
+
+@pytest.mark.parametrize("act", ["gelu", "relu", "resid"])
+def test_gemm_epilogues(act):
+    from hero_b200 import ops
+    m, n, k = 1000, 768, 768
+    a, w = _rand((m, k), seed=4), _rand((n, k), 0.05, seed=5)
+    bias = _rand((n,), 0.5, seed=6, dtype=torch.float32)
+    resid = _rand((m, n), seed=7)
+    out = torch.empty(m, n, dtype=BF16, device=_dev())
+    pre = a.float() @ w.float().t() + bias
+    if act == "gelu":
+        aux = torch.empty(m, n, dtype=BF16, device=_dev())
+        ops.gemm(a, w, out, bias=bias, act=ops.ACT_GELU, aux_out=aux)
+        _close(aux, pre, 2e-2, 1.6e-2, "pre-activation copy")
+        ref = torch.nn.functional.gelu(pre)
+    elif act == "relu":
+        ops.gemm(a, w, out, bias=bias, act=ops.ACT_RELU, resid=resid)
+        ref = torch.relu(pre) + resid.float()
+    else:
+        ops.gemm(a, w, out, bias=bias, resid=resid)
+        ref = pre + resid.float()
+    _close(out, ref, 2e-2, 1.6e-2, f"epilogue {act}")
+
+
+@pytest.mark.parametrize("m,n,k", [(1000, 768, 3072), (16000, 768, 2304), (300, 3072, 768)])
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_gemm_dgrad_b_mnmajor(m, n, k, block_n):
+    """dX[m, n] = dY[m, k] @ W[k, n]  (W stored [k, n]: the nn.Linear weight [out=k, in=n])."""
+    from hero_b200 import ops
+    dy, w = _rand((m, k), seed=8), _rand((k, n), 0.05, seed=9)
+    out = torch.empty(m, n, dtype=BF16, device=_dev())
+    ops.gemm(dy, w, out, b_mn=True, block_n=block_n)
+    _close(out, dy.float() @ w.float(), 2e-2, 1.6e-2, "dgrad")
+
+
+def test_gemm_dgrad_gelu_grad():
+    from hero_b200 import ops
+    m, n, k = 515, 3072, 768
+    dy, w, pre = _rand((m, k), seed=10), _rand((k, n), 0.05, seed=11), _rand((m, n), seed=12)
+    out = torch.empty(m, n, dtype=BF16, device=_dev())
+    ops.gemm(dy, w, out, b_mn=True, act=ops.ACT_GELU_GRAD, aux_in=pre)
+    x = pre.float()
+    dgelu = 0.5 * (1 + torch.erf(x / math.sqrt(2))) + x * torch.exp(-0.5 * x * x) / math.sqrt(
+        2 * math.pi)
+    _close(out, (dy.float() @ w.float()) * dgelu, 2e-2, 1.6e-2, "dgrad*gelu'")
+
+
+@pytest.mark.parametrize("tokens,n_out,k_in", [(1000, 768, 768), (16000, 3072, 768),
+                                               (3333, 768, 3072), (3200, 768, 4352)])
+@pytest.mark.parametrize("k_splits", [0, 1, 3])
+def test_gemm_wgrad_mnmajor(tokens, n_out, k_in, k_splits):
+    """dW[n_out, k_in] += dY[tokens, n_out]^T @ X[tokens, k_in], fp32 accumulate."""
+    from hero_b200 import ops
+    dy, x = _rand((tokens, n_out), 0.1, seed=13), _rand((tokens, k_in), seed=14)
+    out = torch.full((n_out, k_in), 0.5, dtype=torch.float32, device=_dev())
+    ops.gemm(dy, x, out, a_mn=True, b_mn=True, accumulate_f32=True, k_splits=k_splits)
+    ref = 0.5 + dy.float().t() @ x.float()
+    _close(out, ref, 5e-2, 5e-3, "wgrad")
+
+
+def test_gemm_dropout_epilogue_is_deterministic_and_scaled():
+    from hero_b200 import ops
+    m, n, k = 512, 768, 768
+    a, w = _rand((m, k), seed=15), _rand((n, k), 0.05, seed=16)
+    drop = ops.drop_params(0.1, 1234)
+    o1 = torch.empty(m, n, dtype=BF16, device=_dev())
+    o2 = torch.empty_like(o1)
+    ops.gemm(a, w, o1, drop=drop)
+    ops.gemm(a, w, o2, drop=drop)
+    assert torch.equal(o1, o2)
+    ref = a.float() @ w.float().t()
+    kept = o1.float() != 0
+    frac = kept.float().mean().item()
+    assert abs(frac - 0.9) < 0.01, frac
+    _close(o1.float()[kept], (ref / 0.9)[kept], 3e-2, 2e-2, "kept elements scaled by 1/(1-p)")
+
+
+# ------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("h,eps", [(768, 1e-12), (768, 1e-5), (4352, 1e-5), (256, 1e-5)])
+def test_ln_fwd_bwd_plain(h, eps):
+    from hero_b200 import ops
+    n = 1037
+    x = _rand((n, h), 2.0, seed=20)
+    gamma = _rand((h,), 1.0, seed=21, dtype=torch.float32)
+    beta = _rand((h,), 1.0, seed=22, dtype=torch.float32)
+    y = torch.empty(n, h, dtype=BF16, device=_dev())
+    mean = torch.empty(n, device=_dev())
+    rstd = torch.empty(n, device=_dev())
+    ops.ln_fwd(x, gamma, beta, eps, y, n_rows=n, mean=mean, rstd=rstd)
+    xr = x.float().requires_grad_(True)
+    g = gamma.clone().requires_grad_(True)
+    b = beta.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (h,), g, b, eps)
+    _close(y, ref, 2e-2, 1.6e-2, "ln fwd")
+    dy = _rand((n, h), 1.0, seed=23)
+    ref.backward(dy.float())
+    dx = torch.empty(n, h, dtype=BF16, device=_dev())
+    dgamma = torch.zeros(h, device=_dev())
+    dbeta = torch.zeros(h, device=_dev())
+    ops.ln_bwd(dy, x, gamma, mean, rstd, n_rows=n, dx=dx, dgamma=dgamma, dbeta=dbeta)
+    _close(dx, xr.grad, 3e-2, 2e-2, "ln dx")
+    _close(dgamma, g.grad, 0.5, 2e-2, "ln dgamma")
+    _close(dbeta, b.grad, 0.5, 2e-2, "ln dbeta")
+
+
+def test_ln_gather_add_scatter_embedding_form():
+    """Text-embedding form: LN(word[ids] + pos[pid] + type) written to scattered rows."""
+    from hero_b200 import ops
+    h, vocab, n = 768, 1000, 777
+    word = _rand((vocab, h), 0.02, seed=30, dtype=torch.float32)
+    pos = _rand((64, h), 0.02, seed=31, dtype=torch.float32)
+    typ = _rand((h,), 0.02, seed=32, dtype=torch.float32)
+    gamma = _rand((h,), 1.0, seed=33, dtype=torch.float32)
+    beta = _rand((h,), 0.1, seed=34, dtype=torch.float32)
+    g = torch.Generator().manual_seed(35)
+    ids = torch.randint(0, vocab, (n,), generator=g).int().to(_dev())
+    pid = torch.randint(0, 64, (n,), generator=g).int().to(_dev())
+    dst = torch.randperm(n + 50, generator=g)[:n].int().to(_dev())
+    y = torch.zeros(n + 50, h, dtype=BF16, device=_dev())
+    mean = torch.empty(n, device=_dev())
+    rstd = torch.empty(n, device=_dev())
+    ops.ln_fwd(word, gamma, beta, 1e-5, y, n_rows=n, x_rows=ids, add_tab=pos, add_idx=pid,
+               add_vec=typ, y_rows=dst, mean=mean, rstd=rstd)
+    wr = word.clone().requires_grad_(True)
+    pr = pos.clone().requires_grad_(True)
+    s = wr[ids.long()] + pr[pid.long()] + typ
+    ref = torch.nn.functional.layer_norm(s, (h,), gamma, beta, 1e-5)
+    _close(y[dst.long()], ref, 2e-2, 1.6e-2, "embedding ln fwd")
+    dyfull = _rand((n + 50, h), 1.0, seed=36)
+    ref.backward(dyfull[dst.long()].float())
+    dword = torch.zeros_like(word)
+    dpos = torch.zeros_like(pos)
+    dx = torch.empty(n, h, dtype=BF16, device=_dev())
+    ops.ln_bwd(dyfull, word, gamma, mean, rstd, n_rows=n, x_rows=ids, add_tab=pos, add_idx=pid,
+               add_vec=typ, y_rows=dst, dx=dx, d_x_tab=dword, d_add_tab=dpos)
+    _close(dword, wr.grad, 5e-2, 3e-2, "word table grad (atomic scatter)")
+    _close(dpos, pr.grad, 0.3, 3e-2, "pos table grad (atomic scatter)")
+
+
+def test_ln_dropout_mask_matches_between_fwd_and_bwd():
+    from hero_b200 import ops
+    n, h = 512, 768
+    x = _rand((n, h), 1.0, seed=40)
+    gamma = torch.ones(h, device=_dev())
+    beta = torch.zeros(h, device=_dev())
+    drop = ops.drop_params(0.1, 99)
+    y = torch.empty(n, h, dtype=BF16, device=_dev())
+    mean = torch.empty(n, device=_dev())
+    rstd = torch.empty(n, device=_dev())
+    ops.ln_fwd(x, gamma, beta, 1e-5, y, n_rows=n, mean=mean, rstd=rstd, drop=drop)
+    keep = (y.float() != 0)
+    assert abs(keep.float().mean().item() - 0.9) < 0.01
+    # backward of sum(y): dy = 1 -> effective dy is mask/keep; compare with torch using that mask
+    dy = torch.ones(n, h, dtype=BF16, device=_dev())
+    dx = torch.empty(n, h, dtype=BF16, device=_dev())
+    ops.ln_bwd(dy, x, gamma, mean, rstd, n_rows=n, dx=dx, drop=drop)
+    xr = x.float().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (h,), gamma, beta, 1e-5)
+    (ref * keep.float() / 0.9).sum().backward()
+    _close(dx, xr.grad, 3e-2, 3e-2, "ln dx through dropout")
+
+
+# ------------------------------------------------------------------------------ attention
+def _attn_ref(qkv, lens, heads):
+    h = heads * 64
+    outs, off = [], 0
+    for n in lens:
+        blk = qkv[off:off + n]
+        q, k, v = (blk[:, i * h:(i + 1) * h].reshape(n, heads, 64).transpose(0, 1)
+                   for i in range(3))
+        p = torch.softmax(q @ k.transpose(1, 2) / 8.0, dim=-1)
+        outs.append((p @ v).transpose(0, 1).reshape(n, h))
+        off += n
+    return torch.cat(outs, 0)
+
+
+@pytest.mark.parametrize("lens", [[25] * 40, [1, 7, 33, 64, 100, 128, 2, 90], [100] * 8])
+def test_attention_fwd_bwd(lens):
+    from hero_b200 import ops
+    heads = 12
+    ntok = sum(lens)
+    qkv = _rand((ntok, 3 * heads * 64), 1.0, seed=50)
+    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=_dev())
+    ctx = torch.empty(ntok, heads * 64, dtype=BF16, device=_dev())
+    ops.attn_fwd(qkv, cu, ctx, n_seq=len(lens), max_len=max(lens), heads=heads)
+    qr = qkv.float().requires_grad_(True)
+    ref = _attn_ref(qr, lens, heads)
+    _close(ctx, ref, 2e-2, 1.6e-2, "attention fwd")
+    dctx = _rand((ntok, heads * 64), 1.0, seed=51)
+    ref.backward(dctx.float())
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(qkv, cu, dctx, dqkv, n_seq=len(lens), max_len=max(lens), heads=heads)
+    _close(dqkv, qr.grad, 4e-2, 3e-2, "attention bwd")
+
+
+def test_attention_rejects_long_sequences():
+    from hero_b200 import ops, _lib
+    qkv = _rand((200, 3 * 768), seed=52)
+    cu = torch.tensor([0, 200], dtype=torch.int32, device=_dev())
+    ctx = torch.empty(200, 768, dtype=BF16, device=_dev())
+    with pytest.raises(_lib.HeroError):
+        ops.attn_fwd(qkv, cu, ctx, n_seq=1, max_len=200, heads=12)
+
+
+# ------------------------------------------------------------------------------ row utilities
+def test_gather_and_gather_sum_rows():
+    from hero_b200 import ops
+    h = 768
+    src = _rand((500, h), seed=60)
+    g = torch.Generator().manual_seed(61)
+    idx = torch.randint(-1, 500, (700,), generator=g).int().to(_dev())
+    dst = torch.empty(700, h, dtype=BF16, device=_dev())
+    ops.gather_rows(src, idx, dst)
+    ref = torch.where((idx >= 0)[:, None], src[idx.clamp(min=0).long()], torch.zeros_like(dst))
+    assert torch.equal(dst, ref)
+    counts = torch.randint(0, 4, (300,), generator=g)
+    off = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)]).int().to(_dev())
+    cidx = torch.randint(0, 500, (int(counts.sum()),), generator=g).int().to(_dev())
+    out = torch.empty(300, h, dtype=BF16, device=_dev())
+    ops.gather_sum_rows(src, off, cidx, out)
+    ref = torch.zeros(300, h, device=_dev())
+    rows = torch.repeat_interleave(torch.arange(300), counts).to(_dev())
+    ref.index_add_(0, rows, src[cidx.long()].float())
+    _close(out, ref, 2e-2, 1e-2, "gather_sum bf16")
+    out32 = torch.ones(300, h, device=_dev())
+    ops.gather_sum_rows(src, off, cidx, out32)
+    _close(out32, ref + 1.0, 1e-3, 1e-3, "gather_sum f32 accumulate")
+
+
+def test_colsum_relu_bwd_cast():
+    from hero_b200 import ops
+    x = _rand((3201, 768), seed=70)
+    out = torch.ones(768, device=_dev())
+    ops.colsum(x, out)
+    _close(out, 1.0 + x.float().sum(0), 5e-2, 1e-3, "colsum")
+    dy, pre = _rand((100, 768), seed=71), _rand((100, 768), seed=72)
+    o = torch.empty_like(dy)
+    ops.relu_bwd(dy, pre, o)
+    assert torch.equal(o, torch.where(pre.float() > 0, dy, torch.zeros_like(dy)))
+    src = _rand((1000, 77), seed=73, dtype=torch.float32).contiguous()
+    dst = torch.empty(1000, 77, dtype=BF16, device=_dev())
+    ops.cast_bf16(src, dst)
+    assert torch.equal(dst, src.to(BF16))
+
+
+def test_adamw_matches_reference_update_rule():
+    """optim/adamw.py:80-104 restated in torch on the same numbers."""
+    from hero_b200 import ops
+    n = 100003
+    p = _rand((n,), 0.05, seed=80, dtype=torch.float32)
+    g = _rand((n,), 0.01, seed=81, dtype=torch.float32)
+    m = _rand((n,), 0.01, seed=82, dtype=torch.float32)
+    v = _rand((n,), 0.01, seed=83, dtype=torch.float32).abs()
+    lr, b1, b2, eps, wd, t = 1e-4, 0.9, 0.98, 1e-6, 0.01, 7
+    rp, rm, rv = p.clone(), m.clone(), v.clone()
+    rm.mul_(b1).add_(g, alpha=1 - b1)
+    rv.mul_(b2).addcmul_(g, g, value=1 - b2)
+    denom = rv.sqrt().add_(eps)
+    step = lr * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+    rp.addcdiv_(rm, denom, value=-step)
+    rp.add_(rp, alpha=-lr * wd)
+    pb = torch.empty(n, dtype=BF16, device=_dev())
+    ops.adamw_step(p, g, m, v, pb, step_size=step, beta1=b1, beta2=b2, eps=eps, lr_wd=lr * wd)
+    _close(p, rp, 1e-7, 1e-5, "adamw p")
+    _close(m, rm, 1e-8, 1e-5, "adamw m")
+    _close(v, rv, 1e-9, 1e-5, "adamw v")
+    assert torch.equal(pb, p.to(BF16))
+    s = torch.zeros(1, device=_dev())
+    ops.sumsq(g, s)
+    _close(s, (g.double() ** 2).sum().float().reshape(1), 0, 1e-4, "sumsq")
