@@ -387,8 +387,7 @@ extern "C" int hero_gemm_bf16(const hero_gemm_args* g, void* stream) {
   HERO_REQUIRE(g != nullptr, "null args");
   HERO_REQUIRE(g->a && g->b && g->out, "null operand pointer");
   HERO_REQUIRE(g->m > 0 && g->n > 0 && g->k > 0, "empty gemm %dx%dx%d", g->m, g->n, g->k);
-  HERO_REQUIRE(g->k % 8 == 0 && g->n % 8 == 0, "n and k must be multiples of 8 (n=%d k=%d)", g->n,
-               g->k);
+  HERO_REQUIRE(g->n % 8 == 0, "n must be a multiple of 8 (n=%d)", g->n);
   HERO_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0 && g->ld_out % 4 == 0, "unaligned leading dim");
   HERO_REQUIRE(g->act != ACT_GELU_GRAD || g->aux_in != nullptr, "act=3 needs aux_in");
   if (g->a_mn_major) HERO_REQUIRE(g->m % 64 == 0, "MN-major A needs m %% 64 == 0 (m=%d)", g->m);
