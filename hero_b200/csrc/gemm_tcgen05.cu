@@ -53,24 +53,28 @@ struct GemmCfg {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // epilogue staging: per epilogue warp two slabs of 32 rows x 64 bf16 (128 B rows, swizzled)
+  static constexpr int SLAB_BYTES = 32 * 128;
+  static constexpr int STAGING_BYTES = 4 * 2 * SLAB_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + STAGING_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFFSET + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-// Epilogue on 8 consecutive columns of one row.
-template <int ACT, int OUT_F32>
-__device__ __forceinline__ void epilogue8(float (&v)[8], int row, int col, const GemmShape& s,
-                                          const GemmEpilogue& e) {
-  if (e.bias != nullptr) {
+// Epilogue arithmetic on 8 consecutive columns of one row (v in/out). `inb` guards every global
+// read (rows >= M / cols >= N hold don't-care values that the TMA store clips). When `pre` is
+// non-null it receives the packed pre-activation (bias added) for the aux_out copy.
+template <int ACT>
+__device__ __forceinline__ void epilogue_math8(float (&v)[8], uint4* pre, bool inb, int row, int col,
+                                               const GemmShape& s, const GemmEpilogue& e) {
+  if (e.bias != nullptr && inb) {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
     v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
   }
-  if (e.aux_out != nullptr) {
-    uint4 p;
-    p.x = pack_bf16x2(v[0], v[1]); p.y = pack_bf16x2(v[2], v[3]);
-    p.z = pack_bf16x2(v[4], v[5]); p.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(e.aux_out + (long long)row * e.ld_aux_out + col) = p;
+  if (pre != nullptr) {
+    pre->x = pack_bf16x2(v[0], v[1]); pre->y = pack_bf16x2(v[2], v[3]);
+    pre->z = pack_bf16x2(v[4], v[5]); pre->w = pack_bf16x2(v[6], v[7]);
   }
   if (ACT == ACT_GELU) {
 #pragma unroll
@@ -79,7 +83,8 @@ __device__ __forceinline__ void epilogue8(float (&v)[8], int row, int col, const
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
   } else if (ACT == ACT_GELU_GRAD) {
-    const uint4 p = *reinterpret_cast<const uint4*>(e.aux_in + (long long)row * e.ld_aux_in + col);
+    uint4 p = make_uint4(0, 0, 0, 0);
+    if (inb) p = *reinterpret_cast<const uint4*>(e.aux_in + (long long)row * e.ld_aux_in + col);
     const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -94,7 +99,7 @@ __device__ __forceinline__ void epilogue8(float (&v)[8], int row, int col, const
     for (int j = 0; j < 8; ++j)
       v[j] = dropout_keep(e.drop_key, base + j, e.drop_threshold) ? v[j] * e.drop_scale : 0.0f;
   }
-  if (e.resid != nullptr) {
+  if (e.resid != nullptr && inb) {
     const uint4 p = *reinterpret_cast<const uint4*>(e.resid + (long long)row * e.ld_resid + col);
     const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
@@ -104,27 +109,14 @@ __device__ __forceinline__ void epilogue8(float (&v)[8], int row, int col, const
       v[2 * j + 1] += x.y;
     }
   }
-  if (OUT_F32) {
-    float* o = reinterpret_cast<float*>(e.out) + (long long)row * e.ld_out + col;
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]), "f"(v[1]),
-                 "f"(v[2]), "f"(v[3])
-                 : "memory");
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(v[4]),
-                 "f"(v[5]), "f"(v[6]), "f"(v[7])
-                 : "memory");
-  } else {
-    uint4 p;
-    p.x = pack_bf16x2(v[0], v[1]); p.y = pack_bf16x2(v[2], v[3]);
-    p.z = pack_bf16x2(v[4], v[5]); p.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(e.out) + (long long)row * e.ld_out +
-                              col) = p;
-  }
 }
 
 template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT_F32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                    const __grid_constant__ CUtensorMap tmap_b, const GemmShape s,
+                    const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_out,
+                    const __grid_constant__ CUtensorMap tmap_aux, const GemmShape s,
                     const GemmEpilogue e) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
@@ -132,7 +124,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFFSET);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full_bar = bars + 2 * STAGES;
@@ -145,6 +137,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (!OUT_F32) tma_prefetch_desc(&tmap_out);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -237,6 +230,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else {
     // ------------------------------------------------------------- epilogue warps
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    uint8_t* slabs = smem + STAGES * Cfg::STAGE_BYTES + q * (2 * Cfg::SLAB_BYTES);
+    const bool has_aux = (e.aux_out != nullptr);
+    uint32_t slab_it = 0;
     uint32_t local_tile = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
       const int t2 = tile / s.k_splits;
@@ -246,31 +242,81 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t acc_ph = (local_tile >> 1) & 1u;
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after_sync();
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const int row0 = m_blk * BLOCK_M + q * 32;
+      const int row = row0 + lane;
       const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_addr + c * 32, r);
+      for (int c = 0; c < BLOCK_N / 64; ++c) {
+        const int col0 = n_blk * BLOCK_N + c * 64;
+        if (col0 >= s.N) break;  // warp-uniform
+        uint32_t r[2][32];
+        tmem_ld_32x32(t_addr + c * 64, r[0]);
+        tmem_ld_32x32(t_addr + c * 64 + 32, r[1]);
         tmem_ld_wait();
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        if (row < s.M) {
+        if (OUT_F32) {
+          if (row < s.M) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col < s.N) {
-              float v[8];
+            for (int g = 0; g < 8; ++g) {
+              const int col = col0 + g * 8;
+              if (col < s.N) {
+                float v[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-              epilogue8<ACT, OUT_F32>(v, row, col, s, e);
+                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g >> 2][(g & 3) * 8 + j]);
+                epilogue_math8<ACT>(v, nullptr, true, row, col, s, e);
+                float* o = reinterpret_cast<float*>(e.out) + (long long)row * e.ld_out + col;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]),
+                             "f"(v[1]), "f"(v[2]), "f"(v[3])
+                             : "memory");
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4),
+                             "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                             : "memory");
+              }
             }
           }
+        } else {
+          // stage the 32 x 64 bf16 slab(s) in swizzled smem and let TMA write full 128 B rows
+          uint8_t* out_slab;
+          uint8_t* aux_slab = nullptr;
+          if (has_aux) {
+            if (lane == 0) bulk_wait_read<0>();
+            out_slab = slabs;
+            aux_slab = slabs + Cfg::SLAB_BYTES;
+          } else {
+            if (lane == 0) bulk_wait_read<1>();
+            out_slab = slabs + (slab_it & 1u) * Cfg::SLAB_BYTES;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int col = col0 + g * 8;
+            const bool inb = (row < s.M) && (col < s.N);
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g >> 2][(g & 3) * 8 + j]);
+            uint4 pre;
+            epilogue_math8<ACT>(v, has_aux ? &pre : nullptr, inb, row, col, s, e);
+            uint4 pk;
+            pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+            pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+            const int off = lane * 128 + ((g ^ (lane & 7)) << 4);
+            *reinterpret_cast<uint4*>(out_slab + off) = pk;
+            if (has_aux) *reinterpret_cast<uint4*>(aux_slab + off) = pre;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, out_slab, col0, row0);
+            if (has_aux) tma_store_2d(&tmap_aux, aux_slab, col0, row0);
+            bulk_commit();
+          }
+          ++slab_it;
         }
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
+    if (!OUT_F32 && lane == 0) bulk_wait_all();
   }
 
   tc_fence_before_sync();
@@ -332,9 +378,30 @@ static int encode_mnmajor(CUtensorMap* map, const void* ptr, int k, int mn, long
   return HERO_OK;
 }
 
+// bf16 row-major output [rows, cols]: box = 64 cols x 32 rows (one epilogue-warp slab).
+static int encode_out(CUtensorMap* map, const void* ptr, int rows, int cols, long long ld) {
+  auto fn = get_encode_fn();
+  if (!fn) return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled(out %dx%d ld %lld) failed: %d", rows,
+                     cols, ld, (int)r);
+  return HERO_OK;
+}
+
+struct GemmMaps {
+  CUtensorMap a, b, out, aux;
+};
+
 template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT_F32>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& s,
-                  const GemmEpilogue& e, cudaStream_t stream) {
+static int launch(const GemmMaps& tm, const GemmShape& s, const GemmEpilogue& e,
+                  cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, ACT, OUT_F32>;
   static bool attr_set = false;
@@ -347,32 +414,32 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape&
   const int sms = sm_count();
   if (sms <= 0) return set_error(HERO_ERR_NO_DEVICE, "no CUDA device");
   const int grid = total < sms ? total : sms;
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, s, e);
+  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm.a, tm.b, tm.out, tm.aux, s, e);
   HERO_LAUNCH_CHECK();
   return HERO_OK;
 }
 
 template <int BLOCK_N>
-static int dispatch(const hero_gemm_args* g, const CUtensorMap& ta, const CUtensorMap& tb,
-                    const GemmShape& s, const GemmEpilogue& e, cudaStream_t st) {
+static int dispatch(const hero_gemm_args* g, const GemmMaps& tm, const GemmShape& s,
+                    const GemmEpilogue& e, cudaStream_t st) {
   const int layout = g->a_mn_major * 2 + g->b_mn_major;
   if (g->out_f32_accumulate) {
     HERO_REQUIRE(g->act == ACT_NONE, "fp32-accumulate output supports act=0 only");
-    if (layout == 3) return launch<BLOCK_N, 1, 1, ACT_NONE, 1>(ta, tb, s, e, st);
-    if (layout == 0) return launch<BLOCK_N, 0, 0, ACT_NONE, 1>(ta, tb, s, e, st);
+    if (layout == 3) return launch<BLOCK_N, 1, 1, ACT_NONE, 1>(tm, s, e, st);
+    if (layout == 0) return launch<BLOCK_N, 0, 0, ACT_NONE, 1>(tm, s, e, st);
     return set_error(HERO_ERR_INVALID, "fp32-accumulate supports layouts (0,0) and (1,1)");
   }
   if (layout == 0) {
     switch (g->act) {
-      case ACT_NONE: return launch<BLOCK_N, 0, 0, ACT_NONE, 0>(ta, tb, s, e, st);
-      case ACT_GELU: return launch<BLOCK_N, 0, 0, ACT_GELU, 0>(ta, tb, s, e, st);
-      case ACT_RELU: return launch<BLOCK_N, 0, 0, ACT_RELU, 0>(ta, tb, s, e, st);
+      case ACT_NONE: return launch<BLOCK_N, 0, 0, ACT_NONE, 0>(tm, s, e, st);
+      case ACT_GELU: return launch<BLOCK_N, 0, 0, ACT_GELU, 0>(tm, s, e, st);
+      case ACT_RELU: return launch<BLOCK_N, 0, 0, ACT_RELU, 0>(tm, s, e, st);
       default: break;
     }
   } else if (layout == 1) {
     switch (g->act) {
-      case ACT_NONE: return launch<BLOCK_N, 0, 1, ACT_NONE, 0>(ta, tb, s, e, st);
-      case ACT_GELU_GRAD: return launch<BLOCK_N, 0, 1, ACT_GELU_GRAD, 0>(ta, tb, s, e, st);
+      case ACT_NONE: return launch<BLOCK_N, 0, 1, ACT_NONE, 0>(tm, s, e, st);
+      case ACT_GELU_GRAD: return launch<BLOCK_N, 0, 1, ACT_GELU_GRAD, 0>(tm, s, e, st);
       default: break;
     }
   }
@@ -443,20 +510,33 @@ extern "C" int hero_gemm_bf16(const hero_gemm_args* g, void* stream) {
   e.drop_key = g->drop_key;
   e.drop_scale = g->drop_scale;
 
-  CUtensorMap ta, tb;
+  GemmMaps tm;
   int rc;
   if (g->a_mn_major)
-    rc = encode_mnmajor(&ta, g->a, g->k, g->m, g->lda, BLOCK_M);
+    rc = encode_mnmajor(&tm.a, g->a, g->k, g->m, g->lda, BLOCK_M);
   else
-    rc = encode_kmajor(&ta, g->a, g->m, g->k, g->lda, BLOCK_M);
+    rc = encode_kmajor(&tm.a, g->a, g->m, g->k, g->lda, BLOCK_M);
   if (rc) return rc;
   if (g->b_mn_major)
-    rc = encode_mnmajor(&tb, g->b, g->k, g->n, g->ldb, block_n);
+    rc = encode_mnmajor(&tm.b, g->b, g->k, g->n, g->ldb, block_n);
   else
-    rc = encode_kmajor(&tb, g->b, g->n, g->k, g->ldb, block_n);
+    rc = encode_kmajor(&tm.b, g->b, g->n, g->k, g->ldb, block_n);
   if (rc) return rc;
+  if (!g->out_f32_accumulate) {
+    HERO_REQUIRE(g->ld_out % 8 == 0, "bf16 output needs ld_out %% 8 == 0");
+    if ((rc = encode_out(&tm.out, g->out, g->m, g->n, g->ld_out))) return rc;
+    if (g->aux_out) {
+      HERO_REQUIRE(g->ld_aux_out % 8 == 0, "aux_out needs ld %% 8 == 0");
+      if ((rc = encode_out(&tm.aux, g->aux_out, g->m, g->n, g->ld_aux_out))) return rc;
+    } else {
+      tm.aux = tm.out;
+    }
+  } else {
+    tm.out = tm.a;
+    tm.aux = tm.a;
+  }
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return dispatch<256>(g, ta, tb, s, e, st);
-  return dispatch<128>(g, ta, tb, s, e, st);
+  if (block_n == 256) return dispatch<256>(g, tm, s, e, st);
+  return dispatch<128>(g, tm, s, e, st);
 }

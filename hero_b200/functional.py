@@ -1,0 +1,414 @@
+"""Autograd glue: hand-written forward AND backward chains over the C-ABI kernels.
+
+Each Function below replaces one stretch of the reference's module graph (and PyTorch autograd's
+derivative of it) with an explicit sequence of kernel launches on packed (valid-token-only)
+activations. fp32 master parameters enter the Functions only so autograd can route their
+gradients; the arithmetic reads the bf16 working copies held in `ctx_w` objects.
+
+    transformer_stack   BertEncoder.forward           model/layers.py:298-327 (A.4 in SURVEY.md)
+    cross_modal_embed   _compute_img_txt_embeddings   model/encoder.py:256-285 (+ embed.py:28-117)
+    frame_merge         collect_frame_outputs + frame_transform residual  model/model.py:156-212
+    frame_embed         FrameEmbeddings               model/embed.py:146-161
+    pack / unpack       padded <-> packed layouts
+"""
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+class DropoutState:
+    """Per-forward dropout configuration: probabilities + a key stream (fwd and bwd regenerate the
+    same masks from (key, element index); nothing is stored)."""
+
+    def __init__(self, hidden_p=0.0, attn_p=0.0, training=False, base_key=None):
+        self.hidden_p = hidden_p if training else 0.0
+        self.attn_p = attn_p if training else 0.0
+        if base_key is None and (self.hidden_p > 0 or self.attn_p > 0):
+            base_key = int(torch.empty((), dtype=torch.int64).random_().item())
+        self.base = base_key or 0
+        self.count = 0
+
+    def next(self, p):
+        if p <= 0.0:
+            return (0, 0, 1.0)
+        self.count += 1
+        return ops.drop_params(p, (self.base * 2654435761 + self.count * 40503) & 0xFFFFFFFF)
+
+
+def _empty(shape, like, dtype=BF16):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+def _zeros(shape, like, dtype=F32):
+    return torch.zeros(shape, dtype=dtype, device=like.device)
+
+
+# ---------------------------------------------------------------------------------------------
+class LayerWeights:
+    """bf16 working copies + fp32 vectors of one BertLayer (views into the flat buffers)."""
+    __slots__ = ("wqkv", "bqkv", "wo", "bo", "ln1_g", "ln1_b", "w1", "b1", "w2", "b2", "ln2_g",
+                 "ln2_b")
+
+
+class _TransformerStack(torch.autograd.Function):
+    """L x BertLayer on packed tokens. args = (x, cfg, *params) with 16 fp32 params per layer in
+    the order q.w q.b k.w k.b v.w v.b o.w o.b ln1.w ln1.b i.w i.b out.w out.b ln2.w ln2.b."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, *params):
+        layers, cu, n_seq, max_len, heads, eps, drop = (
+            cfg["layers"], cfg["cu"], cfg["n_seq"], cfg["max_len"], cfg["heads"], cfg["eps"],
+            cfg["drop"])
+        M, H = x.shape
+        inter = layers[0].w1.shape[0]
+        need_grad = any(ctx.needs_input_grad)
+        saved = []
+        h = x
+        for lw in layers:
+            qkv = _empty((M, 3 * H), x)
+            ops.gemm(h, lw.wqkv, qkv, bias=lw.bqkv)
+            cx = _empty((M, H), x)
+            d_attn = drop.next(drop.attn_p)
+            ops.attn_fwd(qkv, cu, cx, n_seq=n_seq, max_len=max_len, heads=heads, drop=d_attn)
+            s1 = _empty((M, H), x)
+            d_h1 = drop.next(drop.hidden_p)
+            ops.gemm(cx, lw.wo, s1, bias=lw.bo, resid=h, drop=d_h1)
+            a = _empty((M, H), x)
+            mean1, rstd1 = _empty((M,), x, F32), _empty((M,), x, F32)
+            ops.ln_fwd(s1, lw.ln1_g, lw.ln1_b, eps, a, n_rows=M, mean=mean1, rstd=rstd1)
+            f = _empty((M, inter), x)
+            pre = _empty((M, inter), x) if need_grad else None
+            ops.gemm(a, lw.w1, f, bias=lw.b1, act=ops.ACT_GELU, aux_out=pre)
+            s2 = _empty((M, H), x)
+            d_h2 = drop.next(drop.hidden_p)
+            ops.gemm(f, lw.w2, s2, bias=lw.b2, resid=a, drop=d_h2)
+            out = _empty((M, H), x)
+            mean2, rstd2 = _empty((M,), x, F32), _empty((M,), x, F32)
+            ops.ln_fwd(s2, lw.ln2_g, lw.ln2_b, eps, out, n_rows=M, mean=mean2, rstd=rstd2)
+            if need_grad:
+                saved.append((h, qkv, cx, s1, mean1, rstd1, a, pre, f, s2, mean2, rstd2, d_attn,
+                              d_h1, d_h2))
+            h = out
+        ctx.cfg = cfg
+        ctx.saved = saved
+        return h
+
+    @staticmethod
+    def backward(ctx, dout):
+        cfg = ctx.cfg
+        layers, cu, n_seq, max_len, heads = (cfg["layers"], cfg["cu"], cfg["n_seq"],
+                                             cfg["max_len"], cfg["heads"])
+        dout = dout.contiguous()
+        M, H = dout.shape
+        grads = [None] * (16 * len(layers))
+        dy = dout
+        for li in range(len(layers) - 1, -1, -1):
+            lw = layers[li]
+            (h, qkv, cx, s1, mean1, rstd1, a, pre, f, s2, mean2, rstd2, d_attn, d_h1,
+             d_h2) = ctx.saved[li]
+            inter = lw.w1.shape[0]
+            # LN2 backward: ds2 (residual branch) and ds2 * dropout mask (FFN-down branch)
+            ds2 = _empty((M, H), dy)
+            ds2_d = _empty((M, H), dy) if d_h2[0] else ds2
+            dg2, db2ln = _zeros((H,), dy), _zeros((H,), dy)
+            ops.ln_bwd(dy, s2, lw.ln2_g, mean2, rstd2, n_rows=M, dx=ds2,
+                       dx_drop=ds2_d if d_h2[0] else None, drop2=d_h2, dgamma=dg2, dbeta=db2ln)
+            # FFN down: bias, weight, input grads (input grad fused with gelu')
+            db2 = _zeros((H,), dy)
+            ops.colsum(ds2_d, db2)
+            dw2 = _zeros((H, inter), dy)
+            ops.gemm(ds2_d, f, dw2, a_mn=True, b_mn=True, accumulate_f32=True)
+            dpre = _empty((M, inter), dy)
+            ops.gemm(ds2_d, lw.w2, dpre, b_mn=True, act=ops.ACT_GELU_GRAD, aux_in=pre)
+            # FFN up
+            db1 = _zeros((inter,), dy)
+            ops.colsum(dpre, db1)
+            dw1 = _zeros((inter, H), dy)
+            ops.gemm(dpre, a, dw1, a_mn=True, b_mn=True, accumulate_f32=True)
+            da = _empty((M, H), dy)
+            ops.gemm(dpre, lw.w1, da, b_mn=True, resid=ds2)
+            # LN1 backward
+            ds1 = _empty((M, H), dy)
+            ds1_d = _empty((M, H), dy) if d_h1[0] else ds1
+            dg1, db1ln = _zeros((H,), dy), _zeros((H,), dy)
+            ops.ln_bwd(da, s1, lw.ln1_g, mean1, rstd1, n_rows=M, dx=ds1,
+                       dx_drop=ds1_d if d_h1[0] else None, drop2=d_h1, dgamma=dg1, dbeta=db1ln)
+            # attention output projection
+            dbo = _zeros((H,), dy)
+            ops.colsum(ds1_d, dbo)
+            dwo = _zeros((H, H), dy)
+            ops.gemm(ds1_d, cx, dwo, a_mn=True, b_mn=True, accumulate_f32=True)
+            dcx = _empty((M, H), dy)
+            ops.gemm(ds1_d, lw.wo, dcx, b_mn=True)
+            # attention core
+            dqkv = _empty((M, 3 * H), dy)
+            ops.attn_bwd(qkv, cu, dcx, dqkv, n_seq=n_seq, max_len=max_len, heads=heads,
+                         drop=d_attn)
+            # QKV projection
+            dbqkv = _zeros((3 * H,), dy)
+            ops.colsum(dqkv, dbqkv)
+            dwqkv = _zeros((3 * H, H), dy)
+            ops.gemm(dqkv, h, dwqkv, a_mn=True, b_mn=True, accumulate_f32=True)
+            dx = _empty((M, H), dy)
+            ops.gemm(dqkv, lw.wqkv, dx, b_mn=True, resid=ds1)
+            g = grads
+            o = 16 * li
+            g[o + 0], g[o + 2], g[o + 4] = dwqkv[:H], dwqkv[H:2 * H], dwqkv[2 * H:]
+            g[o + 1], g[o + 3], g[o + 5] = dbqkv[:H], dbqkv[H:2 * H], dbqkv[2 * H:]
+            g[o + 6], g[o + 7] = dwo, dbo
+            g[o + 8], g[o + 9] = dg1, db1ln
+            g[o + 10], g[o + 11] = dw1, db1
+            g[o + 12], g[o + 13] = dw2, db2
+            g[o + 14], g[o + 15] = dg2, db2ln
+            dy = dx
+        ctx.saved = None
+        dx_in = dy if ctx.needs_input_grad[0] else None
+        return (dx_in, None) + tuple(grads)
+
+
+def transformer_stack(x, cfg, params):
+    return _TransformerStack.apply(x, cfg, *params)
+
+
+def _slot_table_grad(dx, off, idx, slot_pos, dtable, tok_pos):
+    """dtable[pos] += sum of dx rows that used position `pos`. Rows are grouped per slot with a
+    CSR gather-sum; `slot_pos` maps slot -> table row (None: fall back to a per-token index_add)."""
+    if slot_pos is None:
+        dtable.index_add_(0, tok_pos.long(), dx.float())
+        return
+    n_slot = off.numel() - 1
+    dslot = torch.zeros((n_slot, dx.shape[1]), dtype=F32, device=dx.device)
+    ops.gather_sum_rows(dx, off, idx, dslot)
+    dtable.index_add_(0, slot_pos[:n_slot].long(), dslot)
+
+
+# ---------------------------------------------------------------------------------------------
+class _CrossModalEmbed(torch.autograd.Function):
+    """Packed cross-modal embeddings. params order:
+    word, pos, type, ln_w, ln_b, [img_lin_w, img_lin_b, img_ln_w, img_ln_b, img_pos, mask_emb,
+    img_out_ln_w, img_out_ln_b]."""
+
+    @staticmethod
+    def forward(ctx, cfg, *params):
+        word, pos, typ, ln_w, ln_b = params[:5]
+        drop = cfg["drop"]
+        n_tok, H = cfg["n_tok"], word.shape[1]
+        emb = torch.empty((n_tok, H), dtype=BF16, device=word.device)
+        type_row = typ[1]
+        st = {}
+        # text tokens: LN(word[id] + pos[pid] + type[1]) -> packed row  (model/embed.py:44-58)
+        n_txt = cfg["n_txt"]
+        if n_txt:
+            st["t_mean"] = torch.empty(n_txt, device=word.device)
+            st["t_rstd"] = torch.empty(n_txt, device=word.device)
+            st["t_drop"] = drop.next(drop.hidden_p)
+            ops.ln_fwd(word, ln_w, ln_b, 1e-5, emb, n_rows=n_txt, x_rows=cfg["txt_ids"],
+                       add_tab=pos, add_idx=cfg["txt_pos"], add_vec=type_row,
+                       y_rows=cfg["txt_tok"], mean=st["t_mean"], rstd=st["t_rstd"],
+                       drop=st["t_drop"])
+        n_img = cfg["n_img"]
+        if n_img:
+            (lin_w, lin_b, iln_w, iln_b, ipos, mask_emb, oln_w, oln_b) = params[5:13]
+            D = iln_w.numel()
+            feats = cfg["img_feats"]                      # fp32 [R*max_vl, D]
+            xn = torch.empty((n_img, D), dtype=BF16, device=word.device)
+            st["i_mean"] = torch.empty(n_img, device=word.device)
+            st["i_rstd"] = torch.empty(n_img, device=word.device)
+            ops.ln_fwd(feats, iln_w, iln_b, 1e-5, xn, n_rows=n_img, x_rows=cfg["img_src"],
+                       add_tab=mask_emb if cfg["img_mask"] is not None else None,
+                       add_idx=cfg["img_mask"], mean=st["i_mean"], rstd=st["i_rstd"])
+            proj = torch.empty((n_img, H), dtype=BF16, device=word.device)
+            ops.gemm(xn, cfg["img_lin_w_bf16"], proj, bias=lin_b)
+            st["o_mean"] = torch.empty(n_img, device=word.device)
+            st["o_rstd"] = torch.empty(n_img, device=word.device)
+            st["o_drop"] = drop.next(drop.hidden_p)
+            ops.ln_fwd(proj, oln_w, oln_b, 1e-5, emb, n_rows=n_img, add_tab=ipos,
+                       add_idx=cfg["img_k"], add_vec=type_row, y_rows=cfg["img_tok"],
+                       mean=st["o_mean"], rstd=st["o_rstd"], drop=st["o_drop"])
+            st["xn"], st["proj"] = xn, proj
+        ctx.cfg, ctx.st = cfg, st
+        ctx.save_for_backward(*params)
+        return emb
+
+    @staticmethod
+    def backward(ctx, demb):
+        cfg, st = ctx.cfg, ctx.st
+        params = ctx.saved_tensors
+        word, pos, typ, ln_w, ln_b = params[:5]
+        demb = demb.contiguous()
+        H = word.shape[1]
+        dev = word.device
+        grads = [None] * len(params)
+        dtyp = torch.zeros_like(typ)
+        n_txt, n_img = cfg["n_txt"], cfg["n_img"]
+        type_row = typ[1]
+        if n_txt:
+            dword = torch.zeros_like(word)
+            dpos = torch.zeros_like(pos)
+            dlnw, dlnb = torch.zeros_like(ln_w), torch.zeros_like(ln_b)
+            dx = torch.empty((n_txt, H), dtype=BF16, device=dev)
+            ops.ln_bwd(demb, word, ln_w, st["t_mean"], st["t_rstd"], n_rows=n_txt,
+                       x_rows=cfg["txt_ids"], add_tab=pos, add_idx=cfg["txt_pos"],
+                       add_vec=type_row, y_rows=cfg["txt_tok"], drop=st["t_drop"], dx=dx,
+                       d_x_tab=dword, x_pad_idx=cfg["pad_idx"], dgamma=dlnw, dbeta=dlnb)
+            # position rows are shared by every sequence: deterministic CSR gather-sum per
+            # text slot, then slot -> position id (identity for the collate's arange ids)
+            _slot_table_grad(dx, cfg["txtpos_off"], cfg["txtpos_idx"], cfg["txt_slot_pos"], dpos,
+                             cfg.get("txt_pos"))
+            ops.colsum(dx, dtyp[1])
+            grads[0], grads[1], grads[3], grads[4] = dword, dpos, dlnw, dlnb
+        if n_img:
+            (lin_w, lin_b, iln_w, iln_b, ipos, mask_emb, oln_w, oln_b) = params[5:13]
+            D = iln_w.numel()
+            dproj = torch.empty((n_img, H), dtype=BF16, device=dev)
+            doln_w, doln_b = torch.zeros_like(oln_w), torch.zeros_like(oln_b)
+            ops.ln_bwd(demb, st["proj"], oln_w, st["o_mean"], st["o_rstd"], n_rows=n_img,
+                       add_tab=ipos, add_idx=cfg["img_k"], add_vec=type_row,
+                       y_rows=cfg["img_tok"], drop=st["o_drop"], dx=dproj, dgamma=doln_w,
+                       dbeta=doln_b)
+            dipos = torch.zeros_like(ipos)
+            _slot_table_grad(dproj, cfg["imgpos_off"], cfg["imgpos_idx"], cfg["img_slot_pos"],
+                             dipos, cfg.get("img_k"))
+            ops.colsum(dproj, dtyp[1])
+            dlin_b = torch.zeros_like(lin_b)
+            ops.colsum(dproj, dlin_b)
+            dlin_w = torch.zeros_like(lin_w)
+            ops.gemm(dproj, st["xn"], dlin_w, a_mn=True, b_mn=True, accumulate_f32=True)
+            # gradient wrt the normalised 4352-d features -> img_LayerNorm gamma/beta (+ mask emb)
+            dxn = torch.empty((n_img, D), dtype=BF16, device=dev)
+            ops.gemm(dproj, cfg["img_lin_w_bf16"], dxn, b_mn=True)
+            diln_w, diln_b = torch.zeros_like(iln_w), torch.zeros_like(iln_b)
+            has_mask = cfg["img_mask"] is not None
+            dmask = torch.zeros_like(mask_emb) if has_mask else None
+            ops.ln_bwd(dxn, cfg["img_feats"], iln_w, st["i_mean"], st["i_rstd"], n_rows=n_img,
+                       x_rows=cfg["img_src"], add_tab=mask_emb if has_mask else None,
+                       add_idx=cfg["img_mask"], d_add_tab=dmask, add_pad_idx=0, dgamma=diln_w,
+                       dbeta=diln_b)
+            grads[5:13] = [dlin_w, dlin_b, diln_w, diln_b, dipos, dmask, doln_w, doln_b]
+        grads[2] = dtyp
+        ctx.st = None
+        return (None,) + tuple(grads)
+
+
+def cross_modal_embed(cfg, params):
+    return _CrossModalEmbed.apply(cfg, *params)
+
+
+# ---------------------------------------------------------------------------------------------
+class _FrameMerge(torch.autograd.Function):
+    """g[c] = relu(LN_4352(c_v[c]) W^T + b) + sum_{f -> c} Hf[f]   (model/model.py:156-212).
+    params: ln_w, ln_b, lin_w, lin_b."""
+
+    @staticmethod
+    def forward(ctx, hf, cfg, ln_w, ln_b, lin_w, lin_b):
+        drop = cfg["drop"]
+        n_c, H = cfg["n_tok"], lin_w.shape[0]
+        D = ln_w.numel()
+        dev = hf.device
+        matched = torch.empty((n_c, H), dtype=BF16, device=dev)
+        ops.gather_sum_rows(hf, cfg["fwd_off"], cfg["fwd_idx"], matched)
+        xn = torch.empty((n_c, D), dtype=BF16, device=dev)
+        mean, rstd = torch.empty(n_c, device=dev), torch.empty(n_c, device=dev)
+        d_in = drop.next(drop.hidden_p)   # LinearLayer: dropout sits between LN and Linear
+        ops.ln_fwd(cfg["feats"], ln_w, ln_b, 1e-5, xn, n_rows=n_c, x_rows=cfg["src"], mean=mean,
+                   rstd=rstd, drop=d_in)
+        g = torch.empty((n_c, H), dtype=BF16, device=dev)
+        pre = torch.empty((n_c, H), dtype=BF16, device=dev)
+        ops.gemm(xn, cfg["lin_w_bf16"], g, bias=lin_b, act=ops.ACT_RELU, resid=matched, aux_out=pre)
+        ctx.cfg = cfg
+        ctx.st = (xn, mean, rstd, pre, d_in)
+        ctx.save_for_backward(ln_w, ln_b, lin_w, lin_b)
+        return g
+
+    @staticmethod
+    def backward(ctx, dg):
+        cfg = ctx.cfg
+        xn, mean, rstd, pre, d_in = ctx.st
+        ln_w, ln_b, lin_w, lin_b = ctx.saved_tensors
+        dg = dg.contiguous()
+        n_c, H = dg.shape
+        dev = dg.device
+        # residual branch: every f token receives the gradient of the clip frames it fed
+        dhf = torch.empty((cfg["n_f_tok"], H), dtype=BF16, device=dev)
+        ops.gather_sum_rows(dg, cfg["bwd_off"], cfg["bwd_idx"], dhf)
+        dpre = torch.empty_like(dg)
+        ops.relu_bwd(dg, pre, dpre)
+        dlin_b = torch.zeros_like(lin_b)
+        ops.colsum(dpre, dlin_b)
+        dlin_w = torch.zeros_like(lin_w)
+        ops.gemm(dpre, xn, dlin_w, a_mn=True, b_mn=True, accumulate_f32=True)
+        dxn = torch.empty((n_c, ln_w.numel()), dtype=BF16, device=dev)
+        ops.gemm(dpre, cfg["lin_w_bf16"], dxn, b_mn=True)
+        dln_w, dln_b = torch.zeros_like(ln_w), torch.zeros_like(ln_b)
+        ops.ln_bwd(dxn, cfg["feats"], ln_w, mean, rstd, n_rows=n_c, x_rows=cfg["src"], drop=d_in,
+                   dgamma=dln_w, dbeta=dln_b)
+        ctx.st = None
+        return dhf, None, dln_w, dln_b, dlin_w, dlin_b
+
+
+def frame_merge(hf, cfg, params):
+    return _FrameMerge.apply(hf, cfg, *params)
+
+
+class _FrameEmbed(torch.autograd.Function):
+    """z = dropout(LN(g + pos[t]))  (model/embed.py:146-161). params: pos, ln_w, ln_b."""
+
+    @staticmethod
+    def forward(ctx, g, cfg, pos, ln_w, ln_b):
+        drop = cfg["drop"]
+        n, H = g.shape
+        z = torch.empty_like(g)
+        mean, rstd = torch.empty(n, device=g.device), torch.empty(n, device=g.device)
+        d = drop.next(drop.hidden_p)
+        ops.ln_fwd(g, ln_w, ln_b, 1e-5, z, n_rows=n, add_tab=pos, add_idx=cfg["t"], mean=mean,
+                   rstd=rstd, drop=d)
+        ctx.cfg, ctx.st = cfg, (mean, rstd, d)
+        ctx.save_for_backward(g, pos, ln_w, ln_b)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        cfg = ctx.cfg
+        mean, rstd, d = ctx.st
+        g, pos, ln_w, ln_b = ctx.saved_tensors
+        dz = dz.contiguous()
+        n, H = dz.shape
+        dgx = torch.empty_like(dz)
+        dln_w, dln_b = torch.zeros_like(ln_w), torch.zeros_like(ln_b)
+        ops.ln_bwd(dz, g, ln_w, mean, rstd, n_rows=n, add_tab=pos, add_idx=cfg["t"], drop=d,
+                   dx=dgx, dgamma=dln_w, dbeta=dln_b)
+        dpos = torch.zeros_like(pos)
+        n_slot = cfg["pos_off"].numel() - 1
+        ops.gather_sum_rows(dgx, cfg["pos_off"], cfg["pos_idx"], dpos[:n_slot])
+        return dgx, None, dpos, dln_w, dln_b
+
+
+def frame_embed(g, cfg, params):
+    return _FrameEmbed.apply(g, cfg, *params)
+
+
+# ---------------------------------------------------------------------------------------------
+class _GatherRows(torch.autograd.Function):
+    """out[i] = idx[i] >= 0 ? src[idx[i]] : 0 with the transposed gather as backward; used for
+    pack (padded -> packed) and unpack (packed -> padded, zeros at padding)."""
+
+    @staticmethod
+    def forward(ctx, src, idx, inv_idx):
+        out = torch.empty((idx.numel(), src.shape[1]), dtype=BF16, device=src.device)
+        ops.gather_rows(src, idx, out)
+        ctx.inv = inv_idx
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dsrc = torch.empty((ctx.inv.numel(), dout.shape[1]), dtype=BF16, device=dout.device)
+        ops.gather_rows(dout.contiguous(), ctx.inv, dsrc)
+        return dsrc, None, None
+
+
+def gather_rows(src, idx, inv_idx):
+    """`inv_idx[j]` = the i with idx[i] == j (or -1): both maps are injective here."""
+    return _GatherRows.apply(src, idx, inv_idx)

@@ -1,0 +1,141 @@
+"""Flat parameter storage: fp32 masters as views of one buffer + a bf16 working mirror.
+
+The reference keeps ~208 separate tensors and pays a pack/all-reduce/unpack copy for its gradient
+exchange (utils/distributed.py:19-46) plus ~10 kernels per tensor in AdamW (optim/adamw.py:80-104).
+Here every nn.Parameter of a module tree becomes a VIEW into one contiguous fp32 buffer (state_dict
+keys and shapes unchanged, `load_state_dict` copies in place), ordered so that each layer's
+query/key/value weights (and biases) are adjacent: the fused QKV GEMM reads them as one
+[3H, H] matrix without any concatenation. A same-layout bf16 mirror feeds the tensor-core
+kernels and is refreshed by ONE cast kernel when the masters changed.
+"""
+import re
+
+import torch
+
+from . import ops
+
+_ALIGN = 64  # elements; keeps every view 128-byte aligned in bf16 (TMA needs 16 B)
+
+
+def _ordered_named_params(module):
+    named = list(module.named_parameters())   # de-duplicated (tied weights appear once)
+    by_name = dict(named)
+    out, placed = [], set()
+    for name, p in named:
+        if name in placed:
+            continue
+        m = re.match(r"(.*attention\.self\.)query\.weight$", name)
+        if m:
+            base = m.group(1)
+            group = [base + s for s in ("query.weight", "key.weight", "value.weight",
+                                        "query.bias", "key.bias", "value.bias")]
+            if all(g in by_name for g in group):
+                for g in group:
+                    out.append((g, by_name[g]))
+                    placed.add(g)
+                continue
+        out.append((name, p))
+        placed.add(name)
+    return out
+
+
+class FlatParams:
+    def __init__(self, module):
+        self.module = module
+        self.flat = None
+        self.mirror = None
+        self.entries = []            # (name, param, offset, numel)
+        self._by_id = {}
+        self.dirty = True
+        self._version_sum = -1
+        self.grad_flat = None
+
+    # ------------------------------------------------------------------ layout
+    def _needs_flatten(self, device):
+        if self.flat is None or self.flat.device != device:
+            return True
+        for _, p, off, n in self.entries[:2] + self.entries[-2:]:
+            if p.data_ptr() != self.flat.data_ptr() + off * 4:
+                return True
+        return len(self.entries) != len(list(self.module.parameters()))
+
+    def ensure(self, device):
+        """(Re)build the flat buffers if parameters were moved / replaced; refresh the mirror."""
+        device = torch.device(device)
+        if self._needs_flatten(device):
+            named = _ordered_named_params(self.module)
+            offs, total = [], 0
+            for _, p in named:
+                offs.append(total)
+                total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            flat = torch.zeros(total, dtype=torch.float32, device=device)
+            self.entries, self._by_id = [], {}
+            with torch.no_grad():
+                for (name, p), off in zip(named, offs):
+                    view = flat[off:off + p.numel()].view(p.shape)
+                    view.copy_(p.data.to(device=device, dtype=torch.float32))
+                    p.data = view
+                    self.entries.append((name, p, off, p.numel()))
+                    self._by_id[id(p)] = (off, p.numel())
+            self.flat = flat
+            self.mirror = torch.empty(total, dtype=torch.bfloat16, device=device)
+            self.grad_flat = None
+            self.dirty = True
+        vs = 0
+        for _, p, _, _ in self.entries:
+            vs += p._version
+        if self.dirty or vs != self._version_sum:
+            ops.cast_bf16(self.flat, self.mirror)
+            self.dirty = False
+            self._version_sum = vs
+        return self
+
+    def mark_dirty(self):
+        self.dirty = True
+
+    # ------------------------------------------------------------------ views
+    def bf16(self, p):
+        off, n = self._by_id[id(p)]
+        return self.mirror[off:off + n].view(p.shape)
+
+    def bf16_span(self, first, count, shape):
+        """bf16 view starting at parameter `first` spanning `count` elements (fused QKV)."""
+        off, _ = self._by_id[id(first)]
+        return self.mirror[off:off + count].view(shape)
+
+    def f32_span(self, first, count, shape):
+        off, _ = self._by_id[id(first)]
+        return self.flat[off:off + count].view(shape)
+
+    def contiguous_after(self, a, b):
+        """True if parameter b starts right where a ends (no alignment gap)."""
+        oa, na = self._by_id[id(a)]
+        ob, _ = self._by_id[id(b)]
+        return oa + na == ob
+
+    # ------------------------------------------------------------------ flat gradients
+    def ensure_flat_grads(self):
+        """Point every p.grad at a view of one flat fp32 buffer (absent grads are zeros), so the
+        data-parallel all-reduce and the fused AdamW run on ONE tensor with no pack/unpack."""
+        if self.grad_flat is None:
+            self.grad_flat = torch.zeros_like(self.flat)
+        for _, p, off, n in self.entries:
+            want = self.grad_flat[off:off + n].view(p.shape)
+            if p.grad is None:
+                p.grad = want
+            elif p.grad.data_ptr() != want.data_ptr():
+                with torch.no_grad():
+                    want.copy_(p.grad)
+                p.grad = want
+        return self.grad_flat
+
+
+def flat_of(module, device):
+    """The FlatParams owning `module`'s parameters: the one installed by the outermost hero_b200
+    module that has run a forward, else a private one."""
+    fp = module.__dict__.get("_hero_flat")
+    if fp is None:
+        fp = FlatParams(module)
+        for m in module.modules():
+            m.__dict__["_hero_flat"] = fp
+    return fp.ensure(device)

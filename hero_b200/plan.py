@@ -1,0 +1,225 @@
+"""Host-side packing plans: padded reference batch layout -> packed (valid-token-only) layout.
+
+The reference pads every subtitle row to the batch maximum and masks padded keys with -10000
+(model/layers.py:299-302); it also re-packs `[frames | pad | text | pad]` into `[frames, text,
+pad]` with torch.gather (model/encoder.py:271-279, index from data/data.py:504-512) and scatters
+frame outputs back to the clip timeline in a Python double loop (model/model.py:156-187). Here all
+of that becomes index arithmetic done ONCE per batch on the host with numpy; the CUDA kernels then
+only ever see valid tokens:
+
+    SeqPlan   which (row, position) pairs are valid, in row-major order -> packed token ids,
+              cu_seqlens for the attention kernel, maps for pack / unpack.
+    FPlan     cross-modal rows: per packed token its source (frame slot or text slot).
+    CPlan     clip rows + the CSR maps replacing collect_frame_outputs (forward gather-sum and its
+              transpose for the backward).
+
+Plans are pure numpy (testable without a GPU); `.to(device)` uploads the int32 index arrays in
+one pinned-memory copy.
+"""
+import numpy as np
+import torch
+
+
+def _np(t):
+    if torch.is_tensor(t):
+        return t.detach().cpu().numpy()
+    return np.asarray(t)
+
+
+class DeviceIndex:
+    """A bundle of int32 index arrays uploaded to the device with a single H2D copy."""
+
+    def __init__(self, arrays, device):
+        names = list(arrays)
+        sizes = [int(arrays[n].size) for n in names]
+        offs = np.concatenate([[0], np.cumsum([(s + 3) // 4 * 4 for s in sizes])]).astype(np.int64)
+        host = torch.empty(int(offs[-1]), dtype=torch.int32,
+                           pin_memory=torch.cuda.is_available() and device.type == "cuda")
+        hv = host.numpy()
+        for n, o, s in zip(names, offs[:-1], sizes):
+            hv[o:o + s] = arrays[n].reshape(-1)
+        self.flat = host.to(device, non_blocking=True)
+        self._host = host  # keep pinned memory alive until the copy is consumed
+        for n, o, s in zip(names, offs[:-1], sizes):
+            setattr(self, n, self.flat[o:o + s])
+
+
+class SeqPlan:
+    """Valid positions of a padded (rows, length) mask, packed row-major."""
+
+    def __init__(self, mask):
+        mask = _np(mask) != 0
+        self.rows, self.length = mask.shape
+        r, c = np.nonzero(mask)                      # row-major order
+        self.tok_row = r.astype(np.int32)
+        self.tok_col = c.astype(np.int32)
+        self.n_tok = int(r.size)
+        lens = mask.sum(1).astype(np.int64)
+        self.lens = lens
+        self.cu = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        self.n_seq = self.rows
+        self.max_len = int(lens.max()) if lens.size else 0
+        self.tok_flat = (r.astype(np.int64) * self.length + c).astype(np.int32)  # packed -> padded
+        p2t = np.full(self.rows * self.length, -1, np.int32)
+        p2t[self.tok_flat] = np.arange(self.n_tok, dtype=np.int32)
+        self.pad_to_tok = p2t                                                    # padded -> packed
+
+    def arrays(self, prefix):
+        return {prefix + "cu": self.cu, prefix + "tok_flat": self.tok_flat,
+                prefix + "pad_to_tok": self.pad_to_tok}
+
+
+def _csr(dst, src, n_dst):
+    """CSR (offsets, indices) listing for each dst all its src, stable in src order."""
+    dst = np.asarray(dst, np.int64)
+    src = np.asarray(src, np.int32)
+    order = np.argsort(dst, kind="stable")
+    counts = np.bincount(dst, minlength=n_dst)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    return off, src[order]
+
+
+class FPlan:
+    """Cross-modal ('repr') rows: frames + subtitle tokens per row, or text-only rows ('txt')."""
+
+    def __init__(self, attn_mask, gather_index=None, max_vl=0, max_sl=None):
+        self.seq = SeqPlan(attn_mask)
+        s = self.seq
+        if gather_index is None:       # text only: position j reads text slot j
+            src = s.tok_col.astype(np.int64)
+            max_vl = 0
+            self.max_sl = s.length if max_sl is None else max_sl
+        else:
+            gi = _np(gather_index).astype(np.int64)
+            src = gi[s.tok_row, s.tok_col]
+            self.max_sl = int(max_sl)
+        self.max_vl = int(max_vl)
+        is_img = src < self.max_vl
+        tok = np.arange(s.n_tok, dtype=np.int32)
+        self.img_tok = tok[is_img]
+        self.img_k = src[is_img].astype(np.int32)                       # frame slot in the row
+        self.img_src = (s.tok_row[is_img].astype(np.int64) * self.max_vl
+                        + src[is_img]).astype(np.int32)                 # row in f_v_feats.view(-1, D)
+        self.txt_tok = tok[~is_img]
+        self.txt_j = (src[~is_img] - self.max_vl).astype(np.int32)
+        self.txt_src = (s.tok_row[~is_img].astype(np.int64) * self.max_sl
+                        + self.txt_j).astype(np.int32)                  # index in input_ids.view(-1)
+        self.n_img = int(self.img_tok.size)
+        self.n_txt = int(self.txt_tok.size)
+
+    def arrays(self, prefix="f_"):
+        a = self.seq.arrays(prefix)
+        a.update({prefix + "img_tok": self.img_tok, prefix + "img_k": self.img_k,
+                  prefix + "img_src": self.img_src, prefix + "txt_tok": self.txt_tok,
+                  prefix + "txt_j": self.txt_j, prefix + "txt_src": self.txt_src})
+        return a
+
+
+class CPlan:
+    """Clip-level rows and the frame-merge maps (collect_frame_outputs as CSR gathers)."""
+
+    def __init__(self, c_attn_mask, fplan, num_subs, sub_idx2frame_idx):
+        self.seq = SeqPlan(c_attn_mask)
+        s = self.seq
+        B, T = s.rows, s.length
+        self.c_src = s.tok_flat                       # row in c_v_feats.view(-1, D)
+        self.c_t = s.tok_col                          # temporal position id
+        # (clip, frame) <- (sub row, slot k): model/model.py:171-186
+        rows, ks, dst = [], [], []
+        start = 0
+        for vid, n_sub in enumerate(num_subs):
+            for sid, frames in sub_idx2frame_idx[vid]:
+                n = len(frames)
+                if n:
+                    rows.extend([start + sid] * n)
+                    ks.extend(range(n))
+                    dst.extend(vid * T + int(t) for t in frames)
+            start += n_sub
+        rows = np.asarray(rows, np.int64)
+        ks = np.asarray(ks, np.int64)
+        dst = np.asarray(dst, np.int64)
+        if dst.size and (dst.max() >= B * T or dst.min() < 0):
+            raise IndexError("sub_idx2frame_idx refers to a frame outside the clip tensor")
+        f_tok = fplan.seq.pad_to_tok[rows * fplan.seq.length + ks] if rows.size else \
+            np.zeros(0, np.int32)
+        c_tok = s.pad_to_tok[dst] if dst.size else np.zeros(0, np.int32)
+        keep = (f_tok >= 0) & (c_tok >= 0)            # masked slots carry no defined value
+        f_tok, c_tok = f_tok[keep], c_tok[keep]
+        self.n_pairs = int(f_tok.size)
+        self.fwd_off, self.fwd_idx = _csr(c_tok, f_tok, s.n_tok)             # c token <- f tokens
+        self.bwd_off, self.bwd_idx = _csr(f_tok, c_tok, fplan.seq.n_tok)     # f token <- c tokens
+
+    def arrays(self, prefix="c_"):
+        a = self.seq.arrays(prefix)
+        a.update({prefix + "src": self.c_src, prefix + "t": self.c_t,
+                  prefix + "fwd_off": self.fwd_off, prefix + "fwd_idx": self.fwd_idx,
+                  prefix + "bwd_off": self.bwd_off, prefix + "bwd_idx": self.bwd_idx})
+        return a
+
+
+def table_csr(idx, n_rows):
+    """CSR listing, for every embedding-table row, the packed tokens that used it (deterministic
+    table gradients via gather-sum instead of contended atomics)."""
+    idx = np.asarray(idx, np.int64)
+    return _csr(idx, np.arange(idx.size, dtype=np.int32), n_rows)
+
+
+class ReprPlan:
+    """Everything HierarchicalVlModel.forward_repr needs for one batch."""
+
+    def __init__(self, batch):
+        max_vl = batch["f_v_feats"].shape[1]
+        max_sl = batch["f_sub_input_ids"].shape[1]
+        self.f = FPlan(batch["f_attn_masks"], batch["f_gather_index"], max_vl, max_sl)
+        self.c = CPlan(batch["c_attn_masks"], self.f, batch["num_subs"],
+                       batch["sub_idx2frame_idx"])
+        self.shape_f = tuple(batch["f_attn_masks"].shape)
+        self.shape_c = tuple(batch["c_attn_masks"].shape)
+        # position-table CSRs for the deterministic embedding gradients
+        self.f_txtpos_off, self.f_txtpos_idx = table_csr(self.f.txt_j, max(max_sl, 1))
+        self.f_imgpos_off, self.f_imgpos_idx = table_csr(self.f.img_k, max(max_vl, 1))
+        self.c_pos_off, self.c_pos_idx = table_csr(self.c.c_t, max(self.shape_c[1], 1))
+        self.dev = None
+
+    def to(self, device):
+        if self.dev is None or self.dev.flat.device != torch.device(device):
+            a = self.f.arrays("f_")
+            a.update(self.c.arrays("c_"))
+            a.update({"f_txtpos_off": self.f_txtpos_off, "f_txtpos_idx": self.f_txtpos_idx,
+                      "f_imgpos_off": self.f_imgpos_off, "f_imgpos_idx": self.f_imgpos_idx,
+                      "c_pos_off": self.c_pos_off, "c_pos_idx": self.c_pos_idx})
+            self.dev = DeviceIndex(a, torch.device(device))
+        return self.dev
+
+
+class TxtPlan:
+    """Text-only rows (CrossModalTrm 'txt' task, and the generic BertEncoder API)."""
+
+    def __init__(self, attn_mask, with_embedding=True):
+        self.f = FPlan(attn_mask)
+        self.shape = tuple(_np(attn_mask).shape)
+        self.with_embedding = with_embedding
+        if with_embedding:
+            self.pos_off, self.pos_idx = table_csr(self.f.txt_j, max(self.shape[1], 1))
+        self.dev = None
+
+    def to(self, device):
+        if self.dev is None or self.dev.flat.device != torch.device(device):
+            a = self.f.arrays("f_")
+            if self.with_embedding:
+                a.update({"pos_off": self.pos_off, "pos_idx": self.pos_idx})
+            self.dev = DeviceIndex(a, torch.device(device))
+        return self.dev
+
+
+PLAN_KEY = "_hero_plan"
+
+
+def attach_plan(batch, kind="repr"):
+    """Collate-side hook: build the plan from HOST tensors (no device sync later) and stash it in
+    the batch dict; `move_to_cuda`-style helpers leave non-tensor values alone."""
+    if kind == "repr":
+        batch[PLAN_KEY] = ReprPlan(batch)
+    else:
+        batch[PLAN_KEY] = TxtPlan(batch["attn_masks"])
+    return batch

@@ -207,6 +207,9 @@ def main():
     model = build_reference_model(full, W)
     vb, qb = synth.syn_tvr_ragged(batch_size=2, seed=77, t_range=(10, 16), s_range=(3, 5),
                                   l_range=(4, 12), q_range=(5, 9))
+    with open(os.path.join(out_dir, "state_dict_keys.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in model.state_dict().items()}, f, indent=0,
+                  sort_keys=True)
     with torch.no_grad():
         clip = model(vb, "repr")
         q_seq = model.f_encoder(qb, "txt")[0]

@@ -1,0 +1,190 @@
+"""TEST INFRASTRUCTURE: torch restatements of the C-ABI contracts (include/hero_b200.h), used to
+exercise the host-side orchestration (plans, autograd chains, module plumbing) on a CPU-only box
+by monkeypatching `hero_b200.ops`. Never imported by the product; dropout is not modelled
+(p must be 0). bf16 rounding is applied where the kernels round, so tolerances stay honest.
+"""
+import math
+
+import torch
+
+BF16 = torch.bfloat16
+
+
+def _ck_drop(drop):
+    assert drop[0] == 0, "fake ops do not model dropout"
+
+
+def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None, resid=None,
+         aux_in=None, aux_out=None, act=0, accumulate_f32=False, drop=(0, 0, 1.0), block_n=0,
+         k_splits=0):
+    _ck_drop(drop)
+    A = a.float().t() if a_mn else a.float()
+    B = b.float() if b_mn else b.float().t()
+    v = A @ B
+    if bias is not None:
+        v = v + bias
+    if aux_out is not None:
+        aux_out.copy_(v.to(BF16))
+    if act == 1:
+        v = v * 0.5 * (1.0 + torch.erf(v / math.sqrt(2.0)))
+    elif act == 2:
+        v = torch.relu(v)
+    elif act == 3:
+        x = aux_in.float()
+        v = v * (0.5 * (1 + torch.erf(x / math.sqrt(2))) +
+                 x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi))
+    if resid is not None:
+        v = v + resid.float()
+    if accumulate_f32:
+        out.add_(v)
+    else:
+        out.copy_(v.to(BF16))
+    return out
+
+
+def _gather_sum(x, n_rows, x_rows, add_tab, add_idx, add_vec):
+    s = x.float()[x_rows.long()] if x_rows is not None else x.float()[:n_rows]
+    if add_tab is not None:
+        s = s + add_tab[add_idx.long()]
+    if add_vec is not None:
+        s = s + add_vec
+    return s
+
+
+def ln_fwd(x, gamma, beta, eps, y, *, n_rows, x_rows=None, add_tab=None, add_idx=None,
+           add_vec=None, y_rows=None, mean=None, rstd=None, drop=(0, 0, 1.0)):
+    _ck_drop(drop)
+    s = _gather_sum(x, n_rows, x_rows, add_tab, add_idx, add_vec)
+    mu = s.mean(-1, keepdim=True)
+    var = ((s - mu) ** 2).mean(-1, keepdim=True)
+    r = torch.rsqrt(var + eps)
+    out = ((s - mu) * r * gamma + beta).to(BF16)
+    if y_rows is not None:
+        y[y_rows.long()] = out
+    else:
+        y[:n_rows] = out
+    if mean is not None:
+        mean.copy_(mu.squeeze(-1))
+    if rstd is not None:
+        rstd.copy_(r.squeeze(-1))
+    return y
+
+
+def ln_bwd(dy, x, gamma, mean, rstd, *, n_rows, x_rows=None, add_tab=None, add_idx=None,
+           add_vec=None, y_rows=None, drop=(0, 0, 1.0), dx=None, dx_drop=None,
+           drop2=(0, 0, 1.0), d_x_tab=None, x_pad_idx=-1, d_add_tab=None, add_pad_idx=-1,
+           dgamma=None, dbeta=None):
+    _ck_drop(drop)
+    _ck_drop(drop2)
+    s = _gather_sum(x, n_rows, x_rows, add_tab, add_idx, add_vec)
+    xh = (s - mean[:, None]) * rstd[:, None]
+    d = dy.float()[y_rows.long()] if y_rows is not None else dy.float()[:n_rows]
+    g = d * gamma
+    c1 = g.mean(-1, keepdim=True)
+    c2 = (g * xh).mean(-1, keepdim=True)
+    dxv = rstd[:, None] * (g - c1 - xh * c2)
+    if dgamma is not None:
+        dgamma.add_((d * xh).sum(0))
+    if dbeta is not None:
+        dbeta.add_(d.sum(0))
+    dxb = dxv.to(BF16)
+    if dx is not None:
+        dx.copy_(dxb)
+    if dx_drop is not None:
+        dx_drop.copy_(dxb)
+    if d_x_tab is not None:
+        keep = x_rows.long() != x_pad_idx
+        d_x_tab.index_add_(0, x_rows.long()[keep], dxv[keep])
+    if d_add_tab is not None and add_tab is not None:
+        keep = add_idx.long() != add_pad_idx
+        d_add_tab.index_add_(0, add_idx.long()[keep], dxv[keep])
+
+
+def _attn_core(qkv, cu, heads):
+    H = heads * 64
+    outs = []
+    cu = cu.tolist()
+    for s in range(len(cu) - 1):
+        blk = qkv[cu[s]:cu[s + 1]]
+        n = blk.shape[0]
+        q, k, v = (blk[:, i * H:(i + 1) * H].reshape(n, heads, 64).transpose(0, 1)
+                   for i in range(3))
+        p = torch.softmax(q @ k.transpose(1, 2) / 8.0, dim=-1)
+        outs.append((p @ v).transpose(0, 1).reshape(n, H))
+    return torch.cat(outs, 0) if outs else qkv.new_zeros((0, H))
+
+
+def attn_fwd(qkv, cu_seqlens, ctx, *, n_seq, max_len, heads, head_dim=64, drop=(0, 0, 1.0)):
+    _ck_drop(drop)
+    assert head_dim == 64 and max_len <= 128
+    ctx.copy_(_attn_core(qkv.float(), cu_seqlens, heads).to(BF16))
+    return ctx
+
+
+def attn_bwd(qkv, cu_seqlens, dctx, dqkv, *, n_seq, max_len, heads, head_dim=64,
+             drop=(0, 0, 1.0)):
+    _ck_drop(drop)
+    with torch.enable_grad():
+        q = qkv.float().detach().requires_grad_(True)
+        out = _attn_core(q, cu_seqlens, heads)
+        out.backward(dctx.float())
+    dqkv.copy_(q.grad.to(BF16))
+    return dqkv
+
+
+def cast_bf16(src, dst):
+    dst.copy_(src.to(BF16))
+    return dst
+
+
+def gather_rows(src, idx, dst):
+    i = idx.long()
+    dst.copy_(torch.where((i >= 0)[:, None], src[i.clamp(min=0)], torch.zeros_like(dst)))
+    return dst
+
+
+def gather_sum_rows(src, off, idx, dst):
+    n = off.numel() - 1
+    counts = (off[1:] - off[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(n), counts)
+    acc = torch.zeros(n, src.shape[-1])
+    acc.index_add_(0, rows, src.float()[idx.long()])
+    if dst.dtype == torch.float32:
+        dst.add_(acc)
+    else:
+        dst.copy_(acc.to(BF16))
+    return dst
+
+
+def colsum(x, out):
+    out.add_(x.float().sum(0))
+    return out
+
+
+def relu_bwd(dy, pre, out):
+    out.copy_(torch.where(pre.float() > 0, dy, torch.zeros_like(dy)))
+    return out
+
+
+def adamw_step(p, g, m, v, p_bf16, *, step_size, beta1, beta2, eps, lr_wd, grad_scale=1.0):
+    gr = g * grad_scale
+    m.mul_(beta1).add_(gr, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(gr, gr, value=1 - beta2)
+    p.addcdiv_(m, v.sqrt() + eps, value=-step_size)
+    if lr_wd > 0:
+        p.add_(p, alpha=-lr_wd)
+    if p_bf16 is not None:
+        p_bf16.copy_(p.to(BF16))
+
+
+def sumsq(x, out):
+    out.add_((x.double() ** 2).sum().float())
+    return out
+
+
+def install(monkeypatch):
+    """Route hero_b200.ops through the torch restatements for the duration of a test."""
+    from hero_b200 import ops
+    for name in ("gemm", "ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd", "cast_bf16", "gather_rows",
+                 "gather_sum_rows", "colsum", "relu_bwd", "adamw_step", "sumsq"):
+        monkeypatch.setattr(ops, name, globals()[name])

@@ -1,0 +1,178 @@
+"""End-to-end parity of the CUDA encoder path against (a) golden fixtures produced by the
+unmodified reference and (b) the CPU oracle on seeded inputs, forward and backward.
+
+Tolerances (bf16 kernels vs fp32 oracle, eval mode, valid positions only):
+  outputs   max-abs <= 6e-2, mean-abs <= 8e-3, per-token cosine >= 0.999
+  gradients per-parameter relative Frobenius error <= 3e-2
+"""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from hero_b200 import synth
+from oracle import hero_oracle as orc
+from tests import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+OUT_MAX, OUT_MEAN, OUT_COS, GRAD_REL = 6e-2, 8e-3, 0.999, 3e-2
+
+
+def _json(tmp_path, d):
+    def cfg(n, v):
+        c = {"attention_probs_dropout_prob": 0.1, "hidden_act": "gelu", "hidden_dropout_prob": 0.1,
+             "hidden_size": d["hidden"], "initializer_range": 0.02,
+             "intermediate_size": d["inter"], "max_position_embeddings": 514,
+             "num_attention_heads": d["heads"], "num_hidden_layers": n, "type_vocab_size": 2}
+        if v:
+            c["vocab_size"] = d["vocab"]
+        return c
+    p = tmp_path / "m.json"
+    p.write_text(json.dumps({"f_config": cfg(d["f_layers"], True),
+                             "c_config": cfg(d["c_layers"], False)}))
+    return str(p)
+
+
+def _build(tmp_path, d, weights):
+    from hero_b200.model import HierarchicalVlModel, VideoModelConfig
+    m = HierarchicalVlModel(VideoModelConfig(_json(tmp_path, d)), vfeat_dim=d["vfeat_dim"],
+                            max_frm_seq_len=d["max_img_len"])
+    missing, unexpected = m.load_state_dict(weights, strict=False)
+    assert not unexpected
+    return m.cuda().eval()
+
+
+def _check_out(got, ref, mask, what):
+    got = got.detach().float().cpu().numpy()[mask]
+    ref = np.asarray(ref)[mask]
+    err = np.abs(got - ref)
+    cos = (got * ref).sum(-1) / (np.linalg.norm(got, axis=-1) * np.linalg.norm(ref, axis=-1))
+    assert err.max() <= OUT_MAX, f"{what}: max abs err {err.max():.4f}"
+    assert err.mean() <= OUT_MEAN, f"{what}: mean abs err {err.mean():.5f}"
+    assert cos.min() >= OUT_COS, f"{what}: min cosine {cos.min():.5f}"
+
+
+def test_config1_cross_modal_layer_matches_reference_golden(tmp_path):
+    fx = gu.load("xm1_config1.npz")
+    d = gu.dims_of(fx)
+    model = _build(tmp_path, d, gu.weights_for(fx))
+    xb = synth.to_device(synth.syn_xm_1(seed=int(fx["seed_batch"])), "cuda")
+    with torch.no_grad():
+        seq, pooled = model.f_encoder(xb, "repr")
+    _check_out(seq, fx["seq_out"], np.ones(seq.shape[:2], bool), "config-1 sequence output")
+    assert np.abs(pooled.float().cpu().numpy() - fx["pooled"]).max() < 3e-2
+
+
+def test_full_depth_encoder_matches_reference_golden(tmp_path):
+    fx = gu.load("hier_full_small.npz")
+    d = gu.dims_of(fx)
+    model = _build(tmp_path, d, gu.weights_for(fx))
+    vb, qb = gu.full_small_batches(fx)
+    with torch.no_grad():
+        clip = model(synth.to_device(vb, "cuda"), "repr")
+        q = model.f_encoder(synth.to_device(qb, "cuda"), "txt")[0]
+    _check_out(clip, fx["clip_out"], vb["c_attn_masks"].bool().numpy(), "clip outputs")
+    _check_out(q, fx["q_seq_out"], qb["attn_masks"].bool().numpy(), "query rows")
+    # padded positions are zeros in this implementation
+    assert float(clip[~vb["c_attn_masks"].bool().cuda()].abs().max()) == 0.0
+
+
+def _oracle_loss_and_grads(P, vb, qb, d, w1, w2):
+    P = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    clip = orc.hierarchical_repr(P, vb, d["f_layers"], d["c_layers"], d["heads"])
+    q = orc.cross_modal_txt(P, "f_encoder.", qb, d["f_layers"], d["heads"])
+    loss = (clip * w1).sum() + (q * w2).sum()
+    loss.backward()
+    return clip.detach(), q.detach(), {k: v.grad for k, v in P.items()}
+
+
+@pytest.mark.parametrize("kind", ["ragged", "dense"])
+def test_forward_backward_vs_oracle(tmp_path, kind):
+    d = dict(hidden=768, inter=3072, heads=12, f_layers=2, c_layers=1, vocab=50272,
+             vfeat_dim=4352, max_img_len=100)
+    shapes = orc.param_shapes(f_layers=2, c_layers=1)
+    P = orc.seeded_weights(shapes, seed=5)
+    if kind == "ragged":
+        vb, qb = synth.syn_tvr_ragged(batch_size=4, seed=99, t_range=(20, 40), s_range=(4, 8),
+                                      l_range=(4, 30), q_range=(6, 20))
+    else:
+        vb, qb = synth.syn_tvr_dense(batch_size=2, seed=7)
+    g = torch.Generator().manual_seed(1)
+    w1 = torch.randn(vb["c_v_feats"].shape[0], vb["c_v_feats"].shape[1], 768, generator=g)
+    w1 = w1 * vb["c_attn_masks"].unsqueeze(-1)
+    w2 = torch.randn(qb["input_ids"].shape[0], qb["input_ids"].shape[1], 768, generator=g)
+    w2 = w2 * qb["attn_masks"].unsqueeze(-1)
+    clip_ref, q_ref, g_ref = _oracle_loss_and_grads(P, vb, qb, d, w1, w2)
+
+    model = _build(tmp_path, d, P)
+    clip = model(synth.to_device(vb, "cuda"), "repr")
+    q = model.f_encoder(synth.to_device(qb, "cuda"), "txt")[0]
+    _check_out(clip, clip_ref.numpy(), vb["c_attn_masks"].bool().numpy(), "clip outputs")
+    _check_out(q, q_ref.numpy(), qb["attn_masks"].bool().numpy(), "query rows")
+    loss = (clip * w1.cuda()).sum() + (q * w2.cuda()).sum()
+    loss.backward()
+    named = dict(model.named_parameters())
+    bad = []
+    for k, gr in g_ref.items():
+        if gr is None or k.endswith("pooler.dense.weight") or k.endswith("pooler.dense.bias") \
+                or "mask_embedding" in k:
+            continue
+        got = named[k].grad
+        assert got is not None, f"no gradient for {k}"
+        num = (got.float().cpu() - gr).norm().item()
+        den = gr.norm().item()
+        if den < 1e-6:
+            assert num < 1e-3, k
+            continue
+        if num / den > GRAD_REL:
+            bad.append((k, round(num / den, 4)))
+    assert not bad, f"gradient mismatch (relative Frobenius) for {bad[:12]} ({len(bad)} total)"
+
+
+def test_generic_bert_encoder_api_padded_in_out(tmp_path):
+    """BertEncoder.forward(hidden (N, L, H), mask) keeps the reference signature."""
+    from hero_b200.encoder import RobertaModelConfig
+    from hero_b200.layers import BertEncoder
+    cfg = RobertaModelConfig(10, hidden_size=768, num_hidden_layers=1, num_attention_heads=12,
+                             intermediate_size=3072)
+    torch.manual_seed(0)
+    enc = BertEncoder(cfg)
+    for p in enc.parameters():
+        torch.nn.init.normal_(p, std=0.02) if p.dim() > 1 else None
+    enc = enc.cuda().eval()
+    P = {"layer.0." + k: v.detach().cpu() for k, v in enc.layer[0].state_dict().items()}
+    g = torch.Generator().manual_seed(2)
+    h = torch.randn(3, 9, 768, generator=g)
+    mask = torch.tensor([[1] * 9, [1] * 4 + [0] * 5, [0, 1, 1, 0, 1, 0, 0, 0, 0]])
+    ref = orc.bert_encoder(h, mask, P, "", 1, 12)
+    with torch.no_grad():
+        out = enc(h.cuda(), mask.cuda())[0]
+    _check_out(out, ref.numpy(), mask.bool().numpy(), "generic encoder")
+
+
+def test_training_mode_dropout_runs_and_is_stochastic(tmp_path):
+    d = dict(hidden=768, inter=3072, heads=12, f_layers=1, c_layers=1, vocab=50272,
+             vfeat_dim=4352, max_img_len=100)
+    P = orc.seeded_weights(orc.param_shapes(f_layers=1, c_layers=1), seed=5)
+    model = _build(tmp_path, d, P)
+    vb, _ = synth.syn_tvr_ragged(batch_size=2, seed=3, t_range=(10, 20), s_range=(2, 4),
+                                 l_range=(4, 10))
+    vbd = synth.to_device(vb, "cuda")
+    with torch.no_grad():
+        ev = model(vbd, "repr")
+    model.train()
+    torch.manual_seed(1)
+    a = model(vbd, "repr")
+    a.float().pow(2).mean().backward()
+    torch.manual_seed(1)
+    b = model(vbd, "repr")
+    torch.manual_seed(2)
+    c = model(vbd, "repr")
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b), "same torch seed must give the same dropout masks"
+    assert not torch.equal(a, c)
+    assert (a - ev).abs().mean() > 1e-3
+    g = model.f_encoder.encoder.layer[0].intermediate.dense.weight.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0

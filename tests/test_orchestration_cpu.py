@@ -1,0 +1,115 @@
+"""Host-side orchestration (plans + autograd chains + module plumbing) checked on CPU against
+the reference-generated golden fixture, with `hero_b200.ops` monkeypatched to torch restatements
+of the C-ABI contracts (tests/fake_ops.py). The CUDA kernels themselves are checked on the GPU
+(tests/test_kernels_gpu.py, tests/test_encoder_gpu.py)."""
+import json
+
+import numpy as np
+import torch
+
+from tests import fake_ops
+from tests import golden_util as gu
+
+
+def _json(tmp_path, d):
+    def cfg(n, v):
+        c = {"attention_probs_dropout_prob": 0.1, "hidden_act": "gelu", "hidden_dropout_prob": 0.1,
+             "hidden_size": d["hidden"], "initializer_range": 0.02,
+             "intermediate_size": d["inter"], "max_position_embeddings": 514,
+             "num_attention_heads": d["heads"], "num_hidden_layers": n, "type_vocab_size": 2}
+        if v:
+            c["vocab_size"] = d["vocab"]
+        return c
+    p = tmp_path / "m.json"
+    p.write_text(json.dumps({"f_config": cfg(d["f_layers"], True),
+                             "c_config": cfg(d["c_layers"], False)}))
+    return str(p)
+
+
+def _model(tmp_path, fx):
+    from hero_b200.model import HierarchicalVlModel, VideoModelConfig
+    d = gu.dims_of(fx)
+    m = HierarchicalVlModel(VideoModelConfig(_json(tmp_path, d)), vfeat_dim=d["vfeat_dim"],
+                            max_frm_seq_len=d["max_img_len"])
+    missing, unexpected = m.load_state_dict(gu.weights_for(fx), strict=False)
+    assert not unexpected
+    return m.eval()
+
+
+def _close(got, ref, mask, atol, what):
+    got = got.detach().float().numpy()[mask]
+    ref = ref[mask]
+    err = np.abs(got - ref).max()
+    assert err <= atol, f"{what}: max abs err {err}"
+
+
+def test_forward_matches_reference_golden(tmp_path, monkeypatch):
+    fake_ops.install(monkeypatch)
+    fx = gu.load("hier_tiny.npz")
+    model = _model(tmp_path, fx)
+    vb, qb = gu.stored_batches(fx)
+    with torch.no_grad():
+        f_seq, pooled = model.f_encoder(vb, "repr")
+        clip = model(vb, "repr")
+        pre = model.forward_repr(vb, encode_clip=False)
+        q = model.f_encoder(qb, "txt")[0]
+    fm = vb["f_attn_masks"].bool().numpy()
+    cm = vb["c_attn_masks"].bool().numpy()
+    _close(f_seq, fx["f_seq_out"], fm, 6e-2, "f_encoder sequence output")
+    _close(clip, fx["clip_out"], cm, 6e-2, "clip outputs")
+    _close(pre, fx["pre_clip"], cm, 8e-2, "pre-temporal features")
+    _close(q, fx["q_seq_out"], qb["attn_masks"].bool().numpy(), 6e-2, "query rows")
+    assert float(clip.numpy()[~cm].max(initial=0.0)) == 0.0
+
+
+def test_backward_matches_reference_golden(tmp_path, monkeypatch):
+    fake_ops.install(monkeypatch)
+    fx = gu.load("hier_tiny.npz")
+    model = _model(tmp_path, fx)
+    vb, qb = gu.stored_batches(fx)
+    clip = model(vb, "repr")
+    q = model.f_encoder(qb, "txt")[0]
+    loss = (clip * torch.from_numpy(fx["loss_w1"])).sum() + (q * torch.from_numpy(fx["loss_w2"])).sum()
+    assert abs(loss.item() - float(fx["loss"])) < 0.05 * max(1.0, abs(float(fx["loss"])))
+    loss.backward()
+    named = dict(model.named_parameters())
+    for k, ref in fx.items():
+        if not k.startswith("grad."):
+            continue
+        g = named[k[5:]].grad
+        assert g is not None, k
+        rel = np.linalg.norm(g.numpy() - ref) / max(np.linalg.norm(ref), 1e-12)
+        assert rel < 4e-2, f"{k}: relative Frobenius error {rel}"
+
+
+def test_generic_bert_encoder_and_temporal_apis(tmp_path, monkeypatch):
+    fake_ops.install(monkeypatch)
+    from oracle import hero_oracle as orc
+    fx = gu.load("hier_tiny.npz")
+    d = gu.dims_of(fx)
+    model = _model(tmp_path, fx)
+    P = gu.weights_for(fx)
+    g = torch.Generator().manual_seed(4)
+    h = torch.randn(3, 7, d["hidden"], generator=g)
+    mask = torch.tensor([[1] * 7, [1, 1, 1, 0, 0, 0, 0], [0, 1, 1, 1, 1, 0, 0]])
+    with torch.no_grad():
+        out = model.c_encoder.encoder(h, mask)[0]
+        tout = model.c_encoder(h, None, mask)
+    ref = orc.bert_encoder(h, mask, P, "c_encoder.encoder.", d["c_layers"], d["heads"])
+    _close(out, ref.numpy(), mask.bool().numpy(), 6e-2, "BertEncoder padded API")
+    tref = orc.temporal_trm(P, "c_encoder.", h, mask, d["c_layers"], d["heads"])
+    _close(tout, tref.numpy(), mask.bool().numpy(), 6e-2, "TemporalTrm.forward")
+
+
+def test_plan_can_be_attached_at_collate_time(tmp_path, monkeypatch):
+    fake_ops.install(monkeypatch)
+    from hero_b200.plan import PLAN_KEY, attach_plan
+    fx = gu.load("hier_tiny.npz")
+    model = _model(tmp_path, fx)
+    vb, _ = gu.stored_batches(fx)
+    with torch.no_grad():
+        a = model(vb, "repr")
+        vb2 = attach_plan(dict(vb))
+        assert PLAN_KEY in vb2
+        b = model(vb2, "repr")
+    assert torch.equal(a, b)

@@ -1,0 +1,100 @@
+"""Host-side packing plans (pure numpy): checked against the padded-layout semantics of the
+reference as restated by the oracle (gather of cat[img, txt]; collect_frame_outputs)."""
+import numpy as np
+import torch
+
+from hero_b200 import synth
+from hero_b200.plan import CPlan, FPlan, ReprPlan, SeqPlan, TxtPlan, table_csr
+from oracle import hero_oracle as orc
+
+
+def _ragged(seed=3, bs=4):
+    return synth.syn_tvr_ragged(batch_size=bs, seed=seed, vfeat_dim=8, vocab=60, t_range=(6, 14),
+                                s_range=(2, 5), l_range=(3, 9), q_range=(3, 8))
+
+
+def test_seqplan_roundtrip():
+    mask = np.array([[1, 1, 0, 0], [0, 1, 1, 1], [0, 0, 0, 0], [1, 0, 1, 0]])
+    sp = SeqPlan(mask)
+    assert sp.n_tok == 7 and sp.max_len == 3
+    assert sp.cu.tolist() == [0, 2, 5, 5, 7]
+    assert sp.tok_flat.tolist() == [0, 1, 5, 6, 7, 12, 14]
+    assert sp.pad_to_tok[sp.tok_flat].tolist() == list(range(7))
+    assert (sp.pad_to_tok >= 0).sum() == 7
+
+
+def test_fplan_matches_gather_of_cat_img_txt():
+    vb, _ = _ragged()
+    R, max_vl = vb["f_v_feats"].shape[:2]
+    max_sl = vb["f_sub_input_ids"].shape[1]
+    fp = FPlan(vb["f_attn_masks"], vb["f_gather_index"], max_vl, max_sl)
+    img_id = torch.arange(R * max_vl).view(R, max_vl)                 # unique id per frame slot
+    txt_id = 10_000 + torch.arange(R * max_sl).view(R, max_sl)         # unique id per text slot
+    ref = torch.gather(torch.cat([img_id, txt_id], 1), 1, vb["f_gather_index"])
+    packed = np.full(fp.seq.n_tok, -1, np.int64)
+    packed[fp.img_tok] = img_id.view(-1).numpy()[fp.img_src]
+    packed[fp.txt_tok] = txt_id.view(-1).numpy()[fp.txt_src]
+    valid = vb["f_attn_masks"].bool().numpy()
+    assert np.array_equal(packed, ref.numpy()[valid])
+    assert fp.n_img + fp.n_txt == fp.seq.n_tok == int(valid.sum())
+    # zero-frame subtitles contribute no image token (their dummy frame is masked)
+    assert fp.n_img == sum(len(fr) for clip in vb["sub_idx2frame_idx"] for _, fr in clip)
+
+
+def test_cplan_equals_collect_frame_outputs_and_its_transpose():
+    vb, _ = _ragged(seed=9, bs=5)
+    plan = ReprPlan(vb)
+    R, n = vb["f_attn_masks"].shape
+    B, T = vb["c_attn_masks"].shape
+    H = 6
+    g = torch.Generator().manual_seed(0)
+    f_out = torch.randn(R, n, H, generator=g)
+    ref = orc.collect_frame_outputs((B, T, H), f_out, vb["num_subs"], vb["sub_idx2frame_idx"])
+    f_packed = f_out.view(-1, H).numpy()[plan.f.seq.tok_flat]
+    c = plan.c
+    got = np.zeros((c.seq.n_tok, H), np.float32)
+    for i in range(c.seq.n_tok):
+        for e in range(c.fwd_off[i], c.fwd_off[i + 1]):
+            got[i] += f_packed[c.fwd_idx[e]]
+    assert np.allclose(got, ref.view(-1, H).numpy()[c.seq.tok_flat], atol=1e-6)
+    # adjoint: <A f, y> == <f, A^T y>
+    y = torch.randn(c.seq.n_tok, H, generator=g).numpy()
+    aty = np.zeros((plan.f.seq.n_tok, H), np.float32)
+    for i in range(plan.f.seq.n_tok):
+        for e in range(c.bwd_off[i], c.bwd_off[i + 1]):
+            aty[i] += y[c.bwd_idx[e]]
+    assert np.isclose((got * y).sum(), (f_packed * aty).sum(), rtol=1e-4)
+
+
+def test_duplicate_frame_assignments_accumulate():
+    """model/model.py:182-184 accumulates when a frame is listed under two subtitles."""
+    gen = torch.Generator().manual_seed(1)
+    clip = synth.make_clip(gen, 6, [[0, 1, 2], [2, 3]], [3, 4], vfeat_dim=8, vocab=50)
+    vb = synth.video_batch([clip])
+    plan = ReprPlan(vb)
+    c = plan.c
+    counts = np.diff(c.fwd_off)
+    assert counts.tolist() == [1, 1, 2, 1, 0, 0]
+
+
+def test_txt_plan_and_table_csr():
+    _, qb = _ragged()
+    tp = TxtPlan(qb["attn_masks"])
+    assert tp.f.n_img == 0 and tp.f.n_txt == int(qb["attn_masks"].sum())
+    ids = qb["input_ids"].view(-1).numpy()[tp.f.txt_src]
+    assert np.array_equal(ids, qb["input_ids"].numpy()[qb["attn_masks"].bool().numpy()])
+    off, idx = table_csr(tp.f.txt_j, qb["attn_masks"].shape[1])
+    for j in range(len(off) - 1):
+        assert all(tp.f.txt_j[t] == j for t in idx[off[j]:off[j + 1]])
+    assert off[-1] == tp.f.n_txt
+
+
+def test_dense_canonical_batch_shapes():
+    vb, qb = synth.syn_tvr_dense(batch_size=2, vfeat_dim=16)
+    assert tuple(vb["f_sub_input_ids"].shape) == (40, 20)
+    assert tuple(vb["f_v_feats"].shape) == (40, 5, 16)
+    assert tuple(vb["f_attn_masks"].shape) == (40, 25)
+    assert tuple(vb["c_v_feats"].shape) == (2, 100, 16)
+    plan = ReprPlan(vb)
+    assert plan.f.seq.n_tok == 40 * 25 and plan.c.seq.n_tok == 200
+    assert plan.c.n_pairs == 200 and plan.f.seq.max_len == 25 and plan.c.seq.max_len == 100
