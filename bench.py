@@ -1,0 +1,398 @@
+"""Headline benchmark: clips/sec, forward + backward of the HERO hierarchical encoder at
+train-tvr-8gpu shapes (BASELINE.json), data-parallel over N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference          # CPU oracle port of the reference path (rank 0)
+
+One step = one pass of the hot path over one synthetic SYN-TVR-dense batch per rank
+(B = 32 clips x 100 frames x 4352-d features, 20 subtitle rows of 5 frames + 20 tokens per clip,
+one 16-token query per clip; hero_finetune dims: 6 cross-modal + 3 temporal layers, H = 768):
+HierarchicalVlModel 'repr' forward + CrossModalTrm 'txt' forward on the query rows, backward of
+both from fixed upstream gradients, and (N > 1) the mean all-reduce of the flat gradient buffer.
+Training mode (dropout 0.1 as in config/train-tvr-8gpu.json). No optimizer step (the metric is
+fwd+bwd); `--with-optimizer` adds the fused AdamW.
+
+`value`   whole-job clips/s with inputs (and the per-batch packing plan, a collate-side product)
+          resident in HBM, CUDA-event timed, max over ranks.
+`e2e`     same metric through the public module API from PINNED HOST batches: per step the packing
+          plan is built on the host, the batch is copied host->device on a side stream (prefetch
+          one step ahead, like the reference's PrefetchLoader, data/loader.py:89-144) and a loss
+          scalar is read back.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+H, INTER, HEADS, F_LAYERS, C_LAYERS, D = 768, 3072, 12, 6, 3, 4352
+METRIC = "clips/sec fwd+bwd HERO encoder (TVR 8gpu shapes)"
+
+
+def model_json(path):
+    def cfg(n, with_vocab):
+        c = {"attention_probs_dropout_prob": 0.1, "hidden_act": "gelu", "hidden_dropout_prob": 0.1,
+             "hidden_size": H, "initializer_range": 0.02, "intermediate_size": INTER,
+             "max_position_embeddings": 514, "num_attention_heads": HEADS, "num_hidden_layers": n,
+             "type_vocab_size": 2}
+        if with_vocab:
+            c["vocab_size"] = 50272
+        return c
+    with open(path, "w") as f:
+        json.dump({"f_config": cfg(F_LAYERS, True), "c_config": cfg(C_LAYERS, False)}, f)
+
+
+def algorithmic_flops_fwd(vb, qb):
+    """SURVEY.md §8d counting rule: valid tokens only, GEMMs + QK^T + PV, multiply-add = 2."""
+    def f_layer(n):
+        return 24 * n * H * H + 4 * n * n * H
+    f_lens = vb["f_attn_masks"].sum(1).tolist()
+    c_lens = vb["c_attn_masks"].sum(1).tolist()
+    q_lens = qb["attn_masks"].sum(1).tolist()
+    n_img = sum(len(fr) for clip in vb["sub_idx2frame_idx"] for _, fr in clip)
+    fl = F_LAYERS * sum(f_layer(n) for n in f_lens) + F_LAYERS * sum(f_layer(n) for n in q_lens)
+    fl += C_LAYERS * sum(f_layer(n) for n in c_lens)
+    fl += 2 * D * H * (n_img + sum(c_lens))
+    return float(fl)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_model(device, seed=0):
+    from hero_b200.model import HierarchicalVlModel, VideoModelConfig
+    torch.manual_seed(seed)
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "hero_finetune.json")
+        model_json(p)
+        model = HierarchicalVlModel(VideoModelConfig(p), vfeat_dim=D, max_frm_seq_len=100)
+    model.initialize()   # random init of the hero_finetune architecture (no checkpoints offline)
+    return model.to(device).train()
+
+
+def run_ours(args):
+    from hero_b200 import distributed as hdist
+    from hero_b200 import ops, synth
+    from hero_b200.params import flat_of
+    from hero_b200.plan import PLAN_KEY, attach_plan
+    from hero_b200.optim import FusedAdamW
+
+    rank, world, local_rank = hdist.init()
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    model = build_model(device, seed=0)
+    flat = flat_of(model, device)
+    hdist.broadcast_tensors([flat.flat], 0)
+    flat.mark_dirty()
+    gflat = flat.ensure_flat_grads()
+    opt = FusedAdamW(flat, lr=1e-4) if args.with_optimizer else None
+
+    B = args.batch_size
+    n_host = 3
+    host = []
+    for i in range(n_host):
+        vb, qb = synth.syn_tvr_dense(batch_size=B, seed=1234 + rank + 1000 * i)
+        for b in (vb, qb):
+            for k, v in b.items():
+                if torch.is_tensor(v):
+                    b[k] = v.pin_memory()
+        host.append((vb, qb))
+    flops_fwd = algorithmic_flops_fwd(*host[0])
+    g = torch.Generator().manual_seed(7)
+    dclip = (torch.randn(B, 100, H, generator=g) * 1e-2).to(device)
+    dq = (torch.randn(B, host[0][1]["input_ids"].shape[1], H, generator=g) * 1e-2).to(device)
+
+    def fwd_bwd(vb_dev, qb_dev):
+        clip = model(vb_dev, "repr")
+        q = model.f_encoder(qb_dev, "txt")[0]
+        torch.autograd.backward([clip, q], [dclip, dq])
+        if world > 1:
+            hdist.all_reduce_flat(gflat)
+        if opt is not None:
+            opt.step()
+        return clip
+
+    # ------------------------------------------------------------- device-resident timing
+    resident = []
+    for vb, qb in host:
+        vb = attach_plan(dict(vb))
+        qb = attach_plan(dict(qb), kind="txt")
+        resident.append((synth.to_device(vb, device), synth.to_device(qb, device)))
+    torch.cuda.synchronize()
+
+    def resident_step(i):
+        gflat.zero_()
+        vb_dev, qb_dev = resident[i % n_host]
+        fwd_bwd(vb_dev, qb_dev)
+
+    for i in range(args.warmup):
+        resident_step(i)
+    ops.reset_launch_count()
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        resident_step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = ops.launch_count() // max(args.steps, 1)
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ------------------------------------------------------------- GEMM-family roofline (live)
+    ops.start_gemm_profile()
+    for i in range(min(args.steps, 5)):
+        resident_step(i)
+    torch.cuda.synchronize()
+    gp = ops.stop_gemm_profile()
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    achieved = gp["flops"] / (gp["ms"] * 1e-3) / 1e12 if gp["ms"] > 0 else 0.0
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tr_path):
+        traffic = json.load(open(tr_path)).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all variants)",
+                "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": round(achieved / peak_tf, 4),
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
+                if peaks else "fallback 1.4 PF/s (of fallback)",
+                "launches_per_step": gp["launches"] // max(min(args.steps, 5), 1),
+                "gemm_share_of_step": round(gp["ms"] / max(min(args.steps, 5), 1) / ms_per_step, 3),
+                "traffic": traffic,
+                "step_algorithmic_tflops": round(3 * flops_fwd * 1e-12, 4),
+                "step_frac_of_peak": round(3 * flops_fwd / (ms_per_step * 1e-3) / 1e12 / peak_tf,
+                                           4)}
+
+    # ------------------------------------------------------------- end-to-end from pinned host
+    copy_stream = torch.cuda.Stream(device)
+
+    def h2d_bytes(b):
+        return sum(v.numel() * v.element_size() for v in b.values() if torch.is_tensor(v))
+
+    def stage(i):
+        vb, qb = host[i % n_host]
+        vb = attach_plan(dict(vb))                      # host-side packing plan, every step
+        qb = attach_plan(dict(qb), kind="txt")
+        with torch.cuda.stream(copy_stream):
+            vb_dev = synth.to_device(vb, device, non_blocking=True)
+            qb_dev = synth.to_device(qb, device, non_blocking=True)
+            vb_dev[PLAN_KEY].to(device)
+            qb_dev[PLAN_KEY].to(device)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return vb_dev, qb_dev, ev
+
+    def e2e_loop(n):
+        out = 0.0
+        nxt = stage(0)
+        for i in range(n):
+            vb_dev, qb_dev, ev = nxt
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            for b in (vb_dev, qb_dev):      # allocator safety across streams (loader.py:135-138)
+                for v in b.values():
+                    if torch.is_tensor(v):
+                        v.record_stream(cur)
+                b[PLAN_KEY].dev.flat.record_stream(cur)
+            if i + 1 < n:
+                nxt = stage(i + 1)                      # prefetch overlaps this step's compute
+            gflat.zero_()
+            clip = fwd_bwd(vb_dev, qb_dev)
+            out = float(clip[0, 0, :8].float().sum().item())   # D2H read of a result scalar
+        return out
+
+    e2e_loop(max(2, args.warmup // 2))
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(t.item())
+    bi = h2d_bytes(host[0][0]) + h2d_bytes(host[0][1])
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(sample_clips=args.cpu_clips, steps=2, warmup=1)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "clips/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "SYN-TVR-dense: HierarchicalVlModel 'repr' + CrossModalTrm 'txt' "
+                                   "fwd+bwd (hero_finetune dims 6+3 layers), per-rank 32 clips x "
+                                   "100 frames x 4352-d + 640 rows x (5 frames + 20 tokens) + 32 "
+                                   "queries x 16 tokens",
+                       "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                       "dropout": 0.1, "optimizer_in_step": bool(args.with_optimizer),
+                       "allreduce_in_step": world > 1,
+                       "l2": "no explicit flush: per-step working set (~0.35 GB weights+grads, "
+                             "~3 GB activations, 111 MB inputs) exceeds the 126 MB L2"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": round(e2e_value, 2), "unit": "clips/s", "h2d_bytes_per_step": bi,
+                    "d2h_bytes_per_step": 4},
+            "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def cpu_baseline(sample_clips=4, steps=2, warmup=1):
+    """The oracle port of the reference path on the host cores: fwd+bwd (autograd) on a bounded
+    sample of the same workload (first `sample_clips` clips of SYN-TVR-dense)."""
+    from hero_b200 import synth
+    from oracle import hero_oracle as orc
+    torch.manual_seed(0)
+    P = orc.seeded_weights(orc.param_shapes(), seed=0)
+    P = {k: v.requires_grad_(True) for k, v in P.items()}
+    vb, qb = synth.syn_tvr_dense(batch_size=sample_clips, seed=1234)
+    g = torch.Generator().manual_seed(7)
+    dclip = torch.randn(sample_clips, 100, H, generator=g) * 1e-2
+    dq = torch.randn(sample_clips, qb["input_ids"].shape[1], H, generator=g) * 1e-2
+
+    def step():
+        for v in P.values():
+            v.grad = None
+        clip = orc.hierarchical_repr(P, vb, F_LAYERS, C_LAYERS, HEADS)
+        q = orc.cross_modal_txt(P, "f_encoder.", qb, F_LAYERS, HEADS)
+        torch.autograd.backward([clip, q], [dclip, dq])
+
+    for _ in range(warmup):
+        step()
+    best = float("inf")
+    t_all = 0.0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        best = min(best, dt)
+        t_all += dt
+    return {"value": round(sample_clips / (t_all / steps), 3), "unit": "clips/s",
+            "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
+            "best_value": round(sample_clips / best, 3),
+            "sample": f"oracle fwd+bwd (fp32, torch CPU autograd) on the first {sample_clips} "
+                      f"clips of SYN-TVR-dense, {steps} timed steps after {warmup} warm-up"}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU path, restated by the oracle port (the Python
+    reference cannot travel to the GPU box), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = max(1, min(args.warmup, 1))
+    cb = cpu_baseline(sample_clips=args.cpu_clips, steps=steps, warmup=warm)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "clips/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": round(1e3 * args.cpu_clips / cb["value"], 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"SYN-TVR-dense sample of {args.cpu_clips} clips per step "
+                                   "(same per-clip shapes as the GPU arm)", "parallelism": "cpu"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-size", type=int, default=32)
+    ap.add_argument("--with-optimizer", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-clips", type=int, default=4)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -290,6 +290,8 @@ class CrossModalTrm(RobertaPreTrainedModel):
         from .plan import FPlan, DeviceIndex, table_csr
         if input_ids is None and img_feat is None:
             raise ValueError("Both img_feat and input_dis are None")
+        if isinstance(_plan, TxtPlan):
+            return _plan.f, _plan.to(attention_mask.device), ("pos_off", "pos_idx", None, None)
         if _plan is not None and hasattr(_plan, "f"):
             return _plan.f, _plan.to(attention_mask.device), None
         if img_feat is None:

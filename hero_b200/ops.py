@@ -15,6 +15,38 @@ ACT_NONE, ACT_GELU, ACT_RELU, ACT_GELU_GRAD = 0, 1, 2, 3
 BF16 = torch.bfloat16
 
 
+_LAUNCHES = 0
+_GEMM_PROF = None
+
+
+def _count(n=1):
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def reset_launch_count():
+    global _LAUNCHES
+    _LAUNCHES = 0
+
+
+def launch_count():
+    """Number of hero_b200 kernels launched since the last reset (bench.py's gpu_launches)."""
+    return _LAUNCHES
+
+
+def start_gemm_profile():
+    """Bracket every GEMM launch with CUDA events on the launching stream (bench.py roofline)."""
+    global _GEMM_PROF
+    _GEMM_PROF = []
+
+
+def stop_gemm_profile():
+    global _GEMM_PROF
+    prof, _GEMM_PROF = _GEMM_PROF or [], None
+    ms = sum(s.elapsed_time(e) for s, e, _ in prof)
+    return {"ms": ms, "flops": float(sum(f for _, _, f in prof)), "launches": len(prof)}
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -73,6 +105,14 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None
     assert out.dtype == (torch.float32 if accumulate_f32 else BF16)
     g.drop_threshold, g.drop_key, g.drop_scale = drop
     g.block_n, g.k_splits = block_n, k_splits
+    _count()
+    if _GEMM_PROF is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        _lib.check(_lib.lib().hero_gemm_bf16(C.byref(g), _stream()))
+        ev1.record()
+        _GEMM_PROF.append((ev0, ev1, 2.0 * m * n * k))
+        return out
     _lib.check(_lib.lib().hero_gemm_bf16(C.byref(g), _stream()))
     return out
 
@@ -106,6 +146,7 @@ def ln_fwd(x, gamma, beta, eps, y, *, n_rows, x_rows=None, add_tab=None, add_idx
     a.y, a.y_rows = _ptr(y), _ptr(y_rows)
     a.mean, a.rstd = _ptr(mean), _ptr(rstd)
     a.drop_threshold, a.drop_key, a.drop_scale = drop
+    _count()
     _lib.check(_lib.lib().hero_ln_fwd(C.byref(a), _stream()))
     return y
 
@@ -125,12 +166,15 @@ def ln_bwd(dy, x, gamma, mean, rstd, *, n_rows, x_rows=None, add_tab=None, add_i
     a.d_x_tab, a.x_pad_idx = _ptr(d_x_tab), x_pad_idx
     a.d_add_tab, a.add_pad_idx = _ptr(d_add_tab), add_pad_idx
     a.dgamma, a.dbeta = _ptr(dgamma), _ptr(dbeta)
+    _count(2 if (h > 768 and (dgamma is not None or dbeta is not None) and
+                 (dx is not None or d_add_tab is not None)) else 1)
     _lib.check(_lib.lib().hero_ln_bwd(C.byref(a), _stream()))
 
 
 def attn_fwd(qkv, cu_seqlens, ctx, *, n_seq, max_len, heads, head_dim=64, drop=(0, 0, 1.0)):
     _require_cuda(qkv, cu_seqlens, ctx)
     assert qkv.dtype == BF16 and cu_seqlens.dtype == torch.int32 and qkv.is_contiguous()
+    _count()
     _lib.check(_lib.lib().hero_attn_fwd(
         _ptr(qkv), _ptr(cu_seqlens), _ptr(ctx), n_seq, max_len, heads, head_dim,
         1.0 / (head_dim ** 0.5), drop[0], drop[1], drop[2], _stream()))
@@ -141,6 +185,7 @@ def attn_bwd(qkv, cu_seqlens, dctx, dqkv, *, n_seq, max_len, heads, head_dim=64,
              drop=(0, 0, 1.0)):
     _require_cuda(qkv, cu_seqlens, dctx, dqkv)
     assert dctx.is_contiguous() and dqkv.is_contiguous()
+    _count()
     _lib.check(_lib.lib().hero_attn_bwd(
         _ptr(qkv), _ptr(cu_seqlens), _ptr(dctx), _ptr(dqkv), n_seq, max_len, heads, head_dim,
         1.0 / (head_dim ** 0.5), drop[0], drop[1], drop[2], _stream()))
@@ -152,6 +197,7 @@ def cast_bf16(src, dst):
     _require_cuda(src, dst)
     assert src.dtype == torch.float32 and dst.dtype == BF16 and src.is_contiguous()
     assert dst.is_contiguous() and src.numel() == dst.numel()
+    _count()
     _lib.check(_lib.lib().hero_cast_f32_to_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()))
     return dst
 
@@ -160,6 +206,7 @@ def gather_rows(src, idx, dst):
     _require_cuda(src, idx, dst)
     assert src.dtype == BF16 and dst.dtype == BF16 and idx.dtype == torch.int32
     h = src.shape[-1]
+    _count()
     _lib.check(_lib.lib().hero_gather_rows_bf16(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), h,
                                                 _stream()))
     return dst
@@ -172,6 +219,7 @@ def gather_sum_rows(src, off, idx, dst):
     n, h = off.numel() - 1, src.shape[-1]
     fn = (_lib.lib().hero_gather_sum_rows_f32 if dst.dtype == torch.float32
           else _lib.lib().hero_gather_sum_rows_bf16)
+    _count()
     _lib.check(fn(_ptr(src), _ptr(off), _ptr(idx), _ptr(dst), n, h, _stream()))
     return dst
 
@@ -180,6 +228,7 @@ def colsum(x, out):
     """out[n] += sum_m x[m, n]  (x bf16 2-D, out fp32)."""
     _require_cuda(x, out)
     assert x.dtype == BF16 and out.dtype == torch.float32 and x.dim() == 2
+    _count()
     _lib.check(_lib.lib().hero_colsum_bf16(_ptr(x), x.stride(0), x.shape[0], x.shape[1],
                                            _ptr(out), _stream()))
     return out
@@ -187,6 +236,7 @@ def colsum(x, out):
 
 def relu_bwd(dy, pre, out):
     _require_cuda(dy, pre, out)
+    _count()
     _lib.check(_lib.lib().hero_relu_bwd_bf16(_ptr(dy), _ptr(pre), _ptr(out), dy.numel(),
                                              _stream()))
     return out
@@ -194,6 +244,7 @@ def relu_bwd(dy, pre, out):
 
 def adamw_step(p, g, m, v, p_bf16, *, step_size, beta1, beta2, eps, lr_wd, grad_scale=1.0):
     _require_cuda(p, g, m, v)
+    _count()
     _lib.check(_lib.lib().hero_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16),
                                           p.numel(), step_size, beta1, beta2, eps, lr_wd,
                                           grad_scale, _stream()))
@@ -201,5 +252,6 @@ def adamw_step(p, g, m, v, p_bf16, *, step_size, beta1, beta2, eps, lr_wd, grad_
 
 def sumsq(x, out):
     _require_cuda(x, out)
+    _count()
     _lib.check(_lib.lib().hero_sumsq_f32(_ptr(x), x.numel(), _ptr(out), _stream()))
     return out

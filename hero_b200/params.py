@@ -36,7 +36,18 @@ def _ordered_named_params(module):
                 continue
         out.append((name, p))
         placed.add(name)
+    # decayed parameters first, then the no-decay set of optim/misc.py:22 (names containing
+    # 'bias' / 'LayerNorm.bias' / 'LayerNorm.weight'): the fused AdamW then needs two launches.
+    # Stable sort keeps q/k/v weights (and q/k/v biases) adjacent.
+    out.sort(key=lambda np_: is_no_decay(np_[0]))
     return out
+
+
+NO_DECAY = ("bias", "LayerNorm.bias", "LayerNorm.weight")
+
+
+def is_no_decay(name):
+    return any(nd in name for nd in NO_DECAY)
 
 
 class FlatParams:
@@ -78,6 +89,10 @@ class FlatParams:
                     self.entries.append((name, p, off, p.numel()))
                     self._by_id[id(p)] = (off, p.numel())
             self.flat = flat
+            self.total = total
+            # first element of the no-decay block (== total when every parameter decays)
+            self.no_decay_start = next((off for (name, _), off in zip(named, offs)
+                                        if is_no_decay(name)), total)
             self.mirror = torch.empty(total, dtype=torch.bfloat16, device=device)
             self.grad_flat = None
             self.dirty = True

@@ -106,10 +106,14 @@ def test_plan_can_be_attached_at_collate_time(tmp_path, monkeypatch):
     from hero_b200.plan import PLAN_KEY, attach_plan
     fx = gu.load("hier_tiny.npz")
     model = _model(tmp_path, fx)
-    vb, _ = gu.stored_batches(fx)
+    vb, qb = gu.stored_batches(fx)
     with torch.no_grad():
         a = model(vb, "repr")
         vb2 = attach_plan(dict(vb))
         assert PLAN_KEY in vb2
         b = model(vb2, "repr")
+        qa = model.f_encoder(qb, "txt")[0]
+        qb2 = attach_plan(dict(qb), kind="txt")
+        qb_out = model.f_encoder(qb2, "txt")[0]
     assert torch.equal(a, b)
+    assert torch.equal(qa, qb_out)
