@@ -22,7 +22,8 @@ namespace hero {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle span
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_GELU_GRAD = 3 };
 
@@ -53,22 +54,26 @@ struct GemmCfg {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers
-  // epilogue staging: per epilogue warp two slabs of 32 rows x 64 bf16 (128 B rows, swizzled)
+  // epilogue staging: one slab of 32 rows x 64 bf16 (128 B rows, swizzled) per epilogue warp
   static constexpr int SLAB_BYTES = 32 * 128;
-  static constexpr int STAGING_BYTES = 4 * 2 * SLAB_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + STAGING_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFFSET + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * SLAB_BYTES;
+  static constexpr int BIAS_OFFSET = STAGES * STAGE_BYTES + STAGING_BYTES;
+  static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;  // per-tile bias slice, double buffered
+  static constexpr int BAR_OFFSET = BIAS_OFFSET + BIAS_BYTES;
+  static constexpr int SMEM_BYTES = BAR_OFFSET + 256 /*barriers*/;
 };
 
-// Epilogue arithmetic on 8 consecutive columns of one row (v in/out). `inb` guards every global
-// read (rows >= M / cols >= N hold don't-care values that the TMA store clips). When `pre` is
-// non-null it receives the packed pre-activation (bias added) for the aux_out copy.
+// Epilogue arithmetic on 8 consecutive columns of one row (v in/out). Operands that come from
+// memory are passed in already loaded (bias from the per-tile smem slice, residual / pre-activation
+// rows batched into registers before the TMEM wait) so no load latency is exposed per group.
 template <int ACT>
-__device__ __forceinline__ void epilogue_math8(float (&v)[8], uint4* pre, bool inb, int row, int col,
-                                               const GemmShape& s, const GemmEpilogue& e) {
-  if (e.bias != nullptr && inb) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(e.bias + col + 4));
+__device__ __forceinline__ void epilogue_math8(float (&v)[8], uint4* pre, const float* bias_s,
+                                               const uint4& aux, bool has_resid, const uint4& res,
+                                               int row, int col, const GemmShape& s,
+                                               const GemmEpilogue& e) {
+  if (bias_s != nullptr) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias_s);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 4);
     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
     v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
   }
@@ -83,9 +88,7 @@ __device__ __forceinline__ void epilogue_math8(float (&v)[8], uint4* pre, bool i
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
   } else if (ACT == ACT_GELU_GRAD) {
-    uint4 p = make_uint4(0, 0, 0, 0);
-    if (inb) p = *reinterpret_cast<const uint4*>(e.aux_in + (long long)row * e.ld_aux_in + col);
-    const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
+    const uint32_t pw[4] = {aux.x, aux.y, aux.z, aux.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 x = unpack_bf16x2(pw[j]);
@@ -93,15 +96,11 @@ __device__ __forceinline__ void epilogue_math8(float (&v)[8], uint4* pre, bool i
       v[2 * j + 1] *= gelu_erf_grad(x.y);
     }
   }
-  if (e.drop_threshold != 0u) {
-    const uint32_t base = (uint32_t)row * (uint32_t)s.N + (uint32_t)col;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      v[j] = dropout_keep(e.drop_key, base + j, e.drop_threshold) ? v[j] * e.drop_scale : 0.0f;
-  }
-  if (e.resid != nullptr && inb) {
-    const uint4 p = *reinterpret_cast<const uint4*>(e.resid + (long long)row * e.ld_resid + col);
-    const uint32_t pw[4] = {p.x, p.y, p.z, p.w};
+  if (e.drop_threshold != 0u)
+    dropout_apply8(v, e.drop_key, (uint32_t)row * (uint32_t)s.N + (uint32_t)col, e.drop_threshold,
+                   e.drop_scale);
+  if (has_resid) {
+    const uint32_t pw[4] = {res.x, res.y, res.z, res.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 x = unpack_bf16x2(pw[j]);
@@ -121,9 +120,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();  // swizzle-128B atoms need a 1024 B aligned base
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFFSET);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
@@ -144,7 +142,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -229,9 +227,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else {
     // ------------------------------------------------------------- epilogue warps
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    uint8_t* slabs = smem + STAGES * Cfg::STAGE_BYTES + q * (2 * Cfg::SLAB_BYTES);
+    // Two warps share each TMEM lane quadrant (hardware: warp w may touch lanes 32*(w%4)..+31) and
+    // split the tile's 64-column slabs between them; 8 warps = 2 per SM sub-partition, which hides
+    // the ALU/MUFU latency of the GELU / dropout / pack arithmetic.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;     // 0 or 1: which slabs of the tile this warp handles
+    const int et = threadIdx.x - 64;      // 0..255 within the epilogue group
+    uint8_t* slab = smem + STAGES * Cfg::STAGE_BYTES + (warp - 2) * Cfg::SLAB_BYTES;
+    float* bias_all = reinterpret_cast<float*>(smem + Cfg::BIAS_OFFSET);
     const bool has_aux = (e.aux_out != nullptr);
+    const bool has_bias = (e.bias != nullptr);
+    const bool has_resid = (ACT != ACT_GELU_GRAD) && (e.resid != nullptr);
     uint32_t slab_it = 0;
     uint32_t local_tile = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
@@ -240,21 +246,51 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int m_blk = t2 / s.num_n_blocks;
       const uint32_t acc = local_tile & 1u;
       const uint32_t acc_ph = (local_tile >> 1) & 1u;
+      float* bias_s = bias_all + acc * BLOCK_N;
+      if (has_bias) {
+        // stage this tile's bias slice once (coalesced) while the main loop is still running
+        if (et < BLOCK_N) {
+          const int col = n_blk * BLOCK_N + et;
+          bias_s[et] = (col < s.N) ? __ldg(e.bias + col) : 0.0f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+      }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after_sync();
       const int row0 = m_blk * BLOCK_M + q * 32;
       const int row = row0 + lane;
+      const bool row_ok = row < s.M;
       const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 64; ++c) {
+      for (int c = half; c < BLOCK_N / 64; c += 2) {
         const int col0 = n_blk * BLOCK_N + c * 64;
         if (col0 >= s.N) break;  // warp-uniform
         uint32_t r[2][32];
         tmem_ld_32x32(t_addr + c * 64, r[0]);
         tmem_ld_32x32(t_addr + c * 64 + 32, r[1]);
+        // batch the per-row global operands of this slab so their latency overlaps the TMEM load
+        uint4 res[8], aux[8];
+        if (ACT != ACT_GELU_GRAD && has_resid) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int col = col0 + g * 8;
+            res[g] = (row_ok && col < s.N)
+                         ? *reinterpret_cast<const uint4*>(e.resid + (long long)row * e.ld_resid + col)
+                         : make_uint4(0, 0, 0, 0);
+          }
+        }
+        if (ACT == ACT_GELU_GRAD) {   // (never combined with a residual: host-checked)
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int col = col0 + g * 8;
+            aux[g] = (row_ok && col < s.N)
+                         ? *reinterpret_cast<const uint4*>(e.aux_in + (long long)row * e.ld_aux_in + col)
+                         : make_uint4(0, 0, 0, 0);
+          }
+        }
         tmem_ld_wait();
         if (OUT_F32) {
-          if (row < s.M) {
+          if (row_ok) {
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               const int col = col0 + g * 8;
@@ -262,7 +298,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g >> 2][(g & 3) * 8 + j]);
-                epilogue_math8<ACT>(v, nullptr, true, row, col, s, e);
+                epilogue_math8<ACT>(v, nullptr, has_bias ? bias_s + c * 64 + g * 8 : nullptr, aux[g],
+                                    has_resid, res[g], row, col, s, e);
                 float* o = reinterpret_cast<float*>(e.out) + (long long)row * e.ld_out + col;
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]),
                              "f"(v[1]), "f"(v[2]), "f"(v[3])
@@ -274,39 +311,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           }
         } else {
-          // stage the 32 x 64 bf16 slab(s) in swizzled smem and let TMA write full 128 B rows
-          uint8_t* out_slab;
-          uint8_t* aux_slab = nullptr;
+          // stage the 32 x 64 bf16 slab in swizzled smem and let TMA write full 128 B rows; the
+          // pre-activation copy (training FFN-up) goes out first through the same buffer
+          uint4 outp[8];
           if (has_aux) {
             if (lane == 0) bulk_wait_read<0>();
-            out_slab = slabs;
-            aux_slab = slabs + Cfg::SLAB_BYTES;
-          } else {
-            if (lane == 0) bulk_wait_read<1>();
-            out_slab = slabs + (slab_it & 1u) * Cfg::SLAB_BYTES;
+            __syncwarp();
           }
-          __syncwarp();
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const int col = col0 + g * 8;
-            const bool inb = (row < s.M) && (col < s.N);
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g >> 2][(g & 3) * 8 + j]);
             uint4 pre;
-            epilogue_math8<ACT>(v, has_aux ? &pre : nullptr, inb, row, col, s, e);
-            uint4 pk;
-            pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
-            pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-            const int off = lane * 128 + ((g ^ (lane & 7)) << 4);
-            *reinterpret_cast<uint4*>(out_slab + off) = pk;
-            if (has_aux) *reinterpret_cast<uint4*>(aux_slab + off) = pre;
+            epilogue_math8<ACT>(v, has_aux ? &pre : nullptr,
+                                has_bias ? bias_s + c * 64 + g * 8 : nullptr, aux[g], has_resid,
+                                res[g], row, col, s, e);
+            outp[g].x = pack_bf16x2(v[0], v[1]); outp[g].y = pack_bf16x2(v[2], v[3]);
+            outp[g].z = pack_bf16x2(v[4], v[5]); outp[g].w = pack_bf16x2(v[6], v[7]);
+            if (has_aux)
+              *reinterpret_cast<uint4*>(slab + lane * 128 + ((g ^ (lane & 7)) << 4)) = pre;
           }
+          if (has_aux) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_aux, slab, col0, row0);
+              bulk_commit();
+            }
+          }
+          if (lane == 0) bulk_wait_read<0>();   // previous store has drained this warp's slab
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<uint4*>(slab + lane * 128 + ((g ^ (lane & 7)) << 4)) = outp[g];
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmap_out, out_slab, col0, row0);
-            if (has_aux) tma_store_2d(&tmap_aux, aux_slab, col0, row0);
+            tma_store_2d(&tmap_out, slab, col0, row0);
             bulk_commit();
           }
           ++slab_it;
@@ -457,6 +500,7 @@ extern "C" int hero_gemm_bf16(const hero_gemm_args* g, void* stream) {
   HERO_REQUIRE(g->n % 8 == 0, "n must be a multiple of 8 (n=%d)", g->n);
   HERO_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0 && g->ld_out % 4 == 0, "unaligned leading dim");
   HERO_REQUIRE(g->act != ACT_GELU_GRAD || g->aux_in != nullptr, "act=3 needs aux_in");
+  HERO_REQUIRE(g->act != ACT_GELU_GRAD || g->resid == nullptr, "act=3 cannot take a residual");
   if (g->a_mn_major) HERO_REQUIRE(g->m % 64 == 0, "MN-major A needs m %% 64 == 0 (m=%d)", g->m);
   if (g->b_mn_major) HERO_REQUIRE(g->n % 64 == 0, "MN-major B needs n %% 64 == 0 (n=%d)", g->n);
 

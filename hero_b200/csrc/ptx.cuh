@@ -210,9 +210,23 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t key, uint32_t idx) {
   h ^= h >> 16;
   return h;
 }
-// keep iff hash >= threshold where threshold = p * 2^32
+// One 32-bit hash decides TWO consecutive elements (16 bits each): keep iff bits16 >= p * 2^16.
+// `threshold` is passed as p * 2^32 (C-ABI) and narrowed here; p = 0.1 -> 6553 / 65536.
 __device__ __forceinline__ bool dropout_keep(uint32_t key, uint32_t idx, uint32_t threshold) {
-  return hash_u32(key, idx) >= threshold;
+  const uint32_t h = hash_u32(key, idx >> 1);
+  const uint32_t bits = (idx & 1u) ? (h >> 16) : (h & 0xFFFFu);
+  return bits >= (threshold >> 16);
+}
+// 8 consecutive elements starting at an even index: 4 hashes. Applies v = keep ? v * scale : 0.
+__device__ __forceinline__ void dropout_apply8(float (&v)[8], uint32_t key, uint32_t idx0,
+                                               uint32_t threshold, float scale) {
+  const uint32_t t16 = threshold >> 16;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t h = hash_u32(key, (idx0 >> 1) + j);
+    v[2 * j] = ((h & 0xFFFFu) >= t16) ? v[2 * j] * scale : 0.0f;
+    v[2 * j + 1] = ((h >> 16) >= t16) ? v[2 * j + 1] * scale : 0.0f;
+  }
 }
 
 // exp2 on the MUFU unit (one op per element is the epilogue's throughput budget on sm_100).

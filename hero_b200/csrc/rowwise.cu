@@ -127,10 +127,8 @@ ln_fwd_kernel(const hero_ln_args a) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * g[j] + b[j];
       if (a.drop_threshold != 0u) {
-        const uint32_t base = (uint32_t)i * (uint32_t)a.h + (uint32_t)e0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = dropout_keep(a.drop_key, base + j, a.drop_threshold) ? o[j] * a.drop_scale : 0.f;
+        dropout_apply8(o, a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0, a.drop_threshold,
+                       a.drop_scale);
       }
       store_bf16x8(y + e0, o);
     }
@@ -172,10 +170,8 @@ ln_bwd_kernel(const hero_ln_args a) {
         load_bf16x8(dy + e0, d);
         load_f32x8(a.gamma + e0, g);
         if (a.drop_threshold != 0u) {
-          const uint32_t base = (uint32_t)i * (uint32_t)a.h + (uint32_t)e0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            d[j] = dropout_keep(a.drop_key, base + j, a.drop_threshold) ? d[j] * a.drop_scale : 0.f;
+          dropout_apply8(d, a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0,
+                         a.drop_threshold, a.drop_scale);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -202,13 +198,11 @@ ln_bwd_kernel(const hero_ln_args a) {
         if (a.dx) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(a.dx) + (long long)i * a.h + e0, dx);
         if (a.dx_drop) {
           float dd[8];
-          const uint32_t base = (uint32_t)i * (uint32_t)a.h + (uint32_t)e0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dd[j] = (a.drop2_threshold == 0u ||
-                     dropout_keep(a.drop2_key, base + j, a.drop2_threshold))
-                        ? dx[j] * (a.drop2_threshold == 0u ? 1.0f : a.drop2_scale)
-                        : 0.f;
+          for (int j = 0; j < 8; ++j) dd[j] = dx[j];
+          if (a.drop2_threshold != 0u)
+            dropout_apply8(dd, a.drop2_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0,
+                           a.drop2_threshold, a.drop2_scale);
           store_bf16x8(reinterpret_cast<__nv_bfloat16*>(a.dx_drop) + (long long)i * a.h + e0, dd);
         }
         if (a.d_x_tab && (int)xrow != a.x_pad_idx) {
@@ -306,11 +300,11 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src,
   reinterpret_cast<uint4*>(dst)[(long long)i * h8 + c] = v;
 }
 
-template <bool OUT_F32>
+// bf16 output: one thread per (row, 8-column chunk) walks the row's (short) CSR list.
 __global__ void gather_sum_rows_kernel(const __nv_bfloat16* __restrict__ src,
                                        const int32_t* __restrict__ off,
-                                       const int32_t* __restrict__ idx, void* __restrict__ dst, int n,
-                                       int h8) {
+                                       const int32_t* __restrict__ idx,
+                                       __nv_bfloat16* __restrict__ dst, int n, int h8) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)n * h8) return;
   const int i = (int)(t / h8), c = (int)(t % h8);
@@ -322,14 +316,31 @@ __global__ void gather_sum_rows_kernel(const __nv_bfloat16* __restrict__ src,
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += v[j];
   }
-  if (OUT_F32) {
-    if (e1 > e0) {
-      float* o = reinterpret_cast<float*>(dst) + ((long long)i * h8 + c) * 8;
+  store_bf16x8(dst + ((long long)i * h8 + c) * 8, acc);
+}
+
+// fp32 accumulate output (embedding-table gradients: few rows, long lists): grid = (row, split);
+// each block sums a slice of the row's list with h/8 threads and adds it with fp32 atomics.
+__global__ void gather_sum_rows_f32_kernel(const __nv_bfloat16* __restrict__ src,
+                                           const int32_t* __restrict__ off,
+                                           const int32_t* __restrict__ idx, float* __restrict__ dst,
+                                           int h8, int per_split) {
+  const int i = blockIdx.x;
+  const int end = off[i + 1];
+  for (int e0 = off[i] + blockIdx.y * per_split; e0 < end; e0 += gridDim.y * per_split) {
+    const int e1 = min(end, e0 + per_split);
+    for (int c = threadIdx.x; c < h8; c += blockDim.x) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int e = e0; e < e1; ++e) {
+        float v[8];
+        load_bf16x8(src + ((long long)idx[e] * h8 + c) * 8, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += acc[j];
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+      float* o = dst + ((long long)i * h8 + c) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(o + j, acc[j]);
     }
-  } else {
-    store_bf16x8(reinterpret_cast<__nv_bfloat16*>(dst) + ((long long)i * h8 + c) * 8, acc);
   }
 }
 
@@ -469,9 +480,10 @@ extern "C" int hero_gather_sum_rows_bf16(const void* src, const int32_t* off, co
   HERO_REQUIRE(src && off && dst && h % 8 == 0, "gather_sum_rows: bad args");
   if (n <= 0) return HERO_OK;
   const long long total = (long long)n * (h / 8);
-  gather_sum_rows_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0,
-                                  reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), off, idx, dst, n, h / 8);
+  gather_sum_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0,
+                           reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), off, idx, reinterpret_cast<__nv_bfloat16*>(dst),
+      n, h / 8);
   HERO_LAUNCH_CHECK();
   return HERO_OK;
 }
@@ -480,10 +492,12 @@ extern "C" int hero_gather_sum_rows_f32(const void* src, const int32_t* off, con
                                         float* dst, int32_t n, int32_t h, void* stream) {
   HERO_REQUIRE(src && off && dst && h % 8 == 0, "gather_sum_rows_f32: bad args");
   if (n <= 0) return HERO_OK;
-  const long long total = (long long)n * (h / 8);
-  gather_sum_rows_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0,
-                                 reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(src), off, idx, dst, n, h / 8);
+  // Lists can be thousands of entries long (every sequence shares a position row): each block
+  // sums 64-entry slices (looping when a list has more than 64 * 64 entries) and adds its partial
+  // with fp32 atomics; rows with short lists cost one early-exit block each.
+  dim3 grid(n, 64);
+  gather_sum_rows_f32_kernel<<<grid, 96, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), off, idx, dst, h / 8, 64);
   HERO_LAUNCH_CHECK();
   return HERO_OK;
 }

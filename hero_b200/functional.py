@@ -46,6 +46,37 @@ def _zeros(shape, like, dtype=F32):
     return torch.zeros(shape, dtype=dtype, device=like.device)
 
 
+def _sink(p):
+    """Where a parameter gradient is accumulated: straight into an existing fp32 `p.grad` (what
+    autograd's AccumulateGrad would do with our result anyway — this skips the zero-fill and the
+    extra add pass; with FlatParams.ensure_flat_grads every grad is a view of one flat buffer), or a
+    fresh zero tensor that is handed back to autograd. Returns (target, value_for_autograd)."""
+    g = p.grad
+    if g is not None and g.dtype == F32 and g.is_contiguous() and not g.requires_grad:
+        return g, None
+    z = torch.zeros_like(p, dtype=F32)
+    return z, z
+
+
+def _fused_sink(ps):
+    """One contiguous accumulation target covering several parameters whose existing grads are
+    adjacent in memory (q/k/v weights or biases in the flat gradient buffer); else None."""
+    gs = [p.grad for p in ps]
+    if any(g is None or g.dtype != F32 or not g.is_contiguous() for g in gs):
+        return None
+    st = gs[0].untyped_storage()
+    base = gs[0].data_ptr()
+    off = 0
+    for g in gs:
+        if g.untyped_storage().data_ptr() != st.data_ptr() or g.data_ptr() != base + off * 4:
+            return None
+        off += g.numel()
+    rows = sum(g.shape[0] for g in gs)
+    out = torch.empty(0, dtype=F32, device=gs[0].device)
+    out.set_(st, gs[0].storage_offset(), (rows,) + tuple(gs[0].shape[1:]))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------
 class LayerWeights:
     """bf16 working copies + fp32 vectors of one BertLayer (views into the flat buffers)."""
@@ -94,6 +125,7 @@ class _TransformerStack(torch.autograd.Function):
             h = out
         ctx.cfg = cfg
         ctx.saved = saved
+        ctx.params = params
         return h
 
     @staticmethod
@@ -101,6 +133,9 @@ class _TransformerStack(torch.autograd.Function):
         cfg = ctx.cfg
         layers, cu, n_seq, max_len, heads = (cfg["layers"], cfg["cu"], cfg["n_seq"],
                                              cfg["max_len"], cfg["heads"])
+        if cfg.get("flat") is not None:
+            cfg["flat"].mark_dirty()        # the masters are about to change (optimizer step)
+        params = ctx.params
         dout = dout.contiguous()
         M, H = dout.shape
         grads = [None] * (16 * len(layers))
@@ -110,36 +145,41 @@ class _TransformerStack(torch.autograd.Function):
             (h, qkv, cx, s1, mean1, rstd1, a, pre, f, s2, mean2, rstd2, d_attn, d_h1,
              d_h2) = ctx.saved[li]
             inter = lw.w1.shape[0]
+            P = params[16 * li:16 * li + 16]
+            g = grads
+            o = 16 * li
             # LN2 backward: ds2 (residual branch) and ds2 * dropout mask (FFN-down branch)
             ds2 = _empty((M, H), dy)
             ds2_d = _empty((M, H), dy) if d_h2[0] else ds2
-            dg2, db2ln = _zeros((H,), dy), _zeros((H,), dy)
+            dg2, g[o + 14] = _sink(P[14])
+            db2ln, g[o + 15] = _sink(P[15])
             ops.ln_bwd(dy, s2, lw.ln2_g, mean2, rstd2, n_rows=M, dx=ds2,
                        dx_drop=ds2_d if d_h2[0] else None, drop2=d_h2, dgamma=dg2, dbeta=db2ln)
             # FFN down: bias, weight, input grads (input grad fused with gelu')
-            db2 = _zeros((H,), dy)
+            db2, g[o + 13] = _sink(P[13])
             ops.colsum(ds2_d, db2)
-            dw2 = _zeros((H, inter), dy)
+            dw2, g[o + 12] = _sink(P[12])
             ops.gemm(ds2_d, f, dw2, a_mn=True, b_mn=True, accumulate_f32=True)
             dpre = _empty((M, inter), dy)
             ops.gemm(ds2_d, lw.w2, dpre, b_mn=True, act=ops.ACT_GELU_GRAD, aux_in=pre)
             # FFN up
-            db1 = _zeros((inter,), dy)
+            db1, g[o + 11] = _sink(P[11])
             ops.colsum(dpre, db1)
-            dw1 = _zeros((inter, H), dy)
+            dw1, g[o + 10] = _sink(P[10])
             ops.gemm(dpre, a, dw1, a_mn=True, b_mn=True, accumulate_f32=True)
             da = _empty((M, H), dy)
             ops.gemm(dpre, lw.w1, da, b_mn=True, resid=ds2)
             # LN1 backward
             ds1 = _empty((M, H), dy)
             ds1_d = _empty((M, H), dy) if d_h1[0] else ds1
-            dg1, db1ln = _zeros((H,), dy), _zeros((H,), dy)
+            dg1, g[o + 8] = _sink(P[8])
+            db1ln, g[o + 9] = _sink(P[9])
             ops.ln_bwd(da, s1, lw.ln1_g, mean1, rstd1, n_rows=M, dx=ds1,
                        dx_drop=ds1_d if d_h1[0] else None, drop2=d_h1, dgamma=dg1, dbeta=db1ln)
             # attention output projection
-            dbo = _zeros((H,), dy)
+            dbo, g[o + 7] = _sink(P[7])
             ops.colsum(ds1_d, dbo)
-            dwo = _zeros((H, H), dy)
+            dwo, g[o + 6] = _sink(P[6])
             ops.gemm(ds1_d, cx, dwo, a_mn=True, b_mn=True, accumulate_f32=True)
             dcx = _empty((M, H), dy)
             ops.gemm(ds1_d, lw.wo, dcx, b_mn=True)
@@ -147,22 +187,20 @@ class _TransformerStack(torch.autograd.Function):
             dqkv = _empty((M, 3 * H), dy)
             ops.attn_bwd(qkv, cu, dcx, dqkv, n_seq=n_seq, max_len=max_len, heads=heads,
                          drop=d_attn)
-            # QKV projection
-            dbqkv = _zeros((3 * H,), dy)
+            # QKV projection (one fused [3H, H] weight gradient, written in place when the three
+            # parameter grads are adjacent views of the flat gradient buffer)
+            dbqkv = _fused_sink([P[1], P[3], P[5]])
+            if dbqkv is None:
+                dbqkv = _zeros((3 * H,), dy)
+                g[o + 1], g[o + 3], g[o + 5] = dbqkv[:H], dbqkv[H:2 * H], dbqkv[2 * H:]
             ops.colsum(dqkv, dbqkv)
-            dwqkv = _zeros((3 * H, H), dy)
+            dwqkv = _fused_sink([P[0], P[2], P[4]])
+            if dwqkv is None:
+                dwqkv = _zeros((3 * H, H), dy)
+                g[o + 0], g[o + 2], g[o + 4] = dwqkv[:H], dwqkv[H:2 * H], dwqkv[2 * H:]
             ops.gemm(dqkv, h, dwqkv, a_mn=True, b_mn=True, accumulate_f32=True)
             dx = _empty((M, H), dy)
             ops.gemm(dqkv, lw.wqkv, dx, b_mn=True, resid=ds1)
-            g = grads
-            o = 16 * li
-            g[o + 0], g[o + 2], g[o + 4] = dwqkv[:H], dwqkv[H:2 * H], dwqkv[2 * H:]
-            g[o + 1], g[o + 3], g[o + 5] = dbqkv[:H], dbqkv[H:2 * H], dbqkv[2 * H:]
-            g[o + 6], g[o + 7] = dwo, dbo
-            g[o + 8], g[o + 9] = dg1, db1ln
-            g[o + 10], g[o + 11] = dw1, db1
-            g[o + 12], g[o + 13] = dw2, db2
-            g[o + 14], g[o + 15] = dg2, db2ln
             dy = dx
         ctx.saved = None
         dx_in = dy if ctx.needs_input_grad[0] else None
@@ -230,25 +268,26 @@ class _CrossModalEmbed(torch.autograd.Function):
                        mean=st["o_mean"], rstd=st["o_rstd"], drop=st["o_drop"])
             st["xn"], st["proj"] = xn, proj
         ctx.cfg, ctx.st = cfg, st
-        ctx.save_for_backward(*params)
+        ctx.params = params      # python refs: backward accumulates into the parameters' .grad
         return emb
 
     @staticmethod
     def backward(ctx, demb):
         cfg, st = ctx.cfg, ctx.st
-        params = ctx.saved_tensors
+        params = ctx.params
         word, pos, typ, ln_w, ln_b = params[:5]
         demb = demb.contiguous()
         H = word.shape[1]
         dev = word.device
         grads = [None] * len(params)
-        dtyp = torch.zeros_like(typ)
+        dtyp, grads[2] = _sink(typ)
         n_txt, n_img = cfg["n_txt"], cfg["n_img"]
         type_row = typ[1]
         if n_txt:
-            dword = torch.zeros_like(word)
-            dpos = torch.zeros_like(pos)
-            dlnw, dlnb = torch.zeros_like(ln_w), torch.zeros_like(ln_b)
+            dword, grads[0] = _sink(word)
+            dpos, grads[1] = _sink(pos)
+            dlnw, grads[3] = _sink(ln_w)
+            dlnb, grads[4] = _sink(ln_b)
             dx = torch.empty((n_txt, H), dtype=BF16, device=dev)
             ops.ln_bwd(demb, word, ln_w, st["t_mean"], st["t_rstd"], n_rows=n_txt,
                        x_rows=cfg["txt_ids"], add_tab=pos, add_idx=cfg["txt_pos"],
@@ -259,37 +298,40 @@ class _CrossModalEmbed(torch.autograd.Function):
             _slot_table_grad(dx, cfg["txtpos_off"], cfg["txtpos_idx"], cfg["txt_slot_pos"], dpos,
                              cfg.get("txt_pos"))
             ops.colsum(dx, dtyp[1])
-            grads[0], grads[1], grads[3], grads[4] = dword, dpos, dlnw, dlnb
         if n_img:
             (lin_w, lin_b, iln_w, iln_b, ipos, mask_emb, oln_w, oln_b) = params[5:13]
             D = iln_w.numel()
             dproj = torch.empty((n_img, H), dtype=BF16, device=dev)
-            doln_w, doln_b = torch.zeros_like(oln_w), torch.zeros_like(oln_b)
+            doln_w, grads[11] = _sink(oln_w)
+            doln_b, grads[12] = _sink(oln_b)
             ops.ln_bwd(demb, st["proj"], oln_w, st["o_mean"], st["o_rstd"], n_rows=n_img,
                        add_tab=ipos, add_idx=cfg["img_k"], add_vec=type_row,
                        y_rows=cfg["img_tok"], drop=st["o_drop"], dx=dproj, dgamma=doln_w,
                        dbeta=doln_b)
-            dipos = torch.zeros_like(ipos)
+            dipos, grads[9] = _sink(ipos)
             _slot_table_grad(dproj, cfg["imgpos_off"], cfg["imgpos_idx"], cfg["img_slot_pos"],
                              dipos, cfg.get("img_k"))
             ops.colsum(dproj, dtyp[1])
-            dlin_b = torch.zeros_like(lin_b)
+            dlin_b, grads[6] = _sink(lin_b)
             ops.colsum(dproj, dlin_b)
-            dlin_w = torch.zeros_like(lin_w)
+            dlin_w, grads[5] = _sink(lin_w)
             ops.gemm(dproj, st["xn"], dlin_w, a_mn=True, b_mn=True, accumulate_f32=True)
             # gradient wrt the normalised 4352-d features -> img_LayerNorm gamma/beta (+ mask emb)
             dxn = torch.empty((n_img, D), dtype=BF16, device=dev)
             ops.gemm(dproj, cfg["img_lin_w_bf16"], dxn, b_mn=True)
-            diln_w, diln_b = torch.zeros_like(iln_w), torch.zeros_like(iln_b)
+            diln_w, grads[7] = _sink(iln_w)
+            diln_b, grads[8] = _sink(iln_b)
             has_mask = cfg["img_mask"] is not None
-            dmask = torch.zeros_like(mask_emb) if has_mask else None
+            dmask = None
+            if has_mask:
+                dmask, grads[10] = _sink(mask_emb)
             ops.ln_bwd(dxn, cfg["img_feats"], iln_w, st["i_mean"], st["i_rstd"], n_rows=n_img,
                        x_rows=cfg["img_src"], add_tab=mask_emb if has_mask else None,
                        add_idx=cfg["img_mask"], d_add_tab=dmask, add_pad_idx=0, dgamma=diln_w,
                        dbeta=diln_b)
-            grads[5:13] = [dlin_w, dlin_b, diln_w, diln_b, dipos, dmask, doln_w, doln_b]
-        grads[2] = dtyp
         ctx.st = None
+        if cfg.get("flat") is not None:
+            cfg["flat"].mark_dirty()
         return (None,) + tuple(grads)
 
 
@@ -320,14 +362,14 @@ class _FrameMerge(torch.autograd.Function):
         ops.gemm(xn, cfg["lin_w_bf16"], g, bias=lin_b, act=ops.ACT_RELU, resid=matched, aux_out=pre)
         ctx.cfg = cfg
         ctx.st = (xn, mean, rstd, pre, d_in)
-        ctx.save_for_backward(ln_w, ln_b, lin_w, lin_b)
+        ctx.params = (ln_w, ln_b, lin_w, lin_b)
         return g
 
     @staticmethod
     def backward(ctx, dg):
         cfg = ctx.cfg
         xn, mean, rstd, pre, d_in = ctx.st
-        ln_w, ln_b, lin_w, lin_b = ctx.saved_tensors
+        ln_w, ln_b, lin_w, lin_b = ctx.params
         dg = dg.contiguous()
         n_c, H = dg.shape
         dev = dg.device
@@ -336,17 +378,18 @@ class _FrameMerge(torch.autograd.Function):
         ops.gather_sum_rows(dg, cfg["bwd_off"], cfg["bwd_idx"], dhf)
         dpre = torch.empty_like(dg)
         ops.relu_bwd(dg, pre, dpre)
-        dlin_b = torch.zeros_like(lin_b)
+        dlin_b, r_lin_b = _sink(lin_b)
         ops.colsum(dpre, dlin_b)
-        dlin_w = torch.zeros_like(lin_w)
+        dlin_w, r_lin_w = _sink(lin_w)
         ops.gemm(dpre, xn, dlin_w, a_mn=True, b_mn=True, accumulate_f32=True)
         dxn = torch.empty((n_c, ln_w.numel()), dtype=BF16, device=dev)
         ops.gemm(dpre, cfg["lin_w_bf16"], dxn, b_mn=True)
-        dln_w, dln_b = torch.zeros_like(ln_w), torch.zeros_like(ln_b)
+        dln_w, r_ln_w = _sink(ln_w)
+        dln_b, r_ln_b = _sink(ln_b)
         ops.ln_bwd(dxn, cfg["feats"], ln_w, mean, rstd, n_rows=n_c, x_rows=cfg["src"], drop=d_in,
                    dgamma=dln_w, dbeta=dln_b)
         ctx.st = None
-        return dhf, None, dln_w, dln_b, dlin_w, dlin_b
+        return dhf, None, r_ln_w, r_ln_b, r_lin_w, r_lin_b
 
 
 def frame_merge(hf, cfg, params):
@@ -366,24 +409,27 @@ class _FrameEmbed(torch.autograd.Function):
         ops.ln_fwd(g, ln_w, ln_b, 1e-5, z, n_rows=n, add_tab=pos, add_idx=cfg["t"], mean=mean,
                    rstd=rstd, drop=d)
         ctx.cfg, ctx.st = cfg, (mean, rstd, d)
-        ctx.save_for_backward(g, pos, ln_w, ln_b)
+        ctx.save_for_backward(g)
+        ctx.params = (pos, ln_w, ln_b)
         return z
 
     @staticmethod
     def backward(ctx, dz):
         cfg = ctx.cfg
         mean, rstd, d = ctx.st
-        g, pos, ln_w, ln_b = ctx.saved_tensors
+        (g,) = ctx.saved_tensors
+        pos, ln_w, ln_b = ctx.params
         dz = dz.contiguous()
         n, H = dz.shape
         dgx = torch.empty_like(dz)
-        dln_w, dln_b = torch.zeros_like(ln_w), torch.zeros_like(ln_b)
+        dln_w, r_ln_w = _sink(ln_w)
+        dln_b, r_ln_b = _sink(ln_b)
         ops.ln_bwd(dz, g, ln_w, mean, rstd, n_rows=n, add_tab=pos, add_idx=cfg["t"], drop=d,
                    dx=dgx, dgamma=dln_w, dbeta=dln_b)
-        dpos = torch.zeros_like(pos)
+        dpos, r_pos = _sink(pos)
         n_slot = cfg["pos_off"].numel() - 1
         ops.gather_sum_rows(dgx, cfg["pos_off"], cfg["pos_idx"], dpos[:n_slot])
-        return dgx, None, dpos, dln_w, dln_b
+        return dgx, None, r_pos, r_ln_w, r_ln_b
 
 
 def frame_embed(g, cfg, params):

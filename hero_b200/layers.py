@@ -159,8 +159,7 @@ class BertEncoder(nn.Module):
         cfg = {"layers": [l.weights(flat) for l in self.layer], "cu": dev_cu, "n_seq": n_seq,
                "max_len": max_len, "heads": self.num_heads, "eps": self.eps, "drop": drop}
         params = [p for l in self.layer for p in l.ordered_params()]
-        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            flat.mark_dirty()   # an optimizer step will follow the backward of this forward
+        cfg["flat"] = flat     # backward marks the bf16 mirror stale (an optimizer step follows)
         return Fn.transformer_stack(x, cfg, params)
 
     def forward(self, hidden_states, attention_mask=None, head_mask=None):

@@ -1,0 +1,105 @@
+"""World-size-2 gloo tests of the data-parallel plumbing (hero_b200/distributed.py) — the N > 1
+path of bench.py minus NCCL. Semantics follow utils/distributed.py and model/pretrain.py:427-447
+of the reference (Horovod allreduce = mean over ranks; allgather concatenates in rank order)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, fn_name, ret):
+    os.environ.update({"RANK": str(rank), "WORLD_SIZE": str(world), "LOCAL_RANK": str(rank),
+                       "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port)})
+    import torch.distributed as dist
+    from hero_b200 import distributed as hd
+    hd.init(backend="gloo")
+    try:
+        ret[rank] = globals()[fn_name](rank, world, hd)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn_name, world=2):
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, fn_name, ret), nprocs=world, join=True)
+    return dict(ret)
+
+
+def _allreduce_case(rank, world, hd):
+    # separate tensors (coalesced path) and views of one flat buffer (in-place path)
+    a = torch.full((5,), float(rank + 1))
+    b = torch.arange(6, dtype=torch.float32).view(2, 3) * (rank + 1)
+    hd.all_reduce_and_rescale_tensors([a, b], 1.0)
+    flat = torch.arange(128 + 64, dtype=torch.float32) * (rank + 1)
+    v1, v2 = flat[:100].view(10, 10), flat[128:128 + 64]
+    hd.all_reduce_and_rescale_tensors([v1, v2], 2.0)
+    return a.tolist(), b.flatten().tolist(), flat.tolist()
+
+
+def test_all_reduce_is_mean_over_ranks_and_rescales():
+    out = _run("_allreduce_case")
+    for r in (0, 1):
+        a, b, flat = out[r]
+        assert a == [1.5] * 5
+        assert b == [x * 1.5 for x in range(6)]
+        assert flat == [x * 1.5 / 2.0 for x in range(192)]
+
+
+def _broadcast_case(rank, world, hd):
+    t1 = torch.full((4,), float(rank + 10))
+    t2 = torch.full((2, 2), float(rank + 20))
+    hd.broadcast_tensors([t1, t2], 0)
+    objs = hd.all_gather_list({"rank": rank, "n": rank * 3})
+    task = hd.any_broadcast("task_%d" % rank, 1)
+    return t1.tolist(), t2.flatten().tolist(), objs, task
+
+
+def test_broadcast_gather_list_and_any_broadcast():
+    out = _run("_broadcast_case")
+    for r in (0, 1):
+        t1, t2, objs, task = out[r]
+        assert t1 == [10.0] * 4 and t2 == [20.0] * 4
+        assert objs == [{"rank": 0, "n": 0}, {"rank": 1, "n": 3}]
+        assert task == "task_1"
+
+
+def _vsm_case(rank, world, hd):
+    n = 2 + rank                       # ranks contribute different row counts
+    x = (torch.arange(n * 3, dtype=torch.float32).view(n, 3) + 100 * rank).requires_grad_(True)
+    y = hd.vsm_allgather(x)
+    w = torch.arange(y.numel(), dtype=torch.float32).view_as(y)
+    (y * w).sum().backward()
+    return y.detach().tolist(), x.grad.tolist()
+
+
+def test_vsm_allgather_forward_concat_backward_own_slice():
+    out = _run("_vsm_case")
+    full = [[0, 1, 2], [3, 4, 5], [100, 101, 102], [103, 104, 105], [106, 107, 108]]
+    w = torch.arange(15, dtype=torch.float32).view(5, 3)
+    for r in (0, 1):
+        y, g = out[r]
+        assert y == [[float(v) for v in row] for row in full]
+    assert out[0][1] == w[0:2].tolist()
+    assert out[1][1] == w[2:5].tolist()
+
+
+def test_single_process_degenerates_to_identity():
+    from hero_b200 import distributed as hd
+    t = torch.ones(3)
+    hd.all_reduce_and_rescale_tensors([t], 2.0)
+    assert t.tolist() == [0.5] * 3
+    assert hd.all_gather_list(7) == [7] and hd.any_broadcast("x", 0) == "x"
+    x = torch.ones(2, 2, requires_grad=True)
+    assert hd.vsm_allgather(x) is x or torch.equal(hd.vsm_allgather(x), x)

@@ -117,3 +117,36 @@ def test_plan_can_be_attached_at_collate_time(tmp_path, monkeypatch):
         qb_out = model.f_encoder(qb2, "txt")[0]
     assert torch.equal(a, b)
     assert torch.equal(qa, qb_out)
+
+
+def test_in_place_gradient_sinks_match_autograd_accumulation(tmp_path, monkeypatch):
+    """With FlatParams.ensure_flat_grads the backward accumulates straight into the flat gradient
+    buffer (no zero-fill / add pass); the result must equal the plain autograd path, and a second
+    backward must accumulate (+=) like autograd does."""
+    fake_ops.install(monkeypatch)
+    from hero_b200.params import flat_of
+    fx = gu.load("hier_tiny.npz")
+    vb, qb = gu.stored_batches(fx)
+    w1, w2 = torch.from_numpy(fx["loss_w1"]), torch.from_numpy(fx["loss_w2"])
+
+    def loss_of(model):
+        clip = model(vb, "repr")
+        q = model.f_encoder(qb, "txt")[0]
+        return (clip * w1).sum() + (q * w2).sum()
+
+    ref = _model(tmp_path, fx)
+    loss_of(ref).backward()
+    ref_grads = {k: p.grad.clone() for k, p in ref.named_parameters() if p.grad is not None}
+
+    model = _model(tmp_path, fx)
+    flat = flat_of(model, torch.device("cpu"))
+    gflat = flat.ensure_flat_grads()
+    loss_of(model).backward()
+    for k, p in model.named_parameters():
+        if k in ref_grads:
+            assert torch.allclose(p.grad, ref_grads[k], rtol=1e-5, atol=1e-6), k
+            assert p.grad.untyped_storage().data_ptr() == gflat.untyped_storage().data_ptr(), k
+    loss_of(model).backward()
+    for k, p in model.named_parameters():
+        if k in ref_grads:
+            assert torch.allclose(p.grad, 2 * ref_grads[k], rtol=1e-4, atol=1e-5), k
