@@ -68,8 +68,9 @@ def _declare(lib):
 
     sig("hero_ln_fwd", C.POINTER(LnArgs), vp)
     sig("hero_ln_bwd", C.POINTER(LnArgs), vp)
-    sig("hero_attn_fwd", vp, vp, vp, i32, i32, i32, i32, f32, u32, u32, f32, vp)
-    sig("hero_attn_bwd", vp, vp, vp, vp, i32, i32, i32, i32, f32, u32, u32, f32, vp)
+    sig("hero_attn_fwd", vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u32, u32, f32, vp)
+    sig("hero_attn_bwd", vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u32, u32, f32,
+        vp)
     sig("hero_cast_f32_to_bf16", vp, vp, i64, vp)
     sig("hero_gather_rows_bf16", vp, vp, vp, i32, i32, vp)
     sig("hero_gather_sum_rows_bf16", vp, vp, vp, vp, i32, i32, vp)

@@ -1,0 +1,557 @@
+// Variable-length multi-head self-attention on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
+//
+// HERO's sequences are short (cross-modal rows ~10-70 tokens, temporal rows <= 100 frames), so a
+// 128-row MMA tile would be mostly empty if it held one sequence. Instead the host packs
+// CONSECUTIVE sequences of the packed token stream into tiles of <= 128 tokens (a sequence never
+// straddles tiles); one CTA handles one (tile, head):
+//
+//   forward   S = Q K^T (128x128x64)  -> per-row softmax restricted to the row's own sequence
+//             (block-diagonal mask = the key-padding mask of model/layers.py:299-302 in the packed
+//             layout) -> P (bf16, smem) -> O = P V (128x64x128) -> ctx
+//   backward  S = Q K^T, dP = dO V^T -> P, dS rows -> dV = P^T dO, dK = dS^T Q, dQ = dS K
+//
+// Q/K/V/dO tiles arrive by TMA (128-byte swizzle); every contraction is a tcgen05.mma with fp32
+// accumulators in TMEM. The transposed operands (P^T, dS^T, V/dO/Q/K as [k][n]) need no copies:
+// the SAME smem tiles are addressed as MN-major operands through the UMMA descriptors.
+// Softmax statistics, exp2, dropout masks and the P / dS tiles never touch HBM.
+//
+// Replaces model/layers.py:129-160 (BertSelfAttention after the QKV projections) and its autograd
+// backward. D_i = sum_j P_ij dP_ij is taken as dO_i . O_i from the saved forward output.
+#include <cuda.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace hero {
+
+constexpr int AT_ROWS = 128;           // tokens per tile
+constexpr int AT_D = 64;               // head dim
+constexpr int AT_TILE_BYTES = AT_ROWS * AT_D * 2;   // 16 KB: one [128 x 64] bf16 operand tile
+constexpr int AT_P_BYTES = AT_ROWS * AT_ROWS * 2;   // 32 KB: one [128 x 128] bf16 tile (2 chunks)
+
+// element (row i, col j) of a [128 x 128] bf16 tile stored as two 64-column chunks of
+// [128 rows x 128 B] with the 128-byte swizzle: byte offset of the 16-byte unit holding cols
+// [8u', 8u'+8) where j = 64*chunk + 8u + (j % 8).
+__device__ __forceinline__ uint32_t p_unit_offset(int row, int chunk, int u) {
+  return chunk * (AT_ROWS * 128) + row * 128 + ((u ^ (row & 7)) << 4);
+}
+
+__device__ __forceinline__ float ex2(float x) { return fast_ex2(x); }
+
+struct AttnTcArgs {
+  const int32_t* tile_tok0;
+  const int32_t* tile_ntok;
+  const int32_t* seq_lo;
+  const int32_t* seq_hi;
+  int heads;
+  int H;
+  float scale_log2;      // log2(e) / sqrt(d)
+  float scale;           // 1 / sqrt(d)
+  uint32_t drop_thr, drop_key;
+  float drop_scale;
+};
+
+// Dropout mask index of probability (query token, head, key position inside the sequence): the
+// same in forward and backward and independent of the tiling.
+__device__ __forceinline__ uint32_t attn_drop_index(int tok, int heads, int head, int jrel) {
+  return ((uint32_t)tok * (uint32_t)heads + (uint32_t)head) * 128u + (uint32_t)jrel;
+}
+
+// ------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(128)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArgs a,
+                   __nv_bfloat16* __restrict__ ctx) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + AT_TILE_BYTES;
+  uint8_t* sV = smem + 2 * AT_TILE_BYTES;
+  uint8_t* sP = smem + 3 * AT_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * AT_TILE_BYTES + AT_P_BYTES);
+  uint64_t* tma_bar = bars;
+  uint64_t* mma_bar = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tile = blockIdx.x, head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tok0 = a.tile_tok0[tile];
+  const int ntok = a.tile_ntok[tile];
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    mbar_init(tma_bar, 1);
+    mbar_init(mma_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(tma_bar, 3 * AT_TILE_BYTES);
+    tma_load_2d(sQ, &tmap_qkv, tma_bar, head * AT_D, tok0);
+    tma_load_2d(sK, &tmap_qkv, tma_bar, a.H + head * AT_D, tok0);
+    tma_load_2d(sV, &tmap_qkv, tma_bar, 2 * a.H + head * AT_D, tok0);
+  }
+  mbar_wait(tma_bar, 0);
+
+  if (threadIdx.x == 0) {
+    tc_fence_after_sync();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+    for (int k = 0; k < AT_D / 16; ++k) {
+      const uint64_t ad = make_sw128_desc(smem_u32(sQ) + k * 32, 16, 1024);
+      const uint64_t bd = make_sw128_desc(smem_u32(sK) + k * 32, 16, 1024);
+      umma_f16(tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(mma_bar);
+  }
+  mbar_wait(mma_bar, 0);
+  tc_fence_after_sync();
+
+  // ---- softmax on this thread's row, restricted to the row's own sequence ----
+  const int i = threadIdx.x;
+  const bool valid = i < ntok;
+  int lo = 0, hi = 0;
+  if (valid) {
+    lo = a.seq_lo[tok0 + i] - tok0;
+    hi = a.seq_hi[tok0 + i] - tok0;
+  }
+  // warp-uniform column range (tcgen05.ld is warp-collective)
+  int wlo = valid ? lo : AT_ROWS, whi = hi;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wlo = min(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
+    whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, o));
+  }
+  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  float mx = -INFINITY;
+  for (int c = 0; c < 4; ++c) {
+    if (c * 32 >= whi || c * 32 + 32 <= wlo) continue;   // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32(t_row + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c * 32 + j;
+      if (col >= lo && col < hi) mx = fmaxf(mx, __uint_as_float(r[j]));
+    }
+  }
+  float sum = 0.f;
+  for (int c = 0; c < 4; ++c) {
+    uint32_t pk[16];
+    const bool touch = !(c * 32 >= whi || c * 32 + 32 <= wlo);   // warp-uniform
+    if (touch) {
+      uint32_t r[32];
+      tmem_ld_32x32(t_row + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float p0 = 0.f, p1 = 0.f;
+        const int col = c * 32 + j;
+        if (col >= lo && col < hi) p0 = ex2((__uint_as_float(r[j]) - mx) * a.scale_log2);
+        if (col + 1 >= lo && col + 1 < hi) p1 = ex2((__uint_as_float(r[j + 1]) - mx) * a.scale_log2);
+        sum += p0 + p1;
+        if (a.drop_thr != 0u) {
+          if (!dropout_keep(a.drop_key, attn_drop_index(tok0 + i, a.heads, head, col - lo),
+                            a.drop_thr))
+            p0 = 0.f;
+          else
+            p0 *= a.drop_scale;
+          if (!dropout_keep(a.drop_key, attn_drop_index(tok0 + i, a.heads, head, col + 1 - lo),
+                            a.drop_thr))
+            p1 = 0.f;
+          else
+            p1 *= a.drop_scale;
+        }
+        pk[j >> 1] = pack_bf16x2(p0, p1);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = 0u;
+    }
+    // 32 columns = 4 units of 16 B inside 64-column chunk (c >> 1), units (c & 1) * 4 + g
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 v = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      *reinterpret_cast<uint4*>(sP + p_unit_offset(i, c >> 1, (c & 1) * 4 + g)) = v;
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    tc_fence_after_sync();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 1);   // A = P (K-major), B = V (MN-major)
+#pragma unroll
+    for (int k = 0; k < AT_ROWS / 16; ++k) {
+      const uint64_t ad =
+          make_sw128_desc(smem_u32(sP) + (k >> 2) * (AT_ROWS * 128) + (k & 3) * 32, 16, 1024);
+      const uint64_t bd = make_sw128_desc(smem_u32(sV) + k * 2048, AT_TILE_BYTES, 1024);
+      umma_f16(tmem + 128, ad, bd, idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(mma_bar);
+  }
+  mbar_wait(mma_bar, 1);
+  tc_fence_after_sync();
+
+  {
+    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32(t_row + 128, r0);
+    tmem_ld_32x32(t_row + 160, r1);
+    tmem_ld_wait();
+    if (valid) {
+      __nv_bfloat16* o = ctx + (long long)(tok0 + i) * a.H + head * AT_D;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(r0[8 * g]) * inv, __uint_as_float(r0[8 * g + 1]) * inv);
+        v.y = pack_bf16x2(__uint_as_float(r0[8 * g + 2]) * inv, __uint_as_float(r0[8 * g + 3]) * inv);
+        v.z = pack_bf16x2(__uint_as_float(r0[8 * g + 4]) * inv, __uint_as_float(r0[8 * g + 5]) * inv);
+        v.w = pack_bf16x2(__uint_as_float(r0[8 * g + 6]) * inv, __uint_as_float(r0[8 * g + 7]) * inv);
+        reinterpret_cast<uint4*>(o)[g] = v;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(r1[8 * g]) * inv, __uint_as_float(r1[8 * g + 1]) * inv);
+        v.y = pack_bf16x2(__uint_as_float(r1[8 * g + 2]) * inv, __uint_as_float(r1[8 * g + 3]) * inv);
+        v.z = pack_bf16x2(__uint_as_float(r1[8 * g + 4]) * inv, __uint_as_float(r1[8 * g + 5]) * inv);
+        v.w = pack_bf16x2(__uint_as_float(r1[8 * g + 6]) * inv, __uint_as_float(r1[8 * g + 7]) * inv);
+        reinterpret_cast<uint4*>(o)[4 + g] = v;
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------ backward
+// TMEM columns: S [0,128)  dP [128,256)  dQ [256,320)  dK [320,384)  dV [384,448)
+__global__ void __launch_bounds__(128)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                   const __grid_constant__ CUtensorMap tmap_do, const AttnTcArgs a,
+                   const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
+                   __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + AT_TILE_BYTES;
+  uint8_t* sV = smem + 2 * AT_TILE_BYTES;
+  uint8_t* sdO = smem + 3 * AT_TILE_BYTES;
+  uint8_t* sP = smem + 4 * AT_TILE_BYTES;
+  uint8_t* sdS = sP + AT_P_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + AT_P_BYTES);
+  uint64_t* tma_bar = bars;
+  uint64_t* mma_bar = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tile = blockIdx.x, head = blockIdx.y;
+  const int warp = threadIdx.x >> 5;
+  const int tok0 = a.tile_tok0[tile];
+  const int ntok = a.tile_ntok[tile];
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(tma_bar, 1);
+    mbar_init(mma_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(tma_bar, 4 * AT_TILE_BYTES);
+    tma_load_2d(sQ, &tmap_qkv, tma_bar, head * AT_D, tok0);
+    tma_load_2d(sK, &tmap_qkv, tma_bar, a.H + head * AT_D, tok0);
+    tma_load_2d(sV, &tmap_qkv, tma_bar, 2 * a.H + head * AT_D, tok0);
+    tma_load_2d(sdO, &tmap_do, tma_bar, head * AT_D, tok0);
+  }
+
+  // D_i = dO_i . O_i straight from global memory while the tiles are in flight
+  const int i = threadIdx.x;
+  const bool valid = i < ntok;
+  float Di = 0.f;
+  int lo = 0, hi = 0;
+  if (valid) {
+    lo = a.seq_lo[tok0 + i] - tok0;
+    hi = a.seq_hi[tok0 + i] - tok0;
+    const uint4* po = reinterpret_cast<const uint4*>(ctx + (long long)(tok0 + i) * a.H + head * AT_D);
+    const uint4* pd = reinterpret_cast<const uint4*>(dctx + (long long)(tok0 + i) * a.H + head * AT_D);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint4 o = po[g], d = pd[g];
+      const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 x = unpack_bf16x2(ow[j]), y = unpack_bf16x2(dw[j]);
+        Di = fmaf(x.x, y.x, Di);
+        Di = fmaf(x.y, y.y, Di);
+      }
+    }
+  }
+  mbar_wait(tma_bar, 0);
+
+  if (threadIdx.x == 0) {
+    tc_fence_after_sync();
+    constexpr uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+#pragma unroll
+    for (int k = 0; k < AT_D / 16; ++k) {   // S = Q K^T
+      const uint64_t ad = make_sw128_desc(smem_u32(sQ) + k * 32, 16, 1024);
+      const uint64_t bd = make_sw128_desc(smem_u32(sK) + k * 32, 16, 1024);
+      umma_f16(tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < AT_D / 16; ++k) {   // dP = dO V^T
+      const uint64_t ad = make_sw128_desc(smem_u32(sdO) + k * 32, 16, 1024);
+      const uint64_t bd = make_sw128_desc(smem_u32(sV) + k * 32, 16, 1024);
+      umma_f16(tmem + 128, ad, bd, idesc, k > 0 ? 1u : 0u);
+    }
+    umma_commit(mma_bar);
+  }
+  mbar_wait(mma_bar, 0);
+  tc_fence_after_sync();
+
+  int wlo = valid ? lo : AT_ROWS, whi = hi;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    wlo = min(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
+    whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, o));
+  }
+  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  float mx = -INFINITY;
+  for (int c = 0; c < 4; ++c) {
+    if (c * 32 >= whi || c * 32 + 32 <= wlo) continue;
+    uint32_t r[32];
+    tmem_ld_32x32(t_row + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c * 32 + j;
+      if (col >= lo && col < hi) mx = fmaxf(mx, __uint_as_float(r[j]));
+    }
+  }
+  float sum = 0.f;
+  for (int c = 0; c < 4; ++c) {
+    if (c * 32 >= whi || c * 32 + 32 <= wlo) continue;
+    uint32_t r[32];
+    tmem_ld_32x32(t_row + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = c * 32 + j;
+      if (col >= lo && col < hi) sum += ex2((__uint_as_float(r[j]) - mx) * a.scale_log2);
+    }
+  }
+  const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+  for (int c = 0; c < 4; ++c) {
+    uint32_t pk[16], dk[16];
+    const bool touch = !(c * 32 >= whi || c * 32 + 32 <= wlo);
+    if (touch) {
+      uint32_t r[32], d[32];
+      tmem_ld_32x32(t_row + c * 32, r);
+      tmem_ld_32x32(t_row + 128 + c * 32, d);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        float pp[2], ds[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int col = c * 32 + j + t;
+          float p = 0.f, dp = 0.f, keep = 1.0f;
+          if (col >= lo && col < hi) {
+            p = ex2((__uint_as_float(r[j + t]) - mx) * a.scale_log2) * inv;
+            dp = __uint_as_float(d[j + t]);
+            if (a.drop_thr != 0u)
+              keep = dropout_keep(a.drop_key, attn_drop_index(tok0 + i, a.heads, head, col - lo),
+                                  a.drop_thr)
+                         ? a.drop_scale
+                         : 0.f;
+          }
+          pp[t] = p * keep;                          // dropped probability (for dV)
+          ds[t] = p * (dp * keep - Di) * a.scale;    // d(raw QK^T score)
+        }
+        pk[j >> 1] = pack_bf16x2(pp[0], pp[1]);
+        dk[j >> 1] = pack_bf16x2(ds[0], ds[1]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = dk[j] = 0u;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t off = p_unit_offset(i, c >> 1, (c & 1) * 4 + g);
+      *reinterpret_cast<uint4*>(sP + off) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      *reinterpret_cast<uint4*>(sdS + off) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before_sync();
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    tc_fence_after_sync();
+    // dQ[i][d] = sum_j dS[i][j] K[j][d] : A = dS K-major, B = K tile as [k=j][n=d] (MN-major)
+    constexpr uint32_t id_q = make_idesc_bf16(128, 64, 0, 1);
+    // dK[j][d] = sum_i dS[i][j] Q[i][d], dV[j][d] = sum_i P[i][j] dO[i][d]:
+    //   A = dS^T / P^T = the same smem tiles read MN-major, B = Q / dO tiles MN-major
+    constexpr uint32_t id_t = make_idesc_bf16(128, 64, 1, 1);
+#pragma unroll
+    for (int k = 0; k < AT_ROWS / 16; ++k) {
+      const uint64_t ad =
+          make_sw128_desc(smem_u32(sdS) + (k >> 2) * (AT_ROWS * 128) + (k & 3) * 32, 16, 1024);
+      const uint64_t bd = make_sw128_desc(smem_u32(sK) + k * 2048, AT_TILE_BYTES, 1024);
+      umma_f16(tmem + 256, ad, bd, id_q, k > 0 ? 1u : 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < AT_ROWS / 16; ++k) {
+      const uint64_t ad = make_sw128_desc(smem_u32(sdS) + k * 2048, AT_ROWS * 128, 1024);
+      const uint64_t bd = make_sw128_desc(smem_u32(sQ) + k * 2048, AT_TILE_BYTES, 1024);
+      umma_f16(tmem + 320, ad, bd, id_t, k > 0 ? 1u : 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < AT_ROWS / 16; ++k) {
+      const uint64_t ad = make_sw128_desc(smem_u32(sP) + k * 2048, AT_ROWS * 128, 1024);
+      const uint64_t bd = make_sw128_desc(smem_u32(sdO) + k * 2048, AT_TILE_BYTES, 1024);
+      umma_f16(tmem + 384, ad, bd, id_t, k > 0 ? 1u : 0u);
+    }
+    umma_commit(mma_bar);
+  }
+  mbar_wait(mma_bar, 1);
+  tc_fence_after_sync();
+
+  // rows of dQ (query i), dK / dV (key i) -> dqkv[tok0 + i, {0, H, 2H} + head * 64 ...]
+#pragma unroll 1
+  for (int part = 0; part < 3; ++part) {
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32(t_row + 256 + part * 64, r0);
+    tmem_ld_32x32(t_row + 256 + part * 64 + 32, r1);
+    tmem_ld_wait();
+    if (valid) {
+      __nv_bfloat16* o = dqkv + (long long)(tok0 + i) * (3 * a.H) + part * a.H + head * AT_D;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(r0[8 * g]), __uint_as_float(r0[8 * g + 1]));
+        v.y = pack_bf16x2(__uint_as_float(r0[8 * g + 2]), __uint_as_float(r0[8 * g + 3]));
+        v.z = pack_bf16x2(__uint_as_float(r0[8 * g + 4]), __uint_as_float(r0[8 * g + 5]));
+        v.w = pack_bf16x2(__uint_as_float(r0[8 * g + 6]), __uint_as_float(r0[8 * g + 7]));
+        reinterpret_cast<uint4*>(o)[g] = v;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(r1[8 * g]), __uint_as_float(r1[8 * g + 1]));
+        v.y = pack_bf16x2(__uint_as_float(r1[8 * g + 2]), __uint_as_float(r1[8 * g + 3]));
+        v.z = pack_bf16x2(__uint_as_float(r1[8 * g + 4]), __uint_as_float(r1[8 * g + 5]));
+        v.w = pack_bf16x2(__uint_as_float(r1[8 * g + 6]), __uint_as_float(r1[8 * g + 7]));
+        reinterpret_cast<uint4*>(o)[4 + g] = v;
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+static int fill_args(AttnTcArgs* a, const int32_t* tile_tok0, const int32_t* tile_ntok,
+                     const int32_t* seq_lo, const int32_t* seq_hi, int heads, int head_dim,
+                     float scale, uint32_t thr, uint32_t key, float dscale) {
+  HERO_REQUIRE(tile_tok0 && tile_ntok && seq_lo && seq_hi, "attn: null plan pointer");
+  HERO_REQUIRE(head_dim == AT_D, "attn: head_dim must be 64 (got %d)", head_dim);
+  HERO_REQUIRE(heads > 0, "attn: bad head count");
+  a->tile_tok0 = tile_tok0;
+  a->tile_ntok = tile_ntok;
+  a->seq_lo = seq_lo;
+  a->seq_hi = seq_hi;
+  a->heads = heads;
+  a->H = heads * head_dim;
+  a->scale = scale;
+  a->scale_log2 = scale * 1.4426950408889634f;
+  a->drop_thr = thr;
+  a->drop_key = key;
+  a->drop_scale = dscale;
+  return HERO_OK;
+}
+
+}  // namespace hero
+
+using namespace hero;
+
+extern "C" int hero_attn_fwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
+                                const int32_t* seq_lo, const int32_t* seq_hi, void* ctx,
+                                int32_t n_tok, int32_t n_tiles, int32_t heads, int32_t head_dim,
+                                float scale, uint32_t drop_threshold, uint32_t drop_key,
+                                float drop_scale, void* stream) {
+  HERO_REQUIRE(qkv && ctx, "attn_fwd: null pointer");
+  if (n_tiles <= 0 || n_tok <= 0) return HERO_OK;
+  AttnTcArgs a;
+  if (int rc = fill_args(&a, tile_tok0, tile_ntok, seq_lo, seq_hi, heads, head_dim, scale,
+                         drop_threshold, drop_key, drop_scale))
+    return rc;
+  CUtensorMap tm;
+  if (int rc = encode_tmap_2d_bf16(&tm, qkv, 3LL * a.H, n_tok, 3LL * a.H, AT_D, AT_ROWS)) return rc;
+  const int smem = 3 * AT_TILE_BYTES + AT_P_BYTES + 64;
+  static bool configured = false;
+  if (!configured) {
+    HERO_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_fwd_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(n_tiles, heads);
+  attn_tc_fwd_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      tm, a, reinterpret_cast<__nv_bfloat16*>(ctx));
+  HERO_LAUNCH_CHECK();
+  return HERO_OK;
+}
+
+extern "C" int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
+                                const int32_t* seq_lo, const int32_t* seq_hi, const void* ctx,
+                                const void* dctx, void* dqkv, int32_t n_tok, int32_t n_tiles,
+                                int32_t heads, int32_t head_dim, float scale,
+                                uint32_t drop_threshold, uint32_t drop_key, float drop_scale,
+                                void* stream) {
+  HERO_REQUIRE(qkv && ctx && dctx && dqkv, "attn_bwd: null pointer");
+  if (n_tiles <= 0 || n_tok <= 0) return HERO_OK;
+  AttnTcArgs a;
+  if (int rc = fill_args(&a, tile_tok0, tile_ntok, seq_lo, seq_hi, heads, head_dim, scale,
+                         drop_threshold, drop_key, drop_scale))
+    return rc;
+  CUtensorMap tq, td;
+  if (int rc = encode_tmap_2d_bf16(&tq, qkv, 3LL * a.H, n_tok, 3LL * a.H, AT_D, AT_ROWS)) return rc;
+  if (int rc = encode_tmap_2d_bf16(&td, dctx, a.H, n_tok, a.H, AT_D, AT_ROWS)) return rc;
+  const int smem = 4 * AT_TILE_BYTES + 2 * AT_P_BYTES + 64;
+  static bool configured = false;
+  if (!configured) {
+    HERO_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(n_tiles, heads);
+  attn_tc_bwd_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      tq, td, a, reinterpret_cast<const __nv_bfloat16*>(ctx),
+      reinterpret_cast<const __nv_bfloat16*>(dctx), reinterpret_cast<__nv_bfloat16*>(dqkv));
+  HERO_LAUNCH_CHECK();
+  return HERO_OK;
+}

@@ -1,3 +1,6 @@
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "common.h"
 
 namespace hero {
@@ -24,6 +27,32 @@ int sm_count() {
     return -HERO_ERR_NO_DEVICE;
   cached = n;
   return n;
+}
+
+int encode_tmap_2d_bf16(void* map, const void* ptr, long long inner, long long outer, long long ld,
+                        int box_inner, int box_outer) {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+            cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled(%lld x %lld, ld %lld) failed: %d", outer,
+                     inner, ld, (int)r);
+  return HERO_OK;
 }
 
 }  // namespace hero

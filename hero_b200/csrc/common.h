@@ -36,4 +36,9 @@ int sm_count();
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// 2-D bf16 tensor map over a row-major [outer, inner] matrix (leading dim `ld` elements) with a
+// 128-byte-swizzled box of box_inner (<= 64) x box_outer elements. `map` is a CUtensorMap.
+int encode_tmap_2d_bf16(void* map, const void* ptr, long long inner, long long outer, long long ld,
+                        int box_inner, int box_outer);
+
 }  // namespace hero

@@ -258,8 +258,7 @@ class CrossModalTrm(RobertaPreTrainedModel):
         if with_img:
             cfg["img_lin_w_bf16"] = flat.bf16(self.img_embeddings.img_linear.weight)
         emb = Fn.cross_modal_embed(cfg, self._embed_params(with_img))
-        return self.encoder.forward_packed(emb, dev.f_cu, fplan.seq.n_seq, fplan.seq.max_len,
-                                           drop)
+        return self.encoder.forward_packed(emb, fplan.seq.attn(dev, "f_"), drop)
 
     def _unpack(self, y, dev, shape):
         out = Fn.gather_rows(y, dev.f_pad_to_tok, dev.f_tok_flat)
@@ -348,7 +347,7 @@ class TemporalTrm(RobertaPreTrainedModel):
         self.apply(self.init_weights)
         self.output_dtype = torch.float32
 
-    def embed_encode_packed(self, g, dev_t, dev_cu, n_seq, max_len, pos_off, pos_idx, drop=None):
+    def embed_encode_packed(self, g, dev_t, att, pos_off, pos_idx, drop=None):
         """g: packed bf16 [n_c_tokens, H] -> FrameEmbeddings -> encoder (packed)."""
         if drop is None:
             drop = self.encoder.dropout_state()
@@ -356,7 +355,7 @@ class TemporalTrm(RobertaPreTrainedModel):
         cfg = {"drop": drop, "t": dev_t, "pos_off": pos_off, "pos_idx": pos_idx}
         z = Fn.frame_embed(g, cfg, [e.position_embeddings.weight, e.LayerNorm.weight,
                                     e.LayerNorm.bias])
-        return self.encoder.forward_packed(z, dev_cu, n_seq, max_len, drop)
+        return self.encoder.forward_packed(z, att, drop)
 
     def forward_encoder(self, embedding_output, attention_mask, pool=False):
         sequence_output = self.encoder(embedding_output, attention_mask)[0]
@@ -382,7 +381,7 @@ class TemporalTrm(RobertaPreTrainedModel):
         dev = DeviceIndex(arrays, clip_level_frame_feat.device)
         flat_in = clip_level_frame_feat.reshape(B * T, H).to(BF16)
         g = Fn.gather_rows(flat_in, dev.c_tok_flat, dev.c_pad_to_tok)
-        y = self.embed_encode_packed(g, dev.c_t, dev.c_cu, sp.n_seq, sp.max_len, dev.c_pos_off,
+        y = self.embed_encode_packed(g, dev.c_t, sp.attn(dev, "c_"), dev.c_pos_off,
                                      dev.c_pos_idx)
         out = Fn.gather_rows(y, dev.c_pad_to_tok, dev.c_tok_flat)
         return out.view(B, T, H).to(_output_dtype(self))

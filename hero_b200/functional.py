@@ -90,9 +90,8 @@ class _TransformerStack(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, cfg, *params):
-        layers, cu, n_seq, max_len, heads, eps, drop = (
-            cfg["layers"], cfg["cu"], cfg["n_seq"], cfg["max_len"], cfg["heads"], cfg["eps"],
-            cfg["drop"])
+        layers, att, heads, eps, drop = (cfg["layers"], cfg["att"], cfg["heads"], cfg["eps"],
+                                         cfg["drop"])
         M, H = x.shape
         inter = layers[0].w1.shape[0]
         need_grad = any(ctx.needs_input_grad)
@@ -103,7 +102,7 @@ class _TransformerStack(torch.autograd.Function):
             ops.gemm(h, lw.wqkv, qkv, bias=lw.bqkv)
             cx = _empty((M, H), x)
             d_attn = drop.next(drop.attn_p)
-            ops.attn_fwd(qkv, cu, cx, n_seq=n_seq, max_len=max_len, heads=heads, drop=d_attn)
+            ops.attn_fwd(qkv, att, cx, heads=heads, drop=d_attn)
             s1 = _empty((M, H), x)
             d_h1 = drop.next(drop.hidden_p)
             ops.gemm(cx, lw.wo, s1, bias=lw.bo, resid=h, drop=d_h1)
@@ -131,8 +130,7 @@ class _TransformerStack(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         cfg = ctx.cfg
-        layers, cu, n_seq, max_len, heads = (cfg["layers"], cfg["cu"], cfg["n_seq"],
-                                             cfg["max_len"], cfg["heads"])
+        layers, att, heads = cfg["layers"], cfg["att"], cfg["heads"]
         if cfg.get("flat") is not None:
             cfg["flat"].mark_dirty()        # the masters are about to change (optimizer step)
         params = ctx.params
@@ -185,8 +183,7 @@ class _TransformerStack(torch.autograd.Function):
             ops.gemm(ds1_d, lw.wo, dcx, b_mn=True)
             # attention core
             dqkv = _empty((M, 3 * H), dy)
-            ops.attn_bwd(qkv, cu, dcx, dqkv, n_seq=n_seq, max_len=max_len, heads=heads,
-                         drop=d_attn)
+            ops.attn_bwd(qkv, att, cx, dcx, dqkv, heads=heads, drop=d_attn)
             # QKV projection (one fused [3H, H] weight gradient, written in place when the three
             # parameter grads are adjacent views of the flat gradient buffer)
             dbqkv = _fused_sink([P[1], P[3], P[5]])

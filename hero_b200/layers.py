@@ -149,15 +149,15 @@ class BertEncoder(nn.Module):
         return Fn.DropoutState(l0.output.dropout.p, l0.attention.self.dropout.p, self.training,
                                base_key)
 
-    def forward_packed(self, x, dev_cu, n_seq, max_len, drop=None):
-        """x: packed bf16 [n_tokens, H]; dev_cu: int32 cu_seqlens on the device."""
+    def forward_packed(self, x, att, drop=None):
+        """x: packed bf16 [n_tokens, H]; att: device attention plan (`SeqPlan.attn`)."""
         if len(self.layer) == 0:
             return x
         flat = flat_of(self, x.device)
         if drop is None:
             drop = self.dropout_state()
-        cfg = {"layers": [l.weights(flat) for l in self.layer], "cu": dev_cu, "n_seq": n_seq,
-               "max_len": max_len, "heads": self.num_heads, "eps": self.eps, "drop": drop}
+        cfg = {"layers": [l.weights(flat) for l in self.layer], "att": att,
+               "heads": self.num_heads, "eps": self.eps, "drop": drop}
         params = [p for l in self.layer for p in l.ordered_params()]
         cfg["flat"] = flat     # backward marks the bf16 mirror stale (an optimizer step follows)
         return Fn.transformer_stack(x, cfg, params)
@@ -172,7 +172,7 @@ class BertEncoder(nn.Module):
         dev = plan.to(hidden_states.device)
         flat_in = hidden_states.reshape(N * L, H).to(BF16)
         x = Fn.gather_rows(flat_in, dev.f_tok_flat, dev.f_pad_to_tok)
-        y = self.forward_packed(x, dev.f_cu, plan.f.seq.n_seq, plan.f.seq.max_len)
+        y = self.forward_packed(x, plan.f.seq.attn(dev, "f_"))
         out = Fn.gather_rows(y, dev.f_pad_to_tok, dev.f_tok_flat)
         return (out.view(N, L, H).to(hidden_states.dtype),)
 

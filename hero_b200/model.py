@@ -147,8 +147,8 @@ class HierarchicalVlModel(VideoPreTrainedModel):
         if not encode_clip:
             return g, dev
         dropc = ce.encoder.dropout_state(drop.base + 104729)
-        y = ce.embed_encode_packed(g, dev.c_t, dev.c_cu, plan.c.seq.n_seq, plan.c.seq.max_len,
-                                   dev.c_pos_off, dev.c_pos_idx, dropc)
+        y = ce.embed_encode_packed(g, dev.c_t, plan.c.seq.attn(dev, "c_"), dev.c_pos_off,
+                                   dev.c_pos_idx, dropc)
         return y, dev
 
     def _unpack_c(self, y, dev, shape):

@@ -171,24 +171,27 @@ def ln_bwd(dy, x, gamma, mean, rstd, *, n_rows, x_rows=None, add_tab=None, add_i
     _lib.check(_lib.lib().hero_ln_bwd(C.byref(a), _stream()))
 
 
-def attn_fwd(qkv, cu_seqlens, ctx, *, n_seq, max_len, heads, head_dim=64, drop=(0, 0, 1.0)):
-    _require_cuda(qkv, cu_seqlens, ctx)
-    assert qkv.dtype == BF16 and cu_seqlens.dtype == torch.int32 and qkv.is_contiguous()
+def attn_fwd(qkv, att, ctx, *, heads, head_dim=64, drop=(0, 0, 1.0)):
+    """ctx = softmax(QK^T / sqrt(d)) V per (sequence, head) on packed tokens; `att` is the device
+    attention plan of `SeqPlan.attn` (tiles of <= 128 tokens + per-token sequence ranges)."""
+    _require_cuda(qkv, ctx)
+    assert qkv.dtype == BF16 and qkv.is_contiguous() and ctx.is_contiguous()
     _count()
     _lib.check(_lib.lib().hero_attn_fwd(
-        _ptr(qkv), _ptr(cu_seqlens), _ptr(ctx), n_seq, max_len, heads, head_dim,
+        _ptr(qkv), _ptr(att["tile_tok0"]), _ptr(att["tile_ntok"]), _ptr(att["seq_lo"]),
+        _ptr(att["seq_hi"]), _ptr(ctx), att["n_tok"], att["n_tiles"], heads, head_dim,
         1.0 / (head_dim ** 0.5), drop[0], drop[1], drop[2], _stream()))
     return ctx
 
 
-def attn_bwd(qkv, cu_seqlens, dctx, dqkv, *, n_seq, max_len, heads, head_dim=64,
-             drop=(0, 0, 1.0)):
-    _require_cuda(qkv, cu_seqlens, dctx, dqkv)
-    assert dctx.is_contiguous() and dqkv.is_contiguous()
+def attn_bwd(qkv, att, ctx, dctx, dqkv, *, heads, head_dim=64, drop=(0, 0, 1.0)):
+    _require_cuda(qkv, ctx, dctx, dqkv)
+    assert dctx.is_contiguous() and dqkv.is_contiguous() and ctx.is_contiguous()
     _count()
     _lib.check(_lib.lib().hero_attn_bwd(
-        _ptr(qkv), _ptr(cu_seqlens), _ptr(dctx), _ptr(dqkv), n_seq, max_len, heads, head_dim,
-        1.0 / (head_dim ** 0.5), drop[0], drop[1], drop[2], _stream()))
+        _ptr(qkv), _ptr(att["tile_tok0"]), _ptr(att["tile_ntok"]), _ptr(att["seq_lo"]),
+        _ptr(att["seq_hi"]), _ptr(ctx), _ptr(dctx), _ptr(dqkv), att["n_tok"], att["n_tiles"],
+        heads, head_dim, 1.0 / (head_dim ** 0.5), drop[0], drop[1], drop[2], _stream()))
     return dqkv
 
 

@@ -20,6 +20,9 @@ import numpy as np
 import torch
 
 
+ATTN_TILE = 128
+
+
 def _np(t):
     if torch.is_tensor(t):
         return t.detach().cpu().numpy()
@@ -63,10 +66,44 @@ class SeqPlan:
         p2t = np.full(self.rows * self.length, -1, np.int32)
         p2t[self.tok_flat] = np.arange(self.n_tok, dtype=np.int32)
         self.pad_to_tok = p2t                                                    # padded -> packed
+        # attention tiling: consecutive sequences packed into tiles of <= 128 tokens (a sequence
+        # never straddles tiles); per token the [lo, hi) range of its own sequence
+        if self.max_len > ATTN_TILE:
+            raise ValueError(f"sequence of {self.max_len} tokens exceeds the attention tile "
+                             f"({ATTN_TILE}); HERO rows are bounded by max_clip_len=100 / short "
+                             "subtitle rows")
+        self.seq_lo = np.repeat(self.cu[:-1], lens).astype(np.int32)
+        self.seq_hi = np.repeat(self.cu[1:], lens).astype(np.int32)
+        t0, tn = [], []
+        start, cur = 0, 0
+        for n in lens.tolist():
+            if n == 0:
+                continue
+            if cur + n > ATTN_TILE:
+                t0.append(start)
+                tn.append(cur)
+                start, cur = start + cur, 0
+            cur += n
+        if cur:
+            t0.append(start)
+            tn.append(cur)
+        self.tile_tok0 = np.asarray(t0, np.int32)
+        self.tile_ntok = np.asarray(tn, np.int32)
+        self.n_tiles = len(t0)
 
     def arrays(self, prefix):
         return {prefix + "cu": self.cu, prefix + "tok_flat": self.tok_flat,
-                prefix + "pad_to_tok": self.pad_to_tok}
+                prefix + "pad_to_tok": self.pad_to_tok, prefix + "seq_lo": self.seq_lo,
+                prefix + "seq_hi": self.seq_hi, prefix + "tile_tok0": self.tile_tok0,
+                prefix + "tile_ntok": self.tile_ntok}
+
+    def attn(self, dev, prefix):
+        """Device-side attention plan consumed by ops.attn_fwd / attn_bwd."""
+        return {"cu": getattr(dev, prefix + "cu"), "seq_lo": getattr(dev, prefix + "seq_lo"),
+                "seq_hi": getattr(dev, prefix + "seq_hi"),
+                "tile_tok0": getattr(dev, prefix + "tile_tok0"),
+                "tile_ntok": getattr(dev, prefix + "tile_ntok"), "n_tiles": self.n_tiles,
+                "n_tok": self.n_tok, "n_seq": self.n_seq, "max_len": self.max_len}
 
 
 def _csr(dst, src, n_dst):

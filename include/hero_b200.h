@@ -156,21 +156,33 @@ int hero_ln_fwd(const hero_ln_args* args, void* stream);
 int hero_ln_bwd(const hero_ln_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * Variable-length multi-head self-attention over packed sequences.
+ * Variable-length multi-head self-attention over packed sequences (tcgen05 / TMEM / TMA).
  *
  * Replaces model/layers.py:129-160 (transpose_for_scores, QK^T/sqrt(d) + additive -10000 key
- * mask, softmax, dropout on probabilities, P·V, head merge). Only valid tokens exist in the packed
- * layout, so the key-padding mask of model/layers.py:299-302 is expressed by cu_seqlens.
- *   qkv  bf16 [n_tokens, 3*heads*head_dim]  (Q | K | V, each head-major inside)
- *   ctx  bf16 [n_tokens, heads*head_dim]
- * Constraints: head_dim == 64, max_len <= 128.
+ * mask, softmax, dropout on probabilities, P·V, head merge) and its backward. Only valid tokens
+ * exist in the packed layout, so the key-padding mask of model/layers.py:299-302 becomes "a row
+ * attends to the tokens of its own sequence".
+ *   qkv   bf16 [n_tok, 3*heads*64]  (Q | K | V, each head-major inside)
+ *   ctx   bf16 [n_tok, heads*64]
+ * Host-built plan (int32, device memory; hero_b200/plan.py SeqPlan):
+ *   tile_tok0[n_tiles], tile_ntok[n_tiles]  consecutive sequences grouped into tiles of <= 128
+ *                                           tokens; a sequence never straddles two tiles
+ *   seq_lo[n_tok], seq_hi[n_tok]            [lo, hi) packed-token range of each token's sequence
+ * One CTA per (tile, head): S = QK^T and O = PV (forward), S, dP, dQ, dK, dV (backward) are
+ * tcgen05.mma contractions with fp32 accumulators in TMEM; probabilities never reach HBM.
+ * Dropout mask index of P[token i, head h, key j] = (i*heads + h)*128 + (j - seq_lo[i]).
+ * The backward takes the saved forward output (D_i = dO_i . O_i).
+ * Constraints: head_dim == 64, sequences <= 128 tokens.
  * ---------------------------------------------------------------------------------------- */
-int hero_attn_fwd(const void* qkv, const int32_t* cu_seqlens, void* ctx, int32_t n_seq,
-                  int32_t max_len, int32_t heads, int32_t head_dim, float scale,
+int hero_attn_fwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
+                  const int32_t* seq_lo, const int32_t* seq_hi, void* ctx, int32_t n_tok,
+                  int32_t n_tiles, int32_t heads, int32_t head_dim, float scale,
                   uint32_t drop_threshold, uint32_t drop_key, float drop_scale, void* stream);
-int hero_attn_bwd(const void* qkv, const int32_t* cu_seqlens, const void* dctx, void* dqkv,
-                  int32_t n_seq, int32_t max_len, int32_t heads, int32_t head_dim, float scale,
-                  uint32_t drop_threshold, uint32_t drop_key, float drop_scale, void* stream);
+int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
+                  const int32_t* seq_lo, const int32_t* seq_hi, const void* ctx, const void* dctx,
+                  void* dqkv, int32_t n_tok, int32_t n_tiles, int32_t heads, int32_t head_dim,
+                  float scale, uint32_t drop_threshold, uint32_t drop_key, float drop_scale,
+                  void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Row utilities (HBM-bound).

@@ -114,19 +114,35 @@ def _attn_core(qkv, cu, heads):
     return torch.cat(outs, 0) if outs else qkv.new_zeros((0, H))
 
 
-def attn_fwd(qkv, cu_seqlens, ctx, *, n_seq, max_len, heads, head_dim=64, drop=(0, 0, 1.0)):
+def _check_att(att):
+    """The tiling must cover the token stream with whole sequences, <= 128 tokens per tile."""
+    t0, tn = att["tile_tok0"].tolist(), att["tile_ntok"].tolist()
+    assert len(t0) == att["n_tiles"] and sum(tn) == att["n_tok"]
+    cu = att["cu"].tolist()
+    bounds = set(cu)
+    pos = 0
+    for a, n in zip(t0, tn):
+        assert a == pos and 0 < n <= 128 and a in bounds and (a + n) in bounds
+        pos += n
+    lo, hi = att["seq_lo"].tolist(), att["seq_hi"].tolist()
+    for s in range(len(cu) - 1):
+        for t in range(cu[s], cu[s + 1]):
+            assert lo[t] == cu[s] and hi[t] == cu[s + 1]
+
+
+def attn_fwd(qkv, att, ctx, *, heads, head_dim=64, drop=(0, 0, 1.0)):
     _ck_drop(drop)
-    assert head_dim == 64 and max_len <= 128
-    ctx.copy_(_attn_core(qkv.float(), cu_seqlens, heads).to(BF16))
+    assert head_dim == 64 and att["max_len"] <= 128
+    _check_att(att)
+    ctx.copy_(_attn_core(qkv.float(), att["cu"], heads).to(BF16))
     return ctx
 
 
-def attn_bwd(qkv, cu_seqlens, dctx, dqkv, *, n_seq, max_len, heads, head_dim=64,
-             drop=(0, 0, 1.0)):
+def attn_bwd(qkv, att, ctx, dctx, dqkv, *, heads, head_dim=64, drop=(0, 0, 1.0)):
     _ck_drop(drop)
     with torch.enable_grad():
         q = qkv.float().detach().requires_grad_(True)
-        out = _attn_core(q, cu_seqlens, heads)
+        out = _attn_core(q, att["cu"], heads)
         out.backward(dctx.float())
     dqkv.copy_(q.grad.to(BF16))
     return dqkv

@@ -218,32 +218,73 @@ def _attn_ref(qkv, lens, heads):
     return torch.cat(outs, 0)
 
 
-@pytest.mark.parametrize("lens", [[25] * 40, [1, 7, 33, 64, 100, 128, 2, 90], [100] * 8])
+def _att_plan(lens):
+    """Device attention plan (tiles + per-token sequence ranges) for packed sequences."""
+    import numpy as np
+    from hero_b200.plan import DeviceIndex, SeqPlan
+    mask = np.zeros((len(lens), max(max(lens), 1)), np.int64)
+    for r, n in enumerate(lens):
+        mask[r, :n] = 1
+    sp = SeqPlan(mask)
+    dev = DeviceIndex(sp.arrays("s_"), _dev())
+    return sp, sp.attn(dev, "s_")
+
+
+@pytest.mark.parametrize("lens", [[25] * 40, [1, 7, 33, 64, 100, 128, 2, 90], [100] * 8,
+                                  [16] * 32, [3, 0, 5, 120, 9]])
 def test_attention_fwd_bwd(lens):
     from hero_b200 import ops
     heads = 12
     ntok = sum(lens)
     qkv = _rand((ntok, 3 * heads * 64), 1.0, seed=50)
-    cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=_dev())
+    sp, att = _att_plan(lens)
+    assert all(n <= 128 for n in sp.tile_ntok) and int(sp.tile_ntok.sum()) == ntok
     ctx = torch.empty(ntok, heads * 64, dtype=BF16, device=_dev())
-    ops.attn_fwd(qkv, cu, ctx, n_seq=len(lens), max_len=max(lens), heads=heads)
+    ops.attn_fwd(qkv, att, ctx, heads=heads)
     qr = qkv.float().requires_grad_(True)
-    ref = _attn_ref(qr, lens, heads)
+    ref = _attn_ref(qr, [n for n in lens if n > 0], heads)
     _close(ctx, ref, 2e-2, 1.6e-2, "attention fwd")
     dctx = _rand((ntok, heads * 64), 1.0, seed=51)
     ref.backward(dctx.float())
     dqkv = torch.empty_like(qkv)
-    ops.attn_bwd(qkv, cu, dctx, dqkv, n_seq=len(lens), max_len=max(lens), heads=heads)
+    ops.attn_bwd(qkv, att, ctx, dctx, dqkv, heads=heads)
     _close(dqkv, qr.grad, 4e-2, 3e-2, "attention bwd")
 
 
+def test_attention_dropout_consistent_between_fwd_and_bwd():
+    """With dropout the forward equals P_drop V for the regenerated mask: check through linearity
+    (ctx is linear in V for fixed Q, K) and that backward's dV matches that same linear map."""
+    from hero_b200 import ops
+    heads, lens = 2, [20, 31, 64, 13]
+    ntok = sum(lens)
+    qkv = _rand((ntok, 3 * heads * 64), 1.0, seed=53)
+    _, att = _att_plan(lens)
+    drop = ops.drop_params(0.1, 4242)
+    c1 = torch.empty(ntok, heads * 64, dtype=BF16, device=_dev())
+    c2 = torch.empty_like(c1)
+    ops.attn_fwd(qkv, att, c1, heads=heads, drop=drop)
+    ops.attn_fwd(qkv, att, c2, heads=heads, drop=drop)
+    assert torch.equal(c1, c2)
+    c0 = torch.empty_like(c1)
+    ops.attn_fwd(qkv, att, c0, heads=heads)
+    assert (c1.float() - c0.float()).abs().mean() > 1e-3          # dropout did something
+    # E[ctx_drop] = ctx: averaged over keys the deviation is zero-mean
+    assert abs((c1.float() - c0.float()).mean().item()) < 5e-3
+    # dV from backward must be the adjoint of V -> ctx_drop: <ctx_drop(V), dO> == <V, dV>
+    dctx = _rand((ntok, heads * 64), 1.0, seed=54)
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(qkv, att, c1, dctx, dqkv, heads=heads, drop=drop)
+    H = heads * 64
+    lhs = (c1.float() * dctx.float()).sum().item()
+    rhs = (qkv[:, 2 * H:].float() * dqkv[:, 2 * H:].float()).sum().item()
+    assert abs(lhs - rhs) <= 2e-2 * max(abs(lhs), 1.0), (lhs, rhs)
+
+
 def test_attention_rejects_long_sequences():
-    from hero_b200 import ops, _lib
-    qkv = _rand((200, 3 * 768), seed=52)
-    cu = torch.tensor([0, 200], dtype=torch.int32, device=_dev())
-    ctx = torch.empty(200, 768, dtype=BF16, device=_dev())
-    with pytest.raises(_lib.HeroError):
-        ops.attn_fwd(qkv, cu, ctx, n_seq=1, max_len=200, heads=12)
+    import numpy as np
+    from hero_b200.plan import SeqPlan
+    with pytest.raises(ValueError):
+        SeqPlan(np.ones((1, 200), np.int64))
 
 
 # ------------------------------------------------------------------------------ row utilities
