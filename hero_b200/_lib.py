@@ -52,6 +52,42 @@ class LnArgs(C.Structure):
     ]
 
 
+class LayerWeights(C.Structure):
+    """Mirror of `hero_layer_weights`."""
+    _fields_ = [(n, C.c_void_p) for n in ("wqkv", "bqkv", "wo", "bo", "ln1_g", "ln1_b", "w1",
+                                            "b1", "w2", "b2", "ln2_g", "ln2_b")]
+
+
+class LayerActs(C.Structure):
+    """Mirror of `hero_layer_acts`."""
+    _fields_ = [(n, C.c_void_p) for n in ("qkv", "cx", "s1", "mean1", "rstd1", "a", "pre", "f",
+                                            "s2", "mean2", "rstd2", "out")]
+
+
+class LayerGrads(C.Structure):
+    """Mirror of `hero_layer_grads`."""
+    _fields_ = [(n, C.c_void_p) for n in ("dwqkv", "dbqkv", "dwo", "dbo", "dln1_g", "dln1_b",
+                                            "dw1", "db1", "dw2", "db2", "dln2_g", "dln2_b")]
+
+
+class StackArgs(C.Structure):
+    """Mirror of `hero_stack_args`."""
+    _fields_ = [
+        ("n_layers", C.c_int32), ("n_tok", C.c_int32), ("hidden", C.c_int32),
+        ("inter", C.c_int32), ("heads", C.c_int32), ("n_tiles", C.c_int32),
+        ("eps", C.c_float),
+        ("weights", C.POINTER(LayerWeights)), ("acts", C.POINTER(LayerActs)),
+        ("grads", C.POINTER(LayerGrads)),
+        ("x", C.c_void_p),
+        ("tile_tok0", C.c_void_p), ("tile_ntok", C.c_void_p), ("seq_lo", C.c_void_p),
+        ("seq_hi", C.c_void_p),
+        ("hidden_drop_threshold", C.c_uint32), ("attn_drop_threshold", C.c_uint32),
+        ("drop_key", C.c_uint32),
+        ("hidden_drop_scale", C.c_float), ("attn_drop_scale", C.c_float),
+        ("dout", C.c_void_p), ("dx", C.c_void_p), ("scratch", C.c_void_p),
+    ]
+
+
 def _declare(lib):
     vp, i32, i64, f32, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint32
     lib.hero_last_error.restype = C.c_char_p
@@ -71,6 +107,10 @@ def _declare(lib):
     sig("hero_attn_fwd", vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u32, u32, f32, vp)
     sig("hero_attn_bwd", vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u32, u32, f32,
         vp)
+    sig("hero_bert_stack_fwd", C.POINTER(StackArgs), vp)
+    sig("hero_bert_stack_bwd", C.POINTER(StackArgs), vp)
+    lib.hero_bert_stack_bwd_scratch_bytes.restype = C.c_int64
+    lib.hero_bert_stack_bwd_scratch_bytes.argtypes = [i32, i32, i32]
     sig("hero_cast_f32_to_bf16", vp, vp, i64, vp)
     sig("hero_gather_rows_bf16", vp, vp, vp, i32, i32, vp)
     sig("hero_gather_sum_rows_bf16", vp, vp, vp, vp, i32, i32, vp)

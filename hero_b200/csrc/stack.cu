@@ -1,0 +1,198 @@
+// Native layer runtime: launches the whole per-layer kernel sequence of a BertLayer stack
+// (forward and backward) from C++, so the host cost per step is a handful of calls instead of
+// hundreds of Python->ctypes round trips. Pure orchestration: every arithmetic step is one of the
+// kernels behind the C-ABI (gemm_tcgen05, attention_tc, rowwise).
+#include <string.h>
+
+#include "common.h"
+
+namespace hero {
+
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_GELU_GRAD = 3 };
+
+static inline uint32_t site_key(uint32_t base, int layer, int site) {
+  uint32_t h = base ^ (0x9E3779B1u * (uint32_t)(layer * 4 + site + 1));
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
+}
+
+struct Gemm {
+  hero_gemm_args g;
+  Gemm(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, int m, int n,
+       int k, void* out, long long ld_out) {
+    memset(&g, 0, sizeof(g));
+    g.a = a; g.lda = lda; g.a_mn_major = a_mn;
+    g.b = b; g.ldb = ldb; g.b_mn_major = b_mn;
+    g.m = m; g.n = n; g.k = k;
+    g.out = out; g.ld_out = ld_out;
+    g.drop_scale = 1.0f;
+  }
+  Gemm& bias(const float* p) { g.bias = p; return *this; }
+  Gemm& resid(const void* p, long long ld) { g.resid = p; g.ld_resid = ld; return *this; }
+  Gemm& act(int a) { g.act = a; return *this; }
+  Gemm& aux_out(void* p, long long ld) { g.aux_out = p; g.ld_aux_out = ld; return *this; }
+  Gemm& aux_in(const void* p, long long ld) { g.aux_in = p; g.ld_aux_in = ld; return *this; }
+  Gemm& drop(uint32_t thr, uint32_t key, float scale) {
+    g.drop_threshold = thr; g.drop_key = key; g.drop_scale = scale; return *this;
+  }
+  Gemm& f32_accumulate() { g.out_f32_accumulate = 1; return *this; }
+  int run(void* stream) { return hero_gemm_bf16(&g, stream); }
+};
+
+static void ln_base(hero_ln_args* a, const void* x, const float* gamma, const float* beta, float eps,
+                    int n_rows, int h, float* mean, float* rstd) {
+  memset(a, 0, sizeof(*a));
+  a->x = x; a->gamma = gamma; a->beta = beta; a->eps = eps;
+  a->n_rows = n_rows; a->h = h; a->mean = mean; a->rstd = rstd;
+  a->x_pad_idx = -1; a->add_pad_idx = -1;
+  a->drop_scale = 1.0f; a->drop2_scale = 1.0f;
+}
+
+#define HERO_TRY(expr)        \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc) return _rc;      \
+  } while (0)
+
+static int check_stack(const hero_stack_args* s, bool bwd) {
+  HERO_REQUIRE(s != nullptr, "null stack args");
+  HERO_REQUIRE(s->n_layers >= 0 && s->n_tok > 0 && s->hidden > 0 && s->inter > 0 && s->heads > 0,
+               "bad stack dims");
+  HERO_REQUIRE(s->hidden == s->heads * 64, "stack: hidden must be heads * 64");
+  HERO_REQUIRE(s->weights && s->acts && s->x, "stack: null weights/acts/x");
+  HERO_REQUIRE(s->tile_tok0 && s->tile_ntok && s->seq_lo && s->seq_hi, "stack: null attention plan");
+  if (bwd) HERO_REQUIRE(s->grads && s->dout && s->scratch, "stack bwd: null grads/dout/scratch");
+  return HERO_OK;
+}
+
+}  // namespace hero
+
+using namespace hero;
+
+extern "C" int64_t hero_bert_stack_bwd_scratch_bytes(int32_t n_tok, int32_t hidden, int32_t inter) {
+  // ds2, ds2_d, da, ds1, ds1_d, dcx, dx_a, dx_b : 8 x [n_tok, H]; dpre [n_tok, I]; dqkv [n_tok, 3H]
+  const int64_t row = (int64_t)(8 + 3) * hidden + inter;
+  return ((int64_t)n_tok * row * 2 + 1023) / 1024 * 1024 + 1024 * 16;
+}
+
+extern "C" int hero_bert_stack_fwd(const hero_stack_args* s, void* stream) {
+  HERO_TRY(check_stack(s, false));
+  const int M = s->n_tok, H = s->hidden, I = s->inter;
+  const float scale = 0.125f;
+  const void* h = s->x;
+  for (int l = 0; l < s->n_layers; ++l) {
+    const hero_layer_weights& W = s->weights[l];
+    const hero_layer_acts& A = s->acts[l];
+    HERO_TRY(Gemm(h, H, 0, W.wqkv, H, 0, M, 3 * H, H, A.qkv, 3 * H).bias(W.bqkv).run(stream));
+    HERO_TRY(hero_attn_fwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, M,
+                           s->n_tiles, s->heads, 64, scale, s->attn_drop_threshold,
+                           site_key(s->drop_key, l, 0), s->attn_drop_scale, stream));
+    HERO_TRY(Gemm(A.cx, H, 0, W.wo, H, 0, M, H, H, A.s1, H)
+                 .bias(W.bo)
+                 .resid(h, H)
+                 .drop(s->hidden_drop_threshold, site_key(s->drop_key, l, 1), s->hidden_drop_scale)
+                 .run(stream));
+    hero_ln_args ln;
+    ln_base(&ln, A.s1, W.ln1_g, W.ln1_b, s->eps, M, H, A.mean1, A.rstd1);
+    ln.y = A.a;
+    HERO_TRY(hero_ln_fwd(&ln, stream));
+    Gemm up(A.a, H, 0, W.w1, H, 0, M, I, H, A.f, I);
+    up.bias(W.b1).act(ACT_GELU);
+    if (A.pre) up.aux_out(A.pre, I);
+    HERO_TRY(up.run(stream));
+    HERO_TRY(Gemm(A.f, I, 0, W.w2, I, 0, M, H, I, A.s2, H)
+                 .bias(W.b2)
+                 .resid(A.a, H)
+                 .drop(s->hidden_drop_threshold, site_key(s->drop_key, l, 2), s->hidden_drop_scale)
+                 .run(stream));
+    ln_base(&ln, A.s2, W.ln2_g, W.ln2_b, s->eps, M, H, A.mean2, A.rstd2);
+    ln.y = A.out;
+    HERO_TRY(hero_ln_fwd(&ln, stream));
+    h = A.out;
+  }
+  return HERO_OK;
+}
+
+extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
+  HERO_TRY(check_stack(s, true));
+  const int M = s->n_tok, H = s->hidden, I = s->inter;
+  const float scale = 0.125f;
+  // carve the scratch buffer (bf16 elements)
+  char* p = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(s->scratch) + 1023) &
+                                    ~static_cast<uintptr_t>(1023));
+  auto take = [&](long long elems) {
+    char* r = p;
+    p += (elems * 2 + 1023) / 1024 * 1024;
+    return reinterpret_cast<void*>(r);
+  };
+  void* ds2 = take((long long)M * H);
+  void* ds2_d = take((long long)M * H);
+  void* da = take((long long)M * H);
+  void* ds1 = take((long long)M * H);
+  void* ds1_d = take((long long)M * H);
+  void* dcx = take((long long)M * H);
+  void* dxa = take((long long)M * H);
+  void* dxb = take((long long)M * H);
+  void* dpre = take((long long)M * I);
+  void* dqkv = take((long long)M * 3 * H);
+
+  const void* dy = s->dout;
+  for (int l = s->n_layers - 1; l >= 0; --l) {
+    const hero_layer_weights& W = s->weights[l];
+    const hero_layer_acts& A = s->acts[l];
+    const hero_layer_grads& G = s->grads[l];
+    const void* h_in = (l == 0) ? s->x : s->acts[l - 1].out;
+    const bool hd = s->hidden_drop_threshold != 0u;
+    HERO_REQUIRE(A.pre != nullptr, "stack bwd: layer %d has no saved FFN pre-activation", l);
+
+    // LN2 backward: ds2 (residual branch) and its dropout-masked copy (FFN-down branch)
+    hero_ln_args ln;
+    ln_base(&ln, A.s2, W.ln2_g, nullptr, s->eps, M, H, A.mean2, A.rstd2);
+    ln.dy = dy; ln.dx = ds2; ln.dgamma = G.dln2_g; ln.dbeta = G.dln2_b;
+    void* g2 = ds2;
+    if (hd) {
+      ln.dx_drop = ds2_d;
+      ln.drop2_threshold = s->hidden_drop_threshold;
+      ln.drop2_key = site_key(s->drop_key, l, 2);
+      ln.drop2_scale = s->hidden_drop_scale;
+      g2 = ds2_d;
+    }
+    HERO_TRY(hero_ln_bwd(&ln, stream));
+    // FFN down
+    HERO_TRY(hero_colsum_bf16(g2, H, M, H, G.db2, stream));
+    HERO_TRY(Gemm(g2, H, 1, A.f, I, 1, H, I, M, G.dw2, I).f32_accumulate().run(stream));
+    HERO_TRY(Gemm(g2, H, 0, W.w2, I, 1, M, I, H, dpre, I).act(ACT_GELU_GRAD).aux_in(A.pre, I).run(stream));
+    // FFN up
+    HERO_TRY(hero_colsum_bf16(dpre, I, M, I, G.db1, stream));
+    HERO_TRY(Gemm(dpre, I, 1, A.a, H, 1, I, H, M, G.dw1, H).f32_accumulate().run(stream));
+    HERO_TRY(Gemm(dpre, I, 0, W.w1, H, 1, M, H, I, da, H).resid(ds2, H).run(stream));
+    // LN1 backward
+    ln_base(&ln, A.s1, W.ln1_g, nullptr, s->eps, M, H, A.mean1, A.rstd1);
+    ln.dy = da; ln.dx = ds1; ln.dgamma = G.dln1_g; ln.dbeta = G.dln1_b;
+    void* g1 = ds1;
+    if (hd) {
+      ln.dx_drop = ds1_d;
+      ln.drop2_threshold = s->hidden_drop_threshold;
+      ln.drop2_key = site_key(s->drop_key, l, 1);
+      ln.drop2_scale = s->hidden_drop_scale;
+      g1 = ds1_d;
+    }
+    HERO_TRY(hero_ln_bwd(&ln, stream));
+    // attention output projection
+    HERO_TRY(hero_colsum_bf16(g1, H, M, H, G.dbo, stream));
+    HERO_TRY(Gemm(g1, H, 1, A.cx, H, 1, H, H, M, G.dwo, H).f32_accumulate().run(stream));
+    HERO_TRY(Gemm(g1, H, 0, W.wo, H, 1, M, H, H, dcx, H).run(stream));
+    // attention core
+    HERO_TRY(hero_attn_bwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, dcx, dqkv,
+                           M, s->n_tiles, s->heads, 64, scale, s->attn_drop_threshold,
+                           site_key(s->drop_key, l, 0), s->attn_drop_scale, stream));
+    // QKV projection
+    HERO_TRY(hero_colsum_bf16(dqkv, 3 * H, M, 3 * H, G.dbqkv, stream));
+    HERO_TRY(Gemm(dqkv, 3 * H, 1, h_in, H, 1, 3 * H, H, M, G.dwqkv, H).f32_accumulate().run(stream));
+    void* dx = (l == 0 && s->dx) ? s->dx : ((l & 1) ? dxa : dxb);
+    if (l > 0 || s->dx)
+      HERO_TRY(Gemm(dqkv, 3 * H, 0, W.wqkv, H, 1, M, H, 3 * H, dx, H).resid(ds1, H).run(stream));
+    dy = dx;
+  }
+  return HERO_OK;
+}

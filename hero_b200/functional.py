@@ -31,11 +31,14 @@ class DropoutState:
         self.base = base_key or 0
         self.count = 0
 
+    def next_key(self):
+        self.count += 1
+        return (self.base * 2654435761 + self.count * 40503) & 0xFFFFFFFF
+
     def next(self, p):
         if p <= 0.0:
             return (0, 0, 1.0)
-        self.count += 1
-        return ops.drop_params(p, (self.base * 2654435761 + self.count * 40503) & 0xFFFFFFFF)
+        return ops.drop_params(p, self.next_key())
 
 
 def _empty(shape, like, dtype=BF16):
@@ -85,123 +88,55 @@ class LayerWeights:
 
 
 class _TransformerStack(torch.autograd.Function):
-    """L x BertLayer on packed tokens. args = (x, cfg, *params) with 16 fp32 params per layer in
-    the order q.w q.b k.w k.b v.w v.b o.w o.b ln1.w ln1.b i.w i.b out.w out.b ln2.w ln2.b."""
+    """L x BertLayer on packed tokens through the native layer runtime (one C call per direction).
+    args = (x, cfg, *params) with 16 fp32 params per layer in the order
+    q.w q.b k.w k.b v.w v.b o.w o.b ln1.w ln1.b i.w i.b out.w out.b ln2.w ln2.b."""
 
     @staticmethod
     def forward(ctx, x, cfg, *params):
-        layers, att, heads, eps, drop = (cfg["layers"], cfg["att"], cfg["heads"], cfg["eps"],
-                                         cfg["drop"])
-        M, H = x.shape
-        inter = layers[0].w1.shape[0]
+        drop = cfg["drop"]
+        dspec = (ops.drop_params(drop.hidden_p, 0), ops.drop_params(drop.attn_p, 0),
+                 drop.next_key())
         need_grad = any(ctx.needs_input_grad)
-        saved = []
-        h = x
-        for lw in layers:
-            qkv = _empty((M, 3 * H), x)
-            ops.gemm(h, lw.wqkv, qkv, bias=lw.bqkv)
-            cx = _empty((M, H), x)
-            d_attn = drop.next(drop.attn_p)
-            ops.attn_fwd(qkv, att, cx, heads=heads, drop=d_attn)
-            s1 = _empty((M, H), x)
-            d_h1 = drop.next(drop.hidden_p)
-            ops.gemm(cx, lw.wo, s1, bias=lw.bo, resid=h, drop=d_h1)
-            a = _empty((M, H), x)
-            mean1, rstd1 = _empty((M,), x, F32), _empty((M,), x, F32)
-            ops.ln_fwd(s1, lw.ln1_g, lw.ln1_b, eps, a, n_rows=M, mean=mean1, rstd=rstd1)
-            f = _empty((M, inter), x)
-            pre = _empty((M, inter), x) if need_grad else None
-            ops.gemm(a, lw.w1, f, bias=lw.b1, act=ops.ACT_GELU, aux_out=pre)
-            s2 = _empty((M, H), x)
-            d_h2 = drop.next(drop.hidden_p)
-            ops.gemm(f, lw.w2, s2, bias=lw.b2, resid=a, drop=d_h2)
-            out = _empty((M, H), x)
-            mean2, rstd2 = _empty((M,), x, F32), _empty((M,), x, F32)
-            ops.ln_fwd(s2, lw.ln2_g, lw.ln2_b, eps, out, n_rows=M, mean=mean2, rstd=rstd2)
-            if need_grad:
-                saved.append((h, qkv, cx, s1, mean1, rstd1, a, pre, f, s2, mean2, rstd2, d_attn,
-                              d_h1, d_h2))
-            h = out
-        ctx.cfg = cfg
-        ctx.saved = saved
-        ctx.params = params
-        return h
+        out, saved = ops.bert_stack_fwd(x, cfg["layers"], cfg["att"], heads=cfg["heads"],
+                                        eps=cfg["eps"], drop=dspec, save=need_grad)
+        ctx.cfg, ctx.dspec, ctx.saved, ctx.params = cfg, dspec, saved, params
+        ctx.x = x
+        return out
 
     @staticmethod
     def backward(ctx, dout):
-        cfg = ctx.cfg
-        layers, att, heads = cfg["layers"], cfg["att"], cfg["heads"]
+        cfg, params = ctx.cfg, ctx.params
         if cfg.get("flat") is not None:
             cfg["flat"].mark_dirty()        # the masters are about to change (optimizer step)
-        params = ctx.params
-        dout = dout.contiguous()
-        M, H = dout.shape
-        grads = [None] * (16 * len(layers))
-        dy = dout
-        for li in range(len(layers) - 1, -1, -1):
-            lw = layers[li]
-            (h, qkv, cx, s1, mean1, rstd1, a, pre, f, s2, mean2, rstd2, d_attn, d_h1,
-             d_h2) = ctx.saved[li]
-            inter = lw.w1.shape[0]
+        n = len(cfg["layers"])
+        H = ctx.x.shape[1]
+        ret = [None] * (16 * n)
+        grads = []
+        for li in range(n):
             P = params[16 * li:16 * li + 16]
-            g = grads
             o = 16 * li
-            # LN2 backward: ds2 (residual branch) and ds2 * dropout mask (FFN-down branch)
-            ds2 = _empty((M, H), dy)
-            ds2_d = _empty((M, H), dy) if d_h2[0] else ds2
-            dg2, g[o + 14] = _sink(P[14])
-            db2ln, g[o + 15] = _sink(P[15])
-            ops.ln_bwd(dy, s2, lw.ln2_g, mean2, rstd2, n_rows=M, dx=ds2,
-                       dx_drop=ds2_d if d_h2[0] else None, drop2=d_h2, dgamma=dg2, dbeta=db2ln)
-            # FFN down: bias, weight, input grads (input grad fused with gelu')
-            db2, g[o + 13] = _sink(P[13])
-            ops.colsum(ds2_d, db2)
-            dw2, g[o + 12] = _sink(P[12])
-            ops.gemm(ds2_d, f, dw2, a_mn=True, b_mn=True, accumulate_f32=True)
-            dpre = _empty((M, inter), dy)
-            ops.gemm(ds2_d, lw.w2, dpre, b_mn=True, act=ops.ACT_GELU_GRAD, aux_in=pre)
-            # FFN up
-            db1, g[o + 11] = _sink(P[11])
-            ops.colsum(dpre, db1)
-            dw1, g[o + 10] = _sink(P[10])
-            ops.gemm(dpre, a, dw1, a_mn=True, b_mn=True, accumulate_f32=True)
-            da = _empty((M, H), dy)
-            ops.gemm(dpre, lw.w1, da, b_mn=True, resid=ds2)
-            # LN1 backward
-            ds1 = _empty((M, H), dy)
-            ds1_d = _empty((M, H), dy) if d_h1[0] else ds1
-            dg1, g[o + 8] = _sink(P[8])
-            db1ln, g[o + 9] = _sink(P[9])
-            ops.ln_bwd(da, s1, lw.ln1_g, mean1, rstd1, n_rows=M, dx=ds1,
-                       dx_drop=ds1_d if d_h1[0] else None, drop2=d_h1, dgamma=dg1, dbeta=db1ln)
-            # attention output projection
-            dbo, g[o + 7] = _sink(P[7])
-            ops.colsum(ds1_d, dbo)
-            dwo, g[o + 6] = _sink(P[6])
-            ops.gemm(ds1_d, cx, dwo, a_mn=True, b_mn=True, accumulate_f32=True)
-            dcx = _empty((M, H), dy)
-            ops.gemm(ds1_d, lw.wo, dcx, b_mn=True)
-            # attention core
-            dqkv = _empty((M, 3 * H), dy)
-            ops.attn_bwd(qkv, att, cx, dcx, dqkv, heads=heads, drop=d_attn)
-            # QKV projection (one fused [3H, H] weight gradient, written in place when the three
-            # parameter grads are adjacent views of the flat gradient buffer)
-            dbqkv = _fused_sink([P[1], P[3], P[5]])
-            if dbqkv is None:
-                dbqkv = _zeros((3 * H,), dy)
-                g[o + 1], g[o + 3], g[o + 5] = dbqkv[:H], dbqkv[H:2 * H], dbqkv[2 * H:]
-            ops.colsum(dqkv, dbqkv)
-            dwqkv = _fused_sink([P[0], P[2], P[4]])
-            if dwqkv is None:
-                dwqkv = _zeros((3 * H, H), dy)
-                g[o + 0], g[o + 2], g[o + 4] = dwqkv[:H], dwqkv[H:2 * H], dwqkv[2 * H:]
-            ops.gemm(dqkv, h, dwqkv, a_mn=True, b_mn=True, accumulate_f32=True)
-            dx = _empty((M, H), dy)
-            ops.gemm(dqkv, lw.wqkv, dx, b_mn=True, resid=ds1)
-            dy = dx
+            g = {}
+            g["dwqkv"] = _fused_sink([P[0], P[2], P[4]])
+            if g["dwqkv"] is None:
+                t = torch.zeros((3 * H, H), dtype=F32, device=dout.device)
+                g["dwqkv"] = t
+                ret[o + 0], ret[o + 2], ret[o + 4] = t[:H], t[H:2 * H], t[2 * H:]
+            g["dbqkv"] = _fused_sink([P[1], P[3], P[5]])
+            if g["dbqkv"] is None:
+                t = torch.zeros((3 * H,), dtype=F32, device=dout.device)
+                g["dbqkv"] = t
+                ret[o + 1], ret[o + 3], ret[o + 5] = t[:H], t[H:2 * H], t[2 * H:]
+            for name, k in (("dwo", 6), ("dbo", 7), ("dln1_g", 8), ("dln1_b", 9), ("dw1", 10),
+                            ("db1", 11), ("dw2", 12), ("db2", 13), ("dln2_g", 14),
+                            ("dln2_b", 15)):
+                g[name], ret[o + k] = _sink(P[k])
+            grads.append(g)
+        dx = ops.bert_stack_bwd(ctx.x, cfg["layers"], cfg["att"], ctx.saved, dout.contiguous(),
+                                grads, heads=cfg["heads"], eps=cfg["eps"], drop=ctx.dspec,
+                                need_dx=ctx.needs_input_grad[0])
         ctx.saved = None
-        dx_in = dy if ctx.needs_input_grad[0] else None
-        return (dx_in, None) + tuple(grads)
+        return (dx, None) + tuple(ret)
 
 
 def transformer_stack(x, cfg, params):

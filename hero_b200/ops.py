@@ -195,6 +195,113 @@ def attn_bwd(qkv, att, ctx, dctx, dqkv, *, heads, head_dim=64, drop=(0, 0, 1.0))
     return dqkv
 
 
+# kernels launched per layer by the native runtime (for bench.py's gpu_launches)
+_STACK_FWD_LAUNCHES, _STACK_BWD_LAUNCHES = 7, 15
+_ACT_FIELDS = ("qkv", "cx", "s1", "mean1", "rstd1", "a", "pre", "f", "s2", "mean2", "rstd2", "out")
+_GRAD_FIELDS = ("dwqkv", "dbqkv", "dwo", "dbo", "dln1_g", "dln1_b", "dw1", "db1", "dw2", "db2",
+                "dln2_g", "dln2_b")
+
+
+def _al(n):
+    return (n + 255) // 256 * 256
+
+
+def _stack_layout(M, H, inter, save):
+    """Byte offsets of one layer's activations inside the workspace slot."""
+    sizes = {"qkv": M * 3 * H * 2, "cx": M * H * 2, "s1": M * H * 2, "mean1": M * 4,
+             "rstd1": M * 4, "a": M * H * 2, "pre": M * inter * 2 if save else 0,
+             "f": M * inter * 2, "s2": M * H * 2, "mean2": M * 4, "rstd2": M * 4,
+             "out": M * H * 2}
+    offs, o = {}, 0
+    for k in _ACT_FIELDS:
+        offs[k] = o
+        o += _al(sizes[k])
+    return offs, o, sizes
+
+
+def _stack_struct(x, layers, att, heads, eps, drop, act_ptrs):
+    n = len(layers)
+    W = (_lib.LayerWeights * n)()
+    A = (_lib.LayerActs * n)()
+    for i, lw in enumerate(layers):
+        w = W[i]
+        w.wqkv, w.bqkv, w.wo, w.bo = (lw.wqkv.data_ptr(), lw.bqkv.data_ptr(), lw.wo.data_ptr(),
+                                      lw.bo.data_ptr())
+        w.ln1_g, w.ln1_b, w.w1, w.b1 = (lw.ln1_g.data_ptr(), lw.ln1_b.data_ptr(),
+                                        lw.w1.data_ptr(), lw.b1.data_ptr())
+        w.w2, w.b2, w.ln2_g, w.ln2_b = (lw.w2.data_ptr(), lw.b2.data_ptr(), lw.ln2_g.data_ptr(),
+                                        lw.ln2_b.data_ptr())
+        a = A[i]
+        for name, ptr in zip(_ACT_FIELDS, act_ptrs[i]):
+            setattr(a, name, ptr)
+    s = _lib.StackArgs()
+    s.n_layers, s.n_tok, s.hidden = n, x.shape[0], x.shape[1]
+    s.inter, s.heads, s.n_tiles = layers[0].w1.shape[0], heads, att["n_tiles"]
+    s.eps = eps
+    s.weights, s.acts = W, A
+    s.x = x.data_ptr()
+    s.tile_tok0, s.tile_ntok = att["tile_tok0"].data_ptr(), att["tile_ntok"].data_ptr()
+    s.seq_lo, s.seq_hi = att["seq_lo"].data_ptr(), att["seq_hi"].data_ptr()
+    (hthr, _, hscale), (athr, _, ascale), key = drop
+    s.hidden_drop_threshold, s.attn_drop_threshold, s.drop_key = hthr, athr, key
+    s.hidden_drop_scale, s.attn_drop_scale = hscale, ascale
+    return s, (W, A)
+
+
+def bert_stack_fwd(x, layers, att, *, heads, eps, drop, save):
+    """All layers of a BertEncoder forward in ONE native call (`hero_bert_stack_fwd`).
+
+    x: packed bf16 [n_tok, H]; layers: functional.LayerWeights per layer; att: attention plan;
+    drop: ((hidden thr, _, scale), (attn thr, _, scale), base key). Returns (out, saved) where
+    `saved` is what bert_stack_bwd needs (None when save is False: activations then ping-pong
+    between two workspace slots)."""
+    _require_cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous()
+    n = len(layers)
+    M, H = x.shape
+    inter = layers[0].w1.shape[0]
+    offs, slot, sizes = _stack_layout(M, H, inter, save)
+    n_slots = n if save else min(n, 2)
+    ws = torch.empty(n_slots * slot, dtype=torch.uint8, device=x.device)
+    base = ws.data_ptr()
+    act_ptrs = []
+    for i in range(n):
+        b = base + (i if save else i % 2) * slot
+        act_ptrs.append([None if (k == "pre" and not save) else b + offs[k] for k in _ACT_FIELDS])
+    s, keep = _stack_struct(x, layers, att, heads, eps, drop, act_ptrs)
+    _count(_STACK_FWD_LAUNCHES * n)
+    _lib.check(_lib.lib().hero_bert_stack_fwd(C.byref(s), _stream()))
+    last = ((n - 1) if save else (n - 1) % 2) * slot + offs["out"]
+    out = ws[last:last + M * H * 2].view(BF16).view(M, H)
+    return out, ((ws, act_ptrs) if save else None)
+
+
+def bert_stack_bwd(x, layers, att, saved, dout, grads, *, heads, eps, drop, need_dx=True):
+    """Backward of the whole stack (`hero_bert_stack_bwd`). grads: per layer a dict of fp32
+    tensors (keys of hero_layer_grads) that are ACCUMULATED into. Returns dx (bf16) or None."""
+    _require_cuda(x, dout)
+    assert dout.dtype == BF16 and dout.is_contiguous()
+    ws, act_ptrs = saved
+    s, keep = _stack_struct(x, layers, att, heads, eps, drop, act_ptrs)
+    n = len(layers)
+    G = (_lib.LayerGrads * n)()
+    for i, gr in enumerate(grads):
+        for name in _GRAD_FIELDS:
+            t = gr[name]
+            assert t.dtype == torch.float32 and t.is_contiguous()
+            setattr(G[i], name, t.data_ptr())
+    s.grads = G
+    s.dout = dout.data_ptr()
+    dx = torch.empty_like(x) if need_dx else None
+    s.dx = None if dx is None else dx.data_ptr()
+    nbytes = _lib.lib().hero_bert_stack_bwd_scratch_bytes(s.n_tok, s.hidden, s.inter)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    s.scratch = scratch.data_ptr()
+    _count(_STACK_BWD_LAUNCHES * n)
+    _lib.check(_lib.lib().hero_bert_stack_bwd(C.byref(s), _stream()))
+    return dx
+
+
 def cast_bf16(src, dst):
     """dst (bf16, same numel) = src (fp32)."""
     _require_cuda(src, dst)

@@ -185,6 +185,80 @@ int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile
                   void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Native layer runtime: a whole stack of BertLayers (model/layers.py:257-327) forward / backward
+ * per call. The reference dispatches ~50 PyTorch ops per layer from Python; even one ctypes call
+ * per kernel left the host as the bottleneck (11 ms of launches per 15 ms step), so the per-layer
+ * launch sequence lives here:
+ *   forward   qkv = x Wqkv^T + b -> attention -> s1 = drop(ctx Wo^T + bo) + x -> a = LN(s1) ->
+ *             f = gelu(a W1^T + b1) (pre-activation kept when `pre` != NULL) ->
+ *             s2 = drop(f W2^T + b2) + a -> out = LN(s2)
+ *   backward  the exact adjoint chain (LN bwd with fused dropout-masked copy, bias column sums,
+ *             split-K wgrads accumulated in fp32 into `grads`, dgrads with fused GELU' / residual
+ *             adds, attention backward)
+ * All buffers are caller-owned device memory; `weights`, `acts`, `grads` are HOST arrays of
+ * n_layers entries. Gradients are ACCUMULATED (+=) into `grads` (point them at zeroed memory or
+ * at the existing .grad buffers). Dropout keys derive from (drop_key, layer, site), identically in
+ * forward and backward; thresholds of 0 disable dropout.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct hero_layer_weights {
+  const void* wqkv;  /* bf16 [3H, H] (query | key | value rows) */
+  const float* bqkv; /* [3H] */
+  const void* wo;    /* bf16 [H, H] */
+  const float* bo;
+  const float* ln1_g;
+  const float* ln1_b;
+  const void* w1;    /* bf16 [I, H] */
+  const float* b1;
+  const void* w2;    /* bf16 [H, I] */
+  const float* b2;
+  const float* ln2_g;
+  const float* ln2_b;
+} hero_layer_weights;
+
+typedef struct hero_layer_acts { /* bf16 unless noted; [n_tok, ...] */
+  void* qkv;    /* [n_tok, 3H] */
+  void* cx;     /* attention output [n_tok, H] */
+  void* s1;     /* pre-LN sum after attention block */
+  float* mean1;
+  float* rstd1;
+  void* a;      /* LN(s1) */
+  void* pre;    /* FFN pre-activation [n_tok, I]; NULL in inference */
+  void* f;      /* gelu(pre) [n_tok, I] */
+  void* s2;     /* pre-LN sum after FFN */
+  float* mean2;
+  float* rstd2;
+  void* out;    /* LN(s2): the layer output */
+} hero_layer_acts;
+
+typedef struct hero_layer_grads { /* fp32, accumulated */
+  float* dwqkv; float* dbqkv; float* dwo; float* dbo; float* dln1_g; float* dln1_b;
+  float* dw1; float* db1; float* dw2; float* db2; float* dln2_g; float* dln2_b;
+} hero_layer_grads;
+
+typedef struct hero_stack_args {
+  int32_t n_layers, n_tok, hidden, inter, heads, n_tiles;
+  float eps;
+  const hero_layer_weights* weights;
+  const hero_layer_acts* acts;
+  const hero_layer_grads* grads; /* backward only */
+  const void* x;                 /* stack input, bf16 [n_tok, H] */
+  const int32_t* tile_tok0;      /* attention plan, see hero_attn_fwd */
+  const int32_t* tile_ntok;
+  const int32_t* seq_lo;
+  const int32_t* seq_hi;
+  uint32_t hidden_drop_threshold, attn_drop_threshold, drop_key;
+  float hidden_drop_scale, attn_drop_scale;
+  /* backward only */
+  const void* dout;              /* bf16 [n_tok, H] gradient of the last layer's output */
+  void* dx;                      /* bf16 [n_tok, H] gradient of x (may be NULL for no input grad) */
+  void* scratch;                 /* >= hero_bert_stack_bwd_scratch_bytes(...) bytes */
+} hero_stack_args;
+
+int hero_bert_stack_fwd(const hero_stack_args* args, void* stream);
+int hero_bert_stack_bwd(const hero_stack_args* args, void* stream);
+int64_t hero_bert_stack_bwd_scratch_bytes(int32_t n_tok, int32_t hidden, int32_t inter);
+
+/* ------------------------------------------------------------------------------------------
  * Row utilities (HBM-bound).
  * ---------------------------------------------------------------------------------------- */
 /* dst[i] = bf16(src[i]); keeps bf16 working copies of the fp32 master weights. */

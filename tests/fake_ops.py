@@ -198,9 +198,77 @@ def sumsq(x, out):
     return out
 
 
+def bert_stack_fwd(x, layers, att, *, heads, eps, drop, save):
+    """Contract of `hero_bert_stack_fwd` (include/hero_b200.h) composed from the per-kernel
+    restatements above; dropout thresholds must be 0."""
+    assert drop[0][0] == 0 and drop[1][0] == 0, "fake ops do not model dropout"
+    M, H = x.shape
+    saved = []
+    h = x
+    for lw in layers:
+        inter = lw.w1.shape[0]
+        qkv = torch.empty(M, 3 * H, dtype=BF16)
+        gemm(h, lw.wqkv, qkv, bias=lw.bqkv)
+        cx = torch.empty(M, H, dtype=BF16)
+        attn_fwd(qkv, att, cx, heads=heads)
+        s1 = torch.empty(M, H, dtype=BF16)
+        gemm(cx, lw.wo, s1, bias=lw.bo, resid=h)
+        a = torch.empty(M, H, dtype=BF16)
+        mean1, rstd1 = torch.empty(M), torch.empty(M)
+        ln_fwd(s1, lw.ln1_g, lw.ln1_b, eps, a, n_rows=M, mean=mean1, rstd=rstd1)
+        f = torch.empty(M, inter, dtype=BF16)
+        pre = torch.empty(M, inter, dtype=BF16) if save else None
+        gemm(a, lw.w1, f, bias=lw.b1, act=1, aux_out=pre)
+        s2 = torch.empty(M, H, dtype=BF16)
+        gemm(f, lw.w2, s2, bias=lw.b2, resid=a)
+        out = torch.empty(M, H, dtype=BF16)
+        mean2, rstd2 = torch.empty(M), torch.empty(M)
+        ln_fwd(s2, lw.ln2_g, lw.ln2_b, eps, out, n_rows=M, mean=mean2, rstd=rstd2)
+        saved.append(dict(h=h, qkv=qkv, cx=cx, s1=s1, mean1=mean1, rstd1=rstd1, a=a, pre=pre, f=f,
+                          s2=s2, mean2=mean2, rstd2=rstd2, out=out))
+        h = out
+    return h, (saved if save else None)
+
+
+def bert_stack_bwd(x, layers, att, saved, dout, grads, *, heads, eps, drop, need_dx=True):
+    """Contract of `hero_bert_stack_bwd`: gradients are accumulated into `grads`."""
+    M, H = dout.shape
+    dy = dout
+    for li in range(len(layers) - 1, -1, -1):
+        lw, S, G = layers[li], saved[li], grads[li]
+        inter = lw.w1.shape[0]
+        ds2 = torch.empty(M, H, dtype=BF16)
+        ln_bwd(dy, S["s2"], lw.ln2_g, S["mean2"], S["rstd2"], n_rows=M, dx=ds2,
+               dgamma=G["dln2_g"], dbeta=G["dln2_b"])
+        colsum(ds2, G["db2"])
+        gemm(ds2, S["f"], G["dw2"], a_mn=True, b_mn=True, accumulate_f32=True)
+        dpre = torch.empty(M, inter, dtype=BF16)
+        gemm(ds2, lw.w2, dpre, b_mn=True, act=3, aux_in=S["pre"])
+        colsum(dpre, G["db1"])
+        gemm(dpre, S["a"], G["dw1"], a_mn=True, b_mn=True, accumulate_f32=True)
+        da = torch.empty(M, H, dtype=BF16)
+        gemm(dpre, lw.w1, da, b_mn=True, resid=ds2)
+        ds1 = torch.empty(M, H, dtype=BF16)
+        ln_bwd(da, S["s1"], lw.ln1_g, S["mean1"], S["rstd1"], n_rows=M, dx=ds1,
+               dgamma=G["dln1_g"], dbeta=G["dln1_b"])
+        colsum(ds1, G["dbo"])
+        gemm(ds1, S["cx"], G["dwo"], a_mn=True, b_mn=True, accumulate_f32=True)
+        dcx = torch.empty(M, H, dtype=BF16)
+        gemm(ds1, lw.wo, dcx, b_mn=True)
+        dqkv = torch.empty(M, 3 * H, dtype=BF16)
+        attn_bwd(S["qkv"], att, S["cx"], dcx, dqkv, heads=heads)
+        colsum(dqkv, G["dbqkv"])
+        gemm(dqkv, S["h"], G["dwqkv"], a_mn=True, b_mn=True, accumulate_f32=True)
+        dx = torch.empty(M, H, dtype=BF16)
+        gemm(dqkv, lw.wqkv, dx, b_mn=True, resid=ds1)
+        dy = dx
+    return dy if need_dx else None
+
+
 def install(monkeypatch):
     """Route hero_b200.ops through the torch restatements for the duration of a test."""
     from hero_b200 import ops
     for name in ("gemm", "ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd", "cast_bf16", "gather_rows",
-                 "gather_sum_rows", "colsum", "relu_bwd", "adamw_step", "sumsq"):
+                 "gather_sum_rows", "colsum", "relu_bwd", "adamw_step", "sumsq", "bert_stack_fwd",
+                 "bert_stack_bwd"):
         monkeypatch.setattr(ops, name, globals()[name])
