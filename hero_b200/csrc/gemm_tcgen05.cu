@@ -14,6 +14,10 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
+
+#include <vector>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -490,9 +494,81 @@ static int dispatch(const hero_gemm_args* g, const GemmMaps& tm, const GemmShape
                    g->a_mn_major, g->b_mn_major, g->act, g->out_f32_accumulate);
 }
 
+// Optional per-launch timing (bench.py roofline): CUDA events on the launching stream around every
+// GEMM launch between hero_gemm_profile_begin() and hero_gemm_profile_end().
+struct GemmProfileRec {
+  int m, n, k, a_mn, b_mn, act, f32;
+};
+struct GemmProfile {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // pairs
+  std::vector<GemmProfileRec> rec;
+  double flops = 0.0;
+  const char* dump_path = nullptr;
+};
+static GemmProfile g_prof;
+
 }  // namespace hero
 
+extern "C" int hero_gemm_profile_begin(void) {
+  using namespace hero;
+  for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+  g_prof.ev.clear();
+  g_prof.rec.clear();
+  g_prof.flops = 0.0;
+  g_prof.on = true;
+  return HERO_OK;
+}
+
+extern "C" int hero_gemm_profile_end(double* ms, double* flops, int64_t* launches) {
+  using namespace hero;
+  g_prof.on = false;
+  double total = 0.0;
+  // HERO_GEMM_PROFILE_DUMP=<path>: per-launch CSV (shape, variant, ms) for tuning
+  const char* path = getenv("HERO_GEMM_PROFILE_DUMP");
+  FILE* f = path ? fopen(path, "w") : nullptr;
+  if (f) fprintf(f, "m,n,k,a_mn,b_mn,act,f32,ms\n");
+  for (size_t i = 0; i + 1 < g_prof.ev.size(); i += 2) {
+    HERO_CUDA_CHECK(cudaEventSynchronize(g_prof.ev[i + 1]));
+    float t = 0.f;
+    HERO_CUDA_CHECK(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
+    total += t;
+    if (f && i / 2 < g_prof.rec.size()) {
+      const GemmProfileRec& r = g_prof.rec[i / 2];
+      fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%.5f\n", r.m, r.n, r.k, r.a_mn, r.b_mn, r.act, r.f32, t);
+    }
+  }
+  if (f) fclose(f);
+  if (ms) *ms = total;
+  if (flops) *flops = g_prof.flops;
+  if (launches) *launches = (int64_t)(g_prof.ev.size() / 2);
+  for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+  g_prof.ev.clear();
+  return HERO_OK;
+}
+
+static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream);
+
 extern "C" int hero_gemm_bf16(const hero_gemm_args* g, void* stream) {
+  using namespace hero;
+  if (!g_prof.on) return hero_gemm_bf16_impl(g, stream);
+  cudaEvent_t e0, e1;
+  HERO_CUDA_CHECK(cudaEventCreate(&e0));
+  HERO_CUDA_CHECK(cudaEventCreate(&e1));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  HERO_CUDA_CHECK(cudaEventRecord(e0, st));
+  const int rc = hero_gemm_bf16_impl(g, stream);
+  HERO_CUDA_CHECK(cudaEventRecord(e1, st));
+  g_prof.ev.push_back(e0);
+  g_prof.ev.push_back(e1);
+  if (g)
+    g_prof.rec.push_back(GemmProfileRec{g->m, g->n, g->k, g->a_mn_major, g->b_mn_major, g->act,
+                                        g->out_f32_accumulate});
+  if (rc == HERO_OK && g) g_prof.flops += 2.0 * (double)g->m * (double)g->n * (double)g->k;
+  return rc;
+}
+
+static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   using namespace hero;
   HERO_REQUIRE(g != nullptr, "null args");
   HERO_REQUIRE(g->a && g->b && g->out, "null operand pointer");

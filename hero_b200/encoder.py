@@ -176,6 +176,12 @@ class CrossModalTrm(RobertaPreTrainedModel):
         self.lm_head.decoder.weight = padded
         self.lm_head.bias = nn.Parameter(bias)
         self.vocab_pad = n_pad
+        self._invalidate_flat()
+
+    def _invalidate_flat(self):
+        fp = self.__dict__.get("_hero_flat")
+        if fp is not None:
+            fp.invalidate()
 
     def init_type_embedding(self):
         new_emb = nn.Embedding(2, self.config.hidden_size)
@@ -184,6 +190,7 @@ class CrossModalTrm(RobertaPreTrainedModel):
         new_emb.weight.data[0, :].copy_(emb)
         new_emb.weight.data[1, :].copy_(emb)
         self.embeddings.token_type_embeddings = new_emb
+        self._invalidate_flat()
 
     # ---- embedding API used by other heads (model/videoQA.py:73, model/violin.py:59) ----
     def _compute_txt_embeddings(self, input_ids, position_ids, txt_type_ids=None):

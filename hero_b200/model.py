@@ -285,3 +285,7 @@ class HeroModel(VideoPreTrainedModel):
             max_img_seq_len=max_frm_seq_len)
         self.v_encoder.f_encoder.pad_vocab()
         self.v_encoder.init_type_embedding()
+        for m in (self, self.v_encoder):
+            fp = m.__dict__.get("_hero_flat")
+            if fp is not None:
+                fp.invalidate()

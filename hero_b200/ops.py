@@ -16,7 +16,6 @@ BF16 = torch.bfloat16
 
 
 _LAUNCHES = 0
-_GEMM_PROF = None
 
 
 def _count(n=1):
@@ -35,16 +34,15 @@ def launch_count():
 
 
 def start_gemm_profile():
-    """Bracket every GEMM launch with CUDA events on the launching stream (bench.py roofline)."""
-    global _GEMM_PROF
-    _GEMM_PROF = []
+    """Bracket every GEMM launch (direct or from the layer runtime) with CUDA events on the
+    launching stream (bench.py roofline); implemented in the library."""
+    _lib.check(_lib.lib().hero_gemm_profile_begin())
 
 
 def stop_gemm_profile():
-    global _GEMM_PROF
-    prof, _GEMM_PROF = _GEMM_PROF or [], None
-    ms = sum(s.elapsed_time(e) for s, e, _ in prof)
-    return {"ms": ms, "flops": float(sum(f for _, _, f in prof)), "launches": len(prof)}
+    ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+    _lib.check(_lib.lib().hero_gemm_profile_end(C.byref(ms), C.byref(fl), C.byref(n)))
+    return {"ms": ms.value, "flops": fl.value, "launches": n.value}
 
 
 def _stream():
@@ -106,13 +104,6 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None
     g.drop_threshold, g.drop_key, g.drop_scale = drop
     g.block_n, g.k_splits = block_n, k_splits
     _count()
-    if _GEMM_PROF is not None:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        _lib.check(_lib.lib().hero_gemm_bf16(C.byref(g), _stream()))
-        ev1.record()
-        _GEMM_PROF.append((ev0, ev1, 2.0 * m * n * k))
-        return out
     _lib.check(_lib.lib().hero_gemm_bf16(C.byref(g), _stream()))
     return out
 

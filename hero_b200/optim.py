@@ -72,7 +72,7 @@ class FusedAdamW:
                            eps=self.eps, lr_wd=lr * grp["weight_decay"], grad_scale=scale)
         # masters changed in place through a flat view: the mirror is already fresh
         self.flat.dirty = False
-        self.flat._version_sum = sum(p._version for _, p, _, _ in self.flat.entries)
+        self.flat._version_sum = sum(p._version for _, p, _, _ in self.flat._probe)
 
     def state_dict(self):
         return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,

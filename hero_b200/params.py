@@ -60,18 +60,30 @@ class FlatParams:
         self.dirty = True
         self._version_sum = -1
         self.grad_flat = None
+        self._stale = False
+        self._probe = []
+        self._hooked = False
 
     # ------------------------------------------------------------------ layout
     def _needs_flatten(self, device):
-        if self.flat is None or self.flat.device != device:
+        """O(1) check: parameters that were moved (.to / .cuda) or replaced (pad_vocab, new
+        modules) no longer point into the flat buffer. Structural edits that keep the sampled
+        parameters in place must call `invalidate()`."""
+        if self.flat is None or self.flat.device != device or self._stale:
             return True
-        for _, p, off, n in self.entries[:2] + self.entries[-2:]:
-            if p.data_ptr() != self.flat.data_ptr() + off * 4:
+        base = self.flat.data_ptr()
+        for _, p, off, n in self._probe:
+            if p.data_ptr() != base + off * 4:
                 return True
-        return len(self.entries) != len(list(self.module.parameters()))
+        return False
+
+    def invalidate(self):
+        self._stale = True
 
     def ensure(self, device):
-        """(Re)build the flat buffers if parameters were moved / replaced; refresh the mirror."""
+        """(Re)build the flat buffers if parameters were moved / replaced; refresh the mirror when
+        the masters may have changed (after a backward, after load_state_dict, or when one of the
+        probed parameters reports a new version)."""
         device = torch.device(device)
         if self._needs_flatten(device):
             named = _ordered_named_params(self.module)
@@ -96,8 +108,15 @@ class FlatParams:
             self.mirror = torch.empty(total, dtype=torch.bfloat16, device=device)
             self.grad_flat = None
             self.dirty = True
+            self._stale = False
+            k = max(1, len(self.entries) // 8)
+            self._probe = self.entries[::k] + self.entries[-1:]
+            if not self._hooked:
+                self.module.register_load_state_dict_post_hook(
+                    lambda module, incompatible: self.mark_dirty())
+                self._hooked = True
         vs = 0
-        for _, p, _, _ in self.entries:
+        for _, p, _, _ in self._probe:
             vs += p._version
         if self.dirty or vs != self._version_sum:
             ops.cast_bf16(self.flat, self.mirror)

@@ -90,6 +90,12 @@ typedef struct hero_gemm_args {
 
 int hero_gemm_bf16(const hero_gemm_args* args, void* stream);
 
+/* Measurement aid for the roofline line of bench.py: between begin and end every GEMM launch (direct
+ * or issued by the layer runtime) is bracketed by CUDA events on its stream; end synchronises and
+ * returns the summed kernel time [ms], the summed 2*M*N*K [FLOP] and the number of launches. */
+int hero_gemm_profile_begin(void);
+int hero_gemm_profile_end(double* ms, double* flops, int64_t* launches);
+
 /* ------------------------------------------------------------------------------------------
  * Fused row kernels: gather + add + LayerNorm (+ dropout) + scatter, one warp per row.
  *
