@@ -9,8 +9,10 @@ train-tvr-8gpu shapes (BASELINE.json), data-parallel over N B200s.
 One step = one pass of the hot path over one synthetic SYN-TVR-dense batch per rank
 (B = 32 clips x 100 frames x 4352-d features, 20 subtitle rows of 5 frames + 20 tokens per clip,
 one 16-token query per clip; hero_finetune dims: 6 cross-modal + 3 temporal layers, H = 768):
-HierarchicalVlModel 'repr' forward + CrossModalTrm 'txt' forward on the query rows, backward of
-both from fixed upstream gradients, and (N > 1) the mean all-reduce of the flat gradient buffer.
+HierarchicalVlModel 'repr' forward + CrossModalTrm 'txt' forward on the query rows (by default
+through `forward_repr_txt`, which runs the query rows in the same cross-modal pass as the video
+rows; `--separate-txt` issues the reference's two calls), backward of both from fixed upstream
+gradients, and (N > 1) the mean all-reduce of the flat gradient buffer.
 Training mode (dropout 0.1 as in config/train-tvr-8gpu.json). No optimizer step (the metric is
 fwd+bwd); `--with-optimizer` adds the fused AdamW.
 
@@ -157,8 +159,11 @@ def run_ours(args):
     dq = (torch.randn(B, host[0][1]["input_ids"].shape[1], H, generator=g) * 1e-2).to(device)
 
     def fwd_bwd(vb_dev, qb_dev):
-        clip = model(vb_dev, "repr")
-        q = model.f_encoder(qb_dev, "txt")[0]
+        if args.separate_txt:      # the reference's two calls (model/pretrain.py:65-70)
+            clip = model(vb_dev, "repr")
+            q = model.f_encoder(qb_dev, "txt")[0]
+        else:                      # same results, query rows share the video rows' GEMMs
+            clip, q = model.forward_repr_txt(vb_dev, qb_dev)
         torch.autograd.backward([clip, q], [dclip, dq])
         if world > 1:
             hdist.all_reduce_flat(gflat)
@@ -301,6 +306,8 @@ def run_ours(args):
                                    "queries x 16 tokens",
                        "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
                        "dropout": 0.1, "optimizer_in_step": bool(args.with_optimizer),
+                       "query_rows": "separate call" if args.separate_txt else
+                       "fused into the video-row pass (forward_repr_txt)",
                        "allreduce_in_step": world > 1,
                        "l2": "no explicit flush: per-step working set (~0.35 GB weights+grads, "
                              "~3 GB activations, 111 MB inputs) exceeds the 126 MB L2"},
@@ -383,6 +390,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-size", type=int, default=32)
     ap.add_argument("--with-optimizer", action="store_true")
+    ap.add_argument("--separate-txt", action="store_true",
+                    help="encode the query rows with a separate f_encoder(batch, 'txt') call")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-clips", type=int, default=4)
     args = ap.parse_args()

@@ -48,7 +48,7 @@ class LnArgs(C.Structure):
         ("drop2_threshold", C.c_uint32), ("drop2_key", C.c_uint32), ("drop2_scale", C.c_float),
         ("d_x_tab", C.c_void_p), ("x_pad_idx", C.c_int32),
         ("d_add_tab", C.c_void_p), ("add_pad_idx", C.c_int32),
-        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("dbias", C.c_void_p),
     ]
 
 

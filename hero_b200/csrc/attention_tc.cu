@@ -91,6 +91,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(tma_bar, 3 * AT_TILE_BYTES);
@@ -277,6 +279,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(tma_bar, 4 * AT_TILE_BYTES);
@@ -520,9 +524,9 @@ extern "C" int hero_attn_fwd(const void* qkv, const int32_t* tile_tok0, const in
     configured = true;
   }
   dim3 grid(n_tiles, heads);
-  attn_tc_fwd_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      tm, a, reinterpret_cast<__nv_bfloat16*>(ctx));
-  HERO_LAUNCH_CHECK();
+  HERO_CUDA_CHECK(launch_pdl(attn_tc_fwd_kernel, grid, dim3(128), smem,
+                             reinterpret_cast<cudaStream_t>(stream), tm, a,
+                             reinterpret_cast<__nv_bfloat16*>(ctx)));
   return HERO_OK;
 }
 
@@ -549,9 +553,10 @@ extern "C" int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const in
     configured = true;
   }
   dim3 grid(n_tiles, heads);
-  attn_tc_bwd_kernel<<<grid, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      tq, td, a, reinterpret_cast<const __nv_bfloat16*>(ctx),
-      reinterpret_cast<const __nv_bfloat16*>(dctx), reinterpret_cast<__nv_bfloat16*>(dqkv));
-  HERO_LAUNCH_CHECK();
+  HERO_CUDA_CHECK(launch_pdl(attn_tc_bwd_kernel, grid, dim3(128), smem,
+                             reinterpret_cast<cudaStream_t>(stream), tq, td, a,
+                             reinterpret_cast<const __nv_bfloat16*>(ctx),
+                             reinterpret_cast<const __nv_bfloat16*>(dctx),
+                             reinterpret_cast<__nv_bfloat16*>(dqkv)));
   return HERO_OK;
 }

@@ -36,6 +36,24 @@ int sm_count();
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Launch with programmatic dependent launch enabled (see ptx.cuh pdl_wait): the kernel MUST call
+// pdl_wait() before its first access to global memory written by earlier work in the stream.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // 2-D bf16 tensor map over a row-major [outer, inner] matrix (leading dim `ld` elements) with a
 // 128-byte-swizzled box of box_inner (<= 64) x box_outer elements. `map` is a CUtensorMap.
 int encode_tmap_2d_bf16(void* map, const void* ptr, long long inner, long long outer, long long ld,

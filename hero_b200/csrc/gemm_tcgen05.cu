@@ -158,6 +158,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above overlapped the tail of the previous kernel (PDL); from here on we touch its
+  // outputs. Let the next kernel start its own prologue right away.
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int total_tiles = s.num_m_blocks * s.num_n_blocks * s.k_splits;
 
@@ -461,8 +465,8 @@ static int launch(const GemmMaps& tm, const GemmShape& s, const GemmEpilogue& e,
   const int sms = sm_count();
   if (sms <= 0) return set_error(HERO_ERR_NO_DEVICE, "no CUDA device");
   const int grid = total < sms ? total : sms;
-  kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm.a, tm.b, tm.out, tm.aux, s, e);
-  HERO_LAUNCH_CHECK();
+  HERO_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, stream, tm.a,
+                             tm.b, tm.out, tm.aux, s, e));
   return HERO_OK;
 }
 

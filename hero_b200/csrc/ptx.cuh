@@ -178,6 +178,17 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
          | (static_cast<uint32_t>(M >> 4) << 24);    // M / 16
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Kernels launched with the programmatic-stream-serialization attribute may start while the
+// previous kernel in the stream is still draining: everything before pdl_wait() (barrier init,
+// TMEM allocation, descriptor prefetch) overlaps that tail; pdl_wait() blocks until the previous
+// grid has completed and its writes are visible. pdl_launch_dependents() lets the NEXT kernel
+// begin its own prologue early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -78,6 +78,8 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float (&v)[
 template <int MAXJ>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const hero_ln_args a) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * LN_WARPS + warp;
   if (i >= a.n_rows) return;
@@ -141,6 +143,8 @@ ln_fwd_kernel(const hero_ln_args a) {
 template <int MAXJ, bool PARAM_GRADS>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const hero_ln_args a) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_warps = gridDim.x * LN_WARPS;
   float dg[PARAM_GRADS ? MAXJ : 1][8], db[PARAM_GRADS ? MAXJ : 1][8];
@@ -245,45 +249,68 @@ ln_bwd_kernel(const hero_ln_args a) {
   }
 }
 
-// Column-parallel dgamma/dbeta for wide rows (H = 4352): block = 32 columns x 8 row lanes.
+// Column-parallel parameter gradients: dgamma += sum_i dy*xhat, dbeta += sum_i dy, and optionally
+// dbias += sum_i dx_drop (the bias gradient of the Linear feeding this LayerNorm). Each thread owns
+// 8 consecutive columns (16-byte loads); block = 32 column groups x 8 row lanes; grid.y splits rows.
+// Runs after the row kernel, whose dx / dx_drop output is still L2-resident.
 __global__ void __launch_bounds__(256)
 ln_param_grad_kernel(const hero_ln_args a, int rows_per_block) {
-  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  pdl_wait();
+  pdl_launch_dependents();
+  const int cg = threadIdx.x & 31;
+  const int col = (blockIdx.x * 32 + cg) * 8;
   const int rl = threadIdx.x >> 5;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(a.n_rows, r0 + rows_per_block);
-  float dg = 0.f, db = 0.f;
+  const bool want_gb = a.dgamma != nullptr || a.dbeta != nullptr;
+  const __nv_bfloat16* dsrc = reinterpret_cast<const __nv_bfloat16*>(a.dx_drop ? a.dx_drop : a.dx);
+  const bool want_bias = a.dbias != nullptr && dsrc != nullptr;
+  float dg[8], db[8], dbi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dg[j] = db[j] = dbi[j] = 0.f;
   if (col < a.h) {
     for (int i = r0 + rl; i < r1; i += 8) {
-      const long long xrow = a.x_rows ? a.x_rows[i] : i;
-      const long long yrow = a.y_rows ? a.y_rows[i] : i;
-      float x = a.x_is_f32 ? __ldg(reinterpret_cast<const float*>(a.x) + xrow * a.h + col)
-                           : __bfloat162float(
-                                 reinterpret_cast<const __nv_bfloat16*>(a.x)[xrow * a.h + col]);
-      if (a.add_tab) x += __ldg(a.add_tab + (long long)a.add_idx[i] * a.h + col);
-      if (a.add_vec) x += __ldg(a.add_vec + col);
-      float d = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.dy)[yrow * a.h + col]);
-      if (a.drop_threshold != 0u)
-        d = dropout_keep(a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)col, a.drop_threshold)
-                ? d * a.drop_scale
-                : 0.f;
-      dg += d * (x - a.mean[i]) * a.rstd[i];
-      db += d;
+      if (want_gb) {
+        const long long xrow = a.x_rows ? a.x_rows[i] : i;
+        const long long yrow = a.y_rows ? a.y_rows[i] : i;
+        const int add_row = a.add_tab ? a.add_idx[i] : 0;
+        float x[8], d[8];
+        ln_load8(a, xrow, add_row, col, x);
+        load_bf16x8(reinterpret_cast<const __nv_bfloat16*>(a.dy) + yrow * a.h + col, d);
+        if (a.drop_threshold != 0u)
+          dropout_apply8(d, a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)col,
+                         a.drop_threshold, a.drop_scale);
+        const float mean = a.mean[i], rstd = a.rstd[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dg[j] += d[j] * (x[j] - mean) * rstd;
+          db[j] += d[j];
+        }
+      }
+      if (want_bias) {
+        float v[8];
+        load_bf16x8(dsrc + (long long)i * a.h + col, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dbi[j] += v[j];
+      }
     }
   }
-  __shared__ float sg[8][33], sb[8][33];
-  sg[rl][threadIdx.x & 31] = dg;
-  sb[rl][threadIdx.x & 31] = db;
-  __syncthreads();
-  if (rl == 0 && col < a.h) {
-    float g = 0.f, b = 0.f;
+  __shared__ float sm[8][32 * 8 + 4];
+  float* outs[3] = {a.dgamma, a.dbeta, want_bias ? a.dbias : nullptr};
+  for (int pass = 0; pass < 3; ++pass) {
+    if (outs[pass] == nullptr) continue;   // block-uniform
+    __syncthreads();
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      g += sg[w][threadIdx.x];
-      b += sb[w][threadIdx.x];
+    for (int j = 0; j < 8; ++j) sm[rl][cg * 8 + j] = pass == 0 ? dg[j] : (pass == 1 ? db[j] : dbi[j]);
+    __syncthreads();
+    const int c = threadIdx.x;
+    const int gcol = blockIdx.x * 256 + c;
+    if (gcol < a.h) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += sm[w][c];
+      atomicAdd(outs[pass] + gcol, t);
     }
-    if (a.dgamma) atomicAdd(a.dgamma + col, g);
-    if (a.dbeta) atomicAdd(a.dbeta + col, b);
   }
 }
 
@@ -291,6 +318,8 @@ ln_param_grad_kernel(const hero_ln_args a, int rows_per_block) {
 __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src,
                                    const int32_t* __restrict__ idx, __nv_bfloat16* __restrict__ dst,
                                    int n, int h8) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)n * h8) return;
   const int i = (int)(t / h8), c = (int)(t % h8);
@@ -305,6 +334,8 @@ __global__ void gather_sum_rows_kernel(const __nv_bfloat16* __restrict__ src,
                                        const int32_t* __restrict__ off,
                                        const int32_t* __restrict__ idx,
                                        __nv_bfloat16* __restrict__ dst, int n, int h8) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)n * h8) return;
   const int i = (int)(t / h8), c = (int)(t % h8);
@@ -325,6 +356,8 @@ __global__ void gather_sum_rows_f32_kernel(const __nv_bfloat16* __restrict__ src
                                            const int32_t* __restrict__ off,
                                            const int32_t* __restrict__ idx, float* __restrict__ dst,
                                            int h8, int per_split) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int i = blockIdx.x;
   const int end = off[i + 1];
   for (int e0 = off[i] + blockIdx.y * per_split; e0 < end; e0 += gridDim.y * per_split) {
@@ -344,31 +377,56 @@ __global__ void gather_sum_rows_f32_kernel(const __nv_bfloat16* __restrict__ src
   }
 }
 
-// out[n] += sum_m x[m, n]: block = 32 columns x 8 row lanes, grid.y splits the rows.
+// out[n] += sum_m x[m, n]. Each thread owns 8 consecutive columns (16-byte loads); a block is
+// 32 column groups (256 columns = 512 B per row, fully coalesced) x 8 row lanes; grid.y splits rows.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int m, int n,
               float* __restrict__ out, int rows_per_block) {
-  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  pdl_wait();
+  pdl_launch_dependents();
+  const int cg = threadIdx.x & 31;
+  const int col = (blockIdx.x * 32 + cg) * 8;
   const int rl = threadIdx.x >> 5;
   const int r0 = blockIdx.y * rows_per_block;
   const int r1 = min(m, r0 + rows_per_block);
-  float s = 0.f;
-  if (col < n)
-    for (int r = r0 + rl; r < r1; r += 8) s += __bfloat162float(x[(long long)r * ld + col]);
-  __shared__ float sm[8][33];
-  sm[rl][threadIdx.x & 31] = s;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < n) {
+    int r = r0 + rl;
+    // two rows in flight per iteration
+    for (; r + 8 < r1; r += 16) {
+      float v0[8], v1[8];
+      load_bf16x8(x + (long long)r * ld + col, v0);
+      load_bf16x8(x + (long long)(r + 8) * ld + col, v1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v0[j] + v1[j];
+    }
+    for (; r < r1; r += 8) {
+      float v0[8];
+      load_bf16x8(x + (long long)r * ld + col, v0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v0[j];
+    }
+  }
+  __shared__ float sm[8][32 * 8 + 4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[rl][cg * 8 + j] = acc[j];
   __syncthreads();
-  if (rl == 0 && col < n) {
+  // thread t sums column t of the block's 256 columns over the 8 row lanes
+  const int c = threadIdx.x;
+  const int gcol = blockIdx.x * 256 + c;
+  if (gcol < n) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += sm[w][threadIdx.x];
-    atomicAdd(out + col, t);
+    for (int w = 0; w < 8; ++w) t += sm[w][c];
+    atomicAdd(out + gcol, t);
   }
 }
 
 __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                 const __nv_bfloat16* __restrict__ pre,
                                 __nv_bfloat16* __restrict__ out, long long n8) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n8) return;
   float d[8], p[8];
@@ -410,10 +468,9 @@ extern "C" int hero_ln_fwd(const hero_ln_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int grid = ceil_div(a->n_rows, LN_WARPS);
   if (a->h <= 768)
-    ln_fwd_kernel<3><<<grid, LN_WARPS * 32, 0, st>>>(*a);
+    HERO_CUDA_CHECK(launch_pdl(ln_fwd_kernel<3>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
   else
-    ln_fwd_kernel<17><<<grid, LN_WARPS * 32, 0, st>>>(*a);
-  HERO_LAUNCH_CHECK();
+    HERO_CUDA_CHECK(launch_pdl(ln_fwd_kernel<17>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
   return HERO_OK;
 }
 
@@ -424,30 +481,25 @@ extern "C" int hero_ln_bwd(const hero_ln_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int sms = sm_count();
   if (sms <= 0) return set_error(HERO_ERR_NO_DEVICE, "no CUDA device");
-  int grid = ceil_div(a->n_rows, LN_WARPS);
-  if (grid > sms * 4) grid = sms * 4;
-  const bool want_param = a->dgamma != nullptr || a->dbeta != nullptr;
-  if (a->h <= 768) {
-    if (want_param)
-      ln_bwd_kernel<3, true><<<grid, LN_WARPS * 32, 0, st>>>(*a);
+  const bool want_rows = a->dx || a->dx_drop || a->d_x_tab || a->d_add_tab;
+  const bool want_cols = a->dgamma || a->dbeta || a->dbias;
+  if (want_rows) {
+    int grid = ceil_div(a->n_rows, LN_WARPS);
+    if (grid > sms * 16) grid = sms * 16;
+    if (a->h <= 768)
+      HERO_CUDA_CHECK(launch_pdl(ln_bwd_kernel<3, false>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
     else
-      ln_bwd_kernel<3, false><<<grid, LN_WARPS * 32, 0, st>>>(*a);
-    HERO_LAUNCH_CHECK();
-  } else {
-    if (a->dx || a->dx_drop || a->d_x_tab || a->d_add_tab) {
-      ln_bwd_kernel<17, false><<<grid, LN_WARPS * 32, 0, st>>>(*a);
-      HERO_LAUNCH_CHECK();
-    }
-    if (want_param) {
-      const int col_blocks = ceil_div(a->h, 32);
-      int row_splits = ceil_div(sms * 8, col_blocks);
-      if (row_splits > ceil_div(a->n_rows, 8)) row_splits = ceil_div(a->n_rows, 8);
-      if (row_splits < 1) row_splits = 1;
-      const int rpb = ceil_div(a->n_rows, row_splits);
-      dim3 g(col_blocks, ceil_div(a->n_rows, rpb));
-      ln_param_grad_kernel<<<g, 256, 0, st>>>(*a, rpb);
-      HERO_LAUNCH_CHECK();
-    }
+      HERO_CUDA_CHECK(launch_pdl(ln_bwd_kernel<17, false>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
+  }
+  if (want_cols) {
+    HERO_REQUIRE(!a->dbias || a->dx || a->dx_drop, "ln_bwd: dbias needs dx or dx_drop");
+    const int col_blocks = ceil_div(a->h, 256);
+    int row_splits = ceil_div(sms * 8, col_blocks);
+    if (row_splits > ceil_div(a->n_rows, 32)) row_splits = ceil_div(a->n_rows, 32);
+    if (row_splits < 1) row_splits = 1;
+    const int rpb = ceil_div(a->n_rows, row_splits);
+    dim3 g(col_blocks, ceil_div(a->n_rows, rpb));
+    HERO_CUDA_CHECK(launch_pdl(ln_param_grad_kernel, g, dim3(256), 0, st, *a, rpb));
   }
   return HERO_OK;
 }
@@ -508,15 +560,16 @@ extern "C" int hero_colsum_bf16(const void* x, int64_t ld, int32_t m, int32_t n,
   if (m <= 0 || n <= 0) return HERO_OK;
   const int sms = sm_count();
   if (sms <= 0) return set_error(HERO_ERR_NO_DEVICE, "no CUDA device");
-  const int col_blocks = ceil_div(n, 32);
+  HERO_REQUIRE(n % 8 == 0 && ld % 8 == 0, "colsum: n and ld must be multiples of 8");
+  const int col_blocks = ceil_div(n, 256);
   int row_splits = ceil_div(sms * 8, col_blocks);
-  if (row_splits > ceil_div(m, 8)) row_splits = ceil_div(m, 8);
+  if (row_splits > ceil_div(m, 32)) row_splits = ceil_div(m, 32);
   if (row_splits < 1) row_splits = 1;
   const int rpb = ceil_div(m, row_splits);
   dim3 g(col_blocks, ceil_div(m, rpb));
-  colsum_kernel<<<g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), ld, m, n, out, rpb);
-  HERO_LAUNCH_CHECK();
+  HERO_CUDA_CHECK(launch_pdl(colsum_kernel, g, dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+                             reinterpret_cast<const __nv_bfloat16*>(x), (long long)ld, m, n, out,
+                             rpb));
   return HERO_OK;
 }
 

@@ -149,6 +149,7 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
     hero_ln_args ln;
     ln_base(&ln, A.s2, W.ln2_g, nullptr, s->eps, M, H, A.mean2, A.rstd2);
     ln.dy = dy; ln.dx = ds2; ln.dgamma = G.dln2_g; ln.dbeta = G.dln2_b;
+    ln.dbias = G.db2;   // bias gradient of the FFN-down Linear = column sums of the masked ds2
     void* g2 = ds2;
     if (hd) {
       ln.dx_drop = ds2_d;
@@ -159,7 +160,6 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
     }
     HERO_TRY(hero_ln_bwd(&ln, stream));
     // FFN down
-    HERO_TRY(hero_colsum_bf16(g2, H, M, H, G.db2, stream));
     HERO_TRY(Gemm(g2, H, 1, A.f, I, 1, H, I, M, G.dw2, I).f32_accumulate().run(stream));
     HERO_TRY(Gemm(g2, H, 0, W.w2, I, 1, M, I, H, dpre, I).act(ACT_GELU_GRAD).aux_in(A.pre, I).run(stream));
     // FFN up
@@ -169,6 +169,7 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
     // LN1 backward
     ln_base(&ln, A.s1, W.ln1_g, nullptr, s->eps, M, H, A.mean1, A.rstd1);
     ln.dy = da; ln.dx = ds1; ln.dgamma = G.dln1_g; ln.dbeta = G.dln1_b;
+    ln.dbias = G.dbo;
     void* g1 = ds1;
     if (hd) {
       ln.dx_drop = ds1_d;
@@ -179,7 +180,6 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
     }
     HERO_TRY(hero_ln_bwd(&ln, stream));
     // attention output projection
-    HERO_TRY(hero_colsum_bf16(g1, H, M, H, G.dbo, stream));
     HERO_TRY(Gemm(g1, H, 1, A.cx, H, 1, H, H, M, G.dwo, H).f32_accumulate().run(stream));
     HERO_TRY(Gemm(g1, H, 0, W.wo, H, 1, M, H, H, dcx, H).run(stream));
     // attention core

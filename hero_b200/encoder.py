@@ -267,6 +267,42 @@ class CrossModalTrm(RobertaPreTrainedModel):
         emb = Fn.cross_modal_embed(cfg, self._embed_params(with_img))
         return self.encoder.forward_packed(emb, fplan.seq.attn(dev, "f_"), drop)
 
+    def encode_packed_joint(self, jplan, rdev, tdev, jdev, batch, txt_batch, drop=None):
+        """One pass of embeddings + encoder over [video rows | query rows] (see plan.JointPlan).
+        Returns the packed bf16 [n_video_tok + n_query_tok, H] output."""
+        device = jdev.flat.device
+        flat = flat_of(self, device)
+        if drop is None:
+            drop = self.encoder.dropout_state()
+        fv, fq = jplan.r.f, jplan.t.f
+        v_ids, q_ids = batch["f_sub_input_ids"], txt_batch["input_ids"]
+        v_pos, q_pos = batch["f_sub_pos_ids"], txt_batch["pos_ids"]
+        cfg_v = self._embed_cfg(fv, rdev, drop, v_ids, v_pos, batch["f_v_feats"],
+                                batch["f_v_pos_ids"], batch["f_v_masks"])
+        cfg_q = self._embed_cfg(fq, tdev, drop, q_ids, q_pos, None, None, None,
+                                pos_keys=("pos_off", "pos_idx", None, None))
+        cfg = dict(cfg_v)
+        cfg["n_tok"], cfg["n_txt"] = jplan.n_tok, jplan.n_txt
+        cfg["txt_ids"] = torch.cat([cfg_v["txt_ids"], cfg_q["txt_ids"]]) if fv.n_txt else \
+            cfg_q["txt_ids"]
+        cfg["txt_pos"] = torch.cat([cfg_v["txt_pos"], cfg_q["txt_pos"]]) if fv.n_txt else \
+            cfg_q["txt_pos"]
+        cfg["txt_tok"] = jdev.j_txt_tok
+        cfg["txtpos_off"], cfg["txtpos_idx"] = jdev.j_txtpos_off, jdev.j_txtpos_idx
+        sv, sq = cfg_v.get("txt_slot_pos"), cfg_q.get("txt_slot_pos")
+        if sv is not None and sq is not None:
+            n = min(sv.numel(), sq.numel())
+            same = bool((sv[:n] == sq[:n]).all()) if n else True    # both are the collate's arange
+            cfg["txt_slot_pos"] = (sv if sv.numel() >= sq.numel() else sq) if same else None
+        else:
+            cfg["txt_slot_pos"] = None
+        with_img = fv.n_img > 0
+        if with_img:
+            cfg["img_lin_w_bf16"] = flat.bf16(self.img_embeddings.img_linear.weight)
+        cfg["flat"] = flat
+        emb = Fn.cross_modal_embed(cfg, self._embed_params(with_img))
+        return self.encoder.forward_packed(emb, jplan.attn(jdev), drop)
+
     def _unpack(self, y, dev, shape):
         out = Fn.gather_rows(y, dev.f_pad_to_tok, dev.f_tok_flat)
         return out.view(shape[0], shape[1], y.shape[1]).to(_output_dtype(self))

@@ -22,7 +22,7 @@ from .encoder import (CrossModalTrm, RobertaModelConfig, RobertaPreTrainedModel,
                       load_pretrained_weight)
 from .layers import GELU, BertLayerNorm, LinearLayer, MLPLayer
 from .params import flat_of
-from .plan import PLAN_KEY, ReprPlan
+from .plan import PLAN_KEY, JointPlan, ReprPlan, TxtPlan
 
 BF16 = torch.bfloat16
 
@@ -120,16 +120,29 @@ class HierarchicalVlModel(VideoPreTrainedModel):
             plan = ReprPlan(batch)      # reads the masks back to the host once (one sync)
         return plan
 
-    def repr_packed(self, batch, plan, encode_clip=True, shuffled_orders=None):
-        """Returns (packed clip-level tensor bf16 [n_c_tokens, H], plan, dev)."""
+    def repr_packed(self, batch, plan, encode_clip=True, txt_batch=None, txt_plan=None):
+        """Returns (packed clip-level tensor bf16 [n_c_tokens, H], dev[, packed query rows]).
+        With `txt_batch` the text-only query rows ride through the cross-modal transformer in the
+        same pass as the video rows (plan.JointPlan)."""
         device = batch["c_v_feats"].device
         dev = plan.to(device)
         flat = flat_of(self, device)
         fe, ce = self.f_encoder, self.c_encoder
         drop = fe.encoder.dropout_state()
-        # cross-modal transformer on packed [frames, text] rows
-        hf = fe.encode_packed(plan.f, dev, batch["f_sub_input_ids"], batch["f_sub_pos_ids"],
-                              batch["f_v_feats"], batch["f_v_pos_ids"], batch["f_v_masks"], drop)
+        yq = None
+        if txt_batch is None:
+            # cross-modal transformer on packed [frames, text] rows
+            hf = fe.encode_packed(plan.f, dev, batch["f_sub_input_ids"], batch["f_sub_pos_ids"],
+                                  batch["f_v_feats"], batch["f_v_pos_ids"], batch["f_v_masks"],
+                                  drop)
+        else:
+            jplan = plan.__dict__.get("_joint")
+            if jplan is None or jplan.t is not txt_plan:
+                jplan = JointPlan(plan, txt_plan)
+                plan.__dict__["_joint"] = jplan
+            y = fe.encode_packed_joint(jplan, dev, txt_plan.to(device), jplan.to(device), batch,
+                                       txt_batch, drop)
+            hf, yq = y[:jplan.n_video_tok], y[jplan.n_video_tok:]
         # frame outputs back onto the clip timeline + projected raw features (residual)
         c_v = batch["c_v_feats"]
         D = c_v.shape[-1]
@@ -145,11 +158,11 @@ class HierarchicalVlModel(VideoPreTrainedModel):
         g = Fn.frame_merge(hf, cfg, [ft.LayerNorm.weight, ft.LayerNorm.bias, ft.net[1].weight,
                                      ft.net[1].bias])
         if not encode_clip:
-            return g, dev
+            return (g, dev) if txt_batch is None else (g, dev, yq)
         dropc = ce.encoder.dropout_state(drop.base + 104729)
         y = ce.embed_encode_packed(g, dev.c_t, plan.c.seq.attn(dev, "c_"), dev.c_pos_off,
                                    dev.c_pos_idx, dropc)
-        return y, dev
+        return (y, dev) if txt_batch is None else (y, dev, yq)
 
     def _unpack_c(self, y, dev, shape):
         out = Fn.gather_rows(y, dev.c_pad_to_tok, dev.c_tok_flat)
@@ -162,6 +175,24 @@ class HierarchicalVlModel(VideoPreTrainedModel):
         plan = self._plan(batch)
         y, dev = self.repr_packed(batch, plan, encode_clip)
         return self._unpack_c(y, dev, plan.shape_c)
+
+    def forward_repr_txt(self, batch, txt_batch, encode_clip=True):
+        """Fused equivalent of
+            clip = self.forward_repr(batch);  q = self.f_encoder(txt_batch, 'txt')[0]
+        (model/pretrain.py:65-70, model/model.py:226-237): the query rows share the cross-modal
+        transformer pass of the video rows. Returns (clip_outputs (B,T,H), query seq (Nq,Lq,H))."""
+        if not isinstance(batch, defaultdict):
+            batch = defaultdict(lambda: None, batch)
+        plan = self._plan(batch)
+        tplan = txt_batch.get(PLAN_KEY) if hasattr(txt_batch, "get") else None
+        if tplan is None:
+            tplan = TxtPlan(txt_batch["attn_masks"])
+        y, dev, yq = self.repr_packed(batch, plan, encode_clip, txt_batch, tplan)
+        clip = self._unpack_c(y, dev, plan.shape_c)
+        tdev = tplan.to(y.device)
+        q = Fn.gather_rows(yq.contiguous(), tdev.f_pad_to_tok, tdev.f_tok_flat)
+        q = q.view(tplan.shape[0], tplan.shape[1], y.shape[1]).to(self.output_dtype)
+        return clip, q
 
     def collect_frame_outputs(self, out_shape, frame_sequence_output, num_subs,
                               sub_idx2frame_idx):
@@ -187,12 +218,10 @@ class HierarchicalVlModel(VideoPreTrainedModel):
 
     def forward_vsm(self, batch):
         """model/model.py:226-237."""
-        clip_outputs = self.forward_repr(batch)
         sub_query_batch = {"input_ids": batch["vsm_query_input_ids"],
                            "pos_ids": batch["vsm_query_pos_ids"],
                            "attn_masks": batch["vsm_query_attn_masks"]}
-        query = self.f_encoder(sub_query_batch, "txt")[0]
-        return clip_outputs, query
+        return self.forward_repr_txt(batch, sub_query_batch)
 
     # ---- pretraining heads (model/model.py:239-336): encoder on CUDA, small heads in torch ----
     def forward_mfm(self, batch, compute_loss=True, loss="regression"):

@@ -157,8 +157,8 @@ def ln_bwd(dy, x, gamma, mean, rstd, *, n_rows, x_rows=None, add_tab=None, add_i
     a.d_x_tab, a.x_pad_idx = _ptr(d_x_tab), x_pad_idx
     a.d_add_tab, a.add_pad_idx = _ptr(d_add_tab), add_pad_idx
     a.dgamma, a.dbeta = _ptr(dgamma), _ptr(dbeta)
-    _count(2 if (h > 768 and (dgamma is not None or dbeta is not None) and
-                 (dx is not None or d_add_tab is not None)) else 1)
+    _count(int(dx is not None or dx_drop is not None or d_x_tab is not None or
+               d_add_tab is not None) + int(dgamma is not None or dbeta is not None))
     _lib.check(_lib.lib().hero_ln_bwd(C.byref(a), _stream()))
 
 
@@ -187,7 +187,7 @@ def attn_bwd(qkv, att, ctx, dctx, dqkv, *, heads, head_dim=64, drop=(0, 0, 1.0))
 
 
 # kernels launched per layer by the native runtime (for bench.py's gpu_launches)
-_STACK_FWD_LAUNCHES, _STACK_BWD_LAUNCHES = 7, 15
+_STACK_FWD_LAUNCHES, _STACK_BWD_LAUNCHES = 7, 15   # bwd: 8 GEMM, 2x2 LN, attn, 2 colsum
 _ACT_FIELDS = ("qkv", "cx", "s1", "mean1", "rstd1", "a", "pre", "f", "s2", "mean2", "rstd2", "out")
 _GRAD_FIELDS = ("dwqkv", "dbqkv", "dwo", "dbo", "dln1_g", "dln1_b", "dw1", "db1", "dw2", "db2",
                 "dln2_g", "dln2_b")

@@ -249,6 +249,51 @@ class TxtPlan:
         return self.dev
 
 
+class JointPlan:
+    """Video rows ('repr') and text-only query rows ('txt') of the SAME CrossModalTrm concatenated
+    into one packed token stream, so both go through the 6 layers as one set of GEMMs (32 query
+    rows x 16 tokens alone would run every GEMM at M = 512, ~10 % tensor utilisation).
+    Query tokens follow the video tokens: packed index = n_video_tokens + query index."""
+
+    def __init__(self, rplan, tplan):
+        self.r, self.t = rplan, tplan
+        fv, fq = rplan.f, tplan.f
+        a = fv.seq.n_tok
+        self.n_video_tok = a
+        self.n_tok = a + fq.seq.n_tok
+        self.n_txt = fv.n_txt + fq.n_txt
+        self.n_img = fv.n_img
+        self.max_vl, self.max_sl_v, self.max_sl_q = fv.max_vl, fv.max_sl, fq.max_sl
+        sv, sq = fv.seq, fq.seq
+        self.n_seq = sv.n_seq + sq.n_seq
+        self.max_len = max(sv.max_len, sq.max_len)
+        self.n_tiles = sv.n_tiles + sq.n_tiles
+        self.arr = {
+            "j_cu": np.concatenate([sv.cu, sq.cu[1:] + a]).astype(np.int32),
+            "j_seq_lo": np.concatenate([sv.seq_lo, sq.seq_lo + a]).astype(np.int32),
+            "j_seq_hi": np.concatenate([sv.seq_hi, sq.seq_hi + a]).astype(np.int32),
+            "j_tile_tok0": np.concatenate([sv.tile_tok0, sq.tile_tok0 + a]).astype(np.int32),
+            "j_tile_ntok": np.concatenate([sv.tile_ntok, sq.tile_ntok]).astype(np.int32),
+            "j_txt_tok": np.concatenate([fv.txt_tok, fq.txt_tok + a]).astype(np.int32),
+            "j_txt_j": np.concatenate([fv.txt_j, fq.txt_j]).astype(np.int32),
+        }
+        n_slot = max(fv.max_sl, fq.max_sl, 1)
+        self.arr["j_txtpos_off"], self.arr["j_txtpos_idx"] = table_csr(self.arr["j_txt_j"], n_slot)
+        self.dev = None
+
+    def to(self, device):
+        device = torch.device(device)
+        if self.dev is None or self.dev.flat.device != device:
+            self.dev = DeviceIndex(self.arr, device)
+        return self.dev
+
+    def attn(self, dev):
+        return {"cu": dev.j_cu, "seq_lo": dev.j_seq_lo, "seq_hi": dev.j_seq_hi,
+                "tile_tok0": dev.j_tile_tok0, "tile_ntok": dev.j_tile_ntok,
+                "n_tiles": self.n_tiles, "n_tok": self.n_tok, "n_seq": self.n_seq,
+                "max_len": self.max_len}
+
+
 PLAN_KEY = "_hero_plan"
 
 

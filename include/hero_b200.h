@@ -156,6 +156,8 @@ typedef struct hero_ln_args {
   int32_t add_pad_idx;     /* -1 = none */
   float* dgamma;           /* f32 [h] or NULL */
   float* dbeta;            /* f32 [h] or NULL */
+  float* dbias;            /* f32 [h] or NULL: += column sums of dx_drop (dx when dx_drop is NULL),
+                              i.e. the bias gradient of the Linear that fed this LayerNorm */
 } hero_ln_args;
 
 int hero_ln_fwd(const hero_ln_args* args, void* stream);

@@ -150,3 +150,29 @@ def test_in_place_gradient_sinks_match_autograd_accumulation(tmp_path, monkeypat
     for k, p in model.named_parameters():
         if k in ref_grads:
             assert torch.allclose(p.grad, 2 * ref_grads[k], rtol=1e-4, atol=1e-5), k
+
+
+def test_fused_repr_txt_equals_separate_calls(tmp_path, monkeypatch):
+    """forward_repr_txt (query rows ride along with the video rows) == the two reference calls,
+    forward and backward."""
+    fake_ops.install(monkeypatch)
+    fx = gu.load("hier_tiny.npz")
+    vb, qb = gu.stored_batches(fx)
+    w1, w2 = torch.from_numpy(fx["loss_w1"]), torch.from_numpy(fx["loss_w2"])
+    ref = _model(tmp_path, fx)
+    clip_r = ref(vb, "repr")
+    q_r = ref.f_encoder(qb, "txt")[0]
+    ((clip_r * w1).sum() + (q_r * w2).sum()).backward()
+    model = _model(tmp_path, fx)
+    clip, q = model.forward_repr_txt(vb, qb)
+    assert torch.allclose(clip, clip_r, atol=2e-2) and torch.allclose(q, q_r, atol=2e-2)
+    cm = vb["c_attn_masks"].bool().numpy()
+    _close(clip, fx["clip_out"], cm, 6e-2, "fused clip outputs")
+    _close(q, fx["q_seq_out"], qb["attn_masks"].bool().numpy(), 6e-2, "fused query rows")
+    ((clip * w1).sum() + (q * w2).sum()).backward()
+    gr = dict(ref.named_parameters())
+    for k, p in model.named_parameters():
+        if gr[k].grad is None:
+            continue
+        rel = (p.grad - gr[k].grad).norm() / gr[k].grad.norm().clamp_min(1e-9)
+        assert rel < 2e-2, (k, float(rel))
