@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
         ("act", C.c_int32), ("out_f32_accumulate", C.c_int32),
         ("drop_threshold", C.c_uint32), ("drop_key", C.c_uint32),
         ("drop_scale", C.c_float),
-        ("block_n", C.c_int32), ("k_splits", C.c_int32),
+        ("block_n", C.c_int32), ("k_splits", C.c_int32), ("cta_pair", C.c_int32),
     ]
 
 

@@ -51,11 +51,14 @@ struct GemmEpilogue {
   float drop_scale;
 };
 
-template <int BLOCK_N>
+// CTA2 = 1: the CTA is half of a pair (cluster of 2) running cta_group::2 MMAs on a 256 x BLOCK_N
+// tile; it stages its own 128 rows of A and BLOCK_N / 2 columns of B per pipeline stage.
+template <int BLOCK_N, int CTA2 = 0>
 struct GemmCfg {
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int STAGES = (BLOCK_N == 256 && !CTA2) ? 4 : 6;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;   // B columns staged by this CTA
+  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers
   // epilogue staging: one slab of 32 rows x 64 bf16 (128 B rows, swizzled) per epilogue warp
@@ -114,15 +117,18 @@ __device__ __forceinline__ void epilogue_math8(float (&v)[8], uint4* pre, const 
   }
 }
 
-template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT_F32>
+template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT_F32, int CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out,
                     const __grid_constant__ CUtensorMap tmap_aux, const GemmShape s,
                     const GemmEpilogue e) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, CTA2>;
   constexpr int STAGES = Cfg::STAGES;
+  // pair rank (0 = leader: issues the MMAs and owns the pipeline "full" / TMEM "empty" barriers)
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = (rank == 0u);
 
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();  // swizzle-128B atoms need a 1024 B aligned base
@@ -146,16 +152,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS);  // one arrive per epilogue warp
+      // one arrive per epilogue warp (of both CTAs on the leader's barrier in pair mode)
+      mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS * (CTA2 ? 2 : 1));
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (CTA2) {
+      tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if (CTA2) cluster_sync(); else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   // everything above overlapped the tail of the previous kernel (PDL); from here on we touch its
@@ -163,13 +175,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   pdl_wait();
   pdl_launch_dependents();
 
+  // persistent schedule over tiles; in pair mode both CTAs of a cluster walk the same tile list
+  // (num_m_blocks then counts 256-row blocks) and the CTA's rank selects its 128-row half
   const int total_tiles = s.num_m_blocks * s.num_n_blocks * s.k_splits;
+  const int first_tile = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
     // ------------------------------------------------------------- TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int ks = tile % s.k_splits;
         const int t2 = tile / s.k_splits;
         const int n_blk = t2 % s.num_n_blocks;
@@ -180,24 +196,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const uint32_t stage = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(&empty_bar[stage], ph ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          if (A_MN)
-            tma_load_3d(sa, &tmap_a, &full_bar[stage], 0, kb * BLOCK_K, m_blk * (BLOCK_M / 64));
-          else
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-          if (B_MN)
-            tma_load_3d(sb, &tmap_b, &full_bar[stage], 0, kb * BLOCK_K, n_blk * (BLOCK_N / 64));
-          else
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          if (CTA2) {
+            // both CTAs' loads complete on the LEADER's barrier, which expects the pair's bytes
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            const int m128 = m_blk * 2 + (int)rank;                       // this CTA's A rows
+            const int n0 = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);   // this CTA's B columns
+            if (A_MN)
+              tma_load_3d_2sm(sa, &tmap_a, &full_bar[stage], 0, kb * BLOCK_K, m128 * (BLOCK_M / 64));
+            else
+              tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m128 * BLOCK_M);
+            if (B_MN)
+              tma_load_3d_2sm(sb, &tmap_b, &full_bar[stage], 0, kb * BLOCK_K, n0 / 64);
+            else
+              tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            if (A_MN)
+              tma_load_3d(sa, &tmap_a, &full_bar[stage], 0, kb * BLOCK_K, m_blk * (BLOCK_M / 64));
+            else
+              tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            if (B_MN)
+              tma_load_3d(sb, &tmap_b, &full_bar[stage], 0, kb * BLOCK_K, n_blk * (BLOCK_N / 64));
+            else
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    // ------------------------------------------------------------- MMA issuer (pair: leader only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N, A_MN, B_MN);
       // K-major: 8-row groups 1024 B apart (SBO), LBO unused (encoded 1 like CUTLASS).
       // MN-major: 64-element MN chunks BLOCK_K*128 B apart (LBO), 8-k groups 1024 B apart (SBO).
       constexpr uint32_t A_LBO = A_MN ? BLOCK_K * 128 : 16;
@@ -206,7 +237,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       constexpr uint32_t B_KSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 2;
       uint32_t it = 0;
       uint32_t local_tile = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++local_tile) {
         const int ks = tile % s.k_splits;
         const int kb0 = (int)(((long long)ks * s.k_blocks) / s.k_splits);
         const int kb1 = (int)(((long long)(ks + 1) * s.k_blocks) / s.k_splits);
@@ -226,11 +257,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_sw128_desc(sa + k * A_KSTEP, A_LBO, 1024);
             const uint64_t bdesc = make_sw128_desc(sb + k * B_KSTEP, B_LBO, 1024);
-            umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CTA2)
+              umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else
+              umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if (CTA2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (CTA2) umma_commit_2sm(&tmem_full_bar[acc]); else umma_commit(&tmem_full_bar[acc]);
       }
     }
   } else {
@@ -248,7 +284,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const bool has_resid = (ACT != ACT_GELU_GRAD) && (e.resid != nullptr);
     uint32_t slab_it = 0;
     uint32_t local_tile = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local_tile) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++local_tile) {
       const int t2 = tile / s.k_splits;
       const int n_blk = t2 % s.num_n_blocks;
       const int m_blk = t2 / s.num_n_blocks;
@@ -265,7 +301,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after_sync();
-      const int row0 = m_blk * BLOCK_M + q * 32;
+      const int row0 = (CTA2 ? m_blk * 2 + (int)rank : m_blk) * BLOCK_M + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < s.M;
       const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
@@ -365,16 +401,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]);
+      }
     }
     if (!OUT_F32 && lane == 0) bulk_wait_all();
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if (CTA2) cluster_sync(); else __syncthreads();   // pair: no CTA may exit while its peer can
+                                                     // still signal its barriers / read its smem
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CTA2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -450,11 +489,11 @@ struct GemmMaps {
   CUtensorMap a, b, out, aux;
 };
 
-template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT_F32>
+template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT_F32, int CTA2>
 static int launch(const GemmMaps& tm, const GemmShape& s, const GemmEpilogue& e,
                   cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N>;
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, ACT, OUT_F32>;
+  using Cfg = GemmCfg<BLOCK_N, CTA2>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, ACT, OUT_F32, CTA2>;
   static bool attr_set = false;
   if (!attr_set) {
     HERO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -464,33 +503,51 @@ static int launch(const GemmMaps& tm, const GemmShape& s, const GemmEpilogue& e,
   const int total = s.num_m_blocks * s.num_n_blocks * s.k_splits;
   const int sms = sm_count();
   if (sms <= 0) return set_error(HERO_ERR_NO_DEVICE, "no CUDA device");
-  const int grid = total < sms ? total : sms;
-  HERO_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), Cfg::SMEM_BYTES, stream, tm.a,
-                             tm.b, tm.out, tm.aux, s, e));
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.numAttrs = 1;
+  if (CTA2) {
+    const int clusters = total < sms / 2 ? total : sms / 2;   // one CTA pair per TPC
+    cfg.gridDim = dim3(2 * clusters);
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  } else {
+    cfg.gridDim = dim3(total < sms ? total : sms);
+  }
+  cfg.attrs = attr;
+  HERO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.out, tm.aux, s, e));
   return HERO_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CTA2>
 static int dispatch(const hero_gemm_args* g, const GemmMaps& tm, const GemmShape& s,
                     const GemmEpilogue& e, cudaStream_t st) {
   const int layout = g->a_mn_major * 2 + g->b_mn_major;
   if (g->out_f32_accumulate) {
     HERO_REQUIRE(g->act == ACT_NONE, "fp32-accumulate output supports act=0 only");
-    if (layout == 3) return launch<BLOCK_N, 1, 1, ACT_NONE, 1>(tm, s, e, st);
-    if (layout == 0) return launch<BLOCK_N, 0, 0, ACT_NONE, 1>(tm, s, e, st);
+    if (layout == 3) return launch<BLOCK_N, 1, 1, ACT_NONE, 1, CTA2>(tm, s, e, st);
+    if (layout == 0) return launch<BLOCK_N, 0, 0, ACT_NONE, 1, CTA2>(tm, s, e, st);
     return set_error(HERO_ERR_INVALID, "fp32-accumulate supports layouts (0,0) and (1,1)");
   }
   if (layout == 0) {
     switch (g->act) {
-      case ACT_NONE: return launch<BLOCK_N, 0, 0, ACT_NONE, 0>(tm, s, e, st);
-      case ACT_GELU: return launch<BLOCK_N, 0, 0, ACT_GELU, 0>(tm, s, e, st);
-      case ACT_RELU: return launch<BLOCK_N, 0, 0, ACT_RELU, 0>(tm, s, e, st);
+      case ACT_NONE: return launch<BLOCK_N, 0, 0, ACT_NONE, 0, CTA2>(tm, s, e, st);
+      case ACT_GELU: return launch<BLOCK_N, 0, 0, ACT_GELU, 0, CTA2>(tm, s, e, st);
+      case ACT_RELU: return launch<BLOCK_N, 0, 0, ACT_RELU, 0, CTA2>(tm, s, e, st);
       default: break;
     }
   } else if (layout == 1) {
     switch (g->act) {
-      case ACT_NONE: return launch<BLOCK_N, 0, 1, ACT_NONE, 0>(tm, s, e, st);
-      case ACT_GELU_GRAD: return launch<BLOCK_N, 0, 1, ACT_GELU_GRAD, 0>(tm, s, e, st);
+      case ACT_NONE: return launch<BLOCK_N, 0, 1, ACT_NONE, 0, CTA2>(tm, s, e, st);
+      case ACT_GELU_GRAD: return launch<BLOCK_N, 0, 1, ACT_GELU_GRAD, 0, CTA2>(tm, s, e, st);
       default: break;
     }
   }
@@ -600,10 +657,13 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
     }
   }
   HERO_REQUIRE(block_n == 128 || block_n == 256, "block_n must be 128 or 256");
+  // CTA pairs (cta_group::2, 256-row tiles) whenever the tile is 256 wide and there is more than
+  // one 128-row block; cta_pair: 0 auto, 1 never, 2 force.
+  const bool pair = (block_n == 256) && (g->cta_pair == 2 || (g->cta_pair == 0 && g->m > 128));
 
   GemmShape s;
   s.M = g->m; s.N = g->n; s.K = g->k;
-  s.num_m_blocks = m_blocks;
+  s.num_m_blocks = pair ? ceil_div(g->m, 2 * BLOCK_M) : m_blocks;
   s.num_n_blocks = ceil_div(g->n, block_n);
   s.k_blocks = ceil_div(g->k, BLOCK_K);
   int k_splits = g->k_splits;
@@ -612,7 +672,8 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   } else if (k_splits <= 0) {
     const int tiles = s.num_m_blocks * s.num_n_blocks;
     k_splits = 1;
-    if (tiles < sms) k_splits = ceil_div(sms, tiles);
+    const int slots = pair ? sms / 2 : sms;   // concurrently resident tiles
+    if (tiles < slots) k_splits = ceil_div(slots, tiles);
     // keep at least 4 k-blocks per split so the pipeline has something to overlap
     if (k_splits > s.k_blocks / 4) k_splits = s.k_blocks / 4;
     if (k_splits < 1) k_splits = 1;
@@ -641,10 +702,11 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   else
     rc = encode_kmajor(&tm.a, g->a, g->m, g->k, g->lda, BLOCK_M);
   if (rc) return rc;
+  const int b_box = pair ? block_n / 2 : block_n;   // a CTA of a pair stages half of the B tile
   if (g->b_mn_major)
-    rc = encode_mnmajor(&tm.b, g->b, g->k, g->n, g->ldb, block_n);
+    rc = encode_mnmajor(&tm.b, g->b, g->k, g->n, g->ldb, b_box);
   else
-    rc = encode_kmajor(&tm.b, g->b, g->n, g->k, g->ldb, block_n);
+    rc = encode_kmajor(&tm.b, g->b, g->n, g->k, g->ldb, b_box);
   if (rc) return rc;
   if (!g->out_f32_accumulate) {
     HERO_REQUIRE(g->ld_out % 8 == 0, "bf16 output needs ld_out %% 8 == 0");
@@ -661,6 +723,7 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   }
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (block_n == 256) return dispatch<256>(g, tm, s, e, st);
-  return dispatch<128>(g, tm, s, e, st);
+  if (pair) return dispatch<256, 1>(g, tm, s, e, st);
+  if (block_n == 256) return dispatch<256, 0>(g, tm, s, e, st);
+  return dispatch<128, 0>(g, tm, s, e, st);
 }

@@ -69,7 +69,7 @@ def drop_params(p, key):
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None, resid=None,
          aux_in=None, aux_out=None, act=ACT_NONE, accumulate_f32=False, drop=(0, 0, 1.0),
-         block_n=0, k_splits=0):
+         block_n=0, k_splits=0, cta_pair=0):
     """out = epilogue(A·B) with the operand conventions of `hero_gemm_args`.
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True) bf16; b: [N,K] (b_mn=False) or [K,N] (b_mn=True).
@@ -102,7 +102,7 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None
     g.out_f32_accumulate = int(accumulate_f32)
     assert out.dtype == (torch.float32 if accumulate_f32 else BF16)
     g.drop_threshold, g.drop_key, g.drop_scale = drop
-    g.block_n, g.k_splits = block_n, k_splits
+    g.block_n, g.k_splits, g.cta_pair = block_n, k_splits, cta_pair
     _count()
     _lib.check(_lib.lib().hero_gemm_bf16(C.byref(g), _stream()))
     return out

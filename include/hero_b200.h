@@ -86,6 +86,8 @@ typedef struct hero_gemm_args {
   float drop_scale;        /* 1 / (1 - p) */
   int32_t block_n;         /* 0 = auto, else 128 or 256 */
   int32_t k_splits;        /* 0 = auto (only > 1 when out_f32_accumulate) */
+  int32_t cta_pair;        /* 0 = auto, 1 = single-CTA tiles, 2 = force CTA pairs (cta_group::2,
+                              256 x 256 tiles; needs block_n 256) */
 } hero_gemm_args;
 
 int hero_gemm_bf16(const hero_gemm_args* args, void* stream);

@@ -16,7 +16,7 @@ def _ck_drop(drop):
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None, resid=None,
          aux_in=None, aux_out=None, act=0, accumulate_f32=False, drop=(0, 0, 1.0), block_n=0,
-         k_splits=0):
+         k_splits=0, cta_pair=0):
     _ck_drop(drop)
     A = a.float().t() if a_mn else a.float()
     B = b.float() if b_mn else b.float().t()

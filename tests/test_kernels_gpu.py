@@ -32,15 +32,15 @@ def _close(got, ref, atol, rtol, what=""):
 @pytest.mark.parametrize("m,n,k", [(128, 256, 64), (300, 768, 768), (16000, 768, 768),
                                    (1000, 2304, 768), (515, 3072, 768), (640, 768, 3072),
                                    (777, 768, 4352), (8, 128, 64)])
-@pytest.mark.parametrize("block_n", [128, 256])
-def test_gemm_forward_kmajor(m, n, k, block_n):
+@pytest.mark.parametrize("block_n,cta_pair", [(128, 1), (256, 1), (256, 2)])
+def test_gemm_forward_kmajor(m, n, k, block_n, cta_pair):
     from hero_b200 import ops
     a, w = _rand((m, k), seed=1), _rand((n, k), 0.05, seed=2)
     bias = _rand((n,), 0.5, seed=3, dtype=torch.float32)
     out = torch.empty(m, n, dtype=BF16, device=_dev())
-    ops.gemm(a, w, out, bias=bias, block_n=block_n)
+    ops.gemm(a, w, out, bias=bias, block_n=block_n, cta_pair=cta_pair)
     ref = a.float() @ w.float().t() + bias
-    _close(out, ref, 2e-2, 1.6e-2, f"gemm fwd {m}x{n}x{k} bn{block_n}")
+    _close(out, ref, 2e-2, 1.6e-2, f"gemm fwd {m}x{n}x{k} bn{block_n} pair{cta_pair}")
 
 
 @pytest.mark.parametrize("act", ["gelu", "relu", "resid"])
@@ -67,13 +67,13 @@ def test_gemm_epilogues(act):
 
 
 @pytest.mark.parametrize("m,n,k", [(1000, 768, 3072), (16000, 768, 2304), (300, 3072, 768)])
-@pytest.mark.parametrize("block_n", [128, 256])
-def test_gemm_dgrad_b_mnmajor(m, n, k, block_n):
+@pytest.mark.parametrize("block_n,cta_pair", [(128, 1), (256, 1), (256, 2)])
+def test_gemm_dgrad_b_mnmajor(m, n, k, block_n, cta_pair):
     """dX[m, n] = dY[m, k] @ W[k, n]  (W stored [k, n]: the nn.Linear weight [out=k, in=n])."""
     from hero_b200 import ops
     dy, w = _rand((m, k), seed=8), _rand((k, n), 0.05, seed=9)
     out = torch.empty(m, n, dtype=BF16, device=_dev())
-    ops.gemm(dy, w, out, b_mn=True, block_n=block_n)
+    ops.gemm(dy, w, out, b_mn=True, block_n=block_n, cta_pair=cta_pair)
     _close(out, dy.float() @ w.float(), 2e-2, 1.6e-2, "dgrad")
 
 
@@ -91,13 +91,14 @@ def test_gemm_dgrad_gelu_grad():
 
 @pytest.mark.parametrize("tokens,n_out,k_in", [(1000, 768, 768), (16000, 3072, 768),
                                                (3333, 768, 3072), (3200, 768, 4352)])
-@pytest.mark.parametrize("k_splits", [0, 1, 3])
-def test_gemm_wgrad_mnmajor(tokens, n_out, k_in, k_splits):
+@pytest.mark.parametrize("k_splits,cta_pair", [(0, 0), (1, 1), (3, 1), (1, 2), (3, 2)])
+def test_gemm_wgrad_mnmajor(tokens, n_out, k_in, k_splits, cta_pair):
     """dW[n_out, k_in] += dY[tokens, n_out]^T @ X[tokens, k_in], fp32 accumulate."""
     from hero_b200 import ops
     dy, x = _rand((tokens, n_out), 0.1, seed=13), _rand((tokens, k_in), seed=14)
     out = torch.full((n_out, k_in), 0.5, dtype=torch.float32, device=_dev())
-    ops.gemm(dy, x, out, a_mn=True, b_mn=True, accumulate_f32=True, k_splits=k_splits)
+    ops.gemm(dy, x, out, a_mn=True, b_mn=True, accumulate_f32=True, k_splits=k_splits,
+             cta_pair=cta_pair)
     ref = 0.5 + dy.float().t() @ x.float()
     _close(out, ref, 5e-2, 5e-3, "wgrad")
 

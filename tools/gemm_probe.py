@@ -32,11 +32,12 @@ def main():
         w = (torch.randn(n, k, device=dev) * 0.05).bfloat16()
         bias = torch.randn(n, device=dev)
         out = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
-        for bn in (128, 256):
+        for bn, pair in ((128, 1), (256, 1), (256, 2)):
             for act in (ops.ACT_NONE, ops.ACT_GELU):
-                med, best = timeit(lambda: ops.gemm(a, w, out, bias=bias, act=act, block_n=bn))
+                med, best = timeit(lambda: ops.gemm(a, w, out, bias=bias, act=act, block_n=bn,
+                                                    cta_pair=pair))
                 tf = 2.0 * m * n * k / (med * 1e-3) / 1e12
-                res.append(dict(kind="fwd", name=name, m=m, n=n, k=k, block_n=bn, act=act,
+                res.append(dict(kind="fwd", name=name, m=m, n=n, k=k, block_n=bn * (pair == 2 and 10 or 1), act=act,
                                 ms=med, best_ms=best, tflops=tf))
                 print(res[-1], flush=True)
         med, best = timeit(lambda: torch.matmul(a, w.t()))
@@ -45,15 +46,17 @@ def main():
         dy = torch.randn(m, n, device=dev).bfloat16()
         dx = torch.empty(m, k, dtype=torch.bfloat16, device=dev)
         if k % 64 == 0:
-            med, best = timeit(lambda: ops.gemm(dy, w, dx, b_mn=True))
-            print(dict(kind="dgrad", name=name, ms=med, tflops=2.0 * m * n * k / (med * 1e-3) / 1e12), flush=True)
+            for pair in (1, 2):
+                med, best = timeit(lambda: ops.gemm(dy, w, dx, b_mn=True, cta_pair=pair))
+                print(dict(kind="dgrad pair%d" % pair, name=name, ms=med, tflops=2.0 * m * n * k / (med * 1e-3) / 1e12), flush=True)
         # wgrad: dW[n,k] += dY^T X
         if m % 64 == 0 or True:
             dw = torch.zeros(n, k, device=dev)
             mm = (m // 64) * 64
             try:
-                med, best = timeit(lambda: ops.gemm(dy[:mm], a[:mm], dw, a_mn=True, b_mn=True, accumulate_f32=True))
-                print(dict(kind="wgrad", name=name, ms=med, tflops=2.0 * mm * n * k / (med * 1e-3) / 1e12), flush=True)
+                for pair in (1, 2):
+                    med, best = timeit(lambda: ops.gemm(dy[:mm], a[:mm], dw, a_mn=True, b_mn=True, accumulate_f32=True, cta_pair=pair))
+                    print(dict(kind="wgrad pair%d" % pair, name=name, ms=med, tflops=2.0 * mm * n * k / (med * 1e-3) / 1e12), flush=True)
             except Exception as ex:
                 print("wgrad failed", name, ex)
     os.makedirs("gpurun_out", exist_ok=True)
