@@ -60,8 +60,8 @@ class LayerWeights(C.Structure):
 
 class LayerActs(C.Structure):
     """Mirror of `hero_layer_acts`."""
-    _fields_ = [(n, C.c_void_p) for n in ("qkv", "cx", "s1", "mean1", "rstd1", "a", "pre", "f",
-                                            "s2", "mean2", "rstd2", "out")]
+    _fields_ = [(n, C.c_void_p) for n in ("qkv", "cx", "lse", "s1", "mean1", "rstd1", "a", "pre",
+                                            "f", "s2", "mean2", "rstd2", "out")]
 
 
 class LayerGrads(C.Structure):
@@ -104,9 +104,9 @@ def _declare(lib):
 
     sig("hero_ln_fwd", C.POINTER(LnArgs), vp)
     sig("hero_ln_bwd", C.POINTER(LnArgs), vp)
-    sig("hero_attn_fwd", vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u32, u32, f32, vp)
-    sig("hero_attn_bwd", vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u32, u32, f32,
-        vp)
+    sig("hero_attn_fwd", vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u32, u32, f32, vp)
+    sig("hero_attn_bwd", vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u32, u32,
+        f32, vp)
     sig("hero_gemm_profile_begin")
     sig("hero_gemm_profile_end", C.POINTER(C.c_double), C.POINTER(C.c_double),
         C.POINTER(C.c_int64))

@@ -60,20 +60,23 @@ __device__ __forceinline__ uint32_t attn_drop_index(int tok, int heads, int head
 // ------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(128)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArgs a,
-                   __nv_bfloat16* __restrict__ ctx) {
+                   __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
+  // 48 KB of operand tiles; P (32 KB) is written over Q|K once S = QK^T has retired, and O reuses
+  // S's TMEM columns, so 4 CTAs fit per SM (smem 49 KB, 128 TMEM columns each) and their TMA /
+  // MMA / softmax phases overlap.
   uint8_t* sQ = smem;
   uint8_t* sK = smem + AT_TILE_BYTES;
   uint8_t* sV = smem + 2 * AT_TILE_BYTES;
-  uint8_t* sP = smem + 3 * AT_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * AT_TILE_BYTES + AT_P_BYTES);
+  uint8_t* sP = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * AT_TILE_BYTES);
   uint64_t* tma_bar = bars;
   uint64_t* mma_bar = bars + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tile = blockIdx.x, head = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const int tok0 = a.tile_tok0[tile];
   const int ntok = a.tile_ntok[tile];
 
@@ -84,7 +87,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, 128);
     tmem_relinquish();
   }
   tc_fence_before_sync();
@@ -196,7 +199,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
       const uint64_t ad =
           make_sw128_desc(smem_u32(sP) + (k >> 2) * (AT_ROWS * 128) + (k & 3) * 32, 16, 1024);
       const uint64_t bd = make_sw128_desc(smem_u32(sV) + k * 2048, AT_TILE_BYTES, 1024);
-      umma_f16(tmem + 128, ad, bd, idesc, k > 0 ? 1u : 0u);
+      umma_f16(tmem, ad, bd, idesc, k > 0 ? 1u : 0u);   // O overwrites S's columns [0, 64)
     }
     umma_commit(mma_bar);
   }
@@ -206,9 +209,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
   {
     const float inv = sum > 0.f ? 1.0f / sum : 0.f;
     uint32_t r0[32], r1[32];
-    tmem_ld_32x32(t_row + 128, r0);
-    tmem_ld_32x32(t_row + 160, r1);
+    tmem_ld_32x32(t_row, r0);
+    tmem_ld_32x32(t_row + 32, r1);
     tmem_ld_wait();
+    if (valid && lse != nullptr)   // log2-domain log-sum-exp of the scaled scores, for the backward
+      lse[(long long)(tok0 + i) * a.heads + head] = mx * a.scale_log2 + log2f(sum);
     if (valid) {
       __nv_bfloat16* o = ctx + (long long)(tok0 + i) * a.H + head * AT_D;
 #pragma unroll
@@ -235,25 +240,31 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
   __syncthreads();
   if (warp == 0) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, 128);
   }
 }
 
 // ------------------------------------------------------------------------------------ backward
-// TMEM columns: S [0,128)  dP [128,256)  dQ [256,320)  dK [320,384)  dV [384,448)
+// TMEM (256 columns): S [0,128) and dP [128,256); once every thread has turned them into P / dS,
+// dQ [0,64), dK [64,128), dV [128,192) reuse the same columns. smem (112 KB): Q, K, V, dO tiles;
+// P's first 64-column chunk is written over V (dead after dP = dO V^T), so two CTAs fit per SM and
+// overlap each other's TMA / MMA / softmax phases. Probabilities are rebuilt from the forward's
+// log-sum-exp in ONE pass over S.
 __global__ void __launch_bounds__(128)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                    const __grid_constant__ CUtensorMap tmap_do, const AttnTcArgs a,
                    const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
-                   __nv_bfloat16* __restrict__ dqkv) {
+                   const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* sQ = smem;
   uint8_t* sK = smem + AT_TILE_BYTES;
   uint8_t* sV = smem + 2 * AT_TILE_BYTES;
   uint8_t* sdO = smem + 3 * AT_TILE_BYTES;
-  uint8_t* sP = smem + 4 * AT_TILE_BYTES;
-  uint8_t* sdS = sP + AT_P_BYTES;
+  // P chunk 0 over V, chunk 1 after dO: chunk stride = 2 tiles
+  uint8_t* sP = sV;
+  constexpr uint32_t P_CHUNK = 2 * AT_TILE_BYTES;
+  uint8_t* sdS = smem + 5 * AT_TILE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + AT_P_BYTES);
   uint64_t* tma_bar = bars;
   uint64_t* mma_bar = bars + 1;
@@ -272,7 +283,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
   tc_fence_before_sync();
@@ -341,31 +352,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, o));
   }
   const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  float mx = -INFINITY;
-  for (int c = 0; c < 4; ++c) {
-    if (c * 32 >= whi || c * 32 + 32 <= wlo) continue;
-    uint32_t r[32];
-    tmem_ld_32x32(t_row + c * 32, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = c * 32 + j;
-      if (col >= lo && col < hi) mx = fmaxf(mx, __uint_as_float(r[j]));
-    }
-  }
-  float sum = 0.f;
-  for (int c = 0; c < 4; ++c) {
-    if (c * 32 >= whi || c * 32 + 32 <= wlo) continue;
-    uint32_t r[32];
-    tmem_ld_32x32(t_row + c * 32, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = c * 32 + j;
-      if (col >= lo && col < hi) sum += ex2((__uint_as_float(r[j]) - mx) * a.scale_log2);
-    }
-  }
-  const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+  const float row_lse = valid ? lse[(long long)(tok0 + i) * a.heads + head] : 0.f;
   for (int c = 0; c < 4; ++c) {
     uint32_t pk[16], dk[16];
     const bool touch = !(c * 32 >= whi || c * 32 + 32 <= wlo);
@@ -382,7 +369,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
           const int col = c * 32 + j + t;
           float p = 0.f, dp = 0.f, keep = 1.0f;
           if (col >= lo && col < hi) {
-            p = ex2((__uint_as_float(r[j + t]) - mx) * a.scale_log2) * inv;
+            p = ex2(__uint_as_float(r[j + t]) * a.scale_log2 - row_lse);
             dp = __uint_as_float(d[j + t]);
             if (a.drop_thr != 0u)
               keep = dropout_keep(a.drop_key, attn_drop_index(tok0 + i, a.heads, head, col - lo),
@@ -402,9 +389,12 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const uint32_t off = p_unit_offset(i, c >> 1, (c & 1) * 4 + g);
-      *reinterpret_cast<uint4*>(sP + off) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-      *reinterpret_cast<uint4*>(sdS + off) = make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
+      const int u = (c & 1) * 4 + g;
+      const uint32_t in_chunk = i * 128 + ((u ^ (i & 7)) << 4);
+      *reinterpret_cast<uint4*>(sP + (c >> 1) * P_CHUNK + in_chunk) =
+          make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      *reinterpret_cast<uint4*>(sdS + (c >> 1) * (AT_ROWS * 128) + in_chunk) =
+          make_uint4(dk[4 * g], dk[4 * g + 1], dk[4 * g + 2], dk[4 * g + 3]);
     }
   }
   fence_proxy_async();
@@ -423,19 +413,19 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       const uint64_t ad =
           make_sw128_desc(smem_u32(sdS) + (k >> 2) * (AT_ROWS * 128) + (k & 3) * 32, 16, 1024);
       const uint64_t bd = make_sw128_desc(smem_u32(sK) + k * 2048, AT_TILE_BYTES, 1024);
-      umma_f16(tmem + 256, ad, bd, id_q, k > 0 ? 1u : 0u);
+      umma_f16(tmem, ad, bd, id_q, k > 0 ? 1u : 0u);
     }
 #pragma unroll
     for (int k = 0; k < AT_ROWS / 16; ++k) {
       const uint64_t ad = make_sw128_desc(smem_u32(sdS) + k * 2048, AT_ROWS * 128, 1024);
       const uint64_t bd = make_sw128_desc(smem_u32(sQ) + k * 2048, AT_TILE_BYTES, 1024);
-      umma_f16(tmem + 320, ad, bd, id_t, k > 0 ? 1u : 0u);
+      umma_f16(tmem + 64, ad, bd, id_t, k > 0 ? 1u : 0u);
     }
 #pragma unroll
     for (int k = 0; k < AT_ROWS / 16; ++k) {
-      const uint64_t ad = make_sw128_desc(smem_u32(sP) + k * 2048, AT_ROWS * 128, 1024);
+      const uint64_t ad = make_sw128_desc(smem_u32(sP) + k * 2048, P_CHUNK, 1024);
       const uint64_t bd = make_sw128_desc(smem_u32(sdO) + k * 2048, AT_TILE_BYTES, 1024);
-      umma_f16(tmem + 384, ad, bd, id_t, k > 0 ? 1u : 0u);
+      umma_f16(tmem + 128, ad, bd, id_t, k > 0 ? 1u : 0u);
     }
     umma_commit(mma_bar);
   }
@@ -446,8 +436,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
 #pragma unroll 1
   for (int part = 0; part < 3; ++part) {
     uint32_t r0[32], r1[32];
-    tmem_ld_32x32(t_row + 256 + part * 64, r0);
-    tmem_ld_32x32(t_row + 256 + part * 64 + 32, r1);
+    tmem_ld_32x32(t_row + part * 64, r0);
+    tmem_ld_32x32(t_row + part * 64 + 32, r1);
     tmem_ld_wait();
     if (valid) {
       __nv_bfloat16* o = dqkv + (long long)(tok0 + i) * (3 * a.H) + part * a.H + head * AT_D;
@@ -475,7 +465,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   __syncthreads();
   if (warp == 0) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, 256);
   }
 }
 
@@ -504,7 +494,7 @@ static int fill_args(AttnTcArgs* a, const int32_t* tile_tok0, const int32_t* til
 using namespace hero;
 
 extern "C" int hero_attn_fwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
-                                const int32_t* seq_lo, const int32_t* seq_hi, void* ctx,
+                                const int32_t* seq_lo, const int32_t* seq_hi, void* ctx, float* lse,
                                 int32_t n_tok, int32_t n_tiles, int32_t heads, int32_t head_dim,
                                 float scale, uint32_t drop_threshold, uint32_t drop_key,
                                 float drop_scale, void* stream) {
@@ -516,7 +506,7 @@ extern "C" int hero_attn_fwd(const void* qkv, const int32_t* tile_tok0, const in
     return rc;
   CUtensorMap tm;
   if (int rc = encode_tmap_2d_bf16(&tm, qkv, 3LL * a.H, n_tok, 3LL * a.H, AT_D, AT_ROWS)) return rc;
-  const int smem = 3 * AT_TILE_BYTES + AT_P_BYTES + 64;
+  const int smem = 3 * AT_TILE_BYTES + 64;
   static bool configured = false;
   if (!configured) {
     HERO_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_fwd_kernel,
@@ -526,17 +516,18 @@ extern "C" int hero_attn_fwd(const void* qkv, const int32_t* tile_tok0, const in
   dim3 grid(n_tiles, heads);
   HERO_CUDA_CHECK(launch_pdl(attn_tc_fwd_kernel, grid, dim3(128), smem,
                              reinterpret_cast<cudaStream_t>(stream), tm, a,
-                             reinterpret_cast<__nv_bfloat16*>(ctx)));
+                             reinterpret_cast<__nv_bfloat16*>(ctx), lse));
   return HERO_OK;
 }
 
 extern "C" int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
                                 const int32_t* seq_lo, const int32_t* seq_hi, const void* ctx,
-                                const void* dctx, void* dqkv, int32_t n_tok, int32_t n_tiles,
+                                const void* dctx, const float* lse, void* dqkv, int32_t n_tok,
+                                int32_t n_tiles,
                                 int32_t heads, int32_t head_dim, float scale,
                                 uint32_t drop_threshold, uint32_t drop_key, float drop_scale,
                                 void* stream) {
-  HERO_REQUIRE(qkv && ctx && dctx && dqkv, "attn_bwd: null pointer");
+  HERO_REQUIRE(qkv && ctx && dctx && dqkv && lse, "attn_bwd: null pointer");
   if (n_tiles <= 0 || n_tok <= 0) return HERO_OK;
   AttnTcArgs a;
   if (int rc = fill_args(&a, tile_tok0, tile_ntok, seq_lo, seq_hi, heads, head_dim, scale,
@@ -545,7 +536,7 @@ extern "C" int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const in
   CUtensorMap tq, td;
   if (int rc = encode_tmap_2d_bf16(&tq, qkv, 3LL * a.H, n_tok, 3LL * a.H, AT_D, AT_ROWS)) return rc;
   if (int rc = encode_tmap_2d_bf16(&td, dctx, a.H, n_tok, a.H, AT_D, AT_ROWS)) return rc;
-  const int smem = 4 * AT_TILE_BYTES + 2 * AT_P_BYTES + 64;
+  const int smem = 5 * AT_TILE_BYTES + AT_P_BYTES + 64;
   static bool configured = false;
   if (!configured) {
     HERO_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_bwd_kernel,
@@ -556,7 +547,7 @@ extern "C" int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const in
   HERO_CUDA_CHECK(launch_pdl(attn_tc_bwd_kernel, grid, dim3(128), smem,
                              reinterpret_cast<cudaStream_t>(stream), tq, td, a,
                              reinterpret_cast<const __nv_bfloat16*>(ctx),
-                             reinterpret_cast<const __nv_bfloat16*>(dctx),
+                             reinterpret_cast<const __nv_bfloat16*>(dctx), lse,
                              reinterpret_cast<__nv_bfloat16*>(dqkv)));
   return HERO_OK;
 }

@@ -659,7 +659,12 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   HERO_REQUIRE(block_n == 128 || block_n == 256, "block_n must be 128 or 256");
   // CTA pairs (cta_group::2, 256-row tiles) whenever the tile is 256 wide and there is more than
   // one 128-row block; cta_pair: 0 auto, 1 never, 2 force.
-  const bool pair = (block_n == 256) && (g->cta_pair == 2 || (g->cta_pair == 0 && g->m > 128));
+  // Measured on B200 (tools/gemm_probe.py): pairs gain 7-15 % when the main loop dominates (long
+  // K: dgrad / FFN-down / every wgrad) and lose ~10 % on short-K tiles with heavy epilogues (the
+  // two CTAs' epilogues are lock-stepped), so auto mode keys on K.
+  const bool pair_auto = g->k >= 1536 && g->m > 128 &&
+                         (g->out_f32_accumulate || m_blocks * ceil_div(g->n, 256) >= sms);
+  const bool pair = (block_n == 256) && (g->cta_pair == 2 || (g->cta_pair == 0 && pair_auto));
 
   GemmShape s;
   s.M = g->m; s.N = g->n; s.K = g->k;

@@ -84,7 +84,7 @@ extern "C" int hero_bert_stack_fwd(const hero_stack_args* s, void* stream) {
     const hero_layer_weights& W = s->weights[l];
     const hero_layer_acts& A = s->acts[l];
     HERO_TRY(Gemm(h, H, 0, W.wqkv, H, 0, M, 3 * H, H, A.qkv, 3 * H).bias(W.bqkv).run(stream));
-    HERO_TRY(hero_attn_fwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, M,
+    HERO_TRY(hero_attn_fwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, A.lse, M,
                            s->n_tiles, s->heads, 64, scale, s->attn_drop_threshold,
                            site_key(s->drop_key, l, 0), s->attn_drop_scale, stream));
     HERO_TRY(Gemm(A.cx, H, 0, W.wo, H, 0, M, H, H, A.s1, H)
@@ -183,8 +183,8 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
     HERO_TRY(Gemm(g1, H, 1, A.cx, H, 1, H, H, M, G.dwo, H).f32_accumulate().run(stream));
     HERO_TRY(Gemm(g1, H, 0, W.wo, H, 1, M, H, H, dcx, H).run(stream));
     // attention core
-    HERO_TRY(hero_attn_bwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, dcx, dqkv,
-                           M, s->n_tiles, s->heads, 64, scale, s->attn_drop_threshold,
+    HERO_TRY(hero_attn_bwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, dcx, A.lse,
+                           dqkv, M, s->n_tiles, s->heads, 64, scale, s->attn_drop_threshold,
                            site_key(s->drop_key, l, 0), s->attn_drop_scale, stream));
     // QKV projection
     HERO_TRY(hero_colsum_bf16(dqkv, 3 * H, M, 3 * H, G.dbqkv, stream));

@@ -162,7 +162,7 @@ def ln_bwd(dy, x, gamma, mean, rstd, *, n_rows, x_rows=None, add_tab=None, add_i
     _lib.check(_lib.lib().hero_ln_bwd(C.byref(a), _stream()))
 
 
-def attn_fwd(qkv, att, ctx, *, heads, head_dim=64, drop=(0, 0, 1.0)):
+def attn_fwd(qkv, att, ctx, *, heads, head_dim=64, drop=(0, 0, 1.0), lse=None):
     """ctx = softmax(QK^T / sqrt(d)) V per (sequence, head) on packed tokens; `att` is the device
     attention plan of `SeqPlan.attn` (tiles of <= 128 tokens + per-token sequence ranges)."""
     _require_cuda(qkv, ctx)
@@ -170,25 +170,27 @@ def attn_fwd(qkv, att, ctx, *, heads, head_dim=64, drop=(0, 0, 1.0)):
     _count()
     _lib.check(_lib.lib().hero_attn_fwd(
         _ptr(qkv), _ptr(att["tile_tok0"]), _ptr(att["tile_ntok"]), _ptr(att["seq_lo"]),
-        _ptr(att["seq_hi"]), _ptr(ctx), att["n_tok"], att["n_tiles"], heads, head_dim,
+        _ptr(att["seq_hi"]), _ptr(ctx), _ptr(lse), att["n_tok"], att["n_tiles"], heads, head_dim,
         1.0 / (head_dim ** 0.5), drop[0], drop[1], drop[2], _stream()))
     return ctx
 
 
-def attn_bwd(qkv, att, ctx, dctx, dqkv, *, heads, head_dim=64, drop=(0, 0, 1.0)):
+def attn_bwd(qkv, att, ctx, dctx, lse, dqkv, *, heads, head_dim=64, drop=(0, 0, 1.0)):
     _require_cuda(qkv, ctx, dctx, dqkv)
     assert dctx.is_contiguous() and dqkv.is_contiguous() and ctx.is_contiguous()
     _count()
     _lib.check(_lib.lib().hero_attn_bwd(
         _ptr(qkv), _ptr(att["tile_tok0"]), _ptr(att["tile_ntok"]), _ptr(att["seq_lo"]),
-        _ptr(att["seq_hi"]), _ptr(ctx), _ptr(dctx), _ptr(dqkv), att["n_tok"], att["n_tiles"],
+        _ptr(att["seq_hi"]), _ptr(ctx), _ptr(dctx), _ptr(lse), _ptr(dqkv), att["n_tok"],
+        att["n_tiles"],
         heads, head_dim, 1.0 / (head_dim ** 0.5), drop[0], drop[1], drop[2], _stream()))
     return dqkv
 
 
 # kernels launched per layer by the native runtime (for bench.py's gpu_launches)
 _STACK_FWD_LAUNCHES, _STACK_BWD_LAUNCHES = 7, 15   # bwd: 8 GEMM, 2x2 LN, attn, 2 colsum
-_ACT_FIELDS = ("qkv", "cx", "s1", "mean1", "rstd1", "a", "pre", "f", "s2", "mean2", "rstd2", "out")
+_ACT_FIELDS = ("qkv", "cx", "lse", "s1", "mean1", "rstd1", "a", "pre", "f", "s2", "mean2", "rstd2",
+               "out")
 _GRAD_FIELDS = ("dwqkv", "dbqkv", "dwo", "dbo", "dln1_g", "dln1_b", "dw1", "db1", "dw2", "db2",
                 "dln2_g", "dln2_b")
 
@@ -199,7 +201,8 @@ def _al(n):
 
 def _stack_layout(M, H, inter, save):
     """Byte offsets of one layer's activations inside the workspace slot."""
-    sizes = {"qkv": M * 3 * H * 2, "cx": M * H * 2, "s1": M * H * 2, "mean1": M * 4,
+    sizes = {"qkv": M * 3 * H * 2, "cx": M * H * 2, "lse": M * (H // 64) * 4 if save else 0,
+             "s1": M * H * 2, "mean1": M * 4,
              "rstd1": M * 4, "a": M * H * 2, "pre": M * inter * 2 if save else 0,
              "f": M * inter * 2, "s2": M * H * 2, "mean2": M * 4, "rstd2": M * 4,
              "out": M * H * 2}
@@ -258,7 +261,8 @@ def bert_stack_fwd(x, layers, att, *, heads, eps, drop, save):
     act_ptrs = []
     for i in range(n):
         b = base + (i if save else i % 2) * slot
-        act_ptrs.append([None if (k == "pre" and not save) else b + offs[k] for k in _ACT_FIELDS])
+        act_ptrs.append([None if (k in ("pre", "lse") and not save) else b + offs[k]
+                         for k in _ACT_FIELDS])
     s, keep = _stack_struct(x, layers, att, heads, eps, drop, act_ptrs)
     _count(_STACK_FWD_LAUNCHES * n)
     _lib.check(_lib.lib().hero_bert_stack_fwd(C.byref(s), _stream()))

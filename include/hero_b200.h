@@ -174,6 +174,9 @@ int hero_ln_bwd(const hero_ln_args* args, void* stream);
  * attends to the tokens of its own sequence".
  *   qkv   bf16 [n_tok, 3*heads*64]  (Q | K | V, each head-major inside)
  *   ctx   bf16 [n_tok, heads*64]
+ *   lse   f32  [n_tok, heads]  log2-domain log-sum-exp of the scaled scores of each (token, head)
+ *                              row; written by the forward (may be NULL in inference), read by the
+ *                              backward, which rebuilds the probabilities in one pass
  * Host-built plan (int32, device memory; hero_b200/plan.py SeqPlan):
  *   tile_tok0[n_tiles], tile_ntok[n_tiles]  consecutive sequences grouped into tiles of <= 128
  *                                           tokens; a sequence never straddles two tiles
@@ -185,14 +188,14 @@ int hero_ln_bwd(const hero_ln_args* args, void* stream);
  * Constraints: head_dim == 64, sequences <= 128 tokens.
  * ---------------------------------------------------------------------------------------- */
 int hero_attn_fwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
-                  const int32_t* seq_lo, const int32_t* seq_hi, void* ctx, int32_t n_tok,
-                  int32_t n_tiles, int32_t heads, int32_t head_dim, float scale,
+                  const int32_t* seq_lo, const int32_t* seq_hi, void* ctx, float* lse,
+                  int32_t n_tok, int32_t n_tiles, int32_t heads, int32_t head_dim, float scale,
                   uint32_t drop_threshold, uint32_t drop_key, float drop_scale, void* stream);
 int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
                   const int32_t* seq_lo, const int32_t* seq_hi, const void* ctx, const void* dctx,
-                  void* dqkv, int32_t n_tok, int32_t n_tiles, int32_t heads, int32_t head_dim,
-                  float scale, uint32_t drop_threshold, uint32_t drop_key, float drop_scale,
-                  void* stream);
+                  const float* lse, void* dqkv, int32_t n_tok, int32_t n_tiles, int32_t heads,
+                  int32_t head_dim, float scale, uint32_t drop_threshold, uint32_t drop_key,
+                  float drop_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Native layer runtime: a whole stack of BertLayers (model/layers.py:257-327) forward / backward
@@ -228,6 +231,7 @@ typedef struct hero_layer_weights {
 typedef struct hero_layer_acts { /* bf16 unless noted; [n_tok, ...] */
   void* qkv;    /* [n_tok, 3H] */
   void* cx;     /* attention output [n_tok, H] */
+  float* lse;   /* f32 [n_tok, heads]: attention log-sum-exp (NULL in inference) */
   void* s1;     /* pre-LN sum after attention block */
   float* mean1;
   float* rstd1;

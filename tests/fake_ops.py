@@ -130,7 +130,7 @@ def _check_att(att):
             assert lo[t] == cu[s] and hi[t] == cu[s + 1]
 
 
-def attn_fwd(qkv, att, ctx, *, heads, head_dim=64, drop=(0, 0, 1.0)):
+def attn_fwd(qkv, att, ctx, *, heads, head_dim=64, drop=(0, 0, 1.0), lse=None):
     _ck_drop(drop)
     assert head_dim == 64 and att["max_len"] <= 128
     _check_att(att)
@@ -138,7 +138,7 @@ def attn_fwd(qkv, att, ctx, *, heads, head_dim=64, drop=(0, 0, 1.0)):
     return ctx
 
 
-def attn_bwd(qkv, att, ctx, dctx, dqkv, *, heads, head_dim=64, drop=(0, 0, 1.0)):
+def attn_bwd(qkv, att, ctx, dctx, lse, dqkv, *, heads, head_dim=64, drop=(0, 0, 1.0)):
     _ck_drop(drop)
     with torch.enable_grad():
         q = qkv.float().detach().requires_grad_(True)
@@ -256,7 +256,7 @@ def bert_stack_bwd(x, layers, att, saved, dout, grads, *, heads, eps, drop, need
         dcx = torch.empty(M, H, dtype=BF16)
         gemm(ds1, lw.wo, dcx, b_mn=True)
         dqkv = torch.empty(M, 3 * H, dtype=BF16)
-        attn_bwd(S["qkv"], att, S["cx"], dcx, dqkv, heads=heads)
+        attn_bwd(S["qkv"], att, S["cx"], dcx, None, dqkv, heads=heads)
         colsum(dqkv, G["dbqkv"])
         gemm(dqkv, S["h"], G["dwqkv"], a_mn=True, b_mn=True, accumulate_f32=True)
         dx = torch.empty(M, H, dtype=BF16)

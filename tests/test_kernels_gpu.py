@@ -241,14 +241,15 @@ def test_attention_fwd_bwd(lens):
     sp, att = _att_plan(lens)
     assert all(n <= 128 for n in sp.tile_ntok) and int(sp.tile_ntok.sum()) == ntok
     ctx = torch.empty(ntok, heads * 64, dtype=BF16, device=_dev())
-    ops.attn_fwd(qkv, att, ctx, heads=heads)
+    lse = torch.empty(ntok, heads, device=_dev())
+    ops.attn_fwd(qkv, att, ctx, heads=heads, lse=lse)
     qr = qkv.float().requires_grad_(True)
     ref = _attn_ref(qr, [n for n in lens if n > 0], heads)
     _close(ctx, ref, 2e-2, 1.6e-2, "attention fwd")
     dctx = _rand((ntok, heads * 64), 1.0, seed=51)
     ref.backward(dctx.float())
     dqkv = torch.empty_like(qkv)
-    ops.attn_bwd(qkv, att, ctx, dctx, dqkv, heads=heads)
+    ops.attn_bwd(qkv, att, ctx, dctx, lse, dqkv, heads=heads)
     _close(dqkv, qr.grad, 4e-2, 3e-2, "attention bwd")
 
 
@@ -263,7 +264,8 @@ def test_attention_dropout_consistent_between_fwd_and_bwd():
     drop = ops.drop_params(0.1, 4242)
     c1 = torch.empty(ntok, heads * 64, dtype=BF16, device=_dev())
     c2 = torch.empty_like(c1)
-    ops.attn_fwd(qkv, att, c1, heads=heads, drop=drop)
+    lse = torch.empty(ntok, heads, device=_dev())
+    ops.attn_fwd(qkv, att, c1, heads=heads, drop=drop, lse=lse)
     ops.attn_fwd(qkv, att, c2, heads=heads, drop=drop)
     assert torch.equal(c1, c2)
     c0 = torch.empty_like(c1)
@@ -274,7 +276,7 @@ def test_attention_dropout_consistent_between_fwd_and_bwd():
     # dV from backward must be the adjoint of V -> ctx_drop: <ctx_drop(V), dO> == <V, dV>
     dctx = _rand((ntok, heads * 64), 1.0, seed=54)
     dqkv = torch.empty_like(qkv)
-    ops.attn_bwd(qkv, att, c1, dctx, dqkv, heads=heads, drop=drop)
+    ops.attn_bwd(qkv, att, c1, dctx, lse, dqkv, heads=heads, drop=drop)
     H = heads * 64
     lhs = (c1.float() * dctx.float()).sum().item()
     rhs = (qkv[:, 2 * H:].float() * dqkv[:, 2 * H:].float()).sum().item()
