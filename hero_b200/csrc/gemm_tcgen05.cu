@@ -84,23 +84,31 @@ __device__ __forceinline__ void epilogue_math8(float (&v)[8], uint4* pre, const 
     v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
     v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
   }
-  if (pre != nullptr) {
+  if (pre != nullptr && ACT != ACT_GELU) {   // pre-activation copy (ReLU backward needs its sign)
     pre->x = pack_bf16x2(v[0], v[1]); pre->y = pack_bf16x2(v[2], v[3]);
     pre->z = pack_bf16x2(v[4], v[5]); pre->w = pack_bf16x2(v[6], v[7]);
   }
   if (ACT == ACT_GELU) {
+    if (pre != nullptr) {   // training: also emit gelu'(x) for the backward's ACT_MUL_AUX epilogue
+      float d[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+      for (int j = 0; j < 8; ++j) v[j] = gelu_erf_with_grad(v[j], d[j]);
+      pre->x = pack_bf16x2(d[0], d[1]); pre->y = pack_bf16x2(d[2], d[3]);
+      pre->z = pack_bf16x2(d[4], d[5]); pre->w = pack_bf16x2(d[6], d[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
+    }
   } else if (ACT == ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
-  } else if (ACT == ACT_GELU_GRAD) {
+  } else if (ACT == ACT_GELU_GRAD) {   // multiply by the saved activation derivative
     const uint32_t pw[4] = {aux.x, aux.y, aux.z, aux.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 x = unpack_bf16x2(pw[j]);
-      v[2 * j] *= gelu_erf_grad(x.x);
-      v[2 * j + 1] *= gelu_erf_grad(x.y);
+      v[2 * j] *= x.x;
+      v[2 * j + 1] *= x.y;
     }
   }
   if (e.drop_threshold != 0u)

@@ -339,6 +339,16 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float h = 0.5f * x * erfc_abs_pow2(fabsf(x));  // 0.5 x erfc(|x|/sqrt2)
   return x >= 0.f ? x - h : h;
 }
+// gelu(x) and its derivative together (the forward FFN-up epilogue saves the derivative so the
+// backward epilogue is a plain multiply): shares the erfc evaluation, one extra MUFU for the pdf.
+__device__ __forceinline__ float gelu_erf_with_grad(float x, float& dgelu) {
+  const float e = 0.5f * erfc_abs_pow2(fabsf(x));   // 0.5 erfc(|x|/sqrt2)
+  const float pdf = 0.3989422804014327f * fast_ex2(-0.72134752044448170f * x * x);
+  const float cdf = x >= 0.f ? 1.0f - e : e;
+  dgelu = fmaf(x, pdf, cdf);
+  const float h = x * e;
+  return x >= 0.f ? x - h : h;
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float e = 0.5f * erfc_abs_pow2(fabsf(x));
   const float cdf = x >= 0.f ? 1.0f - e : e;

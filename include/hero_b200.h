@@ -56,8 +56,10 @@ int hero_sm_count(void);
  *   wgrad    dW = dYᵀ·X    : A = dY (1), B = X  (1), out_f32_accumulate = 1
  * Epilogue, applied in this order on v = acc:
  *   v += bias[n]                                  (bias != NULL; fp32)
- *   if aux_out: aux_out[m,n] = bf16(v)            (pre-activation copy for backward)
- *   act: 0 none | 1 gelu_erf(v) | 2 relu(v) | 3 v * gelu_erf'(aux_in[m,n])
+ *   act: 0 none | 1 gelu_erf(v) | 2 relu(v) | 3 v * aux_in[m,n]
+ *   if aux_out (what the backward needs of the activation):
+ *        act 1: aux_out[m,n] = bf16(gelu_erf'(v))   (consumed by act 3 in the dgrad GEMM)
+ *        else : aux_out[m,n] = bf16(v)              (pre-activation; ReLU backward uses its sign)
  *   dropout: v = keep(m*N+n) ? v * drop_scale : 0 (drop_threshold != 0; keep iff hash>=threshold)
  *   v += resid[m,n]                               (resid != NULL; bf16)
  *   out: bf16 store, or fp32 atomic accumulate (out_f32_accumulate; split-K allowed)
@@ -73,7 +75,7 @@ typedef struct hero_gemm_args {
   const float* bias;     /* [n] or NULL */
   const void* resid;     /* bf16 [m, ld_resid] or NULL */
   int64_t ld_resid;
-  const void* aux_in;    /* bf16 [m, ld_aux_in], required for act == 3 */
+  const void* aux_in;    /* bf16 [m, ld_aux_in], required for act == 3 (saved derivative) */
   int64_t ld_aux_in;
   void* aux_out;         /* bf16 [m, ld_aux_out] or NULL */
   int64_t ld_aux_out;

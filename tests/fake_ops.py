@@ -24,15 +24,18 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None
     if bias is not None:
         v = v + bias
     if aux_out is not None:
-        aux_out.copy_(v.to(BF16))
+        if act == 1:   # saved activation derivative gelu'(v)
+            d = 0.5 * (1 + torch.erf(v / math.sqrt(2))) + \
+                v * torch.exp(-0.5 * v * v) / math.sqrt(2 * math.pi)
+            aux_out.copy_(d.to(BF16))
+        else:
+            aux_out.copy_(v.to(BF16))
     if act == 1:
         v = v * 0.5 * (1.0 + torch.erf(v / math.sqrt(2.0)))
     elif act == 2:
         v = torch.relu(v)
     elif act == 3:
-        x = aux_in.float()
-        v = v * (0.5 * (1 + torch.erf(x / math.sqrt(2))) +
-                 x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi))
+        v = v * aux_in.float()
     if resid is not None:
         v = v + resid.float()
     if accumulate_f32:
