@@ -190,3 +190,47 @@ def test_training_mode_dropout_runs_and_is_stochastic(tmp_path):
     assert (a - ev).abs().mean() > 1e-3
     g = model.f_encoder.encoder.layer[0].intermediate.dense.weight.grad
     assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
+
+
+def test_fused_adamw_follows_reference_rule_with_param_groups():
+    """FusedAdamW on the flat buffer == optim/adamw.py:80-104 per parameter, with the no-decay
+    grouping of optim/misc.py:22 (names containing 'bias' / 'LayerNorm.*'), clipping folded in."""
+    from hero_b200.optim import FusedAdamW
+    from hero_b200.params import flat_of
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.dense = torch.nn.Linear(96, 64)
+            self.LayerNorm = torch.nn.LayerNorm(64)
+            self.proj = torch.nn.Linear(64, 40)
+
+    torch.manual_seed(0)
+    m = Tiny().cuda()
+    flat = flat_of(m, torch.device("cuda"))
+    opt = FusedAdamW(flat, lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01)
+    ref_p = {k: p.detach().cpu().clone() for k, p in m.named_parameters()}
+    ref_m = {k: torch.zeros_like(v) for k, v in ref_p.items()}
+    ref_v = {k: torch.zeros_like(v) for k, v in ref_p.items()}
+    g = torch.Generator().manual_seed(1)
+    for step in range(1, 4):
+        opt.zero_grad()
+        grads = {k: torch.randn(v.shape, generator=g) * 0.1 for k, v in ref_p.items()}
+        for k, p in m.named_parameters():
+            p.grad.copy_(grads[k].cuda())
+        total = torch.sqrt(sum((v.double() ** 2).sum() for v in grads.values())).item()
+        norm = opt.clip_grad_norm_(1.0)
+        assert abs(norm - total) < 1e-3 * total
+        scale = min(1.0, 1.0 / (total + 1e-6))
+        opt.step()
+        for k in ref_p:
+            wd = 0.0 if any(nd in k for nd in ("bias", "LayerNorm.bias", "LayerNorm.weight")) \
+                else 0.01
+            ref_p[k], ref_m[k], ref_v[k] = orc.adamw_step(ref_p[k], grads[k] * scale, ref_m[k],
+                                                          ref_v[k], step, 1e-3, 0.9, 0.98, 1e-6, wd)
+        for k, p in m.named_parameters():
+            err = (p.detach().cpu() - ref_p[k]).abs().max().item()
+            assert err < 2e-6, (k, step, err)
+    # the bf16 working copy was refreshed by the optimizer kernel itself
+    for k, p in m.named_parameters():
+        assert torch.equal(flat.bf16(p), p.detach().to(torch.bfloat16)), k
