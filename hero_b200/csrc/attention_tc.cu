@@ -57,6 +57,37 @@ __device__ __forceinline__ uint32_t attn_drop_index(int tok, int heads, int head
   return ((uint32_t)tok * (uint32_t)heads + (uint32_t)head) * 128u + (uint32_t)jrel;
 }
 
+// Each thread parks its 64-feature row (two 32-column TMEM fragments, optionally scaled) in a
+// swizzled [128 x 128 B] smem tile ...
+__device__ __forceinline__ void stage_row(uint8_t* tile, int row, const uint32_t (&r0)[32],
+                                          const uint32_t (&r1)[32], float scale) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const uint32_t* r = g < 4 ? r0 : r1;
+    const int b = (g & 3) * 8;
+    uint4 v;
+    v.x = pack_bf16x2(__uint_as_float(r[b]) * scale, __uint_as_float(r[b + 1]) * scale);
+    v.y = pack_bf16x2(__uint_as_float(r[b + 2]) * scale, __uint_as_float(r[b + 3]) * scale);
+    v.z = pack_bf16x2(__uint_as_float(r[b + 4]) * scale, __uint_as_float(r[b + 5]) * scale);
+    v.w = pack_bf16x2(__uint_as_float(r[b + 6]) * scale, __uint_as_float(r[b + 7]) * scale);
+    *reinterpret_cast<uint4*>(tile + row * 128 + ((g ^ (row & 7)) << 4)) = v;
+  }
+}
+// ... and the CTA then writes the tile(s) out with every warp covering 4 full 128-byte rows per
+// instruction (a lane-per-row store would touch 32 different lines per instruction and choked the
+// LSU: `lg_throttle` was the top stall of the first version). Rows >= ntok belong to the next tile.
+__device__ __forceinline__ void store_tiles(const uint8_t* tiles, int n_parts, __nv_bfloat16* base,
+                                            long long row_stride, long long part_stride, int ntok) {
+  for (int idx = threadIdx.x; idx < n_parts * AT_ROWS * 8; idx += blockDim.x) {
+    const int part = idx >> 10, row = (idx >> 3) & 127, u = idx & 7;
+    if (row < ntok) {
+      const uint4 v = *reinterpret_cast<const uint4*>(tiles + part * AT_TILE_BYTES + row * 128 +
+                                                      ((u ^ (row & 7)) << 4));
+      *reinterpret_cast<uint4*>(base + row * row_stride + part * part_stride + u * 8) = v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(128)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArgs a,
@@ -214,28 +245,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
     tmem_ld_wait();
     if (valid && lse != nullptr)   // log2-domain log-sum-exp of the scaled scores, for the backward
       lse[(long long)(tok0 + i) * a.heads + head] = mx * a.scale_log2 + log2f(sum);
-    if (valid) {
-      __nv_bfloat16* o = ctx + (long long)(tok0 + i) * a.H + head * AT_D;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 v;
-        v.x = pack_bf16x2(__uint_as_float(r0[8 * g]) * inv, __uint_as_float(r0[8 * g + 1]) * inv);
-        v.y = pack_bf16x2(__uint_as_float(r0[8 * g + 2]) * inv, __uint_as_float(r0[8 * g + 3]) * inv);
-        v.z = pack_bf16x2(__uint_as_float(r0[8 * g + 4]) * inv, __uint_as_float(r0[8 * g + 5]) * inv);
-        v.w = pack_bf16x2(__uint_as_float(r0[8 * g + 6]) * inv, __uint_as_float(r0[8 * g + 7]) * inv);
-        reinterpret_cast<uint4*>(o)[g] = v;
-      }
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 v;
-        v.x = pack_bf16x2(__uint_as_float(r1[8 * g]) * inv, __uint_as_float(r1[8 * g + 1]) * inv);
-        v.y = pack_bf16x2(__uint_as_float(r1[8 * g + 2]) * inv, __uint_as_float(r1[8 * g + 3]) * inv);
-        v.z = pack_bf16x2(__uint_as_float(r1[8 * g + 4]) * inv, __uint_as_float(r1[8 * g + 5]) * inv);
-        v.w = pack_bf16x2(__uint_as_float(r1[8 * g + 6]) * inv, __uint_as_float(r1[8 * g + 7]) * inv);
-        reinterpret_cast<uint4*>(o)[4 + g] = v;
-      }
-    }
+    stage_row(sQ, i, r0, r1, inv);   // Q's tile is dead: P.V has retired
   }
+  __syncthreads();
+  store_tiles(sQ, 1, ctx + (long long)tok0 * a.H + head * AT_D, a.H, 0, ntok);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) {
@@ -252,8 +265,8 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
 // log-sum-exp in ONE pass over S.
 __global__ void __launch_bounds__(128)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
-                   const __grid_constant__ CUtensorMap tmap_do, const AttnTcArgs a,
-                   const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx,
+                   const __grid_constant__ CUtensorMap tmap_do,
+                   const __grid_constant__ CUtensorMap tmap_o, const AttnTcArgs a,
                    const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
@@ -278,6 +291,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_o);
     mbar_init(tma_bar, 1);
     mbar_init(mma_bar, 1);
     fence_barrier_init();
@@ -294,26 +308,32 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(tma_bar, 4 * AT_TILE_BYTES);
+    mbar_arrive_expect_tx(tma_bar, 5 * AT_TILE_BYTES);
     tma_load_2d(sQ, &tmap_qkv, tma_bar, head * AT_D, tok0);
     tma_load_2d(sK, &tmap_qkv, tma_bar, a.H + head * AT_D, tok0);
     tma_load_2d(sV, &tmap_qkv, tma_bar, 2 * a.H + head * AT_D, tok0);
     tma_load_2d(sdO, &tmap_do, tma_bar, head * AT_D, tok0);
+    // the forward output O lands where P's second chunk will be written later: thread i reads
+    // row i of O before it writes row i of P there, so the overlay is row-private
+    tma_load_2d(sP + P_CHUNK, &tmap_o, tma_bar, head * AT_D, tok0);
   }
 
-  // D_i = dO_i . O_i straight from global memory while the tiles are in flight
   const int i = threadIdx.x;
   const bool valid = i < ntok;
-  float Di = 0.f;
   int lo = 0, hi = 0;
   if (valid) {
     lo = a.seq_lo[tok0 + i] - tok0;
     hi = a.seq_hi[tok0 + i] - tok0;
-    const uint4* po = reinterpret_cast<const uint4*>(ctx + (long long)(tok0 + i) * a.H + head * AT_D);
-    const uint4* pd = reinterpret_cast<const uint4*>(dctx + (long long)(tok0 + i) * a.H + head * AT_D);
+  }
+  mbar_wait(tma_bar, 0);
+  // D_i = dO_i . O_i from the swizzled smem tiles (conflict-free 16-byte reads)
+  float Di = 0.f;
+  if (valid) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-      const uint4 o = po[g], d = pd[g];
+      const uint32_t off = i * 128 + ((g ^ (i & 7)) << 4);
+      const uint4 o = *reinterpret_cast<const uint4*>(sP + P_CHUNK + off);
+      const uint4 d = *reinterpret_cast<const uint4*>(sdO + off);
       const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, dw[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -323,7 +343,6 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       }
     }
   }
-  mbar_wait(tma_bar, 0);
 
   if (threadIdx.x == 0) {
     tc_fence_after_sync();
@@ -432,35 +451,18 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   mbar_wait(mma_bar, 1);
   tc_fence_after_sync();
 
-  // rows of dQ (query i), dK / dV (key i) -> dqkv[tok0 + i, {0, H, 2H} + head * 64 ...]
+  // rows of dQ (query i), dK / dV (key i) -> dqkv[tok0 + i, {0, H, 2H} + head * 64 ...]: staged in the
+  // (now dead) Q / K / V tiles, then written with coalesced row stores
 #pragma unroll 1
   for (int part = 0; part < 3; ++part) {
     uint32_t r0[32], r1[32];
     tmem_ld_32x32(t_row + part * 64, r0);
     tmem_ld_32x32(t_row + part * 64 + 32, r1);
     tmem_ld_wait();
-    if (valid) {
-      __nv_bfloat16* o = dqkv + (long long)(tok0 + i) * (3 * a.H) + part * a.H + head * AT_D;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 v;
-        v.x = pack_bf16x2(__uint_as_float(r0[8 * g]), __uint_as_float(r0[8 * g + 1]));
-        v.y = pack_bf16x2(__uint_as_float(r0[8 * g + 2]), __uint_as_float(r0[8 * g + 3]));
-        v.z = pack_bf16x2(__uint_as_float(r0[8 * g + 4]), __uint_as_float(r0[8 * g + 5]));
-        v.w = pack_bf16x2(__uint_as_float(r0[8 * g + 6]), __uint_as_float(r0[8 * g + 7]));
-        reinterpret_cast<uint4*>(o)[g] = v;
-      }
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 v;
-        v.x = pack_bf16x2(__uint_as_float(r1[8 * g]), __uint_as_float(r1[8 * g + 1]));
-        v.y = pack_bf16x2(__uint_as_float(r1[8 * g + 2]), __uint_as_float(r1[8 * g + 3]));
-        v.z = pack_bf16x2(__uint_as_float(r1[8 * g + 4]), __uint_as_float(r1[8 * g + 5]));
-        v.w = pack_bf16x2(__uint_as_float(r1[8 * g + 6]), __uint_as_float(r1[8 * g + 7]));
-        reinterpret_cast<uint4*>(o)[4 + g] = v;
-      }
-    }
+    stage_row(smem + part * AT_TILE_BYTES, i, r0, r1, 1.0f);
   }
+  __syncthreads();
+  store_tiles(smem, 3, dqkv + (long long)tok0 * (3 * a.H) + head * AT_D, 3LL * a.H, a.H, ntok);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) {
@@ -533,9 +535,10 @@ extern "C" int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const in
   if (int rc = fill_args(&a, tile_tok0, tile_ntok, seq_lo, seq_hi, heads, head_dim, scale,
                          drop_threshold, drop_key, drop_scale))
     return rc;
-  CUtensorMap tq, td;
+  CUtensorMap tq, td, to;
   if (int rc = encode_tmap_2d_bf16(&tq, qkv, 3LL * a.H, n_tok, 3LL * a.H, AT_D, AT_ROWS)) return rc;
   if (int rc = encode_tmap_2d_bf16(&td, dctx, a.H, n_tok, a.H, AT_D, AT_ROWS)) return rc;
+  if (int rc = encode_tmap_2d_bf16(&to, ctx, a.H, n_tok, a.H, AT_D, AT_ROWS)) return rc;
   const int smem = 5 * AT_TILE_BYTES + AT_P_BYTES + 64;
   static bool configured = false;
   if (!configured) {
@@ -545,9 +548,7 @@ extern "C" int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const in
   }
   dim3 grid(n_tiles, heads);
   HERO_CUDA_CHECK(launch_pdl(attn_tc_bwd_kernel, grid, dim3(128), smem,
-                             reinterpret_cast<cudaStream_t>(stream), tq, td, a,
-                             reinterpret_cast<const __nv_bfloat16*>(ctx),
-                             reinterpret_cast<const __nv_bfloat16*>(dctx), lse,
+                             reinterpret_cast<cudaStream_t>(stream), tq, td, to, a, lse,
                              reinterpret_cast<__nv_bfloat16*>(dqkv)));
   return HERO_OK;
 }
