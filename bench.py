@@ -158,14 +158,21 @@ def run_ours(args):
     dclip = (torch.randn(B, 100, H, generator=g) * 1e-2).to(device)
     dq = (torch.randn(B, host[0][1]["input_ids"].shape[1], H, generator=g) * 1e-2).to(device)
 
+    bucketer = hdist.GradBucketer(flat) if (world > 1 and not args.no_overlap) else None
+
     def fwd_bwd(vb_dev, qb_dev):
+        if bucketer is not None:   # per-layer gradient exchange overlapped with backward
+            bucketer.__enter__()
         if args.separate_txt:      # the reference's two calls (model/pretrain.py:65-70)
             clip = model(vb_dev, "repr")
             q = model.f_encoder(qb_dev, "txt")[0]
         else:                      # same results, query rows share the video rows' GEMMs
             clip, q = model.forward_repr_txt(vb_dev, qb_dev)
         torch.autograd.backward([clip, q], [dclip, dq])
-        if world > 1:
+        if bucketer is not None:
+            bucketer.__exit__(None, None, None)
+            bucketer.finish()
+        elif world > 1:
             hdist.all_reduce_flat(gflat)
         if opt is not None:
             opt.step()
@@ -325,6 +332,8 @@ def run_ours(args):
                        "query_rows": "separate call" if args.separate_txt else
                        "fused into the video-row pass (forward_repr_txt)",
                        "allreduce_in_step": world > 1,
+                       "allreduce_overlap": ("per-layer buckets during backward"
+                                             if (world > 1 and not args.no_overlap) else "none"),
                        "l2": "no explicit flush: per-step working set (~0.35 GB weights+grads, "
                              "~3 GB activations, 111 MB inputs) exceeds the 126 MB L2"},
             "clocks": clocks, "gpu_launches": launches,
@@ -406,6 +415,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-size", type=int, default=32)
     ap.add_argument("--with-optimizer", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N>1: one all-reduce of the flat gradient after backward (the reference's "
+                         "schedule) instead of per-layer buckets overlapped with backward")
     ap.add_argument("--separate-txt", action="store_true",
                     help="encode the query rows with a separate f_encoder(batch, 'txt') call")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -85,6 +85,7 @@ class StackArgs(C.Structure):
         ("drop_key", C.c_uint32),
         ("hidden_drop_scale", C.c_float), ("attn_drop_scale", C.c_float),
         ("dout", C.c_void_p), ("dx", C.c_void_p), ("scratch", C.c_void_p),
+        ("first_layer", C.c_int32),
     ]
 
 

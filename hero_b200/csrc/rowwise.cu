@@ -75,173 +75,167 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float (&v)[
 }
 
 // ------------------------------------------------------------------ LN forward
-template <int MAXJ>
+// Persistent warps; each iteration a warp handles ROWS independent rows so twice the loads are in
+// flight per warp (the one-row-per-warp version was pure `long_scoreboard` stall: 2.6 TB/s).
+template <int MAXJ, int ROWS>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const hero_ln_args a) {
   pdl_wait();
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * LN_WARPS + warp;
-  if (i >= a.n_rows) return;
-  const long long xrow = a.x_rows ? a.x_rows[i] : i;
-  const int add_row = a.add_tab ? a.add_idx[i] : 0;
-  const long long yrow = a.y_rows ? a.y_rows[i] : i;
-
-  float v[MAXJ][8];
-  float sum = 0.f;
-#pragma unroll
-  for (int c = 0; c < MAXJ; ++c) {
-    const int e0 = (c * 32 + lane) * 8;
-    if (e0 < a.h) {
-      ln_load8(a, xrow, add_row, e0, v[c]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sum += v[c][j];
-    }
-  }
+  const int gw = blockIdx.x * LN_WARPS + warp;
+  const int stride = gridDim.x * LN_WARPS * ROWS;
   const float inv_h = 1.0f / (float)a.h;
-  const float mean = warp_sum(sum) * inv_h;
-  float sq = 0.f;
+  for (int base = gw * ROWS; base < a.n_rows; base += stride) {
+    float v[ROWS][MAXJ][8];
+    float sum[ROWS];
 #pragma unroll
-  for (int c = 0; c < MAXJ; ++c) {
-    const int e0 = (c * 32 + lane) * 8;
-    if (e0 < a.h) {
+    for (int r = 0; r < ROWS; ++r) {
+      const int i = base + r;
+      sum[r] = 0.f;
+      if (i < a.n_rows) {
+        const long long xrow = a.x_rows ? a.x_rows[i] : i;
+        const int add_row = a.add_tab ? a.add_idx[i] : 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[c][j] - mean;
-        sq += d * d;
+        for (int c = 0; c < MAXJ; ++c) {
+          const int e0 = (c * 32 + lane) * 8;
+          if (e0 < a.h) {
+            ln_load8(a, xrow, add_row, e0, v[r][c]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum[r] += v[r][c][j];
+          }
+        }
       }
     }
-  }
-  const float var = warp_sum(sq) * inv_h;
-  const float rstd = rsqrtf(var + a.eps);
-  if (lane == 0) {
-    if (a.mean) a.mean[i] = mean;
-    if (a.rstd) a.rstd[i] = rstd;
-  }
-  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.y) + yrow * a.h;
 #pragma unroll
-  for (int c = 0; c < MAXJ; ++c) {
-    const int e0 = (c * 32 + lane) * 8;
-    if (e0 < a.h) {
-      float g[8], b[8], o[8];
-      load_f32x8(a.gamma + e0, g);
-      load_f32x8(a.beta + e0, b);
+    for (int r = 0; r < ROWS; ++r) {
+      const int i = base + r;
+      if (i >= a.n_rows) break;   // warp-uniform
+      const float mean = warp_sum(sum[r]) * inv_h;
+      float sq = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * g[j] + b[j];
-      if (a.drop_threshold != 0u) {
-        dropout_apply8(o, a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0, a.drop_threshold,
-                       a.drop_scale);
+      for (int c = 0; c < MAXJ; ++c) {
+        const int e0 = (c * 32 + lane) * 8;
+        if (e0 < a.h) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = v[r][c][j] - mean;
+            sq += d * d;
+          }
+        }
       }
-      store_bf16x8(y + e0, o);
+      const float var = warp_sum(sq) * inv_h;
+      const float rstd = rsqrtf(var + a.eps);
+      if (lane == 0) {
+        if (a.mean) a.mean[i] = mean;
+        if (a.rstd) a.rstd[i] = rstd;
+      }
+      const long long yrow = a.y_rows ? a.y_rows[i] : i;
+      __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.y) + yrow * a.h;
+#pragma unroll
+      for (int c = 0; c < MAXJ; ++c) {
+        const int e0 = (c * 32 + lane) * 8;
+        if (e0 < a.h) {
+          float g[8], b[8], o[8];
+          load_f32x8(a.gamma + e0, g);
+          load_f32x8(a.beta + e0, b);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = (v[r][c][j] - mean) * rstd * g[j] + b[j];
+          if (a.drop_threshold != 0u)
+            dropout_apply8(o, a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0,
+                           a.drop_threshold, a.drop_scale);
+          store_bf16x8(y + e0, o);
+        }
+      }
     }
   }
 }
 
-// ------------------------------------------------------------------ LN backward
-// Persistent blocks: each warp walks rows i = gwarp, gwarp + total_warps, ...; with PARAM_GRADS the
-// per-lane column partials of dgamma/dbeta stay in registers and are reduced once per block.
-template <int MAXJ, bool PARAM_GRADS>
+// ------------------------------------------------------------------ LN backward (row part)
+// dx (and its dropout-masked copy / table scatter-adds) per row; persistent warps, ROWS rows per
+// iteration. Parameter and bias gradients are column reductions done by ln_param_grad_kernel.
+template <int MAXJ, int ROWS>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const hero_ln_args a) {
   pdl_wait();
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_warps = gridDim.x * LN_WARPS;
-  float dg[PARAM_GRADS ? MAXJ : 1][8], db[PARAM_GRADS ? MAXJ : 1][8];
-  if (PARAM_GRADS) {
-#pragma unroll
-    for (int c = 0; c < MAXJ; ++c)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dg[c][j] = db[c][j] = 0.f;
-  }
+  const int gw = blockIdx.x * LN_WARPS + warp;
+  const int stride = gridDim.x * LN_WARPS * ROWS;
   const float inv_h = 1.0f / (float)a.h;
 
-  for (int i = blockIdx.x * LN_WARPS + warp; i < a.n_rows; i += total_warps) {
-    const long long xrow = a.x_rows ? a.x_rows[i] : i;
-    const int add_row = a.add_tab ? a.add_idx[i] : 0;
-    const long long yrow = a.y_rows ? a.y_rows[i] : i;
-    const float mean = a.mean[i], rstd = a.rstd[i];
-    const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(a.dy) + yrow * a.h;
-
-    float xh[MAXJ][8], gy[MAXJ][8];
-    float s1 = 0.f, s2 = 0.f;
+  for (int base = gw * ROWS; base < a.n_rows; base += stride) {
+    float xh[ROWS][MAXJ][8], gy[ROWS][MAXJ][8];
+    float s1[ROWS], s2[ROWS], rs[ROWS];
 #pragma unroll
-    for (int c = 0; c < MAXJ; ++c) {
-      const int e0 = (c * 32 + lane) * 8;
-      if (e0 < a.h) {
-        ln_load8(a, xrow, add_row, e0, xh[c]);
-        float d[8], g[8];
-        load_bf16x8(dy + e0, d);
-        load_f32x8(a.gamma + e0, g);
-        if (a.drop_threshold != 0u) {
-          dropout_apply8(d, a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0,
-                         a.drop_threshold, a.drop_scale);
-        }
+    for (int r = 0; r < ROWS; ++r) {
+      const int i = base + r;
+      s1[r] = s2[r] = 0.f;
+      rs[r] = 0.f;
+      if (i < a.n_rows) {
+        const long long xrow = a.x_rows ? a.x_rows[i] : i;
+        const int add_row = a.add_tab ? a.add_idx[i] : 0;
+        const long long yrow = a.y_rows ? a.y_rows[i] : i;
+        const float mean = a.mean[i], rstd = a.rstd[i];
+        rs[r] = rstd;
+        const __nv_bfloat16* dy = reinterpret_cast<const __nv_bfloat16*>(a.dy) + yrow * a.h;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[c][j] = (xh[c][j] - mean) * rstd;
-          if (PARAM_GRADS) {
-            dg[c][j] += d[j] * xh[c][j];
-            db[c][j] += d[j];
+        for (int c = 0; c < MAXJ; ++c) {
+          const int e0 = (c * 32 + lane) * 8;
+          if (e0 < a.h) {
+            ln_load8(a, xrow, add_row, e0, xh[r][c]);
+            float d[8], g[8];
+            load_bf16x8(dy + e0, d);
+            load_f32x8(a.gamma + e0, g);
+            if (a.drop_threshold != 0u)
+              dropout_apply8(d, a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0,
+                             a.drop_threshold, a.drop_scale);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              xh[r][c][j] = (xh[r][c][j] - mean) * rstd;
+              gy[r][c][j] = d[j] * g[j];
+              s1[r] += gy[r][c][j];
+              s2[r] += gy[r][c][j] * xh[r][c][j];
+            }
           }
-          gy[c][j] = d[j] * g[j];
-          s1 += gy[c][j];
-          s2 += gy[c][j] * xh[c][j];
         }
       }
     }
-    const float c1 = warp_sum(s1) * inv_h;
-    const float c2 = warp_sum(s2) * inv_h;
 #pragma unroll
-    for (int c = 0; c < MAXJ; ++c) {
-      const int e0 = (c * 32 + lane) * 8;
-      if (e0 < a.h) {
-        float dx[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dx[j] = rstd * (gy[c][j] - c1 - xh[c][j] * c2);
-        if (a.dx) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(a.dx) + (long long)i * a.h + e0, dx);
-        if (a.dx_drop) {
-          float dd[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dd[j] = dx[j];
-          if (a.drop2_threshold != 0u)
-            dropout_apply8(dd, a.drop2_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0,
-                           a.drop2_threshold, a.drop2_scale);
-          store_bf16x8(reinterpret_cast<__nv_bfloat16*>(a.dx_drop) + (long long)i * a.h + e0, dd);
-        }
-        if (a.d_x_tab && (int)xrow != a.x_pad_idx) {
-          float* t = a.d_x_tab + xrow * a.h + e0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) atomicAdd(t + j, dx[j]);
-        }
-        if (a.d_add_tab && a.add_tab && add_row != a.add_pad_idx) {
-          float* t = a.d_add_tab + (long long)add_row * a.h + e0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) atomicAdd(t + j, dx[j]);
-        }
-      }
-    }
-  }
-
-  if (PARAM_GRADS) {
-    // block reduce over the LN_WARPS warps through smem, then one atomic per column per block
-    __shared__ float red[LN_WARPS][32 * 8 + 1];
-    for (int pass = 0; pass < 2; ++pass) {
-      float* out = pass == 0 ? a.dgamma : a.dbeta;
-      if (out == nullptr) continue;
+    for (int r = 0; r < ROWS; ++r) {
+      const int i = base + r;
+      if (i >= a.n_rows) break;   // warp-uniform
+      const float c1 = warp_sum(s1[r]) * inv_h;
+      const float c2 = warp_sum(s2[r]) * inv_h;
+      const float rstd = rs[r];
+      const long long xrow = a.x_rows ? a.x_rows[i] : i;
+      const int add_row = a.add_tab ? a.add_idx[i] : 0;
 #pragma unroll
       for (int c = 0; c < MAXJ; ++c) {
-        __syncthreads();
+        const int e0 = (c * 32 + lane) * 8;
+        if (e0 < a.h) {
+          float dx[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? dg[c][j] : db[c][j];
-        __syncthreads();
-        for (int t = threadIdx.x; t < 256; t += LN_WARPS * 32) {
-          const int e = c * 256 + t;
-          if (e < a.h) {
-            float s = 0.f;
+          for (int j = 0; j < 8; ++j) dx[j] = rstd * (gy[r][c][j] - c1 - xh[r][c][j] * c2);
+          if (a.dx) store_bf16x8(reinterpret_cast<__nv_bfloat16*>(a.dx) + (long long)i * a.h + e0, dx);
+          if (a.dx_drop) {
+            float dd[8];
 #pragma unroll
-            for (int w = 0; w < LN_WARPS; ++w) s += red[w][t];
-            atomicAdd(out + e, s);
+            for (int j = 0; j < 8; ++j) dd[j] = dx[j];
+            if (a.drop2_threshold != 0u)
+              dropout_apply8(dd, a.drop2_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0,
+                             a.drop2_threshold, a.drop2_scale);
+            store_bf16x8(reinterpret_cast<__nv_bfloat16*>(a.dx_drop) + (long long)i * a.h + e0, dd);
+          }
+          if (a.d_x_tab && (int)xrow != a.x_pad_idx) {
+            float* t = a.d_x_tab + xrow * a.h + e0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(t + j, dx[j]);
+          }
+          if (a.d_add_tab && a.add_tab && add_row != a.add_pad_idx) {
+            float* t = a.d_add_tab + (long long)add_row * a.h + e0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(t + j, dx[j]);
           }
         }
       }
@@ -466,11 +460,17 @@ extern "C" int hero_ln_fwd(const hero_ln_args* a, void* stream) {
   HERO_REQUIRE(a->y && a->beta, "ln_fwd: null y/beta");
   if (a->n_rows <= 0) return HERO_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int grid = ceil_div(a->n_rows, LN_WARPS);
-  if (a->h <= 768)
-    HERO_CUDA_CHECK(launch_pdl(ln_fwd_kernel<3>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
-  else
-    HERO_CUDA_CHECK(launch_pdl(ln_fwd_kernel<17>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
+  const int sms = sm_count();
+  if (sms <= 0) return set_error(HERO_ERR_NO_DEVICE, "no CUDA device");
+  if (a->h <= 768) {
+    int grid = ceil_div(a->n_rows, LN_WARPS * 2);
+    if (grid > sms * 8) grid = sms * 8;
+    HERO_CUDA_CHECK(launch_pdl(ln_fwd_kernel<3, 2>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
+  } else {
+    int grid = ceil_div(a->n_rows, LN_WARPS);
+    if (grid > sms * 8) grid = sms * 8;
+    HERO_CUDA_CHECK(launch_pdl(ln_fwd_kernel<17, 1>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
+  }
   return HERO_OK;
 }
 
@@ -484,12 +484,15 @@ extern "C" int hero_ln_bwd(const hero_ln_args* a, void* stream) {
   const bool want_rows = a->dx || a->dx_drop || a->d_x_tab || a->d_add_tab;
   const bool want_cols = a->dgamma || a->dbeta || a->dbias;
   if (want_rows) {
-    int grid = ceil_div(a->n_rows, LN_WARPS);
-    if (grid > sms * 16) grid = sms * 16;
-    if (a->h <= 768)
-      HERO_CUDA_CHECK(launch_pdl(ln_bwd_kernel<3, false>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
-    else
-      HERO_CUDA_CHECK(launch_pdl(ln_bwd_kernel<17, false>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
+    if (a->h <= 768) {
+      int grid = ceil_div(a->n_rows, LN_WARPS * 2);
+      if (grid > sms * 8) grid = sms * 8;
+      HERO_CUDA_CHECK(launch_pdl(ln_bwd_kernel<3, 2>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
+    } else {
+      int grid = ceil_div(a->n_rows, LN_WARPS);
+      if (grid > sms * 8) grid = sms * 8;
+      HERO_CUDA_CHECK(launch_pdl(ln_bwd_kernel<17, 1>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
+    }
   }
   if (want_cols) {
     HERO_REQUIRE(!a->dbias || a->dx || a->dx_drop, "ln_bwd: dbias needs dx or dx_drop");

@@ -86,11 +86,11 @@ extern "C" int hero_bert_stack_fwd(const hero_stack_args* s, void* stream) {
     HERO_TRY(Gemm(h, H, 0, W.wqkv, H, 0, M, 3 * H, H, A.qkv, 3 * H).bias(W.bqkv).run(stream));
     HERO_TRY(hero_attn_fwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, A.lse, M,
                            s->n_tiles, s->heads, 64, scale, s->attn_drop_threshold,
-                           site_key(s->drop_key, l, 0), s->attn_drop_scale, stream));
+                           site_key(s->drop_key, s->first_layer + l, 0), s->attn_drop_scale, stream));
     HERO_TRY(Gemm(A.cx, H, 0, W.wo, H, 0, M, H, H, A.s1, H)
                  .bias(W.bo)
                  .resid(h, H)
-                 .drop(s->hidden_drop_threshold, site_key(s->drop_key, l, 1), s->hidden_drop_scale)
+                 .drop(s->hidden_drop_threshold, site_key(s->drop_key, s->first_layer + l, 1), s->hidden_drop_scale)
                  .run(stream));
     hero_ln_args ln;
     ln_base(&ln, A.s1, W.ln1_g, W.ln1_b, s->eps, M, H, A.mean1, A.rstd1);
@@ -103,7 +103,7 @@ extern "C" int hero_bert_stack_fwd(const hero_stack_args* s, void* stream) {
     HERO_TRY(Gemm(A.f, I, 0, W.w2, I, 0, M, H, I, A.s2, H)
                  .bias(W.b2)
                  .resid(A.a, H)
-                 .drop(s->hidden_drop_threshold, site_key(s->drop_key, l, 2), s->hidden_drop_scale)
+                 .drop(s->hidden_drop_threshold, site_key(s->drop_key, s->first_layer + l, 2), s->hidden_drop_scale)
                  .run(stream));
     ln_base(&ln, A.s2, W.ln2_g, W.ln2_b, s->eps, M, H, A.mean2, A.rstd2);
     ln.y = A.out;
@@ -154,7 +154,7 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
     if (hd) {
       ln.dx_drop = ds2_d;
       ln.drop2_threshold = s->hidden_drop_threshold;
-      ln.drop2_key = site_key(s->drop_key, l, 2);
+      ln.drop2_key = site_key(s->drop_key, s->first_layer + l, 2);
       ln.drop2_scale = s->hidden_drop_scale;
       g2 = ds2_d;
     }
@@ -174,7 +174,7 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
     if (hd) {
       ln.dx_drop = ds1_d;
       ln.drop2_threshold = s->hidden_drop_threshold;
-      ln.drop2_key = site_key(s->drop_key, l, 1);
+      ln.drop2_key = site_key(s->drop_key, s->first_layer + l, 1);
       ln.drop2_scale = s->hidden_drop_scale;
       g1 = ds1_d;
     }
@@ -185,7 +185,7 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
     // attention core
     HERO_TRY(hero_attn_bwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, dcx, A.lse,
                            dqkv, M, s->n_tiles, s->heads, 64, scale, s->attn_drop_threshold,
-                           site_key(s->drop_key, l, 0), s->attn_drop_scale, stream));
+                           site_key(s->drop_key, s->first_layer + l, 0), s->attn_drop_scale, stream));
     // QKV projection
     HERO_TRY(hero_colsum_bf16(dqkv, 3 * H, M, 3 * H, G.dbqkv, stream));
     HERO_TRY(Gemm(dqkv, 3 * H, 1, h_in, H, 1, 3 * H, H, M, G.dwqkv, H).f32_accumulate().run(stream));

@@ -139,6 +139,115 @@ def any_broadcast(data, root_rank):
     return box[0]
 
 
+class GradBucketer:
+    """Overlaps the data-parallel gradient exchange with the rest of the backward pass.
+
+    The reference all-reduces one flat copy of every gradient AFTER backward has finished
+    (utils/distributed.py:19-46, called at train_vcmr.py:233-239). Here gradients are accumulated
+    in place in FlatParams' flat fp32 buffer, and the hand-written transformer backward reports
+    each layer's parameters as soon as their gradient is final: the ranges of the flat buffer they
+    cover are all-reduced (mean) right away on the communicator's stream while the layers below
+    are still being differentiated. `finish()` reduces every range not covered so far and waits.
+    The result equals one all_reduce_flat(grad_flat) after backward.
+
+    Usage (one step):
+        with bucketer:                 # installs the hook for forward + backward
+            loss = model(...); loss.backward()
+        bucketer.finish(); optimizer.step()
+
+    A parameter used by several forward calls (e.g. c_encoder for video rows and again for query
+    rows) is exchanged only after its LAST backward: forward registers every use (`expect`),
+    backward retires them (`ready`)."""
+
+    def __init__(self, flat, min_elems=1 << 20):
+        self.flat = flat
+        self.min_elems = min_elems       # merge announced ranges into messages of >= 4 MB
+        self.reset()
+
+    def reset(self):
+        self.pending = {}       # id(param) -> forward uses whose backward has not run yet
+        self.done = []          # [a, b) ranges of the flat buffer already handed to the backend
+        self.handles = []
+        self.queue = []         # final but not yet sent ranges (waiting to reach min_elems)
+
+    # ---- hook protocol (hero_b200.functional.GRAD_HOOK) -------------------------------------
+    def expect(self, params):
+        for p in params:
+            self.pending[id(p)] = self.pending.get(id(p), 0) + 1
+
+    def ready(self, params):
+        gf = self.flat.grad_flat
+        if gf is None or size() == 1:
+            return
+        base, spans = gf.data_ptr(), []
+        for p in params:
+            k = id(p)
+            left = self.pending.get(k, 1) - 1
+            self.pending[k] = left
+            ent = self.flat._by_id.get(k)
+            if left > 0 or ent is None or p.grad is None:
+                continue
+            if p.grad.data_ptr() != base + 4 * ent[0]:
+                continue                # gradient does not live in the flat buffer: finish() only
+            spans.append(ent)
+        for off, n in sorted(spans):
+            end = min((off + n + 63) // 64 * 64, self.flat.total)   # alignment padding is zeros
+            if self.queue and off <= self.queue[-1][1]:
+                self.queue[-1][1] = max(self.queue[-1][1], end)
+            else:
+                self.queue.append([off, end])
+        if sum(b - a for a, b in self.queue) >= self.min_elems:
+            self._flush()
+
+    def __enter__(self):
+        from . import functional
+        self.reset()
+        functional.GRAD_HOOK[0] = self
+        return self
+
+    def __exit__(self, *exc):
+        from . import functional
+        functional.GRAD_HOOK[0] = None
+        return False
+
+    # ---- exchange ------------------------------------------------------------------------------
+    def _launch(self, a, b):
+        if b <= a:
+            return
+        buf = self.flat.grad_flat[a:b]
+        if dist.get_backend() == "nccl":
+            self.handles.append((dist.all_reduce(buf, op=dist.ReduceOp.AVG, async_op=True), None))
+        else:
+            self.handles.append((dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True), buf))
+        self.done.append((a, b))
+
+    def _flush(self):
+        for a, b in self.queue:
+            self._launch(a, b)
+        self.queue = []
+
+    def finish(self, rescale_denom=1.0):
+        """Exchange every range not sent so far, wait for all of it (the current stream waits; the
+        host does not block on NCCL) and apply the reference's rescale."""
+        if size() > 1:
+            self.flat.ensure_flat_grads()
+            self._flush()
+            pos = 0
+            for a, b in sorted(self.done):
+                if a > pos:
+                    self._launch(pos, a)
+                pos = max(pos, b)
+            if pos < self.flat.total:
+                self._launch(pos, self.flat.total)
+            for h, buf in self.handles:
+                h.wait()
+                if buf is not None:
+                    buf.div_(size())
+        if rescale_denom != 1.0:
+            self.flat.grad_flat.div_(rescale_denom)
+        self.reset()
+
+
 class VsmAllgather(torch.autograd.Function):
     """model/pretrain.py:427-447: all-gather along dim 0 in rank order (ranks may contribute
     different row counts, as hvd.allgather allows); the backward hands each rank the slice of the

@@ -19,6 +19,12 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 
+# Data-parallel hook (hero_b200.distributed.GradBucketer): forward passes report the parameters
+# they use (`expect`), backward passes report parameters whose gradient contribution is complete
+# (`ready`), so the exchange of a layer's gradients overlaps the backward of the layers below.
+GRAD_HOOK = [None]
+
+
 class DropoutState:
     """Per-forward dropout configuration: probabilities + a key stream (fwd and bwd regenerate the
     same masks from (key, element index); nothing is stored)."""
@@ -102,6 +108,8 @@ class _TransformerStack(torch.autograd.Function):
                                         eps=cfg["eps"], drop=dspec, save=need_grad)
         ctx.cfg, ctx.dspec, ctx.saved, ctx.params = cfg, dspec, saved, params
         ctx.x = x
+        if need_grad and GRAD_HOOK[0] is not None:
+            GRAD_HOOK[0].expect(params)
         return out
 
     @staticmethod
@@ -132,9 +140,20 @@ class _TransformerStack(torch.autograd.Function):
                             ("dln2_b", 15)):
                 g[name], ret[o + k] = _sink(P[k])
             grads.append(g)
-        dx = ops.bert_stack_bwd(ctx.x, cfg["layers"], cfg["att"], ctx.saved, dout.contiguous(),
-                                grads, heads=cfg["heads"], eps=cfg["eps"], drop=ctx.dspec,
-                                need_dx=ctx.needs_input_grad[0])
+        hook = GRAD_HOOK[0]
+        if hook is None:
+            dx = ops.bert_stack_bwd(ctx.x, cfg["layers"], cfg["att"], ctx.saved,
+                                    dout.contiguous(), grads, heads=cfg["heads"], eps=cfg["eps"],
+                                    drop=ctx.dspec, need_dx=ctx.needs_input_grad[0])
+        else:
+            # data-parallel: one native call per layer so each layer's gradients can start their
+            # all-reduce while the layers below are still being differentiated
+            dx = dout.contiguous()
+            for li in range(n - 1, -1, -1):
+                dx = ops.bert_stack_bwd(ctx.x, cfg["layers"], cfg["att"], ctx.saved, dx, grads,
+                                        heads=cfg["heads"], eps=cfg["eps"], drop=ctx.dspec,
+                                        need_dx=(li > 0 or ctx.needs_input_grad[0]), only_layer=li)
+                hook.ready(params[16 * li:16 * li + 16])
         ctx.saved = None
         return (dx, None) + tuple(ret)
 

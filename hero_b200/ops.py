@@ -187,6 +187,21 @@ def attn_bwd(qkv, att, ctx, dctx, lse, dqkv, *, heads, head_dim=64, drop=(0, 0, 
     return dqkv
 
 
+class _PtrTensor:
+    """Minimal stand-in for a tensor that lives inside a workspace (only what _stack_struct
+    reads: data_ptr / shape / device)."""
+
+    def __init__(self, ptr, shape, device):
+        self._ptr, self.shape, self.device = ptr, shape, device
+        self.dtype, self.is_cuda = BF16, True
+
+    def data_ptr(self):
+        return self._ptr
+
+    def is_contiguous(self):
+        return True
+
+
 # kernels launched per layer by the native runtime (for bench.py's gpu_launches)
 _STACK_FWD_LAUNCHES, _STACK_BWD_LAUNCHES = 7, 15   # bwd: 8 GEMM, 2x2 LN, attn, 2 colsum
 _ACT_FIELDS = ("qkv", "cx", "lse", "s1", "mean1", "rstd1", "a", "pre", "f", "s2", "mean2", "rstd2",
@@ -271,13 +286,24 @@ def bert_stack_fwd(x, layers, att, *, heads, eps, drop, save):
     return out, ((ws, act_ptrs) if save else None)
 
 
-def bert_stack_bwd(x, layers, att, saved, dout, grads, *, heads, eps, drop, need_dx=True):
+def bert_stack_bwd(x, layers, att, saved, dout, grads, *, heads, eps, drop, need_dx=True,
+                   only_layer=None):
     """Backward of the whole stack (`hero_bert_stack_bwd`). grads: per layer a dict of fp32
-    tensors (keys of hero_layer_grads) that are ACCUMULATED into. Returns dx (bf16) or None."""
+    tensors (keys of hero_layer_grads) that are ACCUMULATED into. Returns dx (bf16) or None.
+    `only_layer=l` differentiates just layer l (dout = gradient of that layer's output; the
+    result is the gradient of its input): the same native entry point on a one-layer slice."""
     _require_cuda(x, dout)
     assert dout.dtype == BF16 and dout.is_contiguous()
     ws, act_ptrs = saved
+    if only_layer is not None:
+        l = only_layer
+        if l > 0:   # the layer's input is the previous layer's saved output
+            M, H = x.shape
+            prev_out = act_ptrs[l - 1][_ACT_FIELDS.index("out")]
+            x = _PtrTensor(prev_out, (M, H), x.device)
+        layers, act_ptrs, grads = layers[l:l + 1], act_ptrs[l:l + 1], grads[l:l + 1]
     s, keep = _stack_struct(x, layers, att, heads, eps, drop, act_ptrs)
+    s.first_layer = only_layer or 0
     n = len(layers)
     G = (_lib.LayerGrads * n)()
     for i, gr in enumerate(grads):
@@ -287,7 +313,7 @@ def bert_stack_bwd(x, layers, att, saved, dout, grads, *, heads, eps, drop, need
             setattr(G[i], name, t.data_ptr())
     s.grads = G
     s.dout = dout.data_ptr()
-    dx = torch.empty_like(x) if need_dx else None
+    dx = torch.empty((s.n_tok, s.hidden), dtype=BF16, device=dout.device) if need_dx else None
     s.dx = None if dx is None else dx.data_ptr()
     nbytes = _lib.lib().hero_bert_stack_bwd_scratch_bytes(s.n_tok, s.hidden, s.inter)
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)

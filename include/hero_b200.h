@@ -268,6 +268,10 @@ typedef struct hero_stack_args {
   const void* dout;              /* bf16 [n_tok, H] gradient of the last layer's output */
   void* dx;                      /* bf16 [n_tok, H] gradient of x (may be NULL for no input grad) */
   void* scratch;                 /* >= hero_bert_stack_bwd_scratch_bytes(...) bytes */
+  /* Index of weights[0] inside the full encoder (0 for a whole stack). Dropout masks are keyed by
+   * (drop_key, first_layer + l, site), so a caller may run the stack as several slices — e.g. one
+   * backward call per layer to overlap the gradient all-reduce — and get identical masks. */
+  int32_t first_layer;
 } hero_stack_args;
 
 int hero_bert_stack_fwd(const hero_stack_args* args, void* stream);

@@ -233,11 +233,14 @@ def bert_stack_fwd(x, layers, att, *, heads, eps, drop, save):
     return h, (saved if save else None)
 
 
-def bert_stack_bwd(x, layers, att, saved, dout, grads, *, heads, eps, drop, need_dx=True):
-    """Contract of `hero_bert_stack_bwd`: gradients are accumulated into `grads`."""
+def bert_stack_bwd(x, layers, att, saved, dout, grads, *, heads, eps, drop, need_dx=True,
+                   only_layer=None):
+    """Contract of `hero_bert_stack_bwd`: gradients are accumulated into `grads`; `only_layer`
+    differentiates a single layer (dout = gradient of that layer's output)."""
     M, H = dout.shape
     dy = dout
-    for li in range(len(layers) - 1, -1, -1):
+    order = range(len(layers) - 1, -1, -1) if only_layer is None else [only_layer]
+    for li in order:
         lw, S, G = layers[li], saved[li], grads[li]
         inter = lw.w1.shape[0]
         ds2 = torch.empty(M, H, dtype=BF16)

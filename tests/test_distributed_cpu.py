@@ -103,3 +103,60 @@ def test_single_process_degenerates_to_identity():
     assert hd.all_gather_list(7) == [7] and hd.any_broadcast("x", 0) == "x"
     x = torch.ones(2, 2, requires_grad=True)
     assert hd.vsm_allgather(x) is x or torch.equal(hd.vsm_allgather(x), x)
+
+
+class _Patch:
+    """monkeypatch stand-in for spawned workers (nothing to undo: the process exits)."""
+
+    @staticmethod
+    def setattr(obj, name, value):
+        setattr(obj, name, value)
+
+
+def _bucketer_case(rank, world, hd):
+    """Overlapped per-layer exchange == one all-reduce of the flat gradient after backward.
+    f_encoder is used twice per step (video-row subtitles and the query), so its layers may only be
+    exchanged after their second backward."""
+    import tempfile
+    from pathlib import Path
+    from tests import fake_ops, golden_util as gu
+    from tests.test_orchestration_cpu import _model
+    from hero_b200.params import flat_of
+    fake_ops.install(_Patch)
+    fx = gu.load("hier_tiny.npz")
+    vb, qb = gu.stored_batches(fx)
+    w1 = torch.from_numpy(fx["loss_w1"]) * (rank + 1)
+    w2 = torch.from_numpy(fx["loss_w2"]) * (2 - rank)
+
+    def loss_of(model):
+        clip = model(vb, "repr")
+        q = model.f_encoder(qb, "txt")[0]
+        return (clip * w1).sum() + (q * w2).sum()
+
+    out = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for overlapped in (False, True):
+            model = _model(Path(tmp), fx)
+            flat = flat_of(model, torch.device("cpu"))
+            gflat = flat.ensure_flat_grads()
+            if overlapped:
+                bucketer = hd.GradBucketer(flat, min_elems=1)
+                with bucketer:
+                    loss_of(model).backward()
+                    early = len(bucketer.handles)
+                bucketer.finish(rescale_denom=2.0)
+                out.append(early)
+            else:
+                loss_of(model).backward()
+                hd.all_reduce_flat(gflat, 2.0)
+            out.append(gflat.clone())
+    return out
+
+
+def test_grad_bucketer_equals_single_allreduce():
+    res = _run("_bucketer_case")
+    for r in (0, 1):
+        plain, early, bucketed = res[r]
+        assert early >= 2                        # exchanges were issued during backward
+        assert torch.equal(plain, bucketed)
+    assert torch.equal(res[0][2], res[1][2])

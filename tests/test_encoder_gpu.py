@@ -192,6 +192,48 @@ def test_training_mode_dropout_runs_and_is_stochastic(tmp_path):
     assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
 
 
+def test_per_layer_backward_with_grad_hook_is_bit_identical(tmp_path):
+    """The data-parallel schedule (one native backward call per layer + GradBucketer hook) must
+    give the same gradients, bit for bit, as the single whole-stack call — including the dropout
+    masks, which are keyed by the layer's index in the full encoder (hero_stack_args.first_layer)."""
+    from hero_b200 import functional
+    from hero_b200.params import flat_of
+    d = dict(hidden=768, inter=3072, heads=12, f_layers=3, c_layers=2, vocab=50272,
+             vfeat_dim=4352, max_img_len=100)
+    P = orc.seeded_weights(orc.param_shapes(f_layers=3, c_layers=2), seed=6)
+    vb, _ = synth.syn_tvr_ragged(batch_size=2, seed=4, t_range=(10, 20), s_range=(2, 4),
+                                 l_range=(4, 10))
+    vbd = synth.to_device(vb, "cuda")
+
+    class Hook:
+        def __init__(self):
+            self.expected, self.ready_calls = 0, 0
+
+        def expect(self, params):
+            self.expected += len(params)
+
+        def ready(self, params):
+            assert len(params) == 16
+            self.ready_calls += 1
+
+    grads = []
+    for hook in (None, Hook()):
+        model = _build(tmp_path, d, P).train()
+        gflat = flat_of(model, torch.device("cuda")).ensure_flat_grads()
+        functional.GRAD_HOOK[0] = hook
+        try:
+            torch.manual_seed(11)
+            out = model(vbd, "repr")
+            out.float().pow(2).mean().backward()
+        finally:
+            functional.GRAD_HOOK[0] = None
+        grads.append((out.detach().clone(), gflat.clone()))
+    assert hook.ready_calls == 5 and hook.expected == 16 * 5
+    assert torch.equal(grads[0][0], grads[1][0])
+    assert torch.equal(grads[0][1], grads[1][1])
+    assert grads[0][1].abs().sum() > 0
+
+
 def test_fused_adamw_follows_reference_rule_with_param_groups():
     """FusedAdamW on the flat buffer == optim/adamw.py:80-104 per parameter, with the no-decay
     grouping of optim/misc.py:22 (names containing 'bias' / 'LayerNorm.*'), clipping folded in."""
