@@ -53,9 +53,12 @@ struct GemmEpilogue {
 
 // CTA2 = 1: the CTA is half of a pair (cluster of 2) running cta_group::2 MMAs on a 256 x BLOCK_N
 // tile; it stages its own 128 rows of A and BLOCK_N / 2 columns of B per pipeline stage.
-template <int BLOCK_N, int CTA2 = 0>
+// SLABS = 2 (GELU kernels, which store two tensors per tile: the activation and its derivative):
+// a second staging slab per epilogue warp so the two TMA stores of a slab never wait for each
+// other; paid for with one pipeline stage (these are K = hidden tiles, epilogue- not load-bound).
+template <int BLOCK_N, int CTA2 = 0, int SLABS = 1>
 struct GemmCfg {
-  static constexpr int STAGES = (BLOCK_N == 256 && !CTA2) ? 4 : 6;
+  static constexpr int STAGES = ((BLOCK_N == 256 && !CTA2) ? 4 : 6) - (SLABS - 1);
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;   // B columns staged by this CTA
   static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
@@ -63,7 +66,7 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers
   // epilogue staging: one slab of 32 rows x 64 bf16 (128 B rows, swizzled) per epilogue warp
   static constexpr int SLAB_BYTES = 32 * 128;
-  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * SLAB_BYTES;
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * SLAB_BYTES * SLABS;
   static constexpr int BIAS_OFFSET = STAGES * STAGE_BYTES + STAGING_BYTES;
   static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;  // per-tile bias slice, double buffered
   static constexpr int BAR_OFFSET = BIAS_OFFSET + BIAS_BYTES;
@@ -132,7 +135,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_out,
                     const __grid_constant__ CUtensorMap tmap_aux, const GemmShape s,
                     const GemmEpilogue e) {
-  using Cfg = GemmCfg<BLOCK_N, CTA2>;
+  using Cfg = GemmCfg<BLOCK_N, CTA2, (ACT == ACT_GELU) ? 2 : 1>;
   constexpr int STAGES = Cfg::STAGES;
   // pair rank (0 = leader: issues the MMAs and owns the pipeline "full" / TMEM "empty" barriers)
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
@@ -286,6 +289,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int half = (warp - 2) >> 2;     // 0 or 1: which slabs of the tile this warp handles
     const int et = threadIdx.x - 64;      // 0..255 within the epilogue group
     uint8_t* slab = smem + STAGES * Cfg::STAGE_BYTES + (warp - 2) * Cfg::SLAB_BYTES;
+    // second slab (GELU kernels): staging of the derivative tensor
+    uint8_t* slab_aux = (ACT == ACT_GELU) ? slab + NUM_EPI_WARPS * Cfg::SLAB_BYTES : slab;
     float* bias_all = reinterpret_cast<float*>(smem + Cfg::BIAS_OFFSET);
     const bool has_aux = (e.aux_out != nullptr);
     const bool has_bias = (e.bias != nullptr);
@@ -366,8 +371,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           // stage the 32 x 64 bf16 slab in swizzled smem and let TMA write full 128 B rows; the
           // pre-activation copy (training FFN-up) goes out first through the same buffer
           uint4 outp[8];
-          if (has_aux) {
-            if (lane == 0) bulk_wait_read<0>();
+          if (has_aux) {   // the aux slab's previous store (two groups back when double-slabbed)
+            if (lane == 0) { if (ACT == ACT_GELU) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
             __syncwarp();
           }
 #pragma unroll
@@ -383,17 +388,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             outp[g].x = pack_bf16x2(v[0], v[1]); outp[g].y = pack_bf16x2(v[2], v[3]);
             outp[g].z = pack_bf16x2(v[4], v[5]); outp[g].w = pack_bf16x2(v[6], v[7]);
             if (has_aux)
-              *reinterpret_cast<uint4*>(slab + lane * 128 + ((g ^ (lane & 7)) << 4)) = pre;
+              *reinterpret_cast<uint4*>(slab_aux + lane * 128 + ((g ^ (lane & 7)) << 4)) = pre;
           }
           if (has_aux) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmap_aux, slab, col0, row0);
+              tma_store_2d(&tmap_aux, slab_aux, col0, row0);
               bulk_commit();
             }
           }
-          if (lane == 0) bulk_wait_read<0>();   // previous store has drained this warp's slab
+          // the previous store from the out slab has drained (with two slabs the aux store issued
+          // just above may stay in flight)
+          if (lane == 0) {
+            if (ACT == ACT_GELU && has_aux) bulk_wait_read<1>(); else bulk_wait_read<0>();
+          }
           __syncwarp();
 #pragma unroll
           for (int g = 0; g < 8; ++g)
@@ -500,7 +509,7 @@ struct GemmMaps {
 template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT_F32, int CTA2>
 static int launch(const GemmMaps& tm, const GemmShape& s, const GemmEpilogue& e,
                   cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, CTA2>;
+  using Cfg = GemmCfg<BLOCK_N, CTA2, (ACT == ACT_GELU) ? 2 : 1>;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, ACT, OUT_F32, CTA2>;
   static bool attr_set = false;
   if (!attr_set) {

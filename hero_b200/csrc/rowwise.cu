@@ -2,6 +2,8 @@
 // gathers (pack / unpack / frame merge), column sums (bias grads), casts.
 // One warp owns one row; 16-byte vector accesses; fp32 statistics via a true two-pass over
 // registers (mean, then centred sum of squares) like apex FusedLayerNorm / torch.nn.LayerNorm.
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -443,6 +445,15 @@ __global__ void cast_kernel(const float* __restrict__ src, __nv_bfloat16* __rest
   }
 }
 
+// Tuning knob (development only): HERO_LN_ROWS=1 launches one row per warp, non-persistent.
+static int ln_rows_per_warp() {
+  static int v = [] {
+    const char* e = getenv("HERO_LN_ROWS");
+    return (e && e[0] == '1') ? 1 : 2;
+  }();
+  return v;
+}
+
 static int check_ln(const hero_ln_args* a) {
   HERO_REQUIRE(a != nullptr, "null ln args");
   HERO_REQUIRE(a->x && a->gamma, "ln: null x/gamma");
@@ -462,7 +473,10 @@ extern "C" int hero_ln_fwd(const hero_ln_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int sms = sm_count();
   if (sms <= 0) return set_error(HERO_ERR_NO_DEVICE, "no CUDA device");
-  if (a->h <= 768) {
+  if (a->h <= 768 && ln_rows_per_warp() == 1) {
+    HERO_CUDA_CHECK(launch_pdl(ln_fwd_kernel<3, 1>, dim3(ceil_div(a->n_rows, LN_WARPS)),
+                               dim3(LN_WARPS * 32), 0, st, *a));
+  } else if (a->h <= 768) {
     int grid = ceil_div(a->n_rows, LN_WARPS * 2);
     if (grid > sms * 8) grid = sms * 8;
     HERO_CUDA_CHECK(launch_pdl(ln_fwd_kernel<3, 2>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
@@ -484,7 +498,10 @@ extern "C" int hero_ln_bwd(const hero_ln_args* a, void* stream) {
   const bool want_rows = a->dx || a->dx_drop || a->d_x_tab || a->d_add_tab;
   const bool want_cols = a->dgamma || a->dbeta || a->dbias;
   if (want_rows) {
-    if (a->h <= 768) {
+    if (a->h <= 768 && ln_rows_per_warp() == 1) {
+      HERO_CUDA_CHECK(launch_pdl(ln_bwd_kernel<3, 1>, dim3(ceil_div(a->n_rows, LN_WARPS)),
+                                 dim3(LN_WARPS * 32), 0, st, *a));
+    } else if (a->h <= 768) {
       int grid = ceil_div(a->n_rows, LN_WARPS * 2);
       if (grid > sms * 8) grid = sms * 8;
       HERO_CUDA_CHECK(launch_pdl(ln_bwd_kernel<3, 2>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));

@@ -145,7 +145,10 @@ def ln_fwd(x, gamma, beta, eps, y, *, n_rows, x_rows=None, add_tab=None, add_idx
 def ln_bwd(dy, x, gamma, mean, rstd, *, n_rows, x_rows=None, add_tab=None, add_idx=None,
            add_vec=None, y_rows=None, drop=(0, 0, 1.0), dx=None, dx_drop=None,
            drop2=(0, 0, 1.0), d_x_tab=None, x_pad_idx=-1, d_add_tab=None, add_pad_idx=-1,
-           dgamma=None, dbeta=None):
+           dgamma=None, dbeta=None, dbias=None):
+    """Backward of ln_fwd (`hero_ln_bwd`): row gradients dx / dx_drop (dropout-masked copy) and
+    table scatter-adds, parameter gradients dgamma / dbeta (accumulated), and `dbias` (fp32 [h]) +=
+    column sums of dx_drop (else dx) — the bias gradient of the Linear feeding this LayerNorm."""
     _require_cuda(dy, x)
     h = gamma.numel()
     a = _ln_args(x, gamma, None, 0.0, n_rows, h, x_rows, add_tab, add_idx, add_vec)
@@ -156,9 +159,10 @@ def ln_bwd(dy, x, gamma, mean, rstd, *, n_rows, x_rows=None, add_tab=None, add_i
     a.drop2_threshold, a.drop2_key, a.drop2_scale = drop2
     a.d_x_tab, a.x_pad_idx = _ptr(d_x_tab), x_pad_idx
     a.d_add_tab, a.add_pad_idx = _ptr(d_add_tab), add_pad_idx
-    a.dgamma, a.dbeta = _ptr(dgamma), _ptr(dbeta)
+    a.dgamma, a.dbeta, a.dbias = _ptr(dgamma), _ptr(dbeta), _ptr(dbias)
     _count(int(dx is not None or dx_drop is not None or d_x_tab is not None or
-               d_add_tab is not None) + int(dgamma is not None or dbeta is not None))
+               d_add_tab is not None) +
+           int(dgamma is not None or dbeta is not None or dbias is not None))
     _lib.check(_lib.lib().hero_ln_bwd(C.byref(a), _stream()))
 
 

@@ -76,7 +76,7 @@ def ln_fwd(x, gamma, beta, eps, y, *, n_rows, x_rows=None, add_tab=None, add_idx
 def ln_bwd(dy, x, gamma, mean, rstd, *, n_rows, x_rows=None, add_tab=None, add_idx=None,
            add_vec=None, y_rows=None, drop=(0, 0, 1.0), dx=None, dx_drop=None,
            drop2=(0, 0, 1.0), d_x_tab=None, x_pad_idx=-1, d_add_tab=None, add_pad_idx=-1,
-           dgamma=None, dbeta=None):
+           dgamma=None, dbeta=None, dbias=None):
     _ck_drop(drop)
     _ck_drop(drop2)
     s = _gather_sum(x, n_rows, x_rows, add_tab, add_idx, add_vec)
@@ -95,6 +95,8 @@ def ln_bwd(dy, x, gamma, mean, rstd, *, n_rows, x_rows=None, add_tab=None, add_i
         dx.copy_(dxb)
     if dx_drop is not None:
         dx_drop.copy_(dxb)
+    if dbias is not None:
+        dbias.add_(dxb.float().sum(0))
     if d_x_tab is not None:
         keep = x_rows.long() != x_pad_idx
         d_x_tab.index_add_(0, x_rows.long()[keep], dxv[keep])

@@ -192,10 +192,12 @@ def test_training_mode_dropout_runs_and_is_stochastic(tmp_path):
     assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0
 
 
-def test_per_layer_backward_with_grad_hook_is_bit_identical(tmp_path):
+def test_per_layer_backward_with_grad_hook_matches_whole_stack(tmp_path):
     """The data-parallel schedule (one native backward call per layer + GradBucketer hook) must
-    give the same gradients, bit for bit, as the single whole-stack call — including the dropout
-    masks, which are keyed by the layer's index in the full encoder (hero_stack_args.first_layer)."""
+    give the same gradients as the single whole-stack call — including the dropout masks, which
+    are keyed by the layer's index in the full encoder (hero_stack_args.first_layer). Same kernels
+    on the same data: the only difference allowed is the summation order of the split-K fp32
+    atomics of the weight gradients."""
     from hero_b200 import functional
     from hero_b200.params import flat_of
     d = dict(hidden=768, inter=3072, heads=12, f_layers=3, c_layers=2, vocab=50272,
@@ -230,8 +232,9 @@ def test_per_layer_backward_with_grad_hook_is_bit_identical(tmp_path):
         grads.append((out.detach().clone(), gflat.clone()))
     assert hook.ready_calls == 5 and hook.expected == 16 * 5
     assert torch.equal(grads[0][0], grads[1][0])
-    assert torch.equal(grads[0][1], grads[1][1])
-    assert grads[0][1].abs().sum() > 0
+    a, b = grads[0][1], grads[1][1]
+    assert a.abs().sum() > 0
+    assert float((a - b).norm() / a.norm()) < 1e-5
 
 
 def test_fused_adamw_follows_reference_rule_with_param_groups():

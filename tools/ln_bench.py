@@ -1,0 +1,49 @@
+"""Device-time micro-benchmark of the row kernels at bench shapes (CUDA events, buffers rotated
+through > L2 so every launch reads HBM). Usage: [HERO_LN_ROWS=1] python tools/ln_bench.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from hero_b200 import ops
+
+dev = torch.device("cuda:0")
+H = 768
+drop = ops.drop_params(0.1, 77)
+
+
+def timeit(fn, n=40):
+    for i in range(4):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+for M in (16512, 3200):
+    R = 12 if M > 10000 else 40           # rotate through R buffer sets (> 126 MB of L2)
+    xs = [torch.randn(M, H, device=dev).bfloat16() for _ in range(R)]
+    dys = [torch.randn(M, H, device=dev).bfloat16() for _ in range(R)]
+    ys = [torch.empty(M, H, dtype=torch.bfloat16, device=dev) for _ in range(R)]
+    dxs = [torch.empty(M, H, dtype=torch.bfloat16, device=dev) for _ in range(R)]
+    dxd = [torch.empty(M, H, dtype=torch.bfloat16, device=dev) for _ in range(R)]
+    g, b = torch.ones(H, device=dev), torch.zeros(H, device=dev)
+    mean, rstd = torch.empty(M, device=dev), torch.empty(M, device=dev)
+    dg, db, dbias = (torch.zeros(H, device=dev) for _ in range(3))
+    ops.ln_fwd(xs[0], g, b, 1e-12, ys[0], n_rows=M, mean=mean, rstd=rstd)
+    t_f = timeit(lambda i: ops.ln_fwd(xs[i % R], g, b, 1e-12, ys[i % R], n_rows=M, mean=mean,
+                                      rstd=rstd))
+    t_b = timeit(lambda i: ops.ln_bwd(dys[i % R], xs[i % R], g, mean, rstd, n_rows=M,
+                                      dx=dxs[i % R], dx_drop=dxd[i % R], drop2=drop))
+    t_p = timeit(lambda i: ops.ln_bwd(dys[i % R], xs[i % R], g, mean, rstd, n_rows=M,
+                                      dx=dxs[i % R], dx_drop=dxd[i % R], drop2=drop, dgamma=dg,
+                                      dbeta=db, dbias=dbias))
+    t_c = timeit(lambda i: ops.colsum(dys[i % R], dbias))
+    by = M * H * 2 / 1e6
+    print(f"M={M} HERO_LN_ROWS={os.environ.get('HERO_LN_ROWS', '2')}: "
+          f"ln_fwd {t_f:.1f} us ({2 * by / t_f:.0f} GB/s)  ln_bwd rows {t_b:.1f} us "
+          f"({4 * by / t_b:.0f} GB/s)  rows+params {t_p:.1f} us  colsum {t_c:.1f} us "
+          f"({by / t_c:.0f} GB/s)")

@@ -18,7 +18,13 @@ f = torch.empty(M, 3072, dtype=torch.bfloat16, device=dev)
 pre = torch.empty_like(f)
 qkv = torch.empty(M, 2304, dtype=torch.bfloat16, device=dev)
 dw = torch.zeros(3072, 768, device=dev)
+wo = (torch.randn(768, 768, device=dev) * 0.05).bfloat16()
+bo = torch.randn(768, device=dev)
+h = torch.randn(M, 768, device=dev).bfloat16()
+s1 = torch.empty_like(h)
+drop = ops.drop_params(0.1, 99)
 for _ in range(3):
+    ops.gemm(x, wo, s1, bias=bo, resid=h, drop=drop)             # out-proj + dropout + residual
     ops.gemm(x, w1, f, bias=b1, act=ops.ACT_GELU, aux_out=pre)   # FFN-up + erf-GELU (training)
     ops.gemm(x, wq, qkv, bias=bq)                                 # fused QKV
     ops.gemm(f, w1, x, b_mn=True)                                 # dgrad-shaped (K = 3072)
