@@ -129,7 +129,7 @@ __device__ __forceinline__ void epilogue_math8(float (&v)[8], uint4* pre, const 
 }
 
 template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT_F32, int CTA2>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __maxnreg__(200)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out,
@@ -297,6 +297,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const bool has_resid = (ACT != ACT_GELU_GRAD) && (e.resid != nullptr);
     uint32_t slab_it = 0;
     uint32_t local_tile = 0;
+    // Operands that come from global memory are fetched ahead of their use so no load latency
+    // sits on the epilogue's critical path: the bias slice of tile i+1 is read (into a register)
+    // before tile i is processed, and the residual / saved-derivative rows of the NEXT 64-column
+    // slab are requested before the current slab's arithmetic (the first slab's before the wait
+    // for the accumulator, i.e. behind the main loop).
+    const bool has_opnd = has_resid || ACT == ACT_GELU_GRAD;
+    const __nv_bfloat16* opnd_base = (ACT == ACT_GELU_GRAD) ? e.aux_in : e.resid;
+    const long long ld_opnd = (ACT == ACT_GELU_GRAD) ? e.ld_aux_in : e.ld_resid;
+    auto tile_bias = [&](int t) -> float {
+      if (!has_bias || et >= BLOCK_N || t >= total_tiles) return 0.0f;
+      const int col = ((t / s.k_splits) % s.num_n_blocks) * BLOCK_N + et;
+      return (col < s.N) ? __ldg(e.bias + col) : 0.0f;
+    };
+    auto load_opnd = [&](uint4 (&dst)[8], int row, bool row_ok, int col0) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int col = col0 + g * 8;
+        dst[g] = (row_ok && col < s.N)
+                     ? *reinterpret_cast<const uint4*>(opnd_base + (long long)row * ld_opnd + col)
+                     : make_uint4(0, 0, 0, 0);
+      }
+    };
+    float bias_next = tile_bias(first_tile);
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++local_tile) {
       const int t2 = tile / s.k_splits;
       const int n_blk = t2 % s.num_n_blocks;
@@ -304,19 +327,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t acc = local_tile & 1u;
       const uint32_t acc_ph = (local_tile >> 1) & 1u;
       float* bias_s = bias_all + acc * BLOCK_N;
+      const int row0 = (CTA2 ? m_blk * 2 + (int)rank : m_blk) * BLOCK_M + q * 32;
+      const int row = row0 + lane;
+      const bool row_ok = row < s.M;
+      uint4 opnd_next[8];
+      if (has_opnd) load_opnd(opnd_next, row, row_ok, n_blk * BLOCK_N + half * 64);
       if (has_bias) {
-        // stage this tile's bias slice once (coalesced) while the main loop is still running
-        if (et < BLOCK_N) {
-          const int col = n_blk * BLOCK_N + et;
-          bias_s[et] = (col < s.N) ? __ldg(e.bias + col) : 0.0f;
-        }
+        // this tile's bias slice (fetched one tile ago) -> smem; the slot was last read two tiles
+        // back, and every epilogue warp has passed this barrier once since then
+        if (et < BLOCK_N) bias_s[et] = bias_next;
+        bias_next = tile_bias(tile + tile_step);
         asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
       }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after_sync();
-      const int row0 = (CTA2 ? m_blk * 2 + (int)rank : m_blk) * BLOCK_M + q * 32;
-      const int row = row0 + lane;
-      const bool row_ok = row < s.M;
       const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int c = half; c < BLOCK_N / 64; c += 2) {
@@ -325,25 +349,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint32_t r[2][32];
         tmem_ld_32x32(t_addr + c * 64, r[0]);
         tmem_ld_32x32(t_addr + c * 64 + 32, r[1]);
-        // batch the per-row global operands of this slab so their latency overlaps the TMEM load
         uint4 res[8], aux[8];
-        if (ACT != ACT_GELU_GRAD && has_resid) {
+        if (has_opnd) {
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
-            const int col = col0 + g * 8;
-            res[g] = (row_ok && col < s.N)
-                         ? *reinterpret_cast<const uint4*>(e.resid + (long long)row * e.ld_resid + col)
-                         : make_uint4(0, 0, 0, 0);
+            if (ACT == ACT_GELU_GRAD) aux[g] = opnd_next[g]; else res[g] = opnd_next[g];
           }
-        }
-        if (ACT == ACT_GELU_GRAD) {   // (never combined with a residual: host-checked)
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const int col = col0 + g * 8;
-            aux[g] = (row_ok && col < s.N)
-                         ? *reinterpret_cast<const uint4*>(e.aux_in + (long long)row * e.ld_aux_in + col)
-                         : make_uint4(0, 0, 0, 0);
-          }
+          if (c + 2 < BLOCK_N / 64 && col0 + 128 < s.N) load_opnd(opnd_next, row, row_ok, col0 + 128);
         }
         tmem_ld_wait();
         if (OUT_F32) {

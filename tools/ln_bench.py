@@ -1,5 +1,6 @@
 """Device-time micro-benchmark of the row kernels at bench shapes (CUDA events, buffers rotated
-through > L2 so every launch reads HBM). Usage: [HERO_LN_ROWS=1] python tools/ln_bench.py"""
+through > L2 so every launch reads HBM; kernels shorter than ~10 us are host-launch bound here).
+Usage: python tools/ln_bench.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -43,7 +44,6 @@ for M in (16512, 3200):
                                       dbeta=db, dbias=dbias))
     t_c = timeit(lambda i: ops.colsum(dys[i % R], dbias))
     by = M * H * 2 / 1e6
-    print(f"M={M} HERO_LN_ROWS={os.environ.get('HERO_LN_ROWS', '2')}: "
-          f"ln_fwd {t_f:.1f} us ({2 * by / t_f:.0f} GB/s)  ln_bwd rows {t_b:.1f} us "
-          f"({4 * by / t_b:.0f} GB/s)  rows+params {t_p:.1f} us  colsum {t_c:.1f} us "
-          f"({by / t_c:.0f} GB/s)")
+    print(f"M={M}: ln_fwd {t_f:.1f} us ({2 * by / t_f:.2f} TB/s)  ln_bwd rows {t_b:.1f} us "
+          f"({4 * by / t_b:.2f} TB/s)  rows+params {t_p:.1f} us  colsum {t_c:.1f} us "
+          f"({by / t_c:.2f} TB/s)")
