@@ -73,63 +73,51 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = BAR_OFFSET + 256 /*barriers*/;
 };
 
-// Epilogue arithmetic on 8 consecutive columns of one row (v in/out). Operands that come from
-// memory are passed in already loaded (bias from the per-tile smem slice, residual / pre-activation
-// rows batched into registers before the TMEM wait) so no load latency is exposed per group.
-template <int ACT>
-__device__ __forceinline__ void epilogue_math8(float (&v)[8], uint4* pre, const float* bias_s,
-                                               const uint4& aux, bool has_resid, const uint4& res,
-                                               int row, int col, const GemmShape& s,
-                                               const GemmEpilogue& e) {
-  if (bias_s != nullptr) {
-    const float4 b0 = *reinterpret_cast<const float4*>(bias_s);
-    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 4);
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+// Epilogue arithmetic on one 64-column slab of one row (v in/out), organised in phases so that
+// every warp-uniform option (bias / dropout / residual / derivative output) is tested once per slab
+// and the arithmetic inside a phase is straight-line code. Operands that come from memory arrive
+// already loaded: bias from the per-tile smem slice, residual / saved-derivative rows prefetched
+// into registers one slab ahead.
+__device__ __forceinline__ void slab_add_bias(float (&v)[64], const float* bias_s) {
+#pragma unroll
+  for (int g = 0; g < 16; ++g) {
+    const float4 b = *reinterpret_cast<const float4*>(bias_s + g * 4);
+    v[4 * g] += b.x; v[4 * g + 1] += b.y; v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
   }
-  if (pre != nullptr && ACT != ACT_GELU) {   // pre-activation copy (ReLU backward needs its sign)
-    pre->x = pack_bf16x2(v[0], v[1]); pre->y = pack_bf16x2(v[2], v[3]);
-    pre->z = pack_bf16x2(v[4], v[5]); pre->w = pack_bf16x2(v[6], v[7]);
-  }
-  if (ACT == ACT_GELU) {
-    if (pre != nullptr) {   // training: also emit gelu'(x) for the backward's ACT_MUL_AUX epilogue
-      float d[8];
+}
+__device__ __forceinline__ void slab_mul_bf16(float (&v)[64], const uint4 (&m)[8]) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = gelu_erf_with_grad(v[j], d[j]);
-      pre->x = pack_bf16x2(d[0], d[1]); pre->y = pack_bf16x2(d[2], d[3]);
-      pre->z = pack_bf16x2(d[4], d[5]); pre->w = pack_bf16x2(d[6], d[7]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = gelu_erf(v[j]);
-    }
-  } else if (ACT == ACT_RELU) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
-  } else if (ACT == ACT_GELU_GRAD) {   // multiply by the saved activation derivative
-    const uint32_t pw[4] = {aux.x, aux.y, aux.z, aux.w};
+  for (int g = 0; g < 8; ++g) {
+    const uint32_t pw[4] = {m[g].x, m[g].y, m[g].z, m[g].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 x = unpack_bf16x2(pw[j]);
-      v[2 * j] *= x.x;
-      v[2 * j + 1] *= x.y;
-    }
-  }
-  if (e.drop_threshold != 0u)
-    dropout_apply8(v, e.drop_key, (uint32_t)row * (uint32_t)s.N + (uint32_t)col, e.drop_threshold,
-                   e.drop_scale);
-  if (has_resid) {
-    const uint32_t pw[4] = {res.x, res.y, res.z, res.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 x = unpack_bf16x2(pw[j]);
-      v[2 * j] += x.x;
-      v[2 * j + 1] += x.y;
+      v[8 * g + 2 * j] *= x.x;
+      v[8 * g + 2 * j + 1] *= x.y;
     }
   }
 }
+__device__ __forceinline__ void slab_add_bf16(float (&v)[64], const uint4 (&m)[8]) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const uint32_t pw[4] = {m[g].x, m[g].y, m[g].z, m[g].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x = unpack_bf16x2(pw[j]);
+      v[8 * g + 2 * j] += x.x;
+      v[8 * g + 2 * j + 1] += x.y;
+    }
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  return u;
+}
 
 template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT_F32, int CTA2>
-__global__ void __maxnreg__(200)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out,
@@ -297,11 +285,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const bool has_resid = (ACT != ACT_GELU_GRAD) && (e.resid != nullptr);
     uint32_t slab_it = 0;
     uint32_t local_tile = 0;
-    // Operands that come from global memory are fetched ahead of their use so no load latency
-    // sits on the epilogue's critical path: the bias slice of tile i+1 is read (into a register)
-    // before tile i is processed, and the residual / saved-derivative rows of the NEXT 64-column
-    // slab are requested before the current slab's arithmetic (the first slab's before the wait
-    // for the accumulator, i.e. behind the main loop).
+    // The bias slice of tile i+1 is read (into a register) before tile i is processed, so its
+    // latency never sits on the critical path; the residual / saved-derivative rows of a slab are
+    // requested together with the slab's TMEM load. (Requesting them one slab ahead was measured
+    // slower: +32 live registers push the kernel over the 168-register budget of a 10-warp CTA.)
     const bool has_opnd = has_resid || ACT == ACT_GELU_GRAD;
     const __nv_bfloat16* opnd_base = (ACT == ACT_GELU_GRAD) ? e.aux_in : e.resid;
     const long long ld_opnd = (ACT == ACT_GELU_GRAD) ? e.ld_aux_in : e.ld_resid;
@@ -330,8 +317,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int row0 = (CTA2 ? m_blk * 2 + (int)rank : m_blk) * BLOCK_M + q * 32;
       const int row = row0 + lane;
       const bool row_ok = row < s.M;
-      uint4 opnd_next[8];
-      if (has_opnd) load_opnd(opnd_next, row, row_ok, n_blk * BLOCK_N + half * 64);
       if (has_bias) {
         // this tile's bias slice (fetched one tile ago) -> smem; the slot was last read two tiles
         // back, and every epilogue warp has passed this barrier once since then
@@ -349,60 +334,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         uint32_t r[2][32];
         tmem_ld_32x32(t_addr + c * 64, r[0]);
         tmem_ld_32x32(t_addr + c * 64 + 32, r[1]);
-        uint4 res[8], aux[8];
-        if (has_opnd) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (ACT == ACT_GELU_GRAD) aux[g] = opnd_next[g]; else res[g] = opnd_next[g];
-          }
-          if (c + 2 < BLOCK_N / 64 && col0 + 128 < s.N) load_opnd(opnd_next, row, row_ok, col0 + 128);
-        }
+        uint4 opnd[8];
+        if (has_opnd) load_opnd(opnd, row, row_ok, col0);
         tmem_ld_wait();
-        if (OUT_F32) {
-          if (row_ok) {
+        float v[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j >> 5][j & 31]);
+        if (has_bias) slab_add_bias(v, bias_s + c * 64);
+        // activation (compile-time); the training FFN-up also emits gelu'(x) through its own slab
+        if (ACT == ACT_GELU) {
+          if (has_aux) {
+            if (lane == 0) bulk_wait_read<1>();   // the aux slab's previous store (two groups back)
+            __syncwarp();
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-              const int col = col0 + g * 8;
-              if (col < s.N) {
-                float v[8];
+              float d[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g >> 2][(g & 3) * 8 + j]);
-                epilogue_math8<ACT>(v, nullptr, has_bias ? bias_s + c * 64 + g * 8 : nullptr, aux[g],
-                                    has_resid, res[g], row, col, s, e);
-                float* o = reinterpret_cast<float*>(e.out) + (long long)row * e.ld_out + col;
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]),
-                             "f"(v[1]), "f"(v[2]), "f"(v[3])
-                             : "memory");
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4),
-                             "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-                             : "memory");
-              }
+              for (int j = 0; j < 8; ++j) v[8 * g + j] = gelu_erf_with_grad(v[8 * g + j], d[j]);
+              *reinterpret_cast<uint4*>(slab_aux + lane * 128 + ((g ^ (lane & 7)) << 4)) = pack8(d);
             }
-          }
-        } else {
-          // stage the 32 x 64 bf16 slab in swizzled smem and let TMA write full 128 B rows; the
-          // pre-activation copy (training FFN-up) goes out first through the same buffer
-          uint4 outp[8];
-          if (has_aux) {   // the aux slab's previous store (two groups back when double-slabbed)
-            if (lane == 0) { if (ACT == ACT_GELU) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+            fence_proxy_async();
             __syncwarp();
-          }
+            if (lane == 0) {
+              tma_store_2d(&tmap_aux, slab_aux, col0, row0);
+              bulk_commit();
+            }
+          } else {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const int col = col0 + g * 8;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g >> 2][(g & 3) * 8 + j]);
-            uint4 pre;
-            epilogue_math8<ACT>(v, has_aux ? &pre : nullptr,
-                                has_bias ? bias_s + c * 64 + g * 8 : nullptr, aux[g], has_resid,
-                                res[g], row, col, s, e);
-            outp[g].x = pack_bf16x2(v[0], v[1]); outp[g].y = pack_bf16x2(v[2], v[3]);
-            outp[g].z = pack_bf16x2(v[4], v[5]); outp[g].w = pack_bf16x2(v[6], v[7]);
-            if (has_aux)
-              *reinterpret_cast<uint4*>(slab_aux + lane * 128 + ((g ^ (lane & 7)) << 4)) = pre;
+            for (int j = 0; j < 64; ++j) v[j] = gelu_erf(v[j]);
           }
-          if (has_aux) {
+        } else if (ACT == ACT_RELU) {
+          if (has_aux) {   // pre-activation copy (the ReLU backward needs its sign)
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<uint4*>(slab_aux + lane * 128 + ((g ^ (lane & 7)) << 4)) =
+                  pack8(v + 8 * g);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
@@ -410,8 +378,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
               bulk_commit();
             }
           }
-          // the previous store from the out slab has drained (with two slabs the aux store issued
-          // just above may stay in flight)
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else if (ACT == ACT_GELU_GRAD) {   // multiply by the saved activation derivative
+          slab_mul_bf16(v, opnd);
+        }
+        if (e.drop_threshold != 0u) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = v[8 * g + j];
+            dropout_apply8(t, e.drop_key, (uint32_t)row * (uint32_t)s.N + (uint32_t)(col0 + g * 8),
+                           e.drop_threshold, e.drop_scale);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[8 * g + j] = t[j];
+          }
+        }
+        if (has_resid) slab_add_bf16(v, opnd);
+        if (OUT_F32) {
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+              const int col = col0 + g * 4;
+              if (col < s.N) {
+                float* o = reinterpret_cast<float*>(e.out) + (long long)row * e.ld_out + col;
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o),
+                             "f"(v[4 * g]), "f"(v[4 * g + 1]), "f"(v[4 * g + 2]), "f"(v[4 * g + 3])
+                             : "memory");
+              }
+            }
+          }
+        } else {
+          // stage the 32 x 64 bf16 slab in swizzled smem and let TMA write full 128 B rows; the
+          // previous store from this slab must have drained (a derivative store issued just above
+          // from the second slab may stay in flight)
+          uint4 outp[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) outp[g] = pack8(v + 8 * g);
           if (lane == 0) {
             if (ACT == ACT_GELU && has_aux) bulk_wait_read<1>(); else bulk_wait_read<0>();
           }
@@ -690,8 +694,10 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   // one 128-row block; cta_pair: 0 auto, 1 never, 2 force.
   // Measured on B200 (tools/gemm_probe.py): pairs gain 7-15 % when the main loop dominates (long
   // K: dgrad / FFN-down / every wgrad) and lose ~10 % on short-K tiles with heavy epilogues (the
-  // two CTAs' epilogues are lock-stepped), so auto mode keys on K.
-  const bool pair_auto = g->k >= 1536 && g->m > 128 &&
+  // two CTAs' epilogues are lock-stepped), so auto mode keys on K and on the epilogue.
+  // Light epilogues (bias only: the QKV projection) also gain from pairs on short K.
+  const bool heavy_epilogue = g->act != ACT_NONE || g->resid != nullptr || g->drop_threshold != 0u;
+  const bool pair_auto = (g->k >= 1536 || !heavy_epilogue) && g->m > 128 &&
                          (g->out_f32_accumulate || m_blocks * ceil_div(g->n, 256) >= sms);
   const bool pair = (block_n == 256) && (g->cta_pair == 2 || (g->cta_pair == 0 && pair_auto));
 
