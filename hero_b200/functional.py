@@ -118,28 +118,7 @@ class _TransformerStack(torch.autograd.Function):
         if cfg.get("flat") is not None:
             cfg["flat"].mark_dirty()        # the masters are about to change (optimizer step)
         n = len(cfg["layers"])
-        H = ctx.x.shape[1]
-        ret = [None] * (16 * n)
-        grads = []
-        for li in range(n):
-            P = params[16 * li:16 * li + 16]
-            o = 16 * li
-            g = {}
-            g["dwqkv"] = _fused_sink([P[0], P[2], P[4]])
-            if g["dwqkv"] is None:
-                t = torch.zeros((3 * H, H), dtype=F32, device=dout.device)
-                g["dwqkv"] = t
-                ret[o + 0], ret[o + 2], ret[o + 4] = t[:H], t[H:2 * H], t[2 * H:]
-            g["dbqkv"] = _fused_sink([P[1], P[3], P[5]])
-            if g["dbqkv"] is None:
-                t = torch.zeros((3 * H,), dtype=F32, device=dout.device)
-                g["dbqkv"] = t
-                ret[o + 1], ret[o + 3], ret[o + 5] = t[:H], t[H:2 * H], t[2 * H:]
-            for name, k in (("dwo", 6), ("dbo", 7), ("dln1_g", 8), ("dln1_b", 9), ("dw1", 10),
-                            ("db1", 11), ("dw2", 12), ("db2", 13), ("dln2_g", 14),
-                            ("dln2_b", 15)):
-                g[name], ret[o + k] = _sink(P[k])
-            grads.append(g)
+        grads, ret = _stack_sinks(cfg, params, ctx.x.shape[1], dout.device)
         hook = GRAD_HOOK[0]
         if hook is None:
             dx = ops.bert_stack_bwd(ctx.x, cfg["layers"], cfg["att"], ctx.saved,
@@ -156,6 +135,53 @@ class _TransformerStack(torch.autograd.Function):
                 hook.ready(params[16 * li:16 * li + 16])
         ctx.saved = None
         return (dx, None) + tuple(ret)
+
+
+def _stack_sinks(cfg, params, H, device):
+    """Accumulation targets of a stack's 16 n parameter gradients + what to hand back to autograd.
+    When every gradient already lives in an existing fp32 `.grad` (FlatParams.ensure_flat_grads)
+    the targets are the same views every step: they are cached on the encoder (`cfg["cache"]`)
+    and re-validated by pointer (16 n attribute reads instead of rebuilding ~30 views per layer)."""
+    cache = cfg.get("cache")
+    if cache is not None:
+        hit = cache.get("sinks")
+        if hit is not None:
+            ptrs, grads = hit
+            ok = True
+            for p, ptr in zip(params, ptrs):
+                g = p.grad
+                if g is None or g.data_ptr() != ptr:
+                    ok = False
+                    break
+            if ok:
+                return grads, [None] * len(params)
+    n = len(params) // 16
+    ret = [None] * (16 * n)
+    grads = []
+    for li in range(n):
+        P = params[16 * li:16 * li + 16]
+        o = 16 * li
+        g = {}
+        g["dwqkv"] = _fused_sink([P[0], P[2], P[4]])
+        if g["dwqkv"] is None:
+            t = torch.zeros((3 * H, H), dtype=F32, device=device)
+            g["dwqkv"] = t
+            ret[o + 0], ret[o + 2], ret[o + 4] = t[:H], t[H:2 * H], t[2 * H:]
+        g["dbqkv"] = _fused_sink([P[1], P[3], P[5]])
+        if g["dbqkv"] is None:
+            t = torch.zeros((3 * H,), dtype=F32, device=device)
+            g["dbqkv"] = t
+            ret[o + 1], ret[o + 3], ret[o + 5] = t[:H], t[H:2 * H], t[2 * H:]
+        for name, k in (("dwo", 6), ("dbo", 7), ("dln1_g", 8), ("dln1_b", 9), ("dw1", 10),
+                        ("db1", 11), ("dw2", 12), ("db2", 13), ("dln2_g", 14), ("dln2_b", 15)):
+            g[name], ret[o + k] = _sink(P[k])
+        grads.append(g)
+    if cache is not None:
+        if all(r is None for r in ret):     # everything accumulates in place: reusable
+            cache["sinks"] = ([p.grad.data_ptr() for p in params], grads)
+        else:
+            cache.pop("sinks", None)
+    return grads, ret
 
 
 def transformer_stack(x, cfg, params):

@@ -156,9 +156,18 @@ class BertEncoder(nn.Module):
         flat = flat_of(self, x.device)
         if drop is None:
             drop = self.dropout_state()
-        cfg = {"layers": [l.weights(flat) for l in self.layer], "att": att,
-               "heads": self.num_heads, "eps": self.eps, "drop": drop}
-        params = [p for l in self.layer for p in l.ordered_params()]
+        # the per-layer views into the flat buffers and the parameter list only change when the
+        # flat buffers are rebuilt: cache them (saves ~1 ms of Python per step over 9 layers)
+        cache = self.__dict__.setdefault("_packed_cache", {})
+        key = (flat.flat.data_ptr(), flat.mirror.data_ptr(), len(self.layer))
+        if cache.get("key") != key:
+            cache.clear()
+            cache["key"] = key
+            cache["layers"] = [l.weights(flat) for l in self.layer]
+            cache["params"] = [p for l in self.layer for p in l.ordered_params()]
+        params = cache["params"]
+        cfg = {"layers": cache["layers"], "att": att, "heads": self.num_heads, "eps": self.eps,
+               "drop": drop, "cache": cache}
         cfg["flat"] = flat     # backward marks the bf16 mirror stale (an optimizer step follows)
         return Fn.transformer_stack(x, cfg, params)
 

@@ -45,7 +45,15 @@ def stop_gemm_profile():
     return {"ms": ms.value, "flops": fl.value, "launches": n.value}
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream():
+    """Handle of torch's current CUDA stream (the raw getter skips building a Stream object:
+    ~0.5 us instead of ~15 us, on a path called for every launch)."""
+    if _raw_stream is not None and _raw_device is not None:
+        return C.c_void_p(_raw_stream(_raw_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -205,8 +205,9 @@ class ReprPlan:
     """Everything HierarchicalVlModel.forward_repr needs for one batch."""
 
     def __init__(self, batch):
-        max_vl = batch["f_v_feats"].shape[1]
-        max_sl = batch["f_sub_input_ids"].shape[1]
+        # `plan_inputs` dicts carry the two padded lengths instead of the big tensors
+        max_vl = batch["_max_vl"] if "_max_vl" in batch else batch["f_v_feats"].shape[1]
+        max_sl = batch["_max_sl"] if "_max_sl" in batch else batch["f_sub_input_ids"].shape[1]
         self.f = FPlan(batch["f_attn_masks"], batch["f_gather_index"], max_vl, max_sl)
         self.c = CPlan(batch["c_attn_masks"], self.f, batch["num_subs"],
                        batch["sub_idx2frame_idx"])
@@ -295,6 +296,56 @@ class JointPlan:
 
 
 PLAN_KEY = "_hero_plan"
+_REPR_KEYS = ("f_attn_masks", "f_gather_index", "c_attn_masks", "num_subs", "sub_idx2frame_idx")
+
+
+def plan_inputs(batch, kind="repr"):
+    """The small, picklable part of a host batch that a plan is built from (masks and index
+    lists as numpy arrays; none of the feature tensors) — what is shipped to a PlanPool worker."""
+    if kind != "repr":
+        return {"attn_masks": _np(batch["attn_masks"])}
+    d = {k: (_np(batch[k]) if torch.is_tensor(batch[k]) else batch[k]) for k in _REPR_KEYS}
+    d["_max_vl"] = int(batch["f_v_feats"].shape[1])
+    d["_max_sl"] = int(batch["f_sub_input_ids"].shape[1])
+    return d
+
+
+def build_plans(repr_in, txt_in=None):
+    """ReprPlan (+ TxtPlan and the JointPlan of the fused video+query pass) from `plan_inputs`
+    dicts. Pure numpy: runs in collate workers / PlanPool processes."""
+    rplan = ReprPlan(repr_in)
+    if txt_in is None:
+        return rplan, None
+    tplan = TxtPlan(txt_in["attn_masks"])
+    rplan.__dict__["_joint"] = JointPlan(rplan, tplan)
+    return rplan, tplan
+
+
+class PlanPool:
+    """Builds plans in worker processes, the way the reference builds its gather indices inside
+    DataLoader collate workers (data/data.py video_collate, model/model.py:189-193) — the training
+    process only uploads the finished index arrays. `submit` returns a future whose `result()` is
+    (ReprPlan, TxtPlan | None); `attach(future, batch, txt_batch)` stores them in the batch dicts."""
+
+    def __init__(self, workers=2):
+        import concurrent.futures as cf
+        import multiprocessing as mp
+        self._ex = cf.ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn"))
+
+    def submit(self, batch, txt_batch=None):
+        return self._ex.submit(build_plans, plan_inputs(batch),
+                               None if txt_batch is None else plan_inputs(txt_batch, "txt"))
+
+    @staticmethod
+    def attach(future, batch, txt_batch=None):
+        rplan, tplan = future.result()
+        batch[PLAN_KEY] = rplan
+        if txt_batch is not None:
+            txt_batch[PLAN_KEY] = tplan
+        return batch, txt_batch
+
+    def shutdown(self):
+        self._ex.shutdown(wait=False, cancel_futures=True)
 
 
 def attach_plan(batch, kind="repr"):

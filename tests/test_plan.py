@@ -98,3 +98,28 @@ def test_dense_canonical_batch_shapes():
     plan = ReprPlan(vb)
     assert plan.f.seq.n_tok == 40 * 25 and plan.c.seq.n_tok == 200
     assert plan.c.n_pairs == 200 and plan.f.seq.max_len == 25 and plan.c.seq.max_len == 100
+
+
+def test_plan_pool_builds_the_same_plans_in_worker_processes():
+    """PlanPool (collate-side plan building in worker processes) == attach_plan in-process, and
+    the JointPlan of the fused video+query pass arrives prebuilt."""
+    from hero_b200.plan import PLAN_KEY, JointPlan, PlanPool, attach_plan
+    vb, qb = synth.syn_tvr_ragged(batch_size=3, seed=5, t_range=(10, 20), s_range=(2, 4),
+                                  l_range=(4, 10))
+    pool = PlanPool(workers=1)
+    try:
+        fut = pool.submit(vb, qb)
+        vb2, qb2 = PlanPool.attach(fut, dict(vb), dict(qb))
+    finally:
+        pool.shutdown()
+    ref_v = attach_plan(dict(vb))[PLAN_KEY]
+    ref_q = attach_plan(dict(qb), kind="txt")[PLAN_KEY]
+    got_v, got_q = vb2[PLAN_KEY], qb2[PLAN_KEY]
+    for a, b in ((got_v.f.arrays("f_"), ref_v.f.arrays("f_")),
+                 (got_v.c.arrays("c_"), ref_v.c.arrays("c_")),
+                 (got_q.f.arrays("f_"), ref_q.f.arrays("f_")),
+                 (got_v.__dict__["_joint"].arr, JointPlan(ref_v, ref_q).arr)):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    assert got_v.__dict__["_joint"].t is got_q

@@ -20,8 +20,7 @@ dq = torch.randn(32, 16, 768, device=dev) * 1e-2
 
 def step():
     gflat.zero_()
-    clip = model(vbd, "repr")
-    q = model.f_encoder(qbd, "txt")[0]
+    clip, q = model.forward_repr_txt(vbd, qbd)
     torch.autograd.backward([clip, q], [dclip, dq])
 
 
@@ -36,5 +35,5 @@ pr.disable()
 torch.cuda.synchronize()
 for key in ("cumulative", "tottime"):
     s = io.StringIO()
-    pstats.Stats(pr, stream=s).sort_stats(key).print_stats(28)
-    print(s.getvalue()[:6000])
+    pstats.Stats(pr, stream=s).sort_stats(key).print_stats(45)
+    print(s.getvalue()[:9000])
