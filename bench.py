@@ -132,7 +132,8 @@ def run_ours(args):
     from hero_b200 import distributed as hdist
     from hero_b200 import ops, synth
     from hero_b200.params import flat_of
-    from hero_b200.plan import PLAN_KEY, PlanPool, attach_plan
+    from hero_b200.loader import BatchStager, record_plans
+    from hero_b200.plan import PlanPool, attach_plan
     from hero_b200.optim import FusedAdamW
 
     rank, world, local_rank = hdist.init()
@@ -251,7 +252,7 @@ def run_ours(args):
                                            4)}
 
     # ------------------------------------------------------------- end-to-end from pinned host
-    copy_stream = torch.cuda.Stream(device)
+    stager = BatchStager(device, depth=3)
 
     def h2d_bytes(b):
         return sum(v.numel() * v.element_size() for v in b.values() if torch.is_tensor(v))
@@ -278,15 +279,9 @@ def run_ours(args):
         t2 = time.perf_counter()
         stage_t["plan_wait"] += t1 - t0
         stage_t["plan_submit"] += t2 - t1
-        with torch.cuda.stream(copy_stream):
-            vb_dev = synth.to_device(vb, device, non_blocking=True)
-            qb_dev = synth.to_device(qb, device, non_blocking=True)
-            for plan in (vb_dev[PLAN_KEY], qb_dev[PLAN_KEY], vb_dev[PLAN_KEY].__dict__["_joint"]):
-                plan.to(device)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
+        (vb_dev, qb_dev), ev, slot = stager.stage(vb, qb)    # preallocated ring, side stream
         stage_t["h2d_enqueue"] += time.perf_counter() - t2
-        return vb_dev, qb_dev, ev
+        return vb_dev, qb_dev, ev, slot
 
     result_host = torch.zeros(2, dtype=torch.float32).pin_memory()
 
@@ -302,15 +297,10 @@ def run_ours(args):
         nxt = stage(0, n)
         for i in range(n):
             t_a = time.perf_counter()
-            vb_dev, qb_dev, ev = nxt
+            vb_dev, qb_dev, ev, ring_slot = nxt
             cur = torch.cuda.current_stream()
             cur.wait_event(ev)
-            for b in (vb_dev, qb_dev):      # allocator safety across streams (loader.py:135-138)
-                for v in b.values():
-                    if torch.is_tensor(v):
-                        v.record_stream(cur)
-                b[PLAN_KEY].dev.flat.record_stream(cur)
-            vb_dev[PLAN_KEY].__dict__["_joint"].dev.flat.record_stream(cur)
+            record_plans((vb_dev, qb_dev), cur)   # allocator safety across streams
             gflat.zero_()
             t_b = time.perf_counter()
             clip = fwd_bwd(vb_dev, qb_dev)
@@ -319,6 +309,7 @@ def run_ours(args):
             slot.copy_(clip[0, 0, :8].float().sum().reshape(1), non_blocking=True)   # D2H
             done = torch.cuda.Event()
             done.record(cur)
+            stager.release(ring_slot, cur)
             t_d = time.perf_counter()
             if i + 1 < n:
                 nxt = stage(i + 1, n)                   # plan upload + H2D overlap this step's compute

@@ -710,13 +710,25 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   if (!g->out_f32_accumulate) {
     k_splits = 1;
   } else if (k_splits <= 0) {
+    // Split K so that the (tiles x splits) work items fill whole waves of the resident CTAs
+    // (pairs): minimise  waves(s) * (k-blocks per split + epilogue)  over s. The epilogue of a
+    // split-K tile (128 x BLOCK_N fp32 atomics, not overlapped with anything when a CTA owns a
+    // single tile) costs about as much as 10 k-blocks of main loop. Keeps >= 4 k-blocks per
+    // split so the TMA pipeline has something to overlap; ties go to the smaller split count.
     const int tiles = s.num_m_blocks * s.num_n_blocks;
-    k_splits = 1;
     const int slots = pair ? sms / 2 : sms;   // concurrently resident tiles
-    if (tiles < slots) k_splits = ceil_div(slots, tiles);
-    // keep at least 4 k-blocks per split so the pipeline has something to overlap
-    if (k_splits > s.k_blocks / 4) k_splits = s.k_blocks / 4;
-    if (k_splits < 1) k_splits = 1;
+    const int max_s = s.k_blocks / 4 > 1 ? s.k_blocks / 4 : 1;
+    const int epi = 10;
+    long long best_cost = -1;
+    k_splits = 1;
+    for (int sp = 1; sp <= max_s && sp <= 64; ++sp) {
+      const long long waves = ceil_div(tiles * sp, slots);
+      const long long cost = waves * (ceil_div(s.k_blocks, sp) + epi);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        k_splits = sp;
+      }
+    }
   }
   if (k_splits > s.k_blocks) k_splits = s.k_blocks;
   s.k_splits = k_splits;

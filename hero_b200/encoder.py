@@ -292,7 +292,9 @@ class CrossModalTrm(RobertaPreTrainedModel):
         sv, sq = cfg_v.get("txt_slot_pos"), cfg_q.get("txt_slot_pos")
         if sv is not None and sq is not None:
             n = min(sv.numel(), sq.numel())
-            same = bool((sv[:n] == sq[:n]).all()) if n else True    # both are the collate's arange
+            same = jplan.same_slot_pos        # host-side decision of the plan (no device sync)
+            if same is None:                  # plan built from device tensors: compare here
+                same = bool((sv[:n] == sq[:n]).all()) if n else True
             cfg["txt_slot_pos"] = (sv if sv.numel() >= sq.numel() else sq) if same else None
         else:
             cfg["txt_slot_pos"] = None

@@ -29,6 +29,14 @@ def _np(t):
     return np.asarray(t)
 
 
+def _host_ids(t):
+    """Small id tensor -> host int64 array [rows, L], or None if absent / not on the host."""
+    if t is None or (torch.is_tensor(t) and t.device.type != "cpu"):
+        return None
+    a = np.asarray(_np(t), np.int64)
+    return a.reshape(1, -1) if a.ndim == 1 else a
+
+
 class DeviceIndex:
     """A bundle of int32 index arrays uploaded to the device with a single H2D copy."""
 
@@ -217,6 +225,9 @@ class ReprPlan:
         self.f_txtpos_off, self.f_txtpos_idx = table_csr(self.f.txt_j, max(max_sl, 1))
         self.f_imgpos_off, self.f_imgpos_idx = table_csr(self.f.img_k, max(max_vl, 1))
         self.c_pos_off, self.c_pos_idx = table_csr(self.c.c_t, max(self.shape_c[1], 1))
+        # subtitle position ids as the collate made them (lets JointPlan decide on the host
+        # whether video and query rows share one slot -> position table)
+        self.sub_pos = _host_ids(batch.get("f_sub_pos_ids") if hasattr(batch, "get") else None)
         self.dev = None
 
     def to(self, device):
@@ -233,10 +244,11 @@ class ReprPlan:
 class TxtPlan:
     """Text-only rows (CrossModalTrm 'txt' task, and the generic BertEncoder API)."""
 
-    def __init__(self, attn_mask, with_embedding=True):
+    def __init__(self, attn_mask, with_embedding=True, pos_ids=None):
         self.f = FPlan(attn_mask)
         self.shape = tuple(_np(attn_mask).shape)
         self.with_embedding = with_embedding
+        self.pos = _host_ids(pos_ids)
         if with_embedding:
             self.pos_off, self.pos_idx = table_csr(self.f.txt_j, max(self.shape[1], 1))
         self.dev = None
@@ -280,6 +292,14 @@ class JointPlan:
         }
         n_slot = max(fv.max_sl, fq.max_sl, 1)
         self.arr["j_txtpos_off"], self.arr["j_txtpos_idx"] = table_csr(self.arr["j_txt_j"], n_slot)
+        # Do both row kinds use the same slot -> position map (the collate's arange)? Decided here
+        # on the host when the plans saw the position ids; None = unknown (the encoder then has
+        # to compare the device tensors, which costs a device sync per step).
+        self.same_slot_pos = None
+        pv, pq = getattr(rplan, "sub_pos", None), getattr(tplan, "pos", None)
+        if pv is not None and pq is not None and pv.shape[0] == 1 and pq.shape[0] == 1:
+            n = min(pv.shape[1], pq.shape[1])
+            self.same_slot_pos = bool(np.array_equal(pv[0, :n], pq[0, :n]))
         self.dev = None
 
     def to(self, device):
@@ -302,9 +322,14 @@ _REPR_KEYS = ("f_attn_masks", "f_gather_index", "c_attn_masks", "num_subs", "sub
 def plan_inputs(batch, kind="repr"):
     """The small, picklable part of a host batch that a plan is built from (masks and index
     lists as numpy arrays; none of the feature tensors) — what is shipped to a PlanPool worker."""
+    def opt(key):
+        v = batch.get(key) if hasattr(batch, "get") else None
+        return None if v is None else _np(v)
+
     if kind != "repr":
-        return {"attn_masks": _np(batch["attn_masks"])}
+        return {"attn_masks": _np(batch["attn_masks"]), "pos_ids": opt("pos_ids")}
     d = {k: (_np(batch[k]) if torch.is_tensor(batch[k]) else batch[k]) for k in _REPR_KEYS}
+    d["f_sub_pos_ids"] = opt("f_sub_pos_ids")
     d["_max_vl"] = int(batch["f_v_feats"].shape[1])
     d["_max_sl"] = int(batch["f_sub_input_ids"].shape[1])
     return d
@@ -316,7 +341,7 @@ def build_plans(repr_in, txt_in=None):
     rplan = ReprPlan(repr_in)
     if txt_in is None:
         return rplan, None
-    tplan = TxtPlan(txt_in["attn_masks"])
+    tplan = TxtPlan(txt_in["attn_masks"], pos_ids=txt_in.get("pos_ids"))
     rplan.__dict__["_joint"] = JointPlan(rplan, tplan)
     return rplan, tplan
 
@@ -354,5 +379,6 @@ def attach_plan(batch, kind="repr"):
     if kind == "repr":
         batch[PLAN_KEY] = ReprPlan(batch)
     else:
-        batch[PLAN_KEY] = TxtPlan(batch["attn_masks"])
+        batch[PLAN_KEY] = TxtPlan(batch["attn_masks"],
+                                  pos_ids=batch.get("pos_ids") if hasattr(batch, "get") else None)
     return batch

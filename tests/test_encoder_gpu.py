@@ -237,6 +237,58 @@ def test_per_layer_backward_with_grad_hook_matches_whole_stack(tmp_path):
     assert float((a - b).norm() / a.norm()) < 1e-5
 
 
+def test_hot_path_never_synchronises_with_collate_side_plans(tmp_path):
+    """With plans attached on the host (collate / PlanPool) forward + backward must not contain a
+    single device synchronisation — a hidden `.item()` / bool(tensor) drains the launch queue
+    every step. torch's sync debug mode turns any such call into an error."""
+    from hero_b200.params import flat_of
+    from hero_b200.plan import attach_plan
+    d = dict(hidden=768, inter=3072, heads=12, f_layers=2, c_layers=1, vocab=50272,
+             vfeat_dim=4352, max_img_len=100)
+    P = orc.seeded_weights(orc.param_shapes(f_layers=2, c_layers=1), seed=8)
+    model = _build(tmp_path, d, P).train()
+    flat_of(model, torch.device("cuda")).ensure_flat_grads()
+    vb, qb = synth.syn_tvr_ragged(batch_size=2, seed=9, t_range=(10, 20), s_range=(2, 4),
+                                  l_range=(4, 10))
+    vbd = synth.to_device(attach_plan(dict(vb)), "cuda")
+    qbd = synth.to_device(attach_plan(dict(qb), kind="txt"), "cuda")
+    for b in (vbd, qbd):
+        b["_hero_plan"].to("cuda")
+    clip, q = model.forward_repr_txt(vbd, qbd)          # warm-up (flat buffers, caches, joint plan)
+    (clip.float().mean() + q.float().mean()).backward()
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        clip, q = model.forward_repr_txt(vbd, qbd)
+        torch.autograd.backward([clip, q], [torch.ones_like(clip), torch.ones_like(q)])
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    torch.cuda.synchronize()
+    assert torch.isfinite(clip).all()
+
+
+def test_prefetch_loader_stages_batches_with_plans():
+    """hero_b200.loader.PrefetchLoader (data/loader.py:89-144): device batches in order, equal to
+    the host batches, plans attached (in-process here) and uploaded; slots are recycled."""
+    from hero_b200.loader import PrefetchLoader
+    from hero_b200.plan import PLAN_KEY
+    host = []
+    for seed in range(5):
+        vb, qb = synth.syn_tvr_ragged(batch_size=2, seed=20 + seed, t_range=(10, 20),
+                                      s_range=(2, 4), l_range=(4, 10))
+        host.append(({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in vb.items()},
+                     {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in qb.items()}))
+    got = 0
+    for (vbd, qbd), (vb, qb) in zip(PrefetchLoader(host, "cuda:0", depth=3), host):
+        assert vbd[PLAN_KEY].dev is not None and qbd[PLAN_KEY].dev is not None
+        for dev_b, host_b in ((vbd, vb), (qbd, qb)):
+            for k, v in host_b.items():
+                if torch.is_tensor(v):
+                    assert dev_b[k].is_cuda and torch.equal(dev_b[k].cpu(), v), k
+        got += 1
+    assert got == 5
+
+
 def test_fused_adamw_follows_reference_rule_with_param_groups():
     """FusedAdamW on the flat buffer == optim/adamw.py:80-104 per parameter, with the no-decay
     grouping of optim/misc.py:22 (names containing 'bias' / 'LayerNorm.*'), clipping folded in."""
