@@ -51,10 +51,13 @@ struct AttnTcArgs {
   float drop_scale;
 };
 
-// Dropout mask index of probability (query token, head, key position inside the sequence): the
-// same in forward and backward and independent of the tiling.
-__device__ __forceinline__ uint32_t attn_drop_index(int tok, int heads, int head, int jrel) {
-  return ((uint32_t)tok * (uint32_t)heads + (uint32_t)head) * 128u + (uint32_t)jrel;
+// Dropout: ONE 32-bit hash decides the two probabilities (query token, head, tile columns 2u and
+// 2u + 1), 16 bits each; forward and backward regenerate the same words from the same plan.
+// (One hash per element was ~40 % of the softmax instruction count.)
+__device__ __forceinline__ uint32_t attn_drop_word(uint32_t key, int tok, int heads, int head,
+                                                   int col_pair) {
+  return hash_u32(key, ((uint32_t)tok * (uint32_t)heads + (uint32_t)head) * 64u +
+                           (uint32_t)col_pair);
 }
 
 // Each thread parks its 64-feature row (two 32-column TMEM fragments, optionally scaled) in a
@@ -179,6 +182,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
     }
   }
   float sum = 0.f;
+  const uint32_t t16 = a.drop_thr >> 16;
   for (int c = 0; c < 4; ++c) {
     uint32_t pk[16];
     const bool touch = !(c * 32 >= whi || c * 32 + 32 <= wlo);   // warp-uniform
@@ -194,16 +198,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
         if (col + 1 >= lo && col + 1 < hi) p1 = ex2((__uint_as_float(r[j + 1]) - mx) * a.scale_log2);
         sum += p0 + p1;
         if (a.drop_thr != 0u) {
-          if (!dropout_keep(a.drop_key, attn_drop_index(tok0 + i, a.heads, head, col - lo),
-                            a.drop_thr))
-            p0 = 0.f;
-          else
-            p0 *= a.drop_scale;
-          if (!dropout_keep(a.drop_key, attn_drop_index(tok0 + i, a.heads, head, col + 1 - lo),
-                            a.drop_thr))
-            p1 = 0.f;
-          else
-            p1 *= a.drop_scale;
+          const uint32_t h = attn_drop_word(a.drop_key, tok0 + i, a.heads, head, col >> 1);
+          p0 = ((h & 0xFFFFu) >= t16) ? p0 * a.drop_scale : 0.f;
+          p1 = ((h >> 16) >= t16) ? p1 * a.drop_scale : 0.f;
         }
         pk[j >> 1] = pack_bf16x2(p0, p1);
       }
@@ -372,6 +369,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   }
   const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
   const float row_lse = valid ? lse[(long long)(tok0 + i) * a.heads + head] : 0.f;
+  const uint32_t t16 = a.drop_thr >> 16;
+  const float keep_scale = a.drop_thr != 0u ? a.drop_scale : 1.0f;
   for (int c = 0; c < 4; ++c) {
     uint32_t pk[16], dk[16];
     const bool touch = !(c * 32 >= whi || c * 32 + 32 <= wlo);
@@ -383,19 +382,19 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
         float pp[2], ds[2];
+        uint32_t h = 0xFFFFFFFFu;   // both halves >= any threshold: keep
+        if (a.drop_thr != 0u)
+          h = attn_drop_word(a.drop_key, tok0 + i, a.heads, head, (c * 32 + j) >> 1);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           const int col = c * 32 + j + t;
-          float p = 0.f, dp = 0.f, keep = 1.0f;
+          float p = 0.f, dp = 0.f;
           if (col >= lo && col < hi) {
             p = ex2(__uint_as_float(r[j + t]) * a.scale_log2 - row_lse);
             dp = __uint_as_float(d[j + t]);
-            if (a.drop_thr != 0u)
-              keep = dropout_keep(a.drop_key, attn_drop_index(tok0 + i, a.heads, head, col - lo),
-                                  a.drop_thr)
-                         ? a.drop_scale
-                         : 0.f;
           }
+          const uint32_t bits = t ? (h >> 16) : (h & 0xFFFFu);
+          const float keep = (bits >= t16) ? keep_scale : 0.f;
           pp[t] = p * keep;                          // dropped probability (for dV)
           ds[t] = p * (dp * keep - Di) * a.scale;    // d(raw QK^T score)
         }

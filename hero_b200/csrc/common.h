@@ -12,6 +12,9 @@ namespace hero {
 char* error_buffer();
 int set_error(int status, const char* fmt, ...);
 int sm_count();
+// True while hero_gemm_profile_begin/end brackets GEMM launches with timing events (the layer
+// runtime then keeps everything on one stream so per-launch durations do not overlap).
+bool gemm_profile_active();
 
 #define HERO_CUDA_CHECK(expr)                                                              \
   do {                                                                                     \

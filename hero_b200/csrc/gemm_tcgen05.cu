@@ -602,6 +602,8 @@ struct GemmProfile {
 };
 static GemmProfile g_prof;
 
+bool gemm_profile_active() { return g_prof.on; }
+
 }  // namespace hero
 
 extern "C" int hero_gemm_profile_begin(void) {

@@ -48,6 +48,37 @@ static void ln_base(hero_ln_args* a, const void* x, const float* gamma, const fl
   a->drop_scale = 1.0f; a->drop2_scale = 1.0f;
 }
 
+// Weight-gradient stream. The backward of a layer is a dependency chain (LN' -> dgrad GEMMs ->
+// attention') plus four weight-gradient GEMMs and two bias column sums that hang off it and are
+// consumed only by the optimizer. They run on a library-owned second stream, ordered by events,
+// so their CTAs fill the SMs that the chain's kernels leave idle: launch gaps, wave tails, and
+// half of the machine for the 25-block GEMMs of the 3200-token temporal encoder.
+struct SideStream {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ready = nullptr;     // chain -> side: an operand of the next weight gradient exists
+  cudaEvent_t done[2] = {nullptr, nullptr};   // side -> chain: layer's reads of scratch[parity] over
+  cudaEvent_t joined = nullptr;
+};
+
+static int side_stream(SideStream** out) {
+  static SideStream ctx[16];
+  int dev = 0;
+  HERO_CUDA_CHECK(cudaGetDevice(&dev));
+  HERO_REQUIRE(dev >= 0 && dev < 16, "stack: unsupported device ordinal %d", dev);
+  SideStream& c = ctx[dev];
+  if (c.stream == nullptr) {
+    HERO_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    HERO_CUDA_CHECK(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
+    HERO_CUDA_CHECK(cudaEventCreateWithFlags(&c.done[0], cudaEventDisableTiming));
+    HERO_CUDA_CHECK(cudaEventCreateWithFlags(&c.done[1], cudaEventDisableTiming));
+    HERO_CUDA_CHECK(cudaEventCreateWithFlags(&c.joined, cudaEventDisableTiming));
+    c.device = dev;
+  }
+  *out = &c;
+  return HERO_OK;
+}
+
 #define HERO_TRY(expr)        \
   do {                        \
     int _rc = (expr);         \
@@ -70,8 +101,10 @@ static int check_stack(const hero_stack_args* s, bool bwd) {
 using namespace hero;
 
 extern "C" int64_t hero_bert_stack_bwd_scratch_bytes(int32_t n_tok, int32_t hidden, int32_t inter) {
-  // ds2, ds2_d, da, ds1, ds1_d, dcx, dx_a, dx_b : 8 x [n_tok, H]; dpre [n_tok, I]; dqkv [n_tok, 3H]
-  const int64_t row = (int64_t)(8 + 3) * hidden + inter;
+  // per layer parity (x2: the weight-gradient stream may still read layer l's while layer l-1 is
+  // being written): ds2, ds2_d, ds1, ds1_d [n_tok, H], dpre [n_tok, I], dqkv [n_tok, 3H];
+  // single: da, dcx, dx_a, dx_b [n_tok, H]
+  const int64_t row = 2 * ((int64_t)(4 + 3) * hidden + inter) + 4 * (int64_t)hidden;
   return ((int64_t)n_tok * row * 2 + 1023) / 1024 * 1024 + 1024 * 16;
 }
 
@@ -125,16 +158,34 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
     p += (elems * 2 + 1023) / 1024 * 1024;
     return reinterpret_cast<void*>(r);
   };
-  void* ds2 = take((long long)M * H);
-  void* ds2_d = take((long long)M * H);
+  void *ds2_[2], *ds2_d_[2], *ds1_[2], *ds1_d_[2], *dpre_[2], *dqkv_[2];
+  for (int p2 = 0; p2 < 2; ++p2) {
+    ds2_[p2] = take((long long)M * H);
+    ds2_d_[p2] = take((long long)M * H);
+    ds1_[p2] = take((long long)M * H);
+    ds1_d_[p2] = take((long long)M * H);
+    dpre_[p2] = take((long long)M * I);
+    dqkv_[p2] = take((long long)M * 3 * H);
+  }
   void* da = take((long long)M * H);
-  void* ds1 = take((long long)M * H);
-  void* ds1_d = take((long long)M * H);
   void* dcx = take((long long)M * H);
   void* dxa = take((long long)M * H);
   void* dxb = take((long long)M * H);
-  void* dpre = take((long long)M * I);
-  void* dqkv = take((long long)M * 3 * H);
+
+  // weight gradients on the second stream unless per-launch GEMM timing is on
+  cudaStream_t chain = reinterpret_cast<cudaStream_t>(stream);
+  SideStream* side = nullptr;
+  const bool two_streams = !gemm_profile_active();
+  if (two_streams) HERO_TRY(side_stream(&side));
+  void* wstream = two_streams ? reinterpret_cast<void*>(side->stream) : stream;
+  // an operand of the next weight gradient has just been produced on the chain
+  auto publish = [&]() -> int {
+    if (!two_streams) return HERO_OK;
+    HERO_CUDA_CHECK(cudaEventRecord(side->ready, chain));
+    HERO_CUDA_CHECK(cudaStreamWaitEvent(side->stream, side->ready, 0));
+    return HERO_OK;
+  };
+  bool done_recorded[2] = {false, false};
 
   const void* dy = s->dout;
   for (int l = s->n_layers - 1; l >= 0; --l) {
@@ -144,6 +195,12 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
     const void* h_in = (l == 0) ? s->x : s->acts[l - 1].out;
     const bool hd = s->hidden_drop_threshold != 0u;
     HERO_REQUIRE(A.pre != nullptr, "stack bwd: layer %d has no saved FFN pre-activation", l);
+    const int par = l & 1;
+    void *ds2 = ds2_[par], *ds2_d = ds2_d_[par], *ds1 = ds1_[par], *ds1_d = ds1_d_[par];
+    void *dpre = dpre_[par], *dqkv = dqkv_[par];
+    // scratch[par] was last read by the weight gradients of layer l + 2
+    if (two_streams && done_recorded[par])
+      HERO_CUDA_CHECK(cudaStreamWaitEvent(chain, side->done[par], 0));
 
     // LN2 backward: ds2 (residual branch) and its dropout-masked copy (FFN-down branch)
     hero_ln_args ln;
@@ -159,12 +216,14 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
       g2 = ds2_d;
     }
     HERO_TRY(hero_ln_bwd(&ln, stream));
+    HERO_TRY(publish());
     // FFN down
-    HERO_TRY(Gemm(g2, H, 1, A.f, I, 1, H, I, M, G.dw2, I).f32_accumulate().run(stream));
+    HERO_TRY(Gemm(g2, H, 1, A.f, I, 1, H, I, M, G.dw2, I).f32_accumulate().run(wstream));
     HERO_TRY(Gemm(g2, H, 0, W.w2, I, 1, M, I, H, dpre, I).act(ACT_GELU_GRAD).aux_in(A.pre, I).run(stream));
+    HERO_TRY(publish());
     // FFN up
-    HERO_TRY(hero_colsum_bf16(dpre, I, M, I, G.db1, stream));
-    HERO_TRY(Gemm(dpre, I, 1, A.a, H, 1, I, H, M, G.dw1, H).f32_accumulate().run(stream));
+    HERO_TRY(hero_colsum_bf16(dpre, I, M, I, G.db1, wstream));
+    HERO_TRY(Gemm(dpre, I, 1, A.a, H, 1, I, H, M, G.dw1, H).f32_accumulate().run(wstream));
     HERO_TRY(Gemm(dpre, I, 0, W.w1, H, 1, M, H, I, da, H).resid(ds2, H).run(stream));
     // LN1 backward
     ln_base(&ln, A.s1, W.ln1_g, nullptr, s->eps, M, H, A.mean1, A.rstd1);
@@ -179,20 +238,30 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
       g1 = ds1_d;
     }
     HERO_TRY(hero_ln_bwd(&ln, stream));
+    HERO_TRY(publish());
     // attention output projection
-    HERO_TRY(Gemm(g1, H, 1, A.cx, H, 1, H, H, M, G.dwo, H).f32_accumulate().run(stream));
+    HERO_TRY(Gemm(g1, H, 1, A.cx, H, 1, H, H, M, G.dwo, H).f32_accumulate().run(wstream));
     HERO_TRY(Gemm(g1, H, 0, W.wo, H, 1, M, H, H, dcx, H).run(stream));
     // attention core
     HERO_TRY(hero_attn_bwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, dcx, A.lse,
                            dqkv, M, s->n_tiles, s->heads, 64, scale, s->attn_drop_threshold,
                            site_key(s->drop_key, s->first_layer + l, 0), s->attn_drop_scale, stream));
+    HERO_TRY(publish());
     // QKV projection
-    HERO_TRY(hero_colsum_bf16(dqkv, 3 * H, M, 3 * H, G.dbqkv, stream));
-    HERO_TRY(Gemm(dqkv, 3 * H, 1, h_in, H, 1, 3 * H, H, M, G.dwqkv, H).f32_accumulate().run(stream));
+    HERO_TRY(hero_colsum_bf16(dqkv, 3 * H, M, 3 * H, G.dbqkv, wstream));
+    HERO_TRY(Gemm(dqkv, 3 * H, 1, h_in, H, 1, 3 * H, H, M, G.dwqkv, H).f32_accumulate().run(wstream));
+    if (two_streams) {
+      HERO_CUDA_CHECK(cudaEventRecord(side->done[par], side->stream));
+      done_recorded[par] = true;
+    }
     void* dx = (l == 0 && s->dx) ? s->dx : ((l & 1) ? dxa : dxb);
     if (l > 0 || s->dx)
       HERO_TRY(Gemm(dqkv, 3 * H, 0, W.wqkv, H, 1, M, H, 3 * H, dx, H).resid(ds1, H).run(stream));
     dy = dx;
+  }
+  if (two_streams && s->n_layers > 0) {   // every gradient is complete in `stream` order on return
+    HERO_CUDA_CHECK(cudaEventRecord(side->joined, side->stream));
+    HERO_CUDA_CHECK(cudaStreamWaitEvent(chain, side->joined, 0));
   }
   return HERO_OK;
 }
