@@ -1,6 +1,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace hero {
@@ -16,6 +18,14 @@ int set_error(int status, const char* fmt, ...) {
   vsnprintf(error_buffer(), 512, fmt, ap);
   va_end(ap);
   return status;
+}
+
+bool serial_profiling() {
+  static const bool on = [] {
+    const char* v = getenv("HERO_SERIAL_PROFILE");
+    return v != nullptr && v[0] == '1';
+  }();
+  return on;
 }
 
 int sm_count() {

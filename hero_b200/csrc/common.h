@@ -15,6 +15,9 @@ int sm_count();
 // True while hero_gemm_profile_begin/end brackets GEMM launches with timing events (the layer
 // runtime then keeps everything on one stream so per-launch durations do not overlap).
 bool gemm_profile_active();
+// HERO_SERIAL_PROFILE=1 (development): no programmatic dependent launch and a single stream, so a
+// timeline profiler sees every kernel's own duration (tools/step_profile.py).
+bool serial_profiling();
 
 #define HERO_CUDA_CHECK(expr)                                                              \
   do {                                                                                     \
@@ -53,7 +56,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = serial_profiling() ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -542,7 +542,7 @@ static int launch(const GemmMaps& tm, const GemmShape& s, const GemmEpilogue& e,
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = serial_profiling() ? 0 : 1;
   cfg.numAttrs = 1;
   if (CTA2) {
     const int clusters = total < sms / 2 ? total : sms / 2;   // one CTA pair per TPC

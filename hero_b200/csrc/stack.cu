@@ -175,7 +175,7 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
   // weight gradients on the second stream unless per-launch GEMM timing is on
   cudaStream_t chain = reinterpret_cast<cudaStream_t>(stream);
   SideStream* side = nullptr;
-  const bool two_streams = !gemm_profile_active();
+  const bool two_streams = !gemm_profile_active() && !serial_profiling();
   if (two_streams) HERO_TRY(side_stream(&side));
   void* wstream = two_streams ? reinterpret_cast<void*>(side->stream) : stream;
   // an operand of the next weight gradient has just been produced on the chain

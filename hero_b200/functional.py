@@ -115,8 +115,6 @@ class _TransformerStack(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         cfg, params = ctx.cfg, ctx.params
-        if cfg.get("flat") is not None:
-            cfg["flat"].mark_dirty()        # the masters are about to change (optimizer step)
         n = len(cfg["layers"])
         grads, ret = _stack_sinks(cfg, params, ctx.x.shape[1], dout.device)
         hook = GRAD_HOOK[0]
@@ -307,8 +305,6 @@ class _CrossModalEmbed(torch.autograd.Function):
                        add_idx=cfg["img_mask"], d_add_tab=dmask, add_pad_idx=0, dgamma=diln_w,
                        dbeta=diln_b)
         ctx.st = None
-        if cfg.get("flat") is not None:
-            cfg["flat"].mark_dirty()
         return (None,) + tuple(grads)
 
 

@@ -10,6 +10,8 @@ kernels and is refreshed by ONE cast kernel when the masters changed.
 """
 import re
 
+import weakref
+
 import torch
 
 from . import ops
@@ -50,6 +52,24 @@ def is_no_decay(name):
     return any(nd in name for nd in NO_DECAY)
 
 
+# Every live FlatParams; any torch optimizer step marks their bf16 mirrors stale (global post-step
+# hook). The reference's optimizers update `p.data` in place (optim/adamw.py:94-104), which does
+# not bump `p._version`, so the version probe in `ensure` alone would miss them.
+_LIVE = weakref.WeakSet()
+_HOOK = []
+
+
+def _after_optimizer_step(optimizer, args, kwargs):
+    for fp in list(_LIVE):
+        fp.mark_dirty()
+
+
+def _install_optimizer_hook():
+    if not _HOOK:
+        from torch.optim.optimizer import register_optimizer_step_post_hook
+        _HOOK.append(register_optimizer_step_post_hook(_after_optimizer_step))
+
+
 class FlatParams:
     def __init__(self, module):
         self.module = module
@@ -63,6 +83,8 @@ class FlatParams:
         self._stale = False
         self._probe = []
         self._hooked = False
+        _LIVE.add(self)
+        _install_optimizer_hook()
 
     # ------------------------------------------------------------------ layout
     def _needs_flatten(self, device):
@@ -125,6 +147,9 @@ class FlatParams:
         return self
 
     def mark_dirty(self):
+        """The fp32 masters changed: refresh the bf16 mirror before the next forward. Called
+        automatically after every `torch.optim.Optimizer.step()` and `load_state_dict`; call it by
+        hand after editing weights through `p.data` outside an optimizer."""
         self.dirty = True
 
     # ------------------------------------------------------------------ views

@@ -176,3 +176,37 @@ def test_fused_repr_txt_equals_separate_calls(tmp_path, monkeypatch):
             continue
         rel = (p.grad - gr[k].grad).norm() / gr[k].grad.norm().clamp_min(1e-9)
         assert rel < 2e-2, (k, float(rel))
+
+
+def test_bf16_mirror_follows_any_torch_optimizer_step(tmp_path, monkeypatch):
+    """The kernels read a bf16 mirror of the fp32 masters. An optimizer that updates `p.data` in
+    place (the reference's optim/adamw.py:94-104 does; `p._version` does not move) must still be
+    seen by the next forward: FlatParams listens to every torch.optim.Optimizer.step()."""
+    fake_ops.install(monkeypatch)
+    from hero_b200.params import flat_of
+    fx = gu.load("hier_tiny.npz")
+    vb, _ = gu.stored_batches(fx)
+
+    class DataSGD(torch.optim.Optimizer):      # updates through .data like the reference's AdamW
+        def __init__(self, params):
+            super().__init__(params, dict(lr=0.5))
+
+        def step(self, closure=None):
+            for group in self.param_groups:
+                for p in group["params"]:
+                    if p.grad is not None:
+                        p.data.add_(p.grad.data, alpha=-group["lr"])
+
+    model = _model(tmp_path, fx)
+    flat = flat_of(model, torch.device("cpu"))
+    opt = DataSGD(model.parameters())
+    out0 = model(vb, "repr")
+    out0.float().pow(2).mean().backward()
+    assert not flat.dirty
+    opt.step()
+    assert flat.dirty                                  # marked by the global post-step hook
+    out1 = model(vb, "repr")
+    assert (out1 - out0).abs().max() > 1e-3            # the forward saw the new weights
+    fresh = _model(tmp_path, fx)
+    fresh.load_state_dict(model.state_dict())
+    assert torch.equal(fresh(vb, "repr"), out1)
