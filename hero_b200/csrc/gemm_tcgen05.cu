@@ -699,7 +699,11 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   // two CTAs' epilogues are lock-stepped), so auto mode keys on K and on the epilogue.
   // Light epilogues (bias only: the QKV projection) also gain from pairs on short K.
   const bool heavy_epilogue = g->act != ACT_NONE || g->resid != nullptr || g->drop_threshold != 0u;
-  const bool pair_auto = (g->k >= 1536 || !heavy_epilogue) && g->m > 128 &&
+  static const int pair_min_k = [] {   // development knob for A/B runs
+    const char* v = getenv("HERO_GEMM_PAIR_MIN_K");
+    return v ? atoi(v) : 1536;
+  }();
+  const bool pair_auto = (g->k >= pair_min_k || !heavy_epilogue) && g->m > 128 &&
                          (g->out_f32_accumulate || m_blocks * ceil_div(g->n, 256) >= sms);
   const bool pair = (block_n == 256) && (g->cta_pair == 2 || (g->cta_pair == 0 && pair_auto));
 

@@ -33,6 +33,7 @@ class BatchStager:
         self.stream = torch.cuda.Stream(self.device)
         self._bufs = [dict() for _ in range(depth)]
         self._free = [None] * depth
+        self._copied = [None] * depth
         self._n = 0
 
     def stage(self, *host_batches):
@@ -40,6 +41,10 @@ class BatchStager:
         self._n += 1
         bufs = self._bufs[slot]
         out = []
+        if self._copied[slot] is not None:
+            # the host is about to rewrite this slot's pinned index buffers: its previous upload
+            # (depth steps ago) must have left the host side
+            self._copied[slot].synchronize()
         with torch.cuda.stream(self.stream):
             if self._free[slot] is not None:
                 self.stream.wait_event(self._free[slot])
@@ -56,15 +61,29 @@ class BatchStager:
                     else:
                         d[k] = v
                 plan = d.get(PLAN_KEY)
-                if plan is not None:      # index arrays ride on the same stream
-                    plan.to(self.device)
+                if plan is not None:      # index arrays ride on the same stream, through the
+                    plan.dev = None       # slot's own pinned + device buffers
+                    plan.to(self.device, self._staging(bufs, (bi, "plan")))
                     joint = plan.__dict__.get("_joint")
                     if joint is not None:
-                        joint.to(self.device)
+                        joint.dev = None
+                        joint.to(self.device, self._staging(bufs, (bi, "joint")))
                 out.append(d)
             ready = torch.cuda.Event()
             ready.record(self.stream)
+            self._copied[slot] = ready
         return out, ready, slot
+
+    def _staging(self, bufs, key):
+        def get(n):
+            pair = bufs.get(key)
+            if pair is None or pair[0].numel() < n:
+                cap = 1 << max(int(n) - 1, 1).bit_length()
+                pair = (torch.empty(cap, dtype=torch.int32, pin_memory=True),
+                        torch.empty(cap, dtype=torch.int32, device=self.device))
+                bufs[key] = pair
+            return pair
+        return get
 
     def release(self, slot, stream=None):
         ev = torch.cuda.Event()
@@ -73,8 +92,9 @@ class BatchStager:
 
 
 def record_plans(batches, stream):
-    """The plans' (small) index buffers are allocator-managed: tell the allocator that `stream`
-    uses them (data/loader.py:135-138 does this for every tensor of the batch)."""
+    """Plan index buffers that are allocator-managed (uploaded outside a BatchStager): tell the
+    allocator that `stream` uses them (data/loader.py:135-138 does this for every tensor of the
+    batch). Harmless for the stager's own long-lived buffers."""
     for b in batches:
         plan = b.get(PLAN_KEY)
         if plan is None:

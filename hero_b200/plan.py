@@ -38,18 +38,34 @@ def _host_ids(t):
 
 
 class DeviceIndex:
-    """A bundle of int32 index arrays uploaded to the device with a single H2D copy."""
+    """A bundle of int32 index arrays uploaded to the device with a single H2D copy.
 
-    def __init__(self, arrays, device):
+    `staging(n)` (optional) returns a reusable (pinned host, device) pair of int32 buffers with at
+    least n elements. Without it every upload allocates pinned memory; under load the caching host
+    allocator cannot recycle blocks whose copies are still in flight and falls back to
+    cudaHostAlloc — tens of milliseconds and a device synchronisation per call (measured: 30-50 ms
+    holes in the step timeline). loader.BatchStager passes its per-slot buffers."""
+
+    def __init__(self, arrays, device, staging=None):
         names = list(arrays)
         sizes = [int(arrays[n].size) for n in names]
         offs = np.concatenate([[0], np.cumsum([(s + 3) // 4 * 4 for s in sizes])]).astype(np.int64)
-        host = torch.empty(int(offs[-1]), dtype=torch.int32,
-                           pin_memory=torch.cuda.is_available() and device.type == "cuda")
+        total = int(offs[-1])
+        if staging is not None:
+            host_buf, dev_buf = staging(total)
+            host, dst = host_buf[:total], dev_buf[:total]
+        else:
+            host = torch.empty(total, dtype=torch.int32,
+                               pin_memory=torch.cuda.is_available() and device.type == "cuda")
+            dst = None
         hv = host.numpy()
         for n, o, s in zip(names, offs[:-1], sizes):
             hv[o:o + s] = arrays[n].reshape(-1)
-        self.flat = host.to(device, non_blocking=True)
+        if dst is None:
+            self.flat = host.to(device, non_blocking=True)
+        else:
+            dst.copy_(host, non_blocking=True)
+            self.flat = dst
         self._host = host  # keep pinned memory alive until the copy is consumed
         for n, o, s in zip(names, offs[:-1], sizes):
             setattr(self, n, self.flat[o:o + s])
@@ -230,14 +246,14 @@ class ReprPlan:
         self.sub_pos = _host_ids(batch.get("f_sub_pos_ids") if hasattr(batch, "get") else None)
         self.dev = None
 
-    def to(self, device):
+    def to(self, device, staging=None):
         if self.dev is None or self.dev.flat.device != torch.device(device):
             a = self.f.arrays("f_")
             a.update(self.c.arrays("c_"))
             a.update({"f_txtpos_off": self.f_txtpos_off, "f_txtpos_idx": self.f_txtpos_idx,
                       "f_imgpos_off": self.f_imgpos_off, "f_imgpos_idx": self.f_imgpos_idx,
                       "c_pos_off": self.c_pos_off, "c_pos_idx": self.c_pos_idx})
-            self.dev = DeviceIndex(a, torch.device(device))
+            self.dev = DeviceIndex(a, torch.device(device), staging)
         return self.dev
 
 
@@ -253,12 +269,12 @@ class TxtPlan:
             self.pos_off, self.pos_idx = table_csr(self.f.txt_j, max(self.shape[1], 1))
         self.dev = None
 
-    def to(self, device):
+    def to(self, device, staging=None):
         if self.dev is None or self.dev.flat.device != torch.device(device):
             a = self.f.arrays("f_")
             if self.with_embedding:
                 a.update({"pos_off": self.pos_off, "pos_idx": self.pos_idx})
-            self.dev = DeviceIndex(a, torch.device(device))
+            self.dev = DeviceIndex(a, torch.device(device), staging)
         return self.dev
 
 
@@ -302,10 +318,10 @@ class JointPlan:
             self.same_slot_pos = bool(np.array_equal(pv[0, :n], pq[0, :n]))
         self.dev = None
 
-    def to(self, device):
+    def to(self, device, staging=None):
         device = torch.device(device)
         if self.dev is None or self.dev.flat.device != device:
-            self.dev = DeviceIndex(self.arr, device)
+            self.dev = DeviceIndex(self.arr, device, staging)
         return self.dev
 
     def attn(self, dev):
