@@ -350,7 +350,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             for (int g = 0; g < 8; ++g) {
               float d[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[8 * g + j] = gelu_erf_with_grad(v[8 * g + j], d[j]);
+              for (int j = 0; j < 8; j += 2)
+                gelu_erf_with_grad2(v[8 * g + j], v[8 * g + j + 1], d[j], d[j + 1]);
               *reinterpret_cast<uint4*>(slab_aux + lane * 128 + ((g ^ (lane & 7)) << 4)) = pack8(d);
             }
             fence_proxy_async();

@@ -354,6 +354,90 @@ ln_bwd_fast_kernel(const hero_ln_args a) {
   }
 }
 
+// ------------------------------------------------------------------ LN forward, wide rows
+// The 4352-d frame-feature LayerNorms (model/embed.py:108-116, model/layers.py:82-90): a 17 KB fp32
+// row per warp left 3 200 warps with 136 values each in registers (255 regs, 1 TB/s). Here a
+// 256-thread CTA owns a row (<= 3 x 8 elements per thread), CTAs are persistent over rows and
+// keep gamma / beta in registers; mean and centred variance are block reductions.
+constexpr int LNW_THREADS = 256;
+constexpr int LNW_C = 3;   // rows of up to 3 * 256 * 8 = 6144 elements
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();          // red[] may still be read by the previous reduction
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < LNW_THREADS / 32; ++w) t += red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(LNW_THREADS)
+ln_fwd_wide_kernel(const hero_ln_args a) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float red[LNW_THREADS / 32];
+  const float inv_h = 1.0f / (float)a.h;
+  float g[LNW_C][8], b[LNW_C][8];
+#pragma unroll
+  for (int c = 0; c < LNW_C; ++c) {
+    const int e0 = (c * LNW_THREADS + threadIdx.x) * 8;
+    if (e0 < a.h) {
+      load_f32x8(a.gamma + e0, g[c]);
+      load_f32x8(a.beta + e0, b[c]);
+    }
+  }
+  for (int i = blockIdx.x; i < a.n_rows; i += gridDim.x) {
+    const long long xrow = a.x_rows ? a.x_rows[i] : i;
+    const int add_row = a.add_tab ? a.add_idx[i] : 0;
+    float v[LNW_C][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < LNW_C; ++c) {
+      const int e0 = (c * LNW_THREADS + threadIdx.x) * 8;
+      if (e0 < a.h) {
+        ln_load8(a, xrow, add_row, e0, v[c]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += v[c][j];
+      }
+    }
+    const float mean = block_sum_256(sum, red) * inv_h;
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < LNW_C; ++c) {
+      if ((c * LNW_THREADS + threadIdx.x) * 8 < a.h) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[c][j] - mean;
+          sq += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(block_sum_256(sq, red) * inv_h + a.eps);
+    if (threadIdx.x == 0) {
+      if (a.mean) a.mean[i] = mean;
+      if (a.rstd) a.rstd[i] = rstd;
+    }
+    __nv_bfloat16* y =
+        reinterpret_cast<__nv_bfloat16*>(a.y) + (a.y_rows ? a.y_rows[i] : i) * (long long)a.h;
+#pragma unroll
+    for (int c = 0; c < LNW_C; ++c) {
+      const int e0 = (c * LNW_THREADS + threadIdx.x) * 8;
+      if (e0 < a.h) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * g[c][j] + b[c][j];
+        if (a.drop_threshold != 0u)
+          dropout_apply8(o, a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0,
+                         a.drop_threshold, a.drop_scale);
+        store_bf16x8(y + e0, o);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ LN backward (row part)
 // dx (and its dropout-masked copy / table scatter-adds) per row; persistent warps, ROWS rows per
 // iteration. Parameter and bias gradients are column reductions done by ln_param_grad_kernel.
@@ -677,6 +761,9 @@ extern "C" int hero_ln_fwd(const hero_ln_args* a, void* stream) {
   } else if (a->h <= 768) {
     HERO_CUDA_CHECK(launch_pdl(ln_fwd_kernel<3, 1>, dim3(ceil_div(a->n_rows, LN_WARPS)),
                                dim3(LN_WARPS * 32), 0, st, *a));
+  } else if (a->h <= LNW_C * LNW_THREADS * 8 && a->n_rows >= 64) {
+    int grid = a->n_rows < sms * 4 ? a->n_rows : sms * 4;
+    HERO_CUDA_CHECK(launch_pdl(ln_fwd_wide_kernel, dim3(grid), dim3(LNW_THREADS), 0, st, *a));
   } else {
     int grid = ceil_div(a->n_rows, LN_WARPS);
     if (grid > sms * 8) grid = sms * 8;
