@@ -371,6 +371,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   const float row_lse = valid ? lse[(long long)(tok0 + i) * a.heads + head] : 0.f;
   const uint32_t t16 = a.drop_thr >> 16;
   const float keep_scale = a.drop_thr != 0u ? a.drop_scale : 1.0f;
+  const unsigned seq_len = valid ? static_cast<unsigned>(hi - lo) : 0u;
   for (int c = 0; c < 4; ++c) {
     uint32_t pk[16], dk[16];
     const bool touch = !(c * 32 >= whi || c * 32 + 32 <= wlo);
@@ -387,12 +388,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
           h = attn_drop_word(a.drop_key, tok0 + i, a.heads, head, (c * 32 + j) >> 1);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
+          // branch-free: evaluate every column, then select (the per-element branches of the
+          // first version cost ~20 % of the kernel's samples in reconvergence / fetch stalls)
           const int col = c * 32 + j + t;
-          float p = 0.f, dp = 0.f;
-          if (col >= lo && col < hi) {
-            p = ex2(__uint_as_float(r[j + t]) * a.scale_log2 - row_lse);
-            dp = __uint_as_float(d[j + t]);
-          }
+          const bool in_seq = static_cast<unsigned>(col - lo) < seq_len;
+          float p = ex2(fmaf(__uint_as_float(r[j + t]), a.scale_log2, -row_lse));
+          p = in_seq ? p : 0.f;
+          const float dp = __uint_as_float(d[j + t]);
           const uint32_t bits = t ? (h >> 16) : (h & 0xFFFFu);
           const float keep = (bits >= t16) ? keep_scale : 0.f;
           pp[t] = p * keep;                          // dropped probability (for dV)

@@ -695,16 +695,11 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   HERO_REQUIRE(block_n == 128 || block_n == 256, "block_n must be 128 or 256");
   // CTA pairs (cta_group::2, 256-row tiles) whenever the tile is 256 wide and there is more than
   // one 128-row block; cta_pair: 0 auto, 1 never, 2 force.
-  // Measured on B200 (tools/gemm_probe.py): pairs gain 7-15 % when the main loop dominates (long
-  // K: dgrad / FFN-down / every wgrad) and lose ~10 % on short-K tiles with heavy epilogues (the
-  // two CTAs' epilogues are lock-stepped), so auto mode keys on K and on the epilogue.
-  // Light epilogues (bias only: the QKV projection) also gain from pairs on short K.
-  const bool heavy_epilogue = g->act != ACT_NONE || g->resid != nullptr || g->drop_threshold != 0u;
-  static const int pair_min_k = [] {   // development knob for A/B runs
-    const char* v = getenv("HERO_GEMM_PAIR_MIN_K");
-    return v ? atoi(v) : 1536;
-  }();
-  const bool pair_auto = (g->k >= pair_min_k || !heavy_epilogue) && g->m > 128 &&
+  // A single-CTA 128x256 tile needs more L2->SM bandwidth than the fabric delivers at the tensor
+  // peak ("Why pairs"), so every GEMM with enough row blocks to fill the machine runs
+  // as CTA pairs. (Until the remote accumulator-release arrive was made .relaxed, pairs lost ~10 %
+  // on short-K tiles with heavy epilogues: each release compiled to MEMBAR + ERRBAR.)
+  const bool pair_auto = g->m > 128 &&
                          (g->out_f32_accumulate || m_blocks * ceil_div(g->n, 256) >= sms);
   const bool pair = (block_n == 256) && (g->cta_pair == 2 || (g->cta_pair == 0 && pair_auto));
 

@@ -168,8 +168,13 @@ __device__ __forceinline__ void cluster_sync() {
 // In a CTA pair the shared::cluster address of the leader's copy of a smem object is the local
 // shared::cta address with bit 24 cleared (CUTLASS Sm100MmaPeerBitMask).
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+// Relaxed: the only thing this arrival publishes is "my tcgen05.ld's of the accumulator have
+// completed", which the preceding tcgen05.wait::ld + tcgen05.fence::before_thread_sync already
+// order. The default .release at cluster scope compiles to MEMBAR.ALL.CTA + ERRBAR, which waits
+// for every outstanding global store / fp32 atomic of the epilogue (13 % of the samples of a
+// pair-mode GEMM in profiles/r01d).
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(
                    smem_u32(bar) & kPeerBitMask)
                : "memory");
 }

@@ -69,6 +69,16 @@ __device__ __forceinline__ void load_bf16x8(const __nv_bfloat16* p, float (&v)[8
   }
 }
 
+// 8 consecutive fp32 accumulations as two 16-byte vector reductions (one L2 atomic per 4 floats).
+__device__ __forceinline__ void red_add_f32x8(float* p, const float (&v)[8]) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]),
+               "f"(v[2]), "f"(v[3])
+               : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + 4), "f"(v[4]), "f"(v[5]),
+               "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float (&v)[8]) {
   uint4 u;
   u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
@@ -515,14 +525,10 @@ ln_bwd_kernel(const hero_ln_args a) {
             store_bf16x8(reinterpret_cast<__nv_bfloat16*>(a.dx_drop) + (long long)i * a.h + e0, dd);
           }
           if (a.d_x_tab && (int)xrow != a.x_pad_idx) {
-            float* t = a.d_x_tab + xrow * a.h + e0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(t + j, dx[j]);
+            red_add_f32x8(a.d_x_tab + xrow * a.h + e0, dx);
           }
           if (a.d_add_tab && a.add_tab && add_row != a.add_pad_idx) {
-            float* t = a.d_add_tab + (long long)add_row * a.h + e0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) atomicAdd(t + j, dx[j]);
+            red_add_f32x8(a.d_add_tab + (long long)add_row * a.h + e0, dx);
           }
         }
       }
@@ -651,9 +657,7 @@ __global__ void gather_sum_rows_f32_kernel(const __nv_bfloat16* __restrict__ src
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += v[j];
       }
-      float* o = dst + ((long long)i * h8 + c) * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(o + j, acc[j]);
+      red_add_f32x8(dst + ((long long)i * h8 + c) * 8, acc);
     }
   }
 }
