@@ -144,6 +144,12 @@ def run_ours(args):
     flat = flat_of(model, device)
     hdist.broadcast_tensors([flat.flat], 0)
     flat.mark_dirty()
+    # N > 1: gradient buckets travel during backward (peer copies over NVLink; see GradBucketer);
+    # built first because it moves the flat gradient buffer into symmetric memory
+    bucketer = hdist.GradBucketer(flat, min_elems=args.bucket_elems,
+                                  overlap_ctas=args.overlap_ctas,
+                                  transport=args.dp_transport) \
+        if (world > 1 and not args.no_overlap) else None
     gflat = flat.ensure_flat_grads()
     opt = FusedAdamW(flat, lr=1e-4) if args.with_optimizer else None
 
@@ -161,8 +167,6 @@ def run_ours(args):
     g = torch.Generator().manual_seed(7)
     dclip = (torch.randn(B, 100, H, generator=g) * 1e-2).to(device)
     dq = (torch.randn(B, host[0][1]["input_ids"].shape[1], H, generator=g) * 1e-2).to(device)
-
-    bucketer = hdist.GradBucketer(flat) if (world > 1 and not args.no_overlap) else None
 
     def fwd_bwd(vb_dev, qb_dev):
         if bucketer is not None:   # per-layer gradient exchange overlapped with backward
@@ -382,8 +386,11 @@ def run_ours(args):
                        "query_rows": "separate call" if args.separate_txt else
                        "fused into the video-row pass (forward_repr_txt)",
                        "allreduce_in_step": world > 1,
-                       "allreduce_overlap": ("per-layer buckets during backward"
-                                             if (world > 1 and not args.no_overlap) else "none"),
+                       "allreduce_overlap": (("per-layer buckets during backward, "
+                                              + ("peer copies over NVLink (copy engines)"
+                                                 if bucketer.p2p is not None else "NCCL")
+                                              + "; remainder NCCL after backward")
+                                             if bucketer is not None else "none"),
                        "l2": "no explicit flush: per-step working set (~0.35 GB weights+grads, "
                              "~3 GB activations, 111 MB inputs) exceeds the 126 MB L2"},
             "clocks": clocks, "gpu_launches": launches,
@@ -469,6 +476,13 @@ def main():
     ap.add_argument("--no-overlap", action="store_true",
                     help="N>1: one all-reduce of the flat gradient after backward (the reference's "
                          "schedule) instead of per-layer buckets overlapped with backward")
+    ap.add_argument("--dp-transport", default="auto", choices=("auto", "p2p", "nccl"),
+                    help="N>1: how gradient buckets travel during backward (GradBucketer)")
+    ap.add_argument("--bucket-elems", type=int, default=1 << 20,
+                    help="N>1: gradient ranges are exchanged once this many elements are final")
+    ap.add_argument("--overlap-ctas", type=int, default=0,
+                    help="N>1: CTAs of the communicator that exchanges gradient buckets during "
+                         "backward (the compute kernels leave that many SMs free)")
     ap.add_argument("--separate-txt", action="store_true",
                     help="encode the query rows with a separate f_encoder(batch, 'txt') call")
     ap.add_argument("--no-cpu-baseline", action="store_true")

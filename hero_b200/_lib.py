@@ -95,6 +95,8 @@ def _declare(lib):
     lib.hero_last_error.argtypes = []
     lib.hero_version.restype = C.c_int
     lib.hero_sm_count.restype = C.c_int
+    lib.hero_set_sm_limit.restype = C.c_int
+    lib.hero_set_sm_limit.argtypes = [i32]
     lib.hero_gemm_bf16.restype = C.c_int
     lib.hero_gemm_bf16.argtypes = [C.POINTER(GemmArgs), vp]
 
@@ -123,6 +125,7 @@ def _declare(lib):
     sig("hero_relu_bwd_bf16", vp, vp, vp, i64, vp)
     sig("hero_adamw_step", vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp)
     sig("hero_sumsq_f32", vp, i64, vp, vp)
+    sig("hero_reduce_slots_f32", vp, vp, i32, i64, i64, f32, i32, vp)
 
 
 def lib():

@@ -139,6 +139,129 @@ def any_broadcast(data, root_rank):
     return box[0]
 
 
+def bucket_parts(a, b, world, align=64):
+    """Split the flat range [a, b) into `world` consecutive parts of `chunk` elements (a multiple of
+    `align`; the last parts may be short or empty). Returns (parts, chunk)."""
+    n = b - a
+    chunk = (-(-n // world) + align - 1) // align * align
+    parts = [(min(a + r * chunk, b), min(a + (r + 1) * chunk, b)) for r in range(world)]
+    return parts, chunk
+
+
+class PeerExchange:
+    """Mean all-reduce of ranges of the flat gradient buffer with DMA copies over NVLink instead of
+    a communication kernel (the buckets that travel while backward is still running).
+
+    The gradient buffer and a staging buffer live in symmetric memory
+    (torch.distributed._symmetric_memory: every rank maps every peer's allocation). For a bucket
+    [a, b) split into `world` parts, rank r owns part r:
+      1. reduce-scatter: every rank copies its values of part r into a staging slot on rank r
+         (cudaMemcpyAsync to the peer mapping = copy engines, no SMs) and signals r;
+      2. rank r adds the world-1 slots to its own values and scales by 1/world
+         (`hero_reduce_slots_f32`, the only kernel: <= 16 CTAs, HBM-bound);
+      3. all-gather: rank r copies the reduced part into every peer's gradient buffer and signals.
+    Everything is enqueued on one side stream, ordered after the event that marks the bucket
+    final. NCCL kernels cannot do this job beside the GEMMs: the GEMMs run one CTA per SM, a
+    full-speed NCCL kernel wants ~24 SMs, a 4-8 CTA one moves 90-170 GB/s and was measured to finish
+    only after backward (tools/dp_timeline.py, tools/allreduce_probe.py)."""
+
+    def __init__(self, flat, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = flat.flat.device
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:       # newer torch enables every group implicitly
+            pass
+        pad = 64 * self.world
+        self.grad = symm.empty(flat.total + pad, dtype=torch.float32, device=dev)
+        self.stage = symm.empty(flat.total + pad, dtype=torch.float32, device=dev)
+        self.h_grad = symm.rendezvous(self.grad, group.group_name)
+        self.h_stage = symm.rendezvous(self.stage, group.group_name)
+        self.grad.zero_()
+        self.stream = torch.cuda.Stream(dev, priority=-1)
+        self.flat = flat
+        flat.adopt_grad_buffer(self.grad)
+        torch.cuda.synchronize(dev)
+        self.h_grad.barrier(0)
+
+    def fits(self, a, b):
+        _, chunk = bucket_parts(a, b, self.world)
+        return (self.world - 1) * chunk <= b - a      # staging of a bucket stays inside [a, b)
+
+    def exchange(self, a, b):
+        """Enqueue the exchange of [a, b) behind everything already on the current stream."""
+        ready = torch.cuda.Event()
+        ready.record()
+        self.stream.wait_event(ready)
+        with torch.cuda.stream(self.stream):
+            self._scatter(a, b)
+            self._reduce(a, b)
+            self._gather(a, b)
+
+    def _others(self):
+        return [(self.rank + k) % self.world for k in range(1, self.world)]
+
+    def _plan(self, a, b):
+        """Views and peer mappings of a bucket (the same buckets recur every step: cached)."""
+        plans = self.__dict__.setdefault("_plans", {})
+        pl = plans.get((a, b))
+        if pl is None:
+            W, me = self.world, self.rank
+            parts, chunk = bucket_parts(a, b, W)
+            lo, hi = parts[me]
+            pl = {"chunk": chunk, "lo": lo, "hi": hi, "scatter": [], "gather": [],
+                  "wait_gather": [p for p in self._others() if parts[p][1] > parts[p][0]]}
+            for r in self._others():
+                rlo, rhi = parts[r]
+                if rhi > rlo:
+                    slot = (me - r - 1) % W        # 0 .. W-2: which of r's slots is mine
+                    dst = self.h_stage.get_buffer(r, (rhi - rlo,), torch.float32,
+                                                  a + slot * chunk)
+                    pl["scatter"].append((r, dst, self.grad[rlo:rhi]))
+                if hi > lo:
+                    dst = self.h_grad.get_buffer(r, (hi - lo,), torch.float32, lo)
+                    pl["gather"].append((r, dst))
+            if hi > lo:
+                assert (hi - lo) % 4 == 0 and lo % 4 == 0   # FlatParams aligns everything to 64
+                pl["mine"] = self.grad[lo:hi]
+                pl["slots"] = self.stage[a:]
+            plans[(a, b)] = pl
+        return pl
+
+    def _scatter(self, a, b):
+        """1. my values of part r -> r's staging slot for me, then tell r."""
+        for r, dst, src in self._plan(a, b)["scatter"]:
+            dst.copy_(src, non_blocking=True)
+            self.h_stage.put_signal(r, 0)
+
+    def _reduce(self, a, b):
+        """2. once every peer's slice of my part has arrived: mean into my gradients."""
+        from . import ops
+        pl = self._plan(a, b)
+        if pl["hi"] > pl["lo"]:
+            for p in self._others():
+                self.h_stage.wait_signal(p, 0)
+            ops.reduce_slots(pl["mine"], pl["slots"], self.world - 1, pl["chunk"],
+                             1.0 / self.world)
+
+    def _gather(self, a, b):
+        """3. my reduced part -> every peer's gradient buffer; wait for theirs."""
+        pl = self._plan(a, b)
+        for r, dst in pl["gather"]:
+            dst.copy_(pl["mine"], non_blocking=True)
+            self.h_grad.put_signal(r, 0)
+        for p in pl["wait_gather"]:
+            self.h_grad.wait_signal(p, 0)
+
+    def join(self):
+        """Make the current stream wait for every exchange enqueued so far."""
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        torch.cuda.current_stream().wait_event(ev)
+
+
 class GradBucketer:
     """Overlaps the data-parallel gradient exchange with the rest of the backward pass.
 
@@ -159,9 +282,35 @@ class GradBucketer:
     rows) is exchanged only after its LAST backward: forward registers every use (`expect`),
     backward retires them (`ready`)."""
 
-    def __init__(self, flat, min_elems=1 << 20):
+    def __init__(self, flat, min_elems=1 << 20, overlap_ctas=0, transport="auto"):
+        """transport: how buckets travel while backward is running —
+        "p2p" (PeerExchange: symmetric memory + copy engines, NCCL backend only), "nccl"
+        (an extra communicator capped at `overlap_ctas` CTAs, with the compute kernels sized for
+        that many fewer SMs), "auto" = p2p when available else the default communicator.
+        The remainder after backward always goes through the default, full-speed communicator."""
         self.flat = flat
         self.min_elems = min_elems       # merge announced ranges into messages of >= 4 MB
+        self.overlap_ctas = overlap_ctas
+        self.pg = None
+        self.p2p = None
+        nccl = size() > 1 and dist.get_backend() == "nccl"
+        if nccl and transport in ("auto", "p2p"):
+            try:
+                self.p2p = PeerExchange(flat)
+            except Exception as e:          # no symmetric memory on this system
+                if transport == "p2p":
+                    raise
+                import warnings
+                warnings.warn(f"GradBucketer: peer exchange unavailable ({e!r}); using NCCL")
+        if nccl and self.p2p is None and overlap_ctas > 0:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = overlap_ctas
+            opts.config.min_ctas = 1
+            # its CTAs must win the SMs the compute kernels leave free as soon as they are free:
+            # without priority the exchange kernel sat behind the thousands of queued attention /
+            # LayerNorm CTAs and only ran after backward had finished (tools/dp_timeline.py)
+            opts.is_high_priority_stream = True
+            self.pg = dist.new_group(backend="nccl", pg_options=opts)
         self.reset()
 
     def reset(self):
@@ -200,30 +349,40 @@ class GradBucketer:
             self._flush()
 
     def __enter__(self):
-        from . import functional
+        from . import functional, ops
         self.reset()
         functional.GRAD_HOOK[0] = self
+        if self.pg is not None:
+            ops.set_sm_limit(0)
+            ops.set_sm_limit(max(ops.sm_count() - self.overlap_ctas, 1))
         return self
 
     def __exit__(self, *exc):
-        from . import functional
+        from . import functional, ops
         functional.GRAD_HOOK[0] = None
+        if self.pg is not None:
+            ops.set_sm_limit(0)
         return False
 
     # ---- exchange ------------------------------------------------------------------------------
-    def _launch(self, a, b):
+    def _launch(self, a, b, group=None):
         if b <= a:
             return
         buf = self.flat.grad_flat[a:b]
         if dist.get_backend() == "nccl":
-            self.handles.append((dist.all_reduce(buf, op=dist.ReduceOp.AVG, async_op=True), None))
+            self.handles.append((dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=group,
+                                                 async_op=True), None))
         else:
             self.handles.append((dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True), buf))
         self.done.append((a, b))
 
     def _flush(self):
         for a, b in self.queue:
-            self._launch(a, b)
+            if self.p2p is not None and self.p2p.fits(a, b):
+                self.p2p.exchange(a, b)      # beside the backward: copy engines
+                self.done.append((a, b))
+            else:
+                self._launch(a, b, self.pg)  # (capped) communicator
         self.queue = []
 
     def finish(self, rescale_denom=1.0):
@@ -231,7 +390,9 @@ class GradBucketer:
         host does not block on NCCL) and apply the reference's rescale."""
         if size() > 1:
             self.flat.ensure_flat_grads()
-            self._flush()
+            for a, b in self.queue:          # backward is over: full-speed communicator
+                self._launch(a, b)
+            self.queue = []
             pos = 0
             for a, b in sorted(self.done):
                 if a > pos:
@@ -243,6 +404,8 @@ class GradBucketer:
                 h.wait()
                 if buf is not None:
                     buf.div_(size())
+            if self.p2p is not None:
+                self.p2p.join()
         if rescale_denom != 1.0:
             self.flat.grad_flat.div_(rescale_denom)
         self.reset()

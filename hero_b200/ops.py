@@ -33,6 +33,17 @@ def launch_count():
     return _LAUNCHES
 
 
+def sm_count():
+    """SMs the persistent kernels are sized for (the device's count, or the current limit)."""
+    return _lib.lib().hero_sm_count()
+
+
+def set_sm_limit(n):
+    """Size persistent kernels for at most n SMs (0 = all): leaves room for a communication
+    kernel running beside them (`hero_set_sm_limit`)."""
+    _lib.check(_lib.lib().hero_set_sm_limit(int(n)))
+
+
 def start_gemm_profile():
     """Bracket every GEMM launch (direct or from the layer runtime) with CUDA events on the
     launching stream (bench.py roofline); implemented in the library."""
@@ -391,6 +402,16 @@ def adamw_step(p, g, m, v, p_bf16, *, step_size, beta1, beta2, eps, lr_wd, grad_
     _lib.check(_lib.lib().hero_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16),
                                           p.numel(), step_size, beta1, beta2, eps, lr_wd,
                                           grad_scale, _stream()))
+
+
+def reduce_slots(dst, slots, n_slots, slot_stride, scale, max_ctas=16):
+    """dst = (dst + sum of n_slots slices of `slots`, slot_stride apart) * scale, fp32, in place."""
+    _require_cuda(dst, slots)
+    assert dst.dtype == torch.float32 and slots.dtype == torch.float32 and dst.is_contiguous()
+    _count()
+    _lib.check(_lib.lib().hero_reduce_slots_f32(_ptr(dst), _ptr(slots), n_slots, slot_stride,
+                                                dst.numel(), scale, max_ctas, _stream()))
+    return dst
 
 
 def sumsq(x, out):

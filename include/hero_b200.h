@@ -37,6 +37,11 @@ const char* hero_last_error(void);
 int hero_version(void);
 /* Returns SM count of the current device (148 on B200) or a negative hero_status. */
 int hero_sm_count(void);
+/* Size every persistent kernel for at most n SMs (0 = all). The GEMMs run one CTA per SM; while a
+ * communication kernel (NCCL) holds some SMs a full-size grid would need a second wave for the
+ * displaced CTAs. hero_b200.distributed.GradBucketer lowers the limit by the communicator's CTA
+ * count while gradient buckets are exchanged during backward. */
+int hero_set_sm_limit(int32_t n);
 
 /* ------------------------------------------------------------------------------------------
  * GEMM family (tcgen05 / TMEM / TMA).   D[M,N] = epilogue( A · B^T-like contraction )
@@ -312,6 +317,13 @@ int hero_relu_bwd_bf16(const void* dy, const void* pre, void* out, int64_t n, vo
 int hero_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n,
                     float step_size, float beta1, float beta2, float eps, float lr_wd,
                     float grad_scale, void* stream);
+/* dst[i] = (dst[i] + sum_{s < n_slots} slots[s * slot_stride + i]) * scale, i < n (n, stride
+ * multiples of 4), on at most max_ctas CTAs (0: 64). Reduction step of the copy-engine gradient
+ * exchange (hero_b200.distributed.GradBucketer): peers deposit their slices of a bucket in `slots`
+ * over NVLink with DMA copies; this is the only SM work of the exchange
+ * (replaces the Horovod allreduce of utils/distributed.py:19-46 for the overlapped buckets). */
+int hero_reduce_slots_f32(float* dst, const float* slots, int32_t n_slots, int64_t slot_stride,
+                          int64_t n, float scale, int32_t max_ctas, void* stream);
 /* out[0] += sum x^2 (global-norm clipping, train_vcmr.py:258-259). */
 int hero_sumsq_f32(const float* x, int64_t n, float* out, void* stream);
 
