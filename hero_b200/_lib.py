@@ -86,6 +86,7 @@ class StackArgs(C.Structure):
         ("hidden_drop_scale", C.c_float), ("attn_drop_scale", C.c_float),
         ("dout", C.c_void_p), ("dx", C.c_void_p), ("scratch", C.c_void_p),
         ("first_layer", C.c_int32),
+        ("layer_done_events", C.POINTER(C.c_void_p)),
     ]
 
 

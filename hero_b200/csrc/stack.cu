@@ -254,6 +254,11 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
       HERO_CUDA_CHECK(cudaEventRecord(side->done[par], side->stream));
       done_recorded[par] = true;
     }
+    // every parameter gradient of layer l is complete here: the side stream has waited for the
+    // chain's LayerNorm / attention kernels (publish) and has just issued the last weight gradient
+    if (s->layer_done_events != nullptr && s->layer_done_events[l] != nullptr)
+      HERO_CUDA_CHECK(cudaEventRecord(reinterpret_cast<cudaEvent_t>(s->layer_done_events[l]),
+                                      two_streams ? side->stream : chain));
     void* dx = (l == 0 && s->dx) ? s->dx : ((l & 1) ? dxa : dxb);
     if (l > 0 || s->dx)
       HERO_TRY(Gemm(dqkv, 3 * H, 0, W.wqkv, H, 1, M, H, 3 * H, dx, H).resid(ds1, H).run(stream));

@@ -190,11 +190,13 @@ class PeerExchange:
         _, chunk = bucket_parts(a, b, self.world)
         return (self.world - 1) * chunk <= b - a      # staging of a bucket stays inside [a, b)
 
-    def exchange(self, a, b):
-        """Enqueue the exchange of [a, b) behind everything already on the current stream."""
-        ready = torch.cuda.Event()
-        ready.record()
-        self.stream.wait_event(ready)
+    def exchange(self, a, b, event=None):
+        """Enqueue the exchange of [a, b) behind `event` (default: behind everything already on
+        the current stream)."""
+        if event is None:
+            event = torch.cuda.Event()
+            event.record()
+        self.stream.wait_event(event)
         with torch.cuda.stream(self.stream):
             self._scatter(a, b)
             self._reduce(a, b)
@@ -324,7 +326,11 @@ class GradBucketer:
         for p in params:
             self.pending[id(p)] = self.pending.get(id(p), 0) + 1
 
-    def ready(self, params):
+    wants_events = True      # the stack backward stays one native call (functional.py)
+
+    def ready(self, params, event=None):
+        """`event`: CUDA event after which the gradients of `params` are complete (else: complete
+        in current-stream order at the time of the call)."""
         gf = self.flat.grad_flat
         if gf is None or size() == 1:
             return
@@ -346,7 +352,7 @@ class GradBucketer:
             else:
                 self.queue.append([off, end])
         if sum(b - a for a, b in self.queue) >= self.min_elems:
-            self._flush()
+            self._flush(event)
 
     def __enter__(self):
         from . import functional, ops
@@ -376,13 +382,15 @@ class GradBucketer:
             self.handles.append((dist.all_reduce(buf, op=dist.ReduceOp.SUM, async_op=True), buf))
         self.done.append((a, b))
 
-    def _flush(self):
+    def _flush(self, event=None):
         for a, b in self.queue:
             if self.p2p is not None and self.p2p.fits(a, b):
-                self.p2p.exchange(a, b)      # beside the backward: copy engines
+                self.p2p.exchange(a, b, event)   # beside the backward: copy engines
                 self.done.append((a, b))
             else:
-                self._launch(a, b, self.pg)  # (capped) communicator
+                if event is not None:            # NCCL orders itself after the current stream
+                    torch.cuda.current_stream().wait_event(event)
+                self._launch(a, b, self.pg)      # (capped) communicator
         self.queue = []
 
     def finish(self, rescale_denom=1.0):

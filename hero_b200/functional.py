@@ -122,9 +122,18 @@ class _TransformerStack(torch.autograd.Function):
             dx = ops.bert_stack_bwd(ctx.x, cfg["layers"], cfg["att"], ctx.saved,
                                     dout.contiguous(), grads, heads=cfg["heads"], eps=cfg["eps"],
                                     drop=ctx.dspec, need_dx=ctx.needs_input_grad[0])
+        elif getattr(hook, "wants_events", False) and dout.is_cuda:
+            # data-parallel: ONE native call; the runtime records an event per layer where that
+            # layer's gradients are complete, and the exchanges are enqueued behind those events
+            events = _layer_events(cfg, n, dout.device)
+            dx = ops.bert_stack_bwd(ctx.x, cfg["layers"], cfg["att"], ctx.saved,
+                                    dout.contiguous(), grads, heads=cfg["heads"], eps=cfg["eps"],
+                                    drop=ctx.dspec, need_dx=ctx.needs_input_grad[0],
+                                    layer_events=events)
+            for li in range(n - 1, -1, -1):
+                hook.ready(params[16 * li:16 * li + 16], event=events[li])
         else:
-            # data-parallel: one native call per layer so each layer's gradients can start their
-            # all-reduce while the layers below are still being differentiated
+            # hooks without event support: one native call per layer
             dx = dout.contiguous()
             for li in range(n - 1, -1, -1):
                 dx = ops.bert_stack_bwd(ctx.x, cfg["layers"], cfg["att"], ctx.saved, dx, grads,
@@ -133,6 +142,19 @@ class _TransformerStack(torch.autograd.Function):
                 hook.ready(params[16 * li:16 * li + 16])
         ctx.saved = None
         return (dx, None) + tuple(ret)
+
+
+def _layer_events(cfg, n, device):
+    """n reusable CUDA events for `hero_stack_args.layer_done_events` (kept on the encoder)."""
+    cache = cfg.get("cache")
+    events = None if cache is None else cache.get("events")
+    if events is None or len(events) != n:
+        events = [torch.cuda.Event() for _ in range(n)]
+        for e in events:
+            e.record()            # materialise the cudaEvent_t handle
+        if cache is not None:
+            cache["events"] = events
+    return events
 
 
 def _stack_sinks(cfg, params, H, device):

@@ -310,11 +310,13 @@ def bert_stack_fwd(x, layers, att, *, heads, eps, drop, save):
 
 
 def bert_stack_bwd(x, layers, att, saved, dout, grads, *, heads, eps, drop, need_dx=True,
-                   only_layer=None):
+                   only_layer=None, layer_events=None):
     """Backward of the whole stack (`hero_bert_stack_bwd`). grads: per layer a dict of fp32
     tensors (keys of hero_layer_grads) that are ACCUMULATED into. Returns dx (bf16) or None.
     `only_layer=l` differentiates just layer l (dout = gradient of that layer's output; the
-    result is the gradient of its input): the same native entry point on a one-layer slice."""
+    result is the gradient of its input): the same native entry point on a one-layer slice.
+    `layer_events`: one torch.cuda.Event per layer, recorded where that layer's parameter
+    gradients are complete (`hero_stack_args.layer_done_events`)."""
     _require_cuda(x, dout)
     assert dout.dtype == BF16 and dout.is_contiguous()
     ws, act_ptrs = saved
@@ -341,6 +343,10 @@ def bert_stack_bwd(x, layers, att, saved, dout, grads, *, heads, eps, drop, need
     nbytes = _lib.lib().hero_bert_stack_bwd_scratch_bytes(s.n_tok, s.hidden, s.inter)
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     s.scratch = scratch.data_ptr()
+    if layer_events is not None:
+        assert len(layer_events) == n
+        evs = (C.c_void_p * n)(*[e.cuda_event for e in layer_events])
+        s.layer_done_events = evs
     _count(_STACK_BWD_LAUNCHES * n)
     _lib.check(_lib.lib().hero_bert_stack_bwd(C.byref(s), _stream()))
     return dx

@@ -277,6 +277,11 @@ typedef struct hero_stack_args {
    * (drop_key, first_layer + l, site), so a caller may run the stack as several slices — e.g. one
    * backward call per layer to overlap the gradient all-reduce — and get identical masks. */
   int32_t first_layer;
+  /* Backward only, optional: n_layers CUDA events (cudaEvent_t). Event l is recorded at the point
+   * where every parameter gradient of layer l is complete (weight gradients run on the runtime's
+   * second stream), so a data-parallel caller can start exchanging layer l while the layers below
+   * are still being differentiated, from ONE call for the whole stack. */
+  void* const* layer_done_events;
 } hero_stack_args;
 
 int hero_bert_stack_fwd(const hero_stack_args* args, void* stream);

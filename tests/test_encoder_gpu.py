@@ -208,18 +208,24 @@ def test_per_layer_backward_with_grad_hook_matches_whole_stack(tmp_path):
     vbd = synth.to_device(vb, "cuda")
 
     class Hook:
-        def __init__(self):
-            self.expected, self.ready_calls = 0, 0
+        def __init__(self, wants_events=False):
+            self.expected, self.ready_calls, self.events = 0, 0, 0
+            self.wants_events = wants_events
 
         def expect(self, params):
             self.expected += len(params)
 
-        def ready(self, params):
+        def ready(self, params, event=None):
             assert len(params) == 16
             self.ready_calls += 1
+            if event is not None:
+                assert self.wants_events
+                event.synchronize()       # the layer's gradients are complete behind it
+                self.events += 1
 
     grads = []
-    for hook in (None, Hook()):
+    hooks = (None, Hook(), Hook(wants_events=True))
+    for hook in hooks:
         model = _build(tmp_path, d, P).train()
         gflat = flat_of(model, torch.device("cuda")).ensure_flat_grads()
         functional.GRAD_HOOK[0] = hook
@@ -230,11 +236,14 @@ def test_per_layer_backward_with_grad_hook_matches_whole_stack(tmp_path):
         finally:
             functional.GRAD_HOOK[0] = None
         grads.append((out.detach().clone(), gflat.clone()))
-    assert hook.ready_calls == 5 and hook.expected == 16 * 5
-    assert torch.equal(grads[0][0], grads[1][0])
-    a, b = grads[0][1], grads[1][1]
+    for h in hooks[1:]:
+        assert h.ready_calls == 5 and h.expected == 16 * 5
+    assert hooks[1].events == 0 and hooks[2].events == 5   # one native call + one event per layer
+    a = grads[0][1]
     assert a.abs().sum() > 0
-    assert float((a - b).norm() / a.norm()) < 1e-5
+    for out, g in grads[1:]:
+        assert torch.equal(grads[0][0], out)
+        assert float((a - g).norm() / a.norm()) < 1e-5
 
 
 def test_hot_path_never_synchronises_with_collate_side_plans(tmp_path):
