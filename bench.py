@@ -149,7 +149,9 @@ def run_ours(args):
     bucketer = hdist.GradBucketer(flat, min_elems=args.bucket_elems,
                                   overlap_ctas=args.overlap_ctas,
                                   transport=args.dp_transport) \
-        if (world > 1 and not args.no_overlap) else None
+        if (world > 1 and not args.no_overlap and not args.dp_skip_exchange) else None
+    if world > 1 and args.dp_skip_exchange and os.environ.get("HERO_DP_DIAG") == "symm":
+        hdist.PeerExchange(flat)     # diagnostic: gradients in symmetric memory, no exchange
     gflat = flat.ensure_flat_grads()
     opt = FusedAdamW(flat, lr=1e-4) if args.with_optimizer else None
 
@@ -180,7 +182,7 @@ def run_ours(args):
         if bucketer is not None:
             bucketer.__exit__(None, None, None)
             bucketer.finish()
-        elif world > 1:
+        elif world > 1 and not args.dp_skip_exchange:
             hdist.all_reduce_flat(gflat)
         if opt is not None:
             opt.step()
@@ -385,7 +387,7 @@ def run_ours(args):
                        "dropout": 0.1, "optimizer_in_step": bool(args.with_optimizer),
                        "query_rows": "separate call" if args.separate_txt else
                        "fused into the video-row pass (forward_repr_txt)",
-                       "allreduce_in_step": world > 1,
+                       "allreduce_in_step": world > 1 and not args.dp_skip_exchange,
                        "allreduce_overlap": (("per-layer buckets during backward, "
                                               + ("peer copies over NVLink (copy engines)"
                                                  if bucketer.p2p is not None else "NCCL")
@@ -478,6 +480,9 @@ def main():
                          "schedule) instead of per-layer buckets overlapped with backward")
     ap.add_argument("--dp-transport", default="auto", choices=("auto", "p2p", "nccl"),
                     help="N>1: how gradient buckets travel during backward (GradBucketer)")
+    ap.add_argument("--dp-skip-exchange", action="store_true",
+                    help="DIAGNOSTIC (invalid as a result): N>1 without any gradient exchange, to "
+                         "separate per-GPU compute time from communication")
     ap.add_argument("--bucket-elems", type=int, default=1 << 20,
                     help="N>1: gradient ranges are exchanged once this many elements are final")
     ap.add_argument("--overlap-ctas", type=int, default=0,

@@ -16,6 +16,7 @@ torchrun-style environment variables.
 """
 import os
 import pickle
+import sys
 
 import torch
 import torch.distributed as dist
@@ -181,6 +182,7 @@ class PeerExchange:
         self.h_stage = symm.rendezvous(self.stage, group.group_name)
         self.grad.zero_()
         self.stream = torch.cuda.Stream(dev, priority=-1)
+        self.channels = max(1, min(128, self.h_grad.signal_pad_size // (4 * self.world) - 1))
         self.flat = flat
         flat.adopt_grad_buffer(self.grad)
         torch.cuda.synchronize(dev)
@@ -190,16 +192,16 @@ class PeerExchange:
         _, chunk = bucket_parts(a, b, self.world)
         return (self.world - 1) * chunk <= b - a      # staging of a bucket stays inside [a, b)
 
-    def exchange(self, a, b, event=None):
+    def exchange(self, a, b, event=None, reduce_ctas=16):
         """Enqueue the exchange of [a, b) behind `event` (default: behind everything already on
-        the current stream)."""
+        the current stream). `reduce_ctas` caps the reduction kernel (small beside backward)."""
         if event is None:
             event = torch.cuda.Event()
             event.record()
         self.stream.wait_event(event)
         with torch.cuda.stream(self.stream):
             self._scatter(a, b)
-            self._reduce(a, b)
+            self._reduce(a, b, reduce_ctas)
             self._gather(a, b)
 
     def _others(self):
@@ -213,7 +215,11 @@ class PeerExchange:
             W, me = self.world, self.rank
             parts, chunk = bucket_parts(a, b, W)
             lo, hi = parts[me]
+            # one signal channel per bucket (pads hold >= 128 channels): a bucket's signals never
+            # queue behind another bucket's, and the "gathered" acknowledgements can all be
+            # collected at the end of the step instead of stalling the stream after every bucket
             pl = {"chunk": chunk, "lo": lo, "hi": hi, "scatter": [], "gather": [],
+                  "channel": len(plans) % self.channels,
                   "wait_gather": [p for p in self._others() if parts[p][1] > parts[p][0]]}
             for r in self._others():
                 rlo, rhi = parts[r]
@@ -234,31 +240,36 @@ class PeerExchange:
 
     def _scatter(self, a, b):
         """1. my values of part r -> r's staging slot for me, then tell r."""
-        for r, dst, src in self._plan(a, b)["scatter"]:
+        pl = self._plan(a, b)
+        for r, dst, src in pl["scatter"]:
             dst.copy_(src, non_blocking=True)
-            self.h_stage.put_signal(r, 0)
+            self.h_stage.put_signal(r, pl["channel"])
 
-    def _reduce(self, a, b):
+    def _reduce(self, a, b, reduce_ctas=16):
         """2. once every peer's slice of my part has arrived: mean into my gradients."""
         from . import ops
         pl = self._plan(a, b)
         if pl["hi"] > pl["lo"]:
             for p in self._others():
-                self.h_stage.wait_signal(p, 0)
+                self.h_stage.wait_signal(p, pl["channel"])
             ops.reduce_slots(pl["mine"], pl["slots"], self.world - 1, pl["chunk"],
-                             1.0 / self.world)
+                             1.0 / self.world, max_ctas=reduce_ctas)
 
     def _gather(self, a, b):
         """3. my reduced part -> every peer's gradient buffer; wait for theirs."""
         pl = self._plan(a, b)
         for r, dst in pl["gather"]:
             dst.copy_(pl["mine"], non_blocking=True)
-            self.h_grad.put_signal(r, 0)
-        for p in pl["wait_gather"]:
-            self.h_grad.wait_signal(p, 0)
+            self.h_grad.put_signal(r, pl["channel"])
+        self.__dict__.setdefault("_unacked", []).append(pl)
 
     def join(self):
-        """Make the current stream wait for every exchange enqueued so far."""
+        """Collect the peers' "gathered" signals of every bucket of the step, then make the current
+        stream wait for every exchange enqueued so far."""
+        with torch.cuda.stream(self.stream):
+            for pl in self.__dict__.pop("_unacked", []):
+                for p in pl["wait_gather"]:
+                    self.h_grad.wait_signal(p, pl["channel"])
         ev = torch.cuda.Event()
         ev.record(self.stream)
         torch.cuda.current_stream().wait_event(ev)
@@ -295,6 +306,7 @@ class GradBucketer:
         self.overlap_ctas = overlap_ctas
         self.pg = None
         self.p2p = None
+        self.p2p_tail_max_world = 0
         nccl = size() > 1 and dist.get_backend() == "nccl"
         if nccl and transport in ("auto", "p2p"):
             try:
@@ -396,26 +408,51 @@ class GradBucketer:
     def finish(self, rescale_denom=1.0):
         """Exchange every range not sent so far, wait for all of it (the current stream waits; the
         host does not block on NCCL) and apply the reference's rescale."""
+        timing = os.environ.get("HERO_DP_TIMING") == "1"
+        marks = []
+
+        def mark(name):
+            if timing:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
         if size() > 1:
             self.flat.ensure_flat_grads()
-            for a, b in self.queue:          # backward is over: full-speed communicator
-                self._launch(a, b)
+            mark("backward enqueued work done")
+            rest = [tuple(r) for r in self.queue]
             self.queue = []
             pos = 0
             for a, b in sorted(self.done):
                 if a > pos:
-                    self._launch(pos, a)
+                    rest.append((pos, a))
                 pos = max(pos, b)
             if pos < self.flat.total:
-                self._launch(pos, self.flat.total)
+                rest.append((pos, self.flat.total))
+            # After backward nothing competes for SMs: the remainder goes through the full-speed
+            # NCCL communicator (176 MB in 0.5-0.6 ms at N = 2; the peer-copy path was measured at
+            # 0.7-0.8 ms for the same bytes - `p2p_tail_max_world` > 0 re-enables it for A/B runs).
+            for a, b in rest:
+                if self.p2p is not None and size() <= self.p2p_tail_max_world and self.p2p.fits(a, b):
+                    self.p2p.exchange(a, b, reduce_ctas=592)
+                else:
+                    self._launch(a, b)
+            n_tail = len(self.handles)
             for h, buf in self.handles:
                 h.wait()
                 if buf is not None:
                     buf.div_(size())
+            mark(f"remainder through NCCL ({n_tail} calls)")
             if self.p2p is not None:
                 self.p2p.join()
+                mark("peer exchanges joined")
         if rescale_denom != 1.0:
             self.flat.grad_flat.div_(rescale_denom)
+        if timing and marks:
+            torch.cuda.synchronize()
+            print("GradBucketer.finish device ms:",
+                  [(b[0], round(a[1].elapsed_time(b[1]), 3)) for a, b in zip(marks[:-1], marks[1:])],
+                  file=sys.stderr)
         self.reset()
 
 

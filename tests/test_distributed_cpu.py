@@ -200,7 +200,7 @@ def test_peer_exchange_algorithm_on_simulated_ranks(monkeypatch):
         ranks = []
         for r in range(W):
             ex = hd.PeerExchange.__new__(hd.PeerExchange)
-            ex.world, ex.rank, ex.grad, ex.stage = W, r, grads[r], stages[r]
+            ex.world, ex.rank, ex.grad, ex.stage, ex.channels = W, r, grads[r], stages[r], 16
             ex.h_grad, ex.h_stage = Handle(grads), Handle(stages)
             ranks.append(ex)
         buckets = [(0, 64 * 16), (64 * 16, 64 * 17), (64 * 17, 64 * 39), (64 * 39, total)]

@@ -21,7 +21,8 @@ vbd = synth.to_device(attach_plan(dict(vb)), dev)
 qbd = synth.to_device(attach_plan(dict(qb), kind="txt"), dev)
 dclip = torch.randn(32, 100, 768, device=dev) * 1e-2
 dq = torch.randn(32, 16, 768, device=dev) * 1e-2
-bucketer = hdist.GradBucketer(flat, overlap_ctas=ctas)
+bucketer = hdist.GradBucketer(flat)
+gflat = flat.ensure_flat_grads()
 
 
 def step():
@@ -45,6 +46,18 @@ if rank == 0:
     print(f"step span {(t1 - t0) / 1e3:.3f} ms, {len(evs)} device activities")
     comp_end = max(e.time_range.end for e in evs if "nccl" not in e.name.lower())
     print(f"last compute kernel ends at {(comp_end - t0) / 1e3:.3f} ms")
+    bwd_end = max(e.time_range.end for e in evs if "hero::" in e.name or "gemm_tcgen05" in e.name)
+    print(f"last hero kernel ends at {(bwd_end - t0) / 1e3:.3f} ms; activities after "
+          f"{(bwd_end - t0) / 1e3 - 0.3:.3f} ms:")
+    for e in sorted(evs, key=lambda e: e.time_range.start):
+        if e.time_range.end > bwd_end - 300 and "nccl" not in e.name.lower():
+            print(f"  late  start {(e.time_range.start - t0) / 1e3:7.3f}  end "
+                  f"{(e.time_range.end - t0) / 1e3:7.3f}  {e.name[:70]}")
+    cp = [e for e in evs if "memcpy" in e.name.lower() and "dtod" in e.name.lower().replace(" ", "")]
+    if cp:
+        print(f"{len(cp)} DtoD copies: first start {(min(e.time_range.start for e in cp) - t0) / 1e3:.3f}"
+              f" last end {(max(e.time_range.end for e in cp) - t0) / 1e3:.3f} ms, total "
+              f"{sum(e.time_range.elapsed_us() for e in cp) / 1e3:.3f} ms")
     for e in evs:
         if "nccl" in e.name.lower():
             print(f"  nccl  start {(e.time_range.start - t0) / 1e3:7.3f}  end "
