@@ -146,10 +146,11 @@ def run_ours(args):
     flat.mark_dirty()
     # N > 1: gradient buckets travel during backward (peer copies over NVLink; see GradBucketer);
     # built first because it moves the flat gradient buffer into symmetric memory
-    bucketer = hdist.GradBucketer(flat, min_elems=args.bucket_elems,
-                                  overlap_ctas=args.overlap_ctas,
-                                  transport=args.dp_transport) \
-        if (world > 1 and not args.no_overlap and not args.dp_skip_exchange) else None
+    bucketer = None
+    if world > 1 and not args.no_overlap and not args.dp_skip_exchange:
+        bucketer = hdist.overlapped_exchange(flat, transport=args.dp_transport,
+                                             min_elems=args.bucket_elems,
+                                             overlap_ctas=args.overlap_ctas)
     if world > 1 and args.dp_skip_exchange and os.environ.get("HERO_DP_DIAG") == "symm":
         hdist.PeerExchange(flat)     # diagnostic: gradients in symmetric memory, no exchange
     gflat = flat.ensure_flat_grads()
@@ -392,7 +393,9 @@ def run_ours(args):
                                               + ("peer copies over NVLink (copy engines)"
                                                  if bucketer.p2p is not None else "NCCL")
                                               + "; remainder NCCL after backward")
-                                             if bucketer is not None else "none"),
+                                             if bucketer is not None else
+                                             "none: one NCCL all-reduce of the flat gradient "
+                                             "buffer after backward" if world > 1 else "none"),
                        "l2": "no explicit flush: per-step working set (~0.35 GB weights+grads, "
                              "~3 GB activations, 111 MB inputs) exceeds the 126 MB L2"},
             "clocks": clocks, "gpu_launches": launches,

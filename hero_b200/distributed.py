@@ -456,6 +456,30 @@ class GradBucketer:
         self.reset()
 
 
+def overlapped_exchange(flat, transport="auto", **kw):
+    """The gradient-exchange schedule that measured fastest for this world size: a GradBucketer
+    (buckets travel as peer copies during backward) or None = one NCCL all-reduce of the flat
+    buffer after backward (`all_reduce_flat`, the reference's schedule).
+
+    B200 / NVSwitch, 430 MB of fp32 gradients, 6.5 ms of compute per step:
+      N = 2: bucketer 7.23 ms/step, all-reduce after backward 7.32;
+      N = 4: bucketer 8.23, all-reduce after backward 7.65 — every bucket costs 2 (N-1) copies and
+      signals per rank, and NCCL's all-reduce grows by only 0.3 ms from N = 2 to N = 4.
+    So "auto" picks the bucketer for two ranks only; "p2p" / "nccl" force a GradBucketer."""
+    if size() <= 1:
+        return None
+    if transport == "auto":
+        if size() != 2 or dist.get_backend() != "nccl":
+            return None
+        try:
+            return GradBucketer(flat, transport="p2p", **kw)
+        except Exception as e:       # no symmetric memory here: keep the plain schedule
+            import warnings
+            warnings.warn(f"peer-copy gradient exchange unavailable ({e!r}); using all_reduce_flat")
+            return None
+    return GradBucketer(flat, transport=transport, **kw)
+
+
 class VsmAllgather(torch.autograd.Function):
     """model/pretrain.py:427-447: all-gather along dim 0 in rank order (ranks may contribute
     different row counts, as hvd.allgather allows); the backward hands each rank the slice of the
