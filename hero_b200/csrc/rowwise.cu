@@ -11,10 +11,6 @@ namespace hero {
 
 constexpr int LN_WARPS = 4;
 
-struct LnParams {
-  hero_ln_args a;
-};
-
 // Load 8 consecutive elements of the (gathered, summed) pre-LN row into v[8].
 __device__ __forceinline__ void ln_load8(const hero_ln_args& a, long long xrow, int add_row, int e0,
                                          float (&v)[8]) {
@@ -86,9 +82,11 @@ __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float (&v)[
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-// ------------------------------------------------------------------ LN forward
-// Persistent warps; each iteration a warp handles ROWS independent rows so twice the loads are in
-// flight per warp (the one-row-per-warp version was pure `long_scoreboard` stall: 2.6 TB/s).
+// ------------------------------------------------------------------ LN forward (generic)
+// Every option of hero_ln_args: fp32 or bf16 rows, row gather, table / vector adds, row lengths up
+// to MAXJ * 256. One warp per row; ROWS rows per warp iteration (1 in every instantiation: two
+// rows in flight per warp measured slower, 25.9 vs 18.4 us at 16.5 k rows). The transformer-layer
+// LayerNorms take the fast path below, the 4352-wide rows ln_fwd_wide_kernel.
 template <int MAXJ, int ROWS>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const hero_ln_args a) {
@@ -448,9 +446,9 @@ ln_fwd_wide_kernel(const hero_ln_args a) {
   }
 }
 
-// ------------------------------------------------------------------ LN backward (row part)
-// dx (and its dropout-masked copy / table scatter-adds) per row; persistent warps, ROWS rows per
-// iteration. Parameter and bias gradients are column reductions done by ln_param_grad_kernel.
+// ------------------------------------------------------------------ LN backward, generic (rows)
+// dx (and its dropout-masked copy / table scatter-adds) per row, one warp per row. Parameter and
+// bias gradients of this path are column reductions done by ln_param_grad_kernel.
 template <int MAXJ, int ROWS>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const hero_ln_args a) {
