@@ -488,8 +488,10 @@ def main():
     ap.add_argument("--no-overlap", action="store_true",
                     help="N>1: one all-reduce of the flat gradient after backward (the reference's "
                          "schedule) instead of per-layer buckets overlapped with backward")
-    ap.add_argument("--dp-transport", default="auto", choices=("auto", "p2p", "nccl"),
-                    help="N>1: how gradient buckets travel during backward (GradBucketer)")
+    ap.add_argument("--dp-transport", default="none", choices=("none", "p2p", "nccl", "auto"),
+                    help="N>1: 'none' = one NCCL all-reduce of the flat gradient buffer after "
+                         "backward (default, measured fastest end to end); 'p2p' / 'nccl' = "
+                         "GradBucketer: buckets travel during backward")
     ap.add_argument("--dp-skip-exchange", action="store_true",
                     help="DIAGNOSTIC (invalid as a result): N>1 without any gradient exchange, to "
                          "separate per-GPU compute time from communication")

@@ -456,27 +456,21 @@ class GradBucketer:
         self.reset()
 
 
-def overlapped_exchange(flat, transport="auto", **kw):
-    """The gradient-exchange schedule that measured fastest for this world size: a GradBucketer
-    (buckets travel as peer copies during backward) or None = one NCCL all-reduce of the flat
-    buffer after backward (`all_reduce_flat`, the reference's schedule).
+def overlapped_exchange(flat, transport="none", **kw):
+    """The gradient-exchange schedule for a training loop: None = one NCCL all-reduce of the flat
+    buffer after backward (`all_reduce_flat`, the reference's schedule — the default), or a
+    GradBucketer ("p2p": buckets travel as peer copies during backward, "nccl": through a capped
+    communicator).
 
-    B200 / NVSwitch, 430 MB of fp32 gradients, 6.5 ms of compute per step:
-      N = 2: bucketer 7.23 ms/step, all-reduce after backward 7.32;
-      N = 4: bucketer 8.23, all-reduce after backward 7.65 — every bucket costs 2 (N-1) copies and
-      signals per rank, and NCCL's all-reduce grows by only 0.3 ms from N = 2 to N = 4.
-    So "auto" picks the bucketer for two ranks only; "p2p" / "nccl" force a GradBucketer."""
-    if size() <= 1:
+    B200 / NVSwitch, 430 MB of fp32 gradients, 6.4-6.5 ms of compute per step, ms per step:
+      N = 2: bucketer 7.23-7.34 device-resident but 7.96 end to end (its ~100 extra host-side
+             enqueues per step double the host time of a step), all-reduce after backward 7.32;
+      N = 4: bucketer 8.23, all-reduce after backward 7.65 - every bucket costs 2 (N-1) copies and
+             signals per rank, and NCCL's all-reduce grows by only 0.3 ms from N = 2 to N = 4.
+    The bucketer hides its exchanges completely (HERO_DP_TIMING=1) but the 41 % of the bytes that
+    become final only when backward ends stay exposed either way, so it is opt-in."""
+    if size() <= 1 or transport in (None, "none"):
         return None
-    if transport == "auto":
-        if size() != 2 or dist.get_backend() != "nccl":
-            return None
-        try:
-            return GradBucketer(flat, transport="p2p", **kw)
-        except Exception as e:       # no symmetric memory here: keep the plain schedule
-            import warnings
-            warnings.warn(f"peer-copy gradient exchange unavailable ({e!r}); using all_reduce_flat")
-            return None
     return GradBucketer(flat, transport=transport, **kw)
 
 

@@ -126,6 +126,91 @@ def check_collate_layout():
     print("synthetic collate layout == reference video_collate")
 
 
+def heads_fixture(model, dims, vb, out_dir):
+    """Pretraining heads of the reference on the tiny model: MFM regression
+    and NCE (model/model.py:239-289), FOM (:306-336) and MLM (model/encoder.py:355-374). The head
+    parameters are not part of the seeded encoder weights: they are drawn here and stored."""
+    gen = torch.Generator().manual_seed(77)
+    head = {}
+    for k, p in model.named_parameters():
+        if k.startswith(("feat_regress", "fom_output", "mask_embedding", "f_encoder.lm_head.dense",
+                         "f_encoder.lm_head.LayerNorm", "f_encoder.lm_head.bias")):
+            with torch.no_grad():
+                if p.dim() > 1:
+                    p.copy_(torch.randn(p.shape, generator=gen) * 0.05)
+                elif "LayerNorm.weight" in k:
+                    p.copy_(1.0 + torch.randn(p.shape, generator=gen) * 0.05)
+                else:
+                    p.copy_(torch.randn(p.shape, generator=gen) * 0.05)
+            head["head." + k] = p.detach().numpy().copy()
+    with torch.no_grad():
+        model.mask_embedding.weight[0].zero_()          # padding row (init_type_embedding)
+    head["head.mask_embedding.weight"] = model.mask_embedding.weight.detach().numpy().copy()
+    B, T = vb["c_attn_masks"].shape
+    valid = vb["c_attn_masks"].bool()
+    # ---- MFM: mask ~1/3 of the valid frames (at least one masked and one unmasked per clip)
+    c_v_masks = (torch.rand(B, T, generator=gen) < 0.34) & valid
+    for b in range(B):
+        n = int(valid[b].sum())
+        c_v_masks[b, 0], c_v_masks[b, n - 1] = True, False
+    feat_targets = vb["c_v_feats"][c_v_masks].clone()
+
+    def mfm_batch():
+        b = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in vb.items()}
+        b["c_v_masks"], b["feat_targets"] = c_v_masks.clone(), feat_targets.clone()
+        return b
+
+    with torch.no_grad():
+        mffr_pred = model(mfm_batch(), "mffr", compute_loss=False)
+        mffr_loss = model(mfm_batch(), "mffr", compute_loss=True)
+        nce_loss = model(mfm_batch(), "mfm-nce", compute_loss=True)
+    # ---- FOM: permute the valid frames of every clip; a third of the targets ignored (-1)
+    orders = torch.arange(T).repeat(B, 1)
+    targets = torch.full((B, T), -1, dtype=torch.long)
+    for b in range(B):
+        n = int(valid[b].sum())
+        perm = torch.randperm(n, generator=gen)
+        orders[b, :n] = perm
+        keep = torch.rand(n, generator=gen) < 0.67
+        targets[b, :n] = torch.where(keep, perm, torch.full((n,), -1))
+    fb = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in vb.items()}
+    fb["shuffled_orders"], fb["targets"] = orders, targets
+    with torch.no_grad():
+        fom_logits = model(fb, "fom", compute_loss=False)
+        fom_loss = model(fb, "fom", compute_loss=True)
+    # ---- MLM on the cross-modal rows: mask one or two text positions per row
+    am = vb["f_attn_masks"]
+    rows, L = am.shape
+    max_vl = vb["f_v_feats"].shape[1]
+    gi = vb["f_gather_index"]
+    txt_mask_tgt = torch.zeros(rows, L, dtype=torch.bool)
+    for r in range(rows):
+        n = int(am[r].sum())
+        # packed row = [frames, text, filler]: text slots are those gathered from >= max_vl
+        text_pos = [j for j in range(L) if am[r, j] and int(gi[r, j]) >= max_vl]
+        pick = torch.randperm(len(text_pos), generator=gen)[:2 if n > 6 else 1]
+        for i in pick.tolist():
+            txt_mask_tgt[r, text_pos[i]] = True
+    n_masked = int(txt_mask_tgt.sum())
+    txt_labels = torch.randint(5, dims["vocab"] - 8, (n_masked,), generator=gen)
+    mb = {"input_ids": vb["f_sub_input_ids"], "position_ids": vb["f_sub_pos_ids"],
+          "v_feat": vb["f_v_feats"], "f_pos_ids": vb["f_v_pos_ids"], "attn_masks": am,
+          "gather_index": gi, "txt_mask_tgt": txt_mask_tgt, "txt_labels": txt_labels}
+    with torch.no_grad():
+        mlm_scores = model.f_encoder(mb, "mlm", compute_loss=False)
+        mlm_loss = model.f_encoder(mb, "mlm", compute_loss=True)
+    np.savez_compressed(
+        os.path.join(out_dir, "heads_tiny.npz"), **head,
+        c_v_masks=c_v_masks.numpy(), feat_targets=feat_targets.numpy(),
+        mffr_pred=mffr_pred.numpy(), mffr_loss=mffr_loss.numpy(), nce_loss=nce_loss.numpy(),
+        shuffled_orders=orders.numpy(), fom_targets=targets.numpy(),
+        fom_logits=fom_logits.numpy(), fom_loss=np.float64(fom_loss.item()),
+        txt_mask_tgt=txt_mask_tgt.numpy(), txt_labels=txt_labels.numpy(),
+        mlm_scores=mlm_scores.numpy(), mlm_loss=mlm_loss.numpy())
+    print("heads_tiny.npz: mffr", tuple(mffr_pred.shape), "nce", float(nce_loss.mean()),
+          "fom", float(fom_loss), "mlm", tuple(mlm_scores.shape))
+
+
 def np_batch(b):
     return {k: v.numpy() for k, v in b.items() if torch.is_tensor(v)}
 
@@ -184,6 +269,7 @@ def main():
         q_seq_out=q_out[0].detach().numpy(), loss_w1=w1.numpy(), loss_w2=w2.numpy(),
         loss=np.float64(loss.item()), **grads)
     print("hier_tiny.npz: loss", loss.item())
+    heads_fixture(model, tiny, vb, out_dir)
 
     # ---- G3: config 1 (SYN-XM-1), real dims, 1-layer CrossModalTrm -----------------------------
     full1 = dict(hidden=768, inter=3072, heads=12, f_layers=1, c_layers=1, vocab=50272,
