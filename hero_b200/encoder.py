@@ -16,8 +16,9 @@ from torch import nn
 from torch.nn import functional as F
 
 from . import functional as Fn
-from .embed import FrameEmbeddings, ImageEmbeddings, SubEmbeddings
-from .layers import BertEncoder, BertLayerNorm, BertLMPredictionHead, BertPooler
+from .embed import FrameEmbeddings, ImageEmbeddings, QueryFeatEmbeddings, SubEmbeddings
+from .layers import (BertAttention, BertEncoder, BertLayerNorm, BertLMPredictionHead, BertPooler,
+                     LinearLayer, mask_logits)
 from .params import flat_of
 from .plan import PLAN_KEY, TxtPlan
 
@@ -430,3 +431,35 @@ class TemporalTrm(RobertaPreTrainedModel):
                                      dev.c_pos_idx)
         out = Fn.gather_rows(y, dev.c_pad_to_tok, dev.c_tok_flat)
         return out.view(B, T, H).to(_output_dtype(self))
+
+
+class QueryFeatEncoder(nn.Module):
+    """model/encoder.py:426-485: projects query token features, adds positions, one self-attention
+    block, and pools the tokens into ONE vector per query with a learned softmax over positions
+    ("modularized query"). A 'next' row of SURVEY.md 8f: 32 queries x 16 tokens per step, plain
+    torch on whatever device the features live on; parameter names match the reference."""
+
+    def __init__(self, config, qfeat_dim, modularized=True):
+        super().__init__()
+        self.query_input_proj = LinearLayer(qfeat_dim, config.hidden_size, layer_norm=True,
+                                            dropout=config.hidden_dropout_prob, relu=True)
+        self.query_pos_embed = QueryFeatEmbeddings(config)
+        self.query_self_attention = BertAttention(config)
+        self.modularized = modularized
+        if modularized:
+            self.modular_vector_mapping = nn.Linear(config.hidden_size, 1, bias=False)
+
+    def get_modularized_queries(self, query, query_mask, return_modular_att=False):
+        """query (N, L, D), query_mask (N, L) -> (N, D): softmax over the valid positions of a
+        learned per-token score, used as pooling weights."""
+        scores = self.modular_vector_mapping(query)                       # (N, L, 1)
+        att = torch.softmax(mask_logits(scores, query_mask.unsqueeze(2)), dim=1)
+        pooled = (att * query).sum(1)                                      # (N, D)
+        return (pooled, att) if return_modular_att else pooled
+
+    def forward(self, query_feat, query_attn_mask, query_pos_ids=None):
+        dtype = next(self.parameters()).dtype
+        x = self.query_pos_embed(self.query_input_proj(query_feat.to(dtype)))
+        mask = query_attn_mask.to(dtype)
+        attended = self.query_self_attention(x, (1.0 - mask)[:, None, None, :] * -10000.0)[0]
+        return self.get_modularized_queries(attended, mask) if self.modularized else attended

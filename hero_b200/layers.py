@@ -59,6 +59,27 @@ class BertAttention(nn.Module):
         self.self = BertSelfAttention(config)
         self.output = BertSelfOutput(config)
 
+    def forward(self, input_tensor, attention_mask, head_mask=None):
+        """Stand-alone use of one attention block on a padded batch (model/layers.py:124-179,
+        182-231): the query-side `QueryFeatEncoder` runs it on 32 x 16 tokens, far off the hot
+        path, so this is plain torch. `attention_mask` is the additive (N, 1, 1, L) mask of the
+        reference. Returns a 1-tuple like the reference."""
+        if head_mask is not None:
+            raise ValueError("head_mask is not supported (always None in HERO)")
+        sa = self.self
+        N, L, _ = input_tensor.shape
+        x = input_tensor.to(sa.query.weight.dtype)
+
+        def heads(t):
+            return t.view(N, L, sa.num_attention_heads, sa.attention_head_size).transpose(1, 2)
+
+        q, k, v = heads(sa.query(x)), heads(sa.key(x)), heads(sa.value(x))
+        scores = q @ k.transpose(-1, -2) / (sa.attention_head_size ** 0.5)
+        probs = sa.dropout(torch.softmax(scores + attention_mask.to(scores.dtype), dim=-1))
+        ctx = (probs @ v).transpose(1, 2).reshape(N, L, sa.all_head_size)
+        out = self.output
+        return (out.LayerNorm(out.dropout(out.dense(ctx)) + x),)
+
 
 class BertIntermediate(nn.Module):
     def __init__(self, config):
@@ -204,6 +225,11 @@ class LinearLayer(nn.Module):
             x = self.LayerNorm(x)
         x = self.net(x)
         return torch.relu(x) if self.relu else x
+
+
+def mask_logits(target, mask, eps=-1e4):
+    """model/modeling_utils.py:42-43: keep `target` where mask == 1, `eps` elsewhere."""
+    return target * mask + (1 - mask) * eps
 
 
 def gelu(x):

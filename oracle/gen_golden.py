@@ -211,6 +211,104 @@ def heads_fixture(model, dims, vb, out_dir):
           "fom", float(fom_loss), "mlm", tuple(mlm_scores.shape))
 
 
+def vsm_fixture(dims, weights, vb, out_dir):
+    """VSM / VCMR head of the reference (model/pretrain.py, model/vcmr.py) on
+    the tiny encoder: two queries per clip, eval mode (no dropout, 'sum' reductions), span logits,
+    video-level scores and the three losses, plus the hard-negative weighting variant."""
+    from model.vcmr import HeroForVcmr
+    from model.model import VideoModelConfig
+    cfgd = model_json(dims["hidden"], dims["inter"], dims["heads"], dims["f_layers"],
+                      dims["c_layers"], dims["vocab"])
+    cfgd["q_config"] = dict(cfgd["c_config"], num_hidden_layers=1)
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as f:
+        json.dump(cfgd, f)
+        path = f.name
+    config = VideoModelConfig(path)
+    os.unlink(path)
+    model = HeroForVcmr(config, vfeat_dim=dims["vfeat_dim"], max_frm_seq_len=dims["max_img_len"],
+                        lw_neg_ctx=8, lw_neg_q=8, lw_st_ed=0.01, margin=0.1)
+    missing, unexpected = model.load_state_dict(
+        {"v_encoder." + k: v for k, v in weights.items()}, strict=False)
+    assert not unexpected, unexpected
+    gen = torch.Generator().manual_seed(91)
+    head = {}
+    for k, p in model.named_parameters():
+        if k.startswith(("video_query_linear", "video_st_predictor", "video_ed_predictor",
+                         "q_feat_attn")):
+            with torch.no_grad():
+                if "LayerNorm.weight" in k:
+                    p.copy_(1.0 + torch.randn(p.shape, generator=gen) * 0.05)
+                else:
+                    p.copy_(torch.randn(p.shape, generator=gen) * (0.3 if "predictor" in k else 0.05))
+            head["head." + k] = p.detach().numpy().copy()
+    model.eval()
+    B, T = vb["c_attn_masks"].shape
+    k = 2                                           # queries per clip, grouped by clip
+    Lq = 7
+    q_ids = torch.randint(5, dims["vocab"] - 8, (B * k, Lq), generator=gen)
+    q_len = torch.randint(3, Lq + 1, (B * k,), generator=gen)
+    q_mask = (torch.arange(Lq)[None, :] < q_len[:, None]).long()
+    q_ids = q_ids * q_mask + (1 - q_mask)           # padding id 1
+    q_pos = torch.arange(Lq).unsqueeze(0)
+    n_frames = vb["c_attn_masks"].sum(1)
+    st = torch.stack([torch.randint(0, int(n_frames[i // k]), (1,), generator=gen)[0]
+                      for i in range(B * k)])
+    ed = torch.minimum(st + 2, n_frames.repeat_interleave(k) - 1)
+    targets = torch.stack([st, ed], 1)
+    targets[1] = -1                                  # one ignored query
+    q_vidx = torch.arange(B).repeat_interleave(k)
+
+    def batch():
+        b = {kk: (v.clone() if torch.is_tensor(v) else v) for kk, v in vb.items()}
+        b.update(query_input_ids=q_ids, query_pos_ids=q_pos, query_attn_masks=q_mask,
+                 targets=targets, q_vidx=q_vidx)
+        return b
+
+    with torch.no_grad():
+        scores, st_prob, ed_prob = model(batch(), "tvr", compute_loss=False)
+        l_st_ed, l_ctx, l_q = model(batch(), "tvr", compute_loss=True)
+        model.set_hard_negative(True, 2, 10)
+        _, h_ctx, h_q = model(batch(), "tvr", compute_loss=True)
+        model.set_hard_negative(False, 20, 10)
+        model.ranking_loss_type = "lse"
+        _, e_ctx, e_q = model(batch(), "tvr", compute_loss=True)
+        model.ranking_loss_type = "hinge"
+    # second batch: clips of EQUAL length (no padded frames), one query per clip -> the
+    # non-cross span path and a span loss that does not depend on what the encoder leaves at
+    # padded positions (hero_b200 zero-fills them, the reference does not)
+    vbd, qbd = synth.syn_tvr_ragged(batch_size=3, seed=33, vfeat_dim=dims["vfeat_dim"],
+                                    vocab=dims["vocab"] - 7, t_range=(9, 9), s_range=(2, 4),
+                                    l_range=(3, 8), q_range=(3, 7))
+    assert bool(vbd["c_attn_masks"].all())
+    d_targets = torch.tensor([[1, 3], [0, 8], [4, 4]])
+
+    def dense():
+        b = {kk: (v.clone() if torch.is_tensor(v) else v) for kk, v in vbd.items()}
+        b.update(query_input_ids=qbd["input_ids"], query_pos_ids=qbd["pos_ids"],
+                 query_attn_masks=qbd["attn_masks"], targets=d_targets)
+        return b
+
+    with torch.no_grad():
+        d_scores, d_st, d_ed = model(dense(), "tvr", compute_loss=False)
+        d_l_st_ed, d_l_ctx, d_l_q = model(dense(), "tvr", compute_loss=True)
+    dense_np = {"vbd." + k: v for k, v in np_batch(vbd).items()}
+    dense_np.update({"qbd." + k: v for k, v in np_batch(qbd).items()})
+    np.savez_compressed(
+        os.path.join(out_dir, "vsm_tiny.npz"), **head, q_config=json.dumps(cfgd["q_config"]),
+        query_input_ids=q_ids.numpy(), query_pos_ids=q_pos.numpy(),
+        query_attn_masks=q_mask.numpy(), targets=targets.numpy(), q_vidx=q_vidx.numpy(),
+        scores=scores.numpy(), st_prob=st_prob.numpy(), ed_prob=ed_prob.numpy(),
+        loss_st_ed=l_st_ed.numpy(), loss_neg_ctx=l_ctx.numpy(), loss_neg_q=l_q.numpy(),
+        hard_neg_ctx=h_ctx.numpy(), hard_neg_q=h_q.numpy(), lse_neg_ctx=e_ctx.numpy(),
+        lse_neg_q=e_q.numpy(), **dense_np, d_num_subs=json.dumps(vbd["num_subs"]),
+        d_sub_idx2frame_idx=json.dumps(vbd["sub_idx2frame_idx"]), d_targets=d_targets.numpy(),
+        d_scores=d_scores.numpy(), d_st=d_st.numpy(), d_ed=d_ed.numpy(),
+        d_loss_st_ed=d_l_st_ed.numpy(), d_loss_neg_ctx=d_l_ctx.numpy(),
+        d_loss_neg_q=d_l_q.numpy())
+    print("vsm_tiny.npz: scores", tuple(scores.shape), "st", tuple(st_prob.shape),
+          "loss_st_ed", float(l_st_ed.sum()), "ctx", l_ctx.tolist())
+
+
 def np_batch(b):
     return {k: v.numpy() for k, v in b.items() if torch.is_tensor(v)}
 
@@ -270,6 +368,7 @@ def main():
         loss=np.float64(loss.item()), **grads)
     print("hier_tiny.npz: loss", loss.item())
     heads_fixture(model, tiny, vb, out_dir)
+    vsm_fixture(tiny, W, vb, out_dir)
 
     # ---- G3: config 1 (SYN-XM-1), real dims, 1-layer CrossModalTrm -----------------------------
     full1 = dict(hidden=768, inter=3072, heads=12, f_layers=1, c_layers=1, vocab=50272,

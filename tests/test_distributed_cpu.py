@@ -216,3 +216,39 @@ def test_peer_exchange_algorithm_on_simulated_ranks(monkeypatch):
         for a, b in done:
             for r in range(W):
                 assert torch.allclose(grads[r][a:b], want[a:b], atol=1e-6), (W, a, b, r)
+
+
+def _vsm_scores_case(rank, world, hd):
+    """get_video_level_scores with the cross-rank gather: ranks hold clips of different padded
+    lengths; every rank must obtain the scores of ALL queries against ALL clips."""
+    import types
+    from hero_b200.pretrain import HeroForPretraining
+    gen = torch.Generator().manual_seed(5)
+    D = 16
+    data = []
+    for r in range(world):
+        L = 5 + 2 * r
+        q = torch.randn(2, D, generator=gen)
+        ctx = torch.randn(2, L, D, generator=gen)
+        mask = torch.ones(2, L, dtype=torch.long)
+        mask[1, L - 2:] = 0
+        data.append((q, ctx, mask))
+    me = types.SimpleNamespace(training=True, gather_gpus=True)
+    q, ctx, mask = data[rank]
+    got = HeroForPretraining.get_video_level_scores(me, q, ctx, mask)
+    # single-process reference: pad to the longest clip and concatenate in rank order
+    Lmax = max(c.shape[1] for _, c, _ in data)
+    qa = torch.cat([d[0] for d in data])
+    ca = torch.cat([torch.nn.functional.pad(d[1], (0, 0, 0, Lmax - d[1].shape[1])) for d in data])
+    ma = torch.cat([torch.nn.functional.pad(d[2], (0, Lmax - d[2].shape[1])) for d in data])
+    alone = types.SimpleNamespace(training=True, gather_gpus=False)
+    want = HeroForPretraining.get_video_level_scores(alone, qa, ca, ma)
+    return got.tolist(), want.tolist()
+
+
+def test_vsm_video_level_scores_gather_all_ranks():
+    out = _run("_vsm_scores_case")
+    for r in (0, 1):
+        got, want = out[r]
+        assert torch.allclose(torch.tensor(got), torch.tensor(want), atol=1e-6)
+        assert len(got) == 4 and len(got[0]) == 4
