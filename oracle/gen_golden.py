@@ -295,6 +295,7 @@ def vsm_fixture(dims, weights, vb, out_dir):
     dense_np.update({"qbd." + k: v for k, v in np_batch(qbd).items()})
     np.savez_compressed(
         os.path.join(out_dir, "vsm_tiny.npz"), **head, q_config=json.dumps(cfgd["q_config"]),
+        state_dict_shapes=json.dumps({kk: list(v.shape) for kk, v in model.state_dict().items()}),
         query_input_ids=q_ids.numpy(), query_pos_ids=q_pos.numpy(),
         query_attn_masks=q_mask.numpy(), targets=targets.numpy(), q_vidx=q_vidx.numpy(),
         scores=scores.numpy(), st_prob=st_prob.numpy(), ed_prob=ed_prob.numpy(),
