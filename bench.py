@@ -486,8 +486,8 @@ def main():
     ap.add_argument("--batch-size", type=int, default=32)
     ap.add_argument("--with-optimizer", action="store_true")
     ap.add_argument("--no-overlap", action="store_true",
-                    help="N>1: one all-reduce of the flat gradient after backward (the reference's "
-                         "schedule) instead of per-layer buckets overlapped with backward")
+                    help="N>1: force one all-reduce of the flat gradient after backward (already "
+                         "the default; overrides --dp-transport)")
     ap.add_argument("--dp-transport", default="none", choices=("none", "p2p", "nccl", "auto"),
                     help="N>1: 'none' = one NCCL all-reduce of the flat gradient buffer after "
                          "backward (default, measured fastest end to end); 'p2p' / 'nccl' = "

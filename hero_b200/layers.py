@@ -10,7 +10,6 @@ import torch
 from torch import nn
 
 from . import functional as Fn
-from . import ops
 from .params import flat_of
 from .plan import TxtPlan
 

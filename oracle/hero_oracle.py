@@ -26,7 +26,6 @@ standard LayerNorm: biased variance, fp32 statistics.
 import math
 
 import torch
-import torch.nn.functional as F
 
 
 def layer_norm(x, weight, bias, eps):

@@ -4,7 +4,6 @@ of the reference (Horovod allreduce = mean over ranks; allgather concatenates in
 import os
 import socket
 
-import pytest
 import torch
 import torch.multiprocessing as mp
 

@@ -340,3 +340,58 @@ def test_fused_adamw_follows_reference_rule_with_param_groups():
     # the bf16 working copy was refreshed by the optimizer kernel itself
     for k, p in m.named_parameters():
         assert torch.equal(flat.bf16(p), p.detach().to(torch.bfloat16)), k
+
+
+def test_vcmr_head_on_gpu_matches_its_cpu_orchestration(tmp_path, monkeypatch):
+    """hero_b200.pretrain.HeroForVcmr (VSM / VCMR head) on the CUDA encoder:
+    same outputs as the same module run on CPU with hero_b200.ops routed to the torch
+    restatements of the kernel contracts (tests/fake_ops.py) — that CPU path is what
+    tests/test_heads_cpu.py pins against the reference. Full hidden size, 1 + 1 + 1 layers."""
+    from hero_b200.model import VideoModelConfig
+    from hero_b200.pretrain import HeroForVcmr
+    from tests import fake_ops
+    d = dict(hidden=768, inter=3072, heads=12, f_layers=1, c_layers=1, vocab=50272,
+             vfeat_dim=4352, max_img_len=100)
+    cfg = json.load(open(_json(tmp_path, d)))
+    cfg["q_config"] = dict(cfg["c_config"])
+    path = tmp_path / "vcmr.json"
+    path.write_text(json.dumps(cfg))
+    P = orc.seeded_weights(orc.param_shapes(f_layers=1, c_layers=1), seed=12)
+
+    def build():
+        torch.manual_seed(3)               # identical random head parameters in both builds
+        m = HeroForVcmr(VideoModelConfig(str(path)), vfeat_dim=4352, max_frm_seq_len=100,
+                        lw_neg_ctx=8, lw_neg_q=8, lw_st_ed=0.01)
+        m.load_state_dict({"v_encoder." + k: v for k, v in P.items()}, strict=False)
+        return m.eval()
+
+    vb, qb = synth.syn_tvr_ragged(batch_size=3, seed=14, t_range=(10, 16), s_range=(2, 4),
+                                  l_range=(4, 10), q_range=(4, 8))
+    targets = torch.tensor([[1, 3], [0, 5], [2, 2]])
+
+    def batch(dev):
+        b = synth.to_device(dict(vb), dev) if dev != "cpu" else dict(vb)
+        for k, v in (("query_input_ids", qb["input_ids"]), ("query_pos_ids", qb["pos_ids"]),
+                     ("query_attn_masks", qb["attn_masks"]), ("targets", targets)):
+            b[k] = v.to(dev)
+        return b
+
+    gpu = build().cuda()
+    with torch.no_grad():
+        s_g, st_g, ed_g = gpu(batch("cuda"), "tvr", compute_loss=False)
+        losses_g = gpu(batch("cuda"), "tvr", compute_loss=True)
+    head_sd = {k: v.cpu() for k, v in gpu.state_dict().items()}
+    fake_ops.install(monkeypatch)
+    cpu = build()
+    cpu.load_state_dict(head_sd)
+    with torch.no_grad():
+        s_c, st_c, ed_c = cpu(batch("cpu"), "tvr", compute_loss=False)
+        losses_c = cpu(batch("cpu"), "tvr", compute_loss=True)
+    assert s_g.shape == (3, 3) and st_g.shape == st_c.shape
+    assert float((s_g.cpu() - s_c).abs().max()) < 2e-2
+    valid = vb["c_attn_masks"].bool()
+    for a, b in ((st_g, st_c), (ed_g, ed_c)):
+        diff = (a.float().cpu() - b.float())[valid].abs().max()
+        assert float(diff) <= 3e-2 * float(b.float()[valid].abs().max()) + 3e-2
+    for a, b in zip(losses_g, losses_c):
+        assert float((a.float().cpu() - b.float()).abs().max()) < 0.2

@@ -4,7 +4,7 @@ import numpy as np
 import torch
 
 from hero_b200 import synth
-from hero_b200.plan import CPlan, FPlan, ReprPlan, SeqPlan, TxtPlan, table_csr
+from hero_b200.plan import FPlan, ReprPlan, SeqPlan, TxtPlan, table_csr
 from oracle import hero_oracle as orc
 
 

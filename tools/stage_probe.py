@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from hero_b200 import synth
 from hero_b200.loader import BatchStager
-from hero_b200.plan import PLAN_KEY, DeviceIndex, build_plans, plan_inputs
+from hero_b200.plan import DeviceIndex, build_plans, plan_inputs
 
 dev = torch.device("cuda:0")
 vb, qb = synth.syn_tvr_dense(batch_size=32, seed=1)
