@@ -107,6 +107,12 @@ def load_pretrained_weight(model, state_dict):
     if errors:
         raise RuntimeError("Error(s) in loading state_dict for {}:\n\t{}".format(
             model.__class__.__name__, "\n\t".join(errors)))
+    # the copies above went through state_dict views: tell the flat-parameter manager (if the
+    # model has already run) that its bf16 working copy is stale
+    for m in model.modules():
+        fp = m.__dict__.get("_hero_flat")
+        if fp is not None:
+            fp.mark_dirty()
     return model
 
 

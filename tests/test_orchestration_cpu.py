@@ -210,3 +210,33 @@ def test_bf16_mirror_follows_any_torch_optimizer_step(tmp_path, monkeypatch):
     fresh = _model(tmp_path, fx)
     fresh.load_state_dict(model.state_dict())
     assert torch.equal(fresh(vb, "repr"), out1)
+
+
+def test_fp16_checkpoint_round_trip_after_the_model_has_run(tmp_path, monkeypatch):
+    """checkpoints are written with the reference's conventions
+    (utils/save.py:117-130: plain state_dict + a 'vocab_padded' flag, fp16 tensors on disk for the
+    released weights) and must load into a model whose flat buffers already exist — the bf16
+    working copy has to follow."""
+    fake_ops.install(monkeypatch)
+    from hero_b200.encoder import load_pretrained_weight
+    fx = gu.load("hier_tiny.npz")
+    vb, _ = gu.stored_batches(fx)
+    src = _model(tmp_path, fx)
+    ckpt = {k: v.half() for k, v in src.state_dict().items()}
+    ckpt["vocab_padded"] = True
+    path = tmp_path / "model_step_1.pt"
+    torch.save(ckpt, str(path))
+
+    dst = _model(tmp_path, fx)
+    with torch.no_grad():
+        for p in dst.parameters():
+            p.mul_(0.5)                       # some other weights ...
+    out_other = dst(vb, "repr")               # ... and the flat buffers + bf16 mirror exist
+    load_pretrained_weight(dst, torch.load(str(path)))
+    out_loaded = dst(vb, "repr")
+    for (k, a), (_, b) in zip(dst.state_dict().items(), src.state_dict().items()):
+        assert torch.equal(a, b.half().to(a.dtype)), k
+    want = src(vb, "repr")
+    m = vb["c_attn_masks"].bool()
+    assert (out_loaded - out_other)[m].abs().max() > 1e-2
+    assert (out_loaded - want)[m].abs().max() < 6e-2          # fp16-rounded weights, bf16 math
