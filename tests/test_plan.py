@@ -123,3 +123,31 @@ def test_plan_pool_builds_the_same_plans_in_worker_processes():
         for k in a:
             assert np.array_equal(a[k], b[k]), k
     assert got_v.__dict__["_joint"].t is got_q
+
+
+def test_prefetch_loader_attaches_plans_in_order_without_cuda():
+    """hero_b200.loader.PrefetchLoader._with_plans (the host half of the loader): batches come out
+    in order, a plan attached by the collate function is kept, a missing one is built (here in
+    process), single dicts and (video, query) pairs are both accepted."""
+    from hero_b200.loader import PrefetchLoader
+    from hero_b200.plan import PLAN_KEY, attach_plan
+    items = []
+    for seed in range(4):
+        vb, qb = synth.syn_tvr_ragged(batch_size=2, seed=40 + seed, t_range=(8, 12),
+                                      s_range=(2, 3), l_range=(3, 6))
+        vb["_tag"] = seed
+        items.append((vb, qb) if seed % 2 == 0 else vb)
+    pre = attach_plan(dict(items[1]))[PLAN_KEY]
+    items[1][PLAN_KEY] = pre
+    ld = PrefetchLoader.__new__(PrefetchLoader)
+    ld.pool = None
+    out = list(ld._with_plans(iter(items)))
+    assert [(b[0] if isinstance(b, tuple) else b)["_tag"] for b in out] == [0, 1, 2, 3]
+    assert isinstance(out[0], tuple) and not isinstance(out[1], tuple)
+    assert out[1][PLAN_KEY] is pre
+    for b in out:
+        vb = b[0] if isinstance(b, tuple) else b
+        assert vb[PLAN_KEY] is not None
+        if isinstance(b, tuple):
+            assert b[1][PLAN_KEY] is not None
+    assert PLAN_KEY not in items[0][0]          # the loader works on copies of the dicts
