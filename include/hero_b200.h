@@ -10,8 +10,10 @@
  *   - plain C types only: device pointers, sizes, strides in ELEMENTS unless a name says bytes.
  *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns 0 on
  *     success or a non-zero hero_status; hero_last_error() describes the last failure of the
- *     calling thread. No hidden allocation, no global mutable state besides cached device
- *     attributes and TMA descriptor encode entry points.
+ *     calling thread. No hidden allocation; global state is limited to cached device
+ *     attributes, the TMA descriptor encode entry point, the optional SM limit, and the layer
+ *     runtime's second stream + events per device (hero_bert_stack_bwd, always joined into the
+ *     caller's stream before the call returns).
  *   - "bf16" buffers are raw uint16 bfloat16; "f32" are float.
  *   - token-major packed layout: activations are [n_tokens, hidden] with only VALID (unmasked)
  *     tokens present; sequences are described by cu_seqlens[n_seq + 1] (int32 prefix sums).
@@ -39,8 +41,8 @@ int hero_version(void);
 int hero_sm_count(void);
 /* Size every persistent kernel for at most n SMs (0 = all). The GEMMs run one CTA per SM; while a
  * communication kernel (NCCL) holds some SMs a full-size grid would need a second wave for the
- * displaced CTAs. hero_b200.distributed.GradBucketer lowers the limit by the communicator's CTA
- * count while gradient buckets are exchanged during backward. */
+ * displaced CTAs. Used by hero_b200.distributed.GradBucketer(transport="nccl") while gradient
+ * buckets are exchanged beside the backward kernels. */
 int hero_set_sm_limit(int32_t n);
 
 /* ------------------------------------------------------------------------------------------
@@ -190,7 +192,9 @@ int hero_ln_bwd(const hero_ln_args* args, void* stream);
  *   seq_lo[n_tok], seq_hi[n_tok]            [lo, hi) packed-token range of each token's sequence
  * One CTA per (tile, head): S = QK^T and O = PV (forward), S, dP, dQ, dK, dV (backward) are
  * tcgen05.mma contractions with fp32 accumulators in TMEM; probabilities never reach HBM.
- * Dropout mask index of P[token i, head h, key j] = (i*heads + h)*128 + (j - seq_lo[i]).
+ * Dropout: one 32-bit counter hash per (token i, head h, pair of tile columns 2u, 2u+1), 16 bits
+ * per probability, word index ((i*heads + h)*64 + u); forward and backward regenerate the same
+ * words from the same plan.
  * The backward takes the saved forward output (D_i = dO_i . O_i).
  * Constraints: head_dim == 64, sequences <= 128 tokens.
  * ---------------------------------------------------------------------------------------- */
@@ -243,7 +247,7 @@ typedef struct hero_layer_acts { /* bf16 unless noted; [n_tok, ...] */
   float* mean1;
   float* rstd1;
   void* a;      /* LN(s1) */
-  void* pre;    /* FFN pre-activation [n_tok, I]; NULL in inference */
+  void* pre;    /* gelu'(FFN pre-activation) [n_tok, I], saved for the backward; NULL in inference */
   void* f;      /* gelu(pre) [n_tok, I] */
   void* s2;     /* pre-LN sum after FFN */
   float* mean2;
