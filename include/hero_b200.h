@@ -108,7 +108,10 @@ int hero_gemm_profile_begin(void);
 int hero_gemm_profile_end(double* ms, double* flops, int64_t* launches);
 
 /* ------------------------------------------------------------------------------------------
- * Fused row kernels: gather + add + LayerNorm (+ dropout) + scatter, one warp per row.
+ * Fused row kernels: gather + add + LayerNorm (+ dropout) + scatter. One entry point per
+ * direction; the library picks the kernel (persistent register-resident fast path for plain bf16
+ * rows of <= 768 columns incl. a one-pass backward with dgamma / dbeta / dbias, CTA-per-row kernel
+ * for the 4352-wide rows, generic warp-per-row kernel otherwise).
  *
  * Replaces apex FusedLayerNorm and the embedding sums around it:
  *   model/layers.py:178,253      LN(dropout(dense(x)) + residual), eps 1e-12 (post-GEMM form:
