@@ -1,5 +1,7 @@
 """Prints error statistics of the CUDA encoder vs the CPU oracle / reference goldens (used to
-choose and justify the tolerances written in tests/test_encoder_gpu.py)."""
+choose and justify the tolerances written in tests/test_encoder_gpu.py). Lives under tests/
+because it calls the oracle (test infrastructure); run as `python tests/parity_report.py` on a GPU
+box. Not collected by pytest (no test_ prefix)."""
 import json
 import os
 import sys

@@ -7,7 +7,7 @@ Tolerances (bf16 kernels vs fp32 oracle, eval mode, valid positions only):
   gradients per-parameter relative Frobenius error <= 3e-2, except
             * frame_transform.* <= 6e-2: these four gradients are ill-conditioned in bf16 — the
               oracle itself run under torch CPU bf16 autocast shows 4.2e-2 / 4.2e-2 / 3.8e-2 /
-              3.7e-2 on the dense case (tools/parity_report.py; ours: 4.2e-2 / 4.1e-2 / 3.7e-2 /
+              3.7e-2 on the dense case (tests/parity_report.py; ours: 4.2e-2 / 4.1e-2 / 3.7e-2 /
               3.7e-2), i.e. the bound is 1.5x the bf16 yardstick as SURVEY.md §8c prescribes;
             * attention.self.key.bias: the exact gradient is identically zero (softmax is
               invariant to a per-query constant), so it is checked in absolute terms.
