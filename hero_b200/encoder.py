@@ -207,7 +207,10 @@ class CrossModalTrm(RobertaPreTrainedModel):
     # ---- packed hot path -------------------------------------------------------------------
     def _embed_cfg(self, fplan, dev, drop, input_ids, position_ids, img_feat, img_pos_ids,
                    img_masks, pos_keys=("f_txtpos_off", "f_txtpos_idx", "f_imgpos_off",
-                                        "f_imgpos_idx")):
+                                        "f_imgpos_idx"), shared_feats=None):
+        """`shared_feats`: clip-level frame features (B, T, D) to read the frame slots from when
+        the batch carries no `f_v_feats` (plan.ReprPlan maps every packed frame token to its
+        clip frame)."""
         device = dev.flat.device
         cfg = {"drop": drop, "n_tok": fplan.seq.n_tok, "n_txt": fplan.n_txt,
                "n_img": fplan.n_img, "pad_idx": self.embeddings.padding_idx, "img_mask": None}
@@ -227,12 +230,20 @@ class CrossModalTrm(RobertaPreTrainedModel):
             cfg["txtpos_off"] = getattr(dev, pos_keys[0])
             cfg["txtpos_idx"] = getattr(dev, pos_keys[1])
         if fplan.n_img:
+            img_src = dev.f_img_src
+            if img_feat is None:
+                if shared_feats is None:
+                    raise ValueError("batch has neither f_v_feats nor c_v_feats for the frame slots")
+                if img_masks is not None:
+                    raise ValueError("frame masking (f_v_masks) needs the f_v_feats copy: the MFM "
+                                     "path overwrites c_v_feats in place (model/model.py:244-247)")
+                img_feat, img_src = shared_feats, dev.f_img_src_c
             D = img_feat.shape[-1]
             feats = img_feat.reshape(-1, D)
             if feats.dtype != torch.float32:
                 feats = feats.float()
             cfg["img_feats"] = feats.contiguous()
-            cfg["img_src"] = dev.f_img_src
+            cfg["img_src"] = img_src
             cfg["img_tok"] = dev.f_img_tok
             if img_pos_ids is None:
                 cfg["img_k"] = dev.f_img_k
@@ -259,13 +270,15 @@ class CrossModalTrm(RobertaPreTrainedModel):
         return params
 
     def encode_packed(self, fplan, dev, input_ids, position_ids, img_feat=None, img_pos_ids=None,
-                      img_masks=None, drop=None, pos_keys=None):
+                      img_masks=None, drop=None, pos_keys=None, shared_feats=None):
         """Embeddings + encoder on packed tokens -> bf16 [n_tokens, H]."""
         device = dev.flat.device
         flat = flat_of(self, device)
         if drop is None:
             drop = self.encoder.dropout_state()
         kw = {} if pos_keys is None else {"pos_keys": pos_keys}
+        if shared_feats is not None:
+            kw["shared_feats"] = shared_feats
         cfg = self._embed_cfg(fplan, dev, drop, input_ids, position_ids, img_feat, img_pos_ids,
                               img_masks, **kw)
         with_img = fplan.n_img > 0
@@ -285,7 +298,9 @@ class CrossModalTrm(RobertaPreTrainedModel):
         v_ids, q_ids = batch["f_sub_input_ids"], txt_batch["input_ids"]
         v_pos, q_pos = batch["f_sub_pos_ids"], txt_batch["pos_ids"]
         cfg_v = self._embed_cfg(fv, rdev, drop, v_ids, v_pos, batch["f_v_feats"],
-                                batch["f_v_pos_ids"], batch["f_v_masks"])
+                                batch["f_v_pos_ids"], batch["f_v_masks"],
+                                shared_feats=batch["c_v_feats"] if batch["f_v_feats"] is None
+                                else None)
         cfg_q = self._embed_cfg(fq, tdev, drop, q_ids, q_pos, None, None, None,
                                 pos_keys=("pos_off", "pos_idx", None, None))
         cfg = dict(cfg_v)

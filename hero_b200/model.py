@@ -134,7 +134,8 @@ class HierarchicalVlModel(VideoPreTrainedModel):
             # cross-modal transformer on packed [frames, text] rows
             hf = fe.encode_packed(plan.f, dev, batch["f_sub_input_ids"], batch["f_sub_pos_ids"],
                                   batch["f_v_feats"], batch["f_v_pos_ids"], batch["f_v_masks"],
-                                  drop)
+                                  drop, shared_feats=batch["c_v_feats"]
+                                  if batch["f_v_feats"] is None else None)
         else:
             jplan = plan.__dict__.get("_joint")
             if jplan is None or jplan.t is not txt_plan:
@@ -226,6 +227,9 @@ class HierarchicalVlModel(VideoPreTrainedModel):
     # ---- pretraining heads (model/model.py:239-336): encoder on CUDA, small heads in torch ----
     def forward_mfm(self, batch, compute_loss=True, loss="regression"):
         assert loss in ["regression", "nce"]
+        if batch["f_v_feats"] is None:
+            raise ValueError("MFM needs the batch's own f_v_feats: c_v_feats is overwritten in "
+                             "place below and cannot also serve the subtitle-level frame slots")
         c_v_feats = batch["c_v_feats"]
         c_v_mask = batch["c_v_masks"]
         c_v_feats.masked_fill_(c_v_mask.unsqueeze(-1), 0)      # in place, like the reference

@@ -29,6 +29,17 @@ def _np(t):
     return np.asarray(t)
 
 
+def _max_vl_of(batch):
+    """Padded number of frame slots per subtitle row: from the plan inputs, the frame features, or
+    (batches without f_v_feats) the (1, max_vl) frame position ids of the collate."""
+    if "_max_vl" in batch:
+        return int(batch["_max_vl"])
+    fv = batch.get("f_v_feats") if hasattr(batch, "get") else batch["f_v_feats"]
+    if fv is not None:
+        return int(fv.shape[1])
+    return int(batch["f_v_pos_ids"].shape[-1])
+
+
 def _host_ids(t):
     """Small id tensor -> host int64 array [rows, L], or None if absent / not on the host."""
     if t is None or (torch.is_tensor(t) and t.device.type != "cpu"):
@@ -201,6 +212,10 @@ class CPlan:
         dst = np.asarray(dst, np.int64)
         if dst.size and (dst.max() >= B * T or dst.min() < 0):
             raise IndexError("sub_idx2frame_idx refers to a frame outside the clip tensor")
+        # (sub row, slot) -> row of c_v_feats.view(-1, D); -1 where the slot holds no clip frame
+        self.frame_source = np.full(fplan.seq.rows * max(fplan.max_vl, 1), -1, np.int32)
+        if rows.size:
+            self.frame_source[rows * fplan.max_vl + ks] = dst
         f_tok = fplan.seq.pad_to_tok[rows * fplan.seq.length + ks] if rows.size else \
             np.zeros(0, np.int32)
         c_tok = s.pad_to_tok[dst] if dst.size else np.zeros(0, np.int32)
@@ -230,11 +245,16 @@ class ReprPlan:
 
     def __init__(self, batch):
         # `plan_inputs` dicts carry the two padded lengths instead of the big tensors
-        max_vl = batch["_max_vl"] if "_max_vl" in batch else batch["f_v_feats"].shape[1]
+        max_vl = _max_vl_of(batch)
         max_sl = batch["_max_sl"] if "_max_sl" in batch else batch["f_sub_input_ids"].shape[1]
         self.f = FPlan(batch["f_attn_masks"], batch["f_gather_index"], max_vl, max_sl)
         self.c = CPlan(batch["c_attn_masks"], self.f, batch["num_subs"],
                        batch["sub_idx2frame_idx"])
+        # Every frame slot of a subtitle row is a copy of a clip frame (data/data.py:380-395 fills
+        # f_v_feats with index_select(c_v_feats, frames)): row of c_v_feats.view(-1, D) behind each
+        # packed frame token, so a batch may omit `f_v_feats` altogether (half the H2D bytes).
+        self.f.img_src_c = self.c.frame_source[self.f.img_src] if self.f.n_img else \
+            np.zeros(0, np.int32)
         self.shape_f = tuple(batch["f_attn_masks"].shape)
         self.shape_c = tuple(batch["c_attn_masks"].shape)
         # position-table CSRs for the deterministic embedding gradients
@@ -249,6 +269,7 @@ class ReprPlan:
     def to(self, device, staging=None):
         if self.dev is None or self.dev.flat.device != torch.device(device):
             a = self.f.arrays("f_")
+            a["f_img_src_c"] = self.f.img_src_c
             a.update(self.c.arrays("c_"))
             a.update({"f_txtpos_off": self.f_txtpos_off, "f_txtpos_idx": self.f_txtpos_idx,
                       "f_imgpos_off": self.f_imgpos_off, "f_imgpos_idx": self.f_imgpos_idx,
@@ -346,7 +367,7 @@ def plan_inputs(batch, kind="repr"):
         return {"attn_masks": _np(batch["attn_masks"]), "pos_ids": opt("pos_ids")}
     d = {k: (_np(batch[k]) if torch.is_tensor(batch[k]) else batch[k]) for k in _REPR_KEYS}
     d["f_sub_pos_ids"] = opt("f_sub_pos_ids")
-    d["_max_vl"] = int(batch["f_v_feats"].shape[1])
+    d["_max_vl"] = _max_vl_of(batch)
     d["_max_sl"] = int(batch["f_sub_input_ids"].shape[1])
     return d
 

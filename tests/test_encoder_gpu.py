@@ -395,3 +395,23 @@ def test_vcmr_head_on_gpu_matches_its_cpu_orchestration(tmp_path, monkeypatch):
         assert float(diff) <= 3e-2 * float(b.float()[valid].abs().max()) + 3e-2
     for a, b in zip(losses_g, losses_c):
         assert float((a.float().cpu() - b.float()).abs().max()) < 0.2
+
+
+def test_batch_without_f_v_feats_on_gpu(tmp_path):
+    """A batch that omits `f_v_feats` (the subtitle-level copies of the clip frames) gives the
+    same forward as the legacy batch: the frame slots are read from `c_v_feats` through the plan."""
+    d = dict(hidden=768, inter=3072, heads=12, f_layers=1, c_layers=1, vocab=50272,
+             vfeat_dim=4352, max_img_len=100)
+    P = orc.seeded_weights(orc.param_shapes(f_layers=1, c_layers=1), seed=15)
+    model = _build(tmp_path, d, P)
+    vb, qb = synth.syn_tvr_ragged(batch_size=3, seed=16, t_range=(10, 18), s_range=(2, 4),
+                                  l_range=(4, 10))
+    full = synth.to_device(dict(vb), "cuda")
+    slim = {k: v for k, v in full.items() if k != "f_v_feats"}
+    qd = synth.to_device(dict(qb), "cuda")
+    with torch.no_grad():
+        a = model(full, "repr")
+        b = model(slim, "repr")
+        a2, qa = model.forward_repr_txt(full, qd)
+        b2, qb2 = model.forward_repr_txt(slim, qd)
+    assert torch.equal(a, b) and torch.equal(a2, b2) and torch.equal(qa, qb2)

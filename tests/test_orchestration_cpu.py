@@ -240,3 +240,42 @@ def test_fp16_checkpoint_round_trip_after_the_model_has_run(tmp_path, monkeypatc
     m = vb["c_attn_masks"].bool()
     assert (out_loaded - out_other)[m].abs().max() > 1e-2
     assert (out_loaded - want)[m].abs().max() < 6e-2          # fp16-rounded weights, bf16 math
+
+
+def test_batch_without_f_v_feats_reads_the_clip_frames(tmp_path, monkeypatch):
+    """SURVEY.md 8f rank 2 (first step): `f_v_feats` is a row gather of `c_v_feats`; a batch that
+    omits it (half the host->device bytes) must give exactly the same outputs and gradients, on
+    the plain and on the fused query path. MFM keeps requiring it (c_v_feats is masked in place)."""
+    import pytest
+    fake_ops.install(monkeypatch)
+    fx = gu.load("hier_tiny.npz")
+    vb, qb = gu.stored_batches(fx)
+    slim = {k: v for k, v in vb.items() if k != "f_v_feats"}
+    w1 = torch.from_numpy(fx["loss_w1"])
+
+    def run(batch, fused):
+        model = _model(tmp_path, fx)
+        if fused:
+            clip, q = model.forward_repr_txt(batch, qb)
+        else:
+            clip, q = model(batch, "repr"), None
+        (clip * w1).sum().backward()
+        grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        return clip.detach(), q, grads
+
+    for fused in (False, True):
+        a, qa, ga = run(vb, fused)
+        b, qb_out, gb = run(slim, fused)
+        assert torch.equal(a, b)
+        if fused:
+            assert torch.equal(qa, qb_out)
+        assert ga.keys() == gb.keys()
+        for k in ga:
+            assert torch.equal(ga[k], gb[k]), k
+    model = _model(tmp_path, fx)
+    mb = dict(slim)
+    mb["c_v_masks"] = torch.zeros_like(vb["c_attn_masks"], dtype=torch.bool)
+    mb["c_v_masks"][:, 0] = True
+    mb["feat_targets"] = vb["c_v_feats"][mb["c_v_masks"]]
+    with pytest.raises(ValueError):
+        model(mb, "mffr")

@@ -151,3 +151,21 @@ def test_prefetch_loader_attaches_plans_in_order_without_cuda():
         if isinstance(b, tuple):
             assert b[1][PLAN_KEY] is not None
     assert PLAN_KEY not in items[0][0]          # the loader works on copies of the dicts
+
+
+def test_frame_slots_map_back_to_clip_frames():
+    """ReprPlan.f.img_src_c: every packed frame token of the subtitle rows points at the clip frame
+    it was copied from (data/data.py fills f_v_feats with index_select(c_v_feats, frames)), so a
+    batch may drop `f_v_feats`; without it max_vl comes from f_v_pos_ids."""
+    vb, _ = synth.syn_tvr_ragged(batch_size=4, seed=61, t_range=(9, 15), s_range=(2, 5),
+                                 l_range=(3, 7))
+    plan = ReprPlan(vb)
+    D = vb["c_v_feats"].shape[-1]
+    from_f = vb["f_v_feats"].reshape(-1, D)[torch.from_numpy(plan.f.img_src).long()]
+    from_c = vb["c_v_feats"].reshape(-1, D)[torch.from_numpy(plan.f.img_src_c).long()]
+    assert plan.f.n_img > 0 and (plan.f.img_src_c >= 0).all()
+    assert torch.equal(from_f, from_c)
+    slim = {k: v for k, v in vb.items() if k != "f_v_feats"}
+    plan2 = ReprPlan(slim)
+    assert plan2.f.max_vl == plan.f.max_vl
+    assert np.array_equal(plan2.f.img_src_c, plan.f.img_src_c)
