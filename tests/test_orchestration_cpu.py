@@ -279,3 +279,76 @@ def test_batch_without_f_v_feats_reads_the_clip_frames(tmp_path, monkeypatch):
     mb["feat_targets"] = vb["c_v_feats"][mb["c_v_masks"]]
     with pytest.raises(ValueError):
         model(mb, "mffr")
+
+
+def test_fused_adamw_host_logic_groups_clipping_and_state_dict(monkeypatch):
+    """FusedAdamW's host side on CPU (kernels replaced by their torch restatements): two launches
+    over the decay / no-decay ranges == the reference rule per parameter (optim/adamw.py:80-104,
+    grouping optim/misc.py:22), global-norm clipping folded into the update, the training loop's
+    `for g in optimizer.param_groups: g['lr'] = ...` (train_vcmr.py:245-247), and a
+    state_dict round trip (utils/save.py TrainingRestorer)."""
+    from oracle import hero_oracle as orc
+    fake_ops.install(monkeypatch)
+    from hero_b200.optim import FusedAdamW
+    from hero_b200.params import flat_of
+
+    class Tiny(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.dense = torch.nn.Linear(96, 64)
+            self.LayerNorm = torch.nn.LayerNorm(64)
+            self.proj = torch.nn.Linear(64, 40)
+
+    def make():
+        torch.manual_seed(0)
+        m = Tiny()
+        flat = flat_of(m, torch.device("cpu"))
+        return m, flat, FusedAdamW(flat, lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01)
+
+    m, flat, opt = make()
+    assert flat.no_decay_start < flat.total and len(opt.param_groups) == 2
+    ref_p = {k: p.detach().clone() for k, p in m.named_parameters()}
+    ref_m = {k: torch.zeros_like(v) for k, v in ref_p.items()}
+    ref_v = {k: torch.zeros_like(v) for k, v in ref_p.items()}
+    g = torch.Generator().manual_seed(1)
+    lrs = [1e-3, 5e-4, 2e-3]
+    saved = None
+    for step in range(1, 4):
+        opt.zero_grad()
+        grads = {k: torch.randn(v.shape, generator=g) * 0.1 for k, v in ref_p.items()}
+        for k, p in m.named_parameters():
+            p.grad.copy_(grads[k])
+        for grp in opt.param_groups:
+            grp["lr"] = lrs[step - 1]
+        total = torch.sqrt(sum((v.double() ** 2).sum() for v in grads.values())).item()
+        assert abs(opt.clip_grad_norm_(1.0) - total) < 1e-3 * total
+        scale = min(1.0, 1.0 / (total + 1e-6))
+        opt.step()
+        for k in ref_p:
+            wd = 0.0 if ("bias" in k or "LayerNorm" in k) else 0.01
+            ref_p[k], ref_m[k], ref_v[k] = orc.adamw_step(ref_p[k], grads[k] * scale, ref_m[k],
+                                                          ref_v[k], step, lrs[step - 1], 0.9, 0.98,
+                                                          1e-6, wd)
+        for k, p in m.named_parameters():
+            assert (p.detach() - ref_p[k]).abs().max() < 2e-6, (k, step)
+        if step == 2:
+            saved = ({k: v.clone() if torch.is_tensor(v) else v for k, v in
+                      opt.state_dict().items()}, {k: v.clone() for k, v in m.state_dict().items()},
+                     grads)
+    assert not flat.dirty                              # the optimizer refreshed the bf16 mirror
+    for k, p in m.named_parameters():
+        assert torch.equal(flat.bf16(p), p.detach().to(torch.bfloat16)), k
+    # resume from the step-2 snapshot and repeat step 3: same parameters
+    m2, flat2, opt2 = make()
+    m2.load_state_dict(saved[1])
+    opt2.load_state_dict(saved[0])
+    assert opt2.step_count == 2
+    opt2.zero_grad()
+    for k, p in m2.named_parameters():
+        p.grad.copy_(grads[k])                         # `grads`: the step-3 gradients
+    for grp in opt2.param_groups:
+        grp["lr"] = lrs[2]
+    opt2.clip_grad_norm_(1.0)
+    opt2.step()
+    for (k, a), (_, b) in zip(m2.named_parameters(), m.named_parameters()):
+        assert (a.detach() - b.detach()).abs().max() < 1e-7, k
