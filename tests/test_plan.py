@@ -169,3 +169,45 @@ def test_frame_slots_map_back_to_clip_frames():
     plan2 = ReprPlan(slim)
     assert plan2.f.max_vl == plan.f.max_vl
     assert np.array_equal(plan2.f.img_src_c, plan.f.img_src_c)
+
+
+def test_plan_invariants_on_random_batches():
+    """Property test (hypothesis): for random ragged batches — including subtitles without frames,
+    frames matched by no subtitle or by several, single-token rows — the plan is a bijection
+    between packed tokens and valid padded positions, attention tiles partition the token stream
+    without splitting a sequence, the two frame-merge CSRs are transposes of each other, and the
+    joint (video + query) plan is the concatenation of its parts."""
+    from hypothesis import given, settings, strategies as st
+    from hero_b200.plan import ATTN_TILE, JointPlan
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.integers(0, 10_000), st.integers(1, 5))
+    def check(seed, bs):
+        vb, qb = synth.syn_tvr_ragged(batch_size=bs, seed=seed, vfeat_dim=8, vocab=60,
+                                      t_range=(3, 40), s_range=(1, 6), l_range=(1, 9),
+                                      q_range=(1, 8))
+        rp, tp = ReprPlan(vb), TxtPlan(qb["attn_masks"], pos_ids=qb["pos_ids"])
+        for sp, mask in ((rp.f.seq, vb["f_attn_masks"]), (rp.c.seq, vb["c_attn_masks"]),
+                         (tp.f.seq, qb["attn_masks"])):
+            valid = np.flatnonzero(mask.numpy().reshape(-1))
+            assert np.array_equal(np.sort(sp.tok_flat), valid)            # bijection
+            assert np.array_equal(sp.pad_to_tok[sp.tok_flat], np.arange(sp.n_tok))
+            assert sp.tile_ntok.sum() == sp.n_tok and (sp.tile_ntok <= ATTN_TILE).all()
+            assert np.array_equal(sp.tile_tok0, np.concatenate([[0], np.cumsum(sp.tile_ntok)[:-1]]))
+            starts = set(sp.cu[:-1].tolist()) | {sp.n_tok}
+            assert all(int(t) in starts for t in sp.tile_tok0)            # tiles start at sequences
+            assert ((sp.seq_hi - sp.seq_lo) == np.repeat(sp.lens, sp.lens)).all()
+        c = rp.c
+        fwd = {(int(i), int(c.fwd_idx[e])) for i in range(c.seq.n_tok)
+               for e in range(c.fwd_off[i], c.fwd_off[i + 1])}
+        bwd = {(int(c.bwd_idx[e]), int(j)) for j in range(rp.f.seq.n_tok)
+               for e in range(c.bwd_off[j], c.bwd_off[j + 1])}
+        assert fwd == bwd and len(fwd) == c.n_pairs
+        assert (rp.f.img_src_c >= 0).all()
+        jp = JointPlan(rp, tp)
+        a = rp.f.seq.n_tok
+        assert jp.n_tok == a + tp.f.seq.n_tok and jp.n_tiles == rp.f.seq.n_tiles + tp.f.seq.n_tiles
+        assert np.array_equal(jp.arr["j_seq_lo"][a:], tp.f.seq.seq_lo + a)
+        assert jp.same_slot_pos in (True, False)
+
+    check()
