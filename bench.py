@@ -4,7 +4,7 @@ train-tvr-8gpu shapes (BASELINE.json), data-parallel over N B200s.
     python bench.py --gpus 1 --steps 20 --warmup 5
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference          # CPU oracle port of the reference path (rank 0)
+    python bench.py --impl reference          # the UNMODIFIED reference's CPU path (rank 0)
 
 One step = one pass of the hot path over one synthetic SYN-TVR-dense batch per rank
 (B = 32 clips x 100 frames x 4352-d features, 20 subtitle rows of 5 frames + 20 tokens per clip,
@@ -13,8 +13,9 @@ HierarchicalVlModel 'repr' forward + CrossModalTrm 'txt' forward on the query ro
 through `forward_repr_txt`, which runs the query rows in the same cross-modal pass as the video
 rows; `--separate-txt` issues the reference's two calls), backward of both from fixed upstream
 gradients, and (N > 1) the mean all-reduce of the flat gradient buffer.
-Training mode (dropout 0.1 as in config/train-tvr-8gpu.json). No optimizer step (the metric is
-fwd+bwd); `--with-optimizer` adds the fused AdamW.
+Training mode (dropout 0.1 as in config/train-tvr-8gpu.json). No optimizer step inside `value`
+(the metric is fwd+bwd); BASELINE configs 2 (fwd-only) and 3 (fwd+bwd+AdamW+clip) are timed in the
+same run and reported under `extra`.
 
 `value`   whole-job clips/s with inputs (and the per-batch packing plan, a collate-side product)
           resident in HBM, CUDA-event timed, max over ranks.
@@ -24,11 +25,19 @@ fwd+bwd); `--with-optimizer` adds the fused AdamW.
           plan's index arrays are copied host->device on a side stream (prefetch one step ahead,
           like the reference's PrefetchLoader, data/loader.py:89-144) and a loss scalar is read
           back. The loader is primed (two plans in flight) when the timed region starts.
+`gpu_reference`  the UNMODIFIED reference modules (staged in git-ignored baseline/_ref by
+          baseline/stage_ref.py; apex FusedLayerNorm -> torch.nn.LayerNorm, Horovod ->
+          torch.distributed shim) doing the same step on the same GPU(s) in the same run under
+          torch.autocast(bfloat16): the PyTorch-GPU baseline of BASELINE.json's north star.
+`cpu_baseline` / `--impl reference`  the same reference modules on the host cores (fp32); falls
+          back to the oracle port (kind "port") only if baseline/_ref was not staged.
 """
 import argparse
 import collections
+import gc
 import json
 import os
+import statistics
 import subprocess
 import sys
 import tempfile
@@ -73,10 +82,11 @@ def algorithmic_flops_fwd(vb, qb):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (rank 0's GPU)."""
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t_marks = []
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -85,7 +95,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -94,16 +104,22 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def window(self, t0, t1):
+        """Only samples taken between t0 and t1 (perf_counter) count as 'during the region'."""
+        self.t_marks.append((t0, t1))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if self.t_marks and not any(a - 0.06 <= t <= b + 0.06 for a, b in self.t_marks):
+                continue
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -128,6 +144,38 @@ def build_model(device, seed=0):
     return model.to(device).train()
 
 
+def _max_over_ranks(x, device, world):
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def timed_loop(step_fn, steps, device, world, sampler=None):
+    """barrier + synchronize immediately before the first event, one event per step, synchronize +
+    barrier after; returns (total ms = max over ranks, median per-step ms of THIS rank, host
+    enqueue ms per step)."""
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    evs[0].record()
+    for i in range(steps):
+        step_fn(i)
+        evs[i + 1].record()
+    host_ms = (time.perf_counter() - t0) * 1e3 / max(steps, 1)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    if world > 1:
+        torch.distributed.barrier()
+    if sampler is not None:
+        sampler.window(t0, t1)
+    total = evs[0].elapsed_time(evs[-1])
+    gaps = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    return _max_over_ranks(total, device, world), statistics.median(gaps), host_ms, gaps
+
+
 def run_ours(args):
     from hero_b200 import distributed as hdist
     from hero_b200 import ops, synth
@@ -144,17 +192,15 @@ def run_ours(args):
     flat = flat_of(model, device)
     hdist.broadcast_tensors([flat.flat], 0)
     flat.mark_dirty()
-    # N > 1: gradient buckets travel during backward (peer copies over NVLink; see GradBucketer);
-    # built first because it moves the flat gradient buffer into symmetric memory
     bucketer = None
-    if world > 1 and not args.no_overlap and not args.dp_skip_exchange:
+    if world > 1 and args.dp_transport != "none" and not args.dp_skip_exchange:
         bucketer = hdist.overlapped_exchange(flat, transport=args.dp_transport,
                                              min_elems=args.bucket_elems,
                                              overlap_ctas=args.overlap_ctas)
-    if world > 1 and args.dp_skip_exchange and os.environ.get("HERO_DP_DIAG") == "symm":
-        hdist.PeerExchange(flat)     # diagnostic: gradients in symmetric memory, no exchange
     gflat = flat.ensure_flat_grads()
-    opt = FusedAdamW(flat, lr=1e-4) if args.with_optimizer else None
+    exchange = None
+    if world > 1 and bucketer is None and not args.dp_skip_exchange:
+        exchange = hdist.FlatGradExchange(flat, wire=args.dp_wire)
 
     B = args.batch_size
     n_host = 3
@@ -170,8 +216,10 @@ def run_ours(args):
     g = torch.Generator().manual_seed(7)
     dclip = (torch.randn(B, 100, H, generator=g) * 1e-2).to(device)
     dq = (torch.randn(B, host[0][1]["input_ids"].shape[1], H, generator=g) * 1e-2).to(device)
+    accum = max(1, args.accum)
+    state = {"micro": 0}
 
-    def fwd_bwd(vb_dev, qb_dev):
+    def fwd_bwd(vb_dev, qb_dev, opt=None, clip_norm=None):
         if bucketer is not None:   # per-layer gradient exchange overlapped with backward
             bucketer.__enter__()
         if args.separate_txt:      # the reference's two calls (model/pretrain.py:65-70)
@@ -180,12 +228,16 @@ def run_ours(args):
         else:                      # same results, query rows share the video rows' GEMMs
             clip, q = model.forward_repr_txt(vb_dev, qb_dev)
         torch.autograd.backward([clip, q], [dclip, dq])
+        state["micro"] += 1
+        boundary = state["micro"] % accum == 0     # gradient_accumulation_steps (train_vcmr.py:233)
         if bucketer is not None:
             bucketer.__exit__(None, None, None)
             bucketer.finish()
-        elif world > 1 and not args.dp_skip_exchange:
-            hdist.all_reduce_flat(gflat)
-        if opt is not None:
+        elif exchange is not None and boundary:
+            exchange.all_reduce()
+        if opt is not None and boundary:
+            if clip_norm is not None:
+                opt.clip_grad_norm_device_(clip_norm)
             opt.step()
         return clip
 
@@ -198,84 +250,130 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     def resident_step(i):
-        gflat.zero_()
+        if state["micro"] % accum == 0:
+            gflat.zero_()
         vb_dev, qb_dev = resident[i % n_host]
         fwd_bwd(vb_dev, qb_dev)
 
+    # known-answer test of the gradient exchange on this job's ranks / transport (raises on a
+    # mismatch): every rank must end with the mean of the per-rank patterns, bit-identical
+    allreduce_check = None
+    if world > 1 and exchange is not None:
+        allreduce_check = exchange.self_check()
     for i in range(args.warmup):
         resident_step(i)
     ops.reset_launch_count()
-    sampler = ClockSampler(local_rank)
-    if world > 1:
-        torch.distributed.barrier()
-    torch.cuda.synchronize()
-    sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    h0 = time.perf_counter()
-    for i in range(args.steps):
-        resident_step(i)
-    host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / max(args.steps, 1)
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        torch.distributed.barrier()
-    ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    state["micro"] = 0
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()           # forks nvidia-smi BEFORE the barrier that opens the timed region
+        time.sleep(0.2)
+    ms_total, ms_median, host_enqueue_ms, gaps = timed_loop(resident_step, args.steps, device,
+                                                            world, sampler)
     launches = ops.launch_count() // max(args.steps, 1)
-    t = torch.tensor([ms], dtype=torch.float64, device=device)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
     # ------------------------------------------------------------- GEMM-family roofline (live)
     # (the layer runtime keeps everything on one stream while GEMM launches are being timed, so
-    # durations do not overlap; the share below is taken against THIS pass's own step time)
+    # durations do not overlap). Runs for >= ~2 s so clocks settle where a long job runs, which is
+    # what the "sustained" peak in MEASURED_PEAKS.json was measured under; both fractions reported.
+    prof_steps = max(5, min(int(2000.0 / max(ms_per_step * 1.15, 1e-3)), 400))
     ops.start_gemm_profile()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tp0 = time.perf_counter()
     p0.record()
-    for i in range(min(args.steps, 5)):
+    for i in range(prof_steps):
         resident_step(i)
     p1.record()
     torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.window(tp0, time.perf_counter())
     gp = ops.stop_gemm_profile()
-    profiled_step_ms = p0.elapsed_time(p1) / max(min(args.steps, 5), 1)
+    profiled_step_ms = p0.elapsed_time(p1) / prof_steps
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
         peaks = json.load(open(pk_path))
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    burst_tf = peaks.get("bf16_tflops", 1693.7)
     achieved = gp["flops"] / (gp["ms"] * 1e-3) / 1e12 if gp["ms"] > 0 else 0.0
-    traffic = None
+    traffic, traffic_src = None, None
     tr_path = os.path.join(ROOT, "profiles", "gemm_traffic.json")
     if os.path.exists(tr_path):
-        traffic = json.load(open(tr_path)).get("dram_bytes_per_launch")
+        tj = json.load(open(tr_path))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all variants)",
                 "achieved": round(achieved, 1), "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": round(achieved / peak_tf, 4),
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
-                if peaks else "fallback 1.4 PF/s (of fallback)",
-                "launches_per_step": gp["launches"] // max(min(args.steps, 5), 1),
-                "gemm_share_of_step": round(gp["ms"] / max(min(args.steps, 5), 1) /
-                                            profiled_step_ms, 3),
-                "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured); the "
+                               "roofline pass runs >= 2 s" if peaks else
+                               "fallback 1.4 PF/s (of fallback)",
+                "frac_of_burst_peak": round(achieved / burst_tf, 4),
+                "profiled_steps": prof_steps,
+                "launches_per_step": gp["launches"] // prof_steps,
+                "gemm_share_of_step": round(gp["ms"] / prof_steps / profiled_step_ms, 3),
+                "traffic": traffic, "traffic_source": traffic_src,
                 "step_algorithmic_tflops": round(3 * flops_fwd * 1e-12, 4),
                 "step_frac_of_peak": round(3 * flops_fwd / (ms_per_step * 1e-3) / 1e12 / peak_tf,
                                            4)}
 
+    # ------------------------------------------------------------- BASELINE configs 2 and 3
+    extra = {}
+    if not args.no_extra:
+        k_extra = max(5, min(args.steps, 20))
+        # config 3: fwd + bwd + global-norm clip + fused AdamW (train_vcmr.py:240-262)
+        opt = FusedAdamW(flat, lr=1e-5)
+
+        def opt_step(i):
+            if state["micro"] % accum == 0:
+                gflat.zero_()
+            fwd_bwd(*resident[i % n_host], opt=opt, clip_norm=1.0)
+        for i in range(3):
+            opt_step(i)
+        t_ms, med, _, _ = timed_loop(opt_step, k_extra, device, world)
+        extra["fwd_bwd_adamw"] = {
+            "value": round(world * B / (t_ms / k_extra * 1e-3), 2), "unit": "clips/s",
+            "ms_per_step": round(t_ms / k_extra, 4), "median_ms_per_step": round(med, 4),
+            "steps": k_extra, "what": "BASELINE config 3: fwd+bwd"
+            + (" + gradient all-reduce" if world > 1 else "")
+            + " + global-norm clip (1.0) + fused AdamW, device-resident inputs"}
+        del opt
+        # config 2: forward only, eval mode, no autograd graph
+        model.eval()
+
+        def fwd_only(i):
+            with torch.no_grad():
+                vb_dev, qb_dev = resident[i % n_host]
+                model.forward_repr_txt(vb_dev, qb_dev)
+        for i in range(3):
+            fwd_only(i)
+        t_ms, med, _, _ = timed_loop(fwd_only, k_extra, device, world)
+        extra["fwd_only_eval"] = {
+            "value": round(world * B / (t_ms / k_extra * 1e-3), 2), "unit": "clips/s",
+            "ms_per_step": round(t_ms / k_extra, 4), "median_ms_per_step": round(med, 4),
+            "steps": k_extra,
+            "frac_of_peak": round(flops_fwd / (t_ms / k_extra * 1e-3) / 1e12 / peak_tf, 4),
+            "what": "BASELINE config 2: full encoder forward only (eval mode, no_grad)"}
+        model.train()
+        flat.mark_dirty()       # the optimizer moved the weights; mirror refreshed by its kernel
+        state["micro"] = 0
+
     # ------------------------------------------------------------- end-to-end from pinned host
     stager = BatchStager(device, depth=3)
+    slim = not args.e2e_legacy_batch
+    # The e2e arm ships the packed-layout batch: `f_v_feats` is a row gather of
+    # `c_v_feats` (data/data.py:380-395), so the batch omits it and the plan maps every frame slot
+    # to its clip frame — half the host->device bytes, identical results
+    # (tests/test_encoder_gpu.py::test_batch_without_f_v_feats_on_gpu). --e2e-legacy-batch ships it.
+    e2e_host = []
+    for vb, qb in host:
+        vb2 = {k: v for k, v in vb.items() if not (slim and k == "f_v_feats")}
+        e2e_host.append((vb2, qb))
 
     def h2d_bytes(b):
         return sum(v.numel() * v.element_size() for v in b.values() if torch.is_tensor(v))
 
-    # Packing plans are built per step, from that step's masks, in worker processes — the
-    # reference builds its gather indices in DataLoader collate workers (data/data.py) — two steps
-    # ahead of their use; the training process uploads the finished index arrays.
-    # (If the worker pool cannot start or dies, plans are built in this process instead — slower,
-    # but the run still produces its line; `config.e2e_plans` says which.)
     loader_state = {"pool": None, "mode": "loader worker processes (PlanPool, 3 workers)"}
     try:
         loader_state["pool"] = PlanPool(workers=3)
@@ -284,7 +382,7 @@ def run_ours(args):
     plan_futs = collections.deque()
 
     def submit_plan(i):
-        vb, qb = host[i % n_host]
+        vb, qb = e2e_host[i % n_host]
         pool = loader_state["pool"]
         try:
             plan_futs.append(pool.submit(vb, qb) if pool is not None else None)
@@ -306,7 +404,7 @@ def run_ours(args):
 
     def stage(i, total):
         t0 = time.perf_counter()
-        vb, qb = host[i % n_host]
+        vb, qb = e2e_host[i % n_host]
         vb, qb = plans_for(plan_futs.popleft(), dict(vb), dict(qb))
         t1 = time.perf_counter()
         if i + 2 < total:
@@ -327,7 +425,6 @@ def run_ours(args):
         after step i+1 has been enqueued (one-step-lagged logging), so the host never idles the
         GPU; all n results are read."""
         out, pending = 0.0, None
-        dbg = True     # host phase times go to stderr (diagnostics; the JSON line stays on stdout)
         tt = collections.defaultdict(float)
         dones = []
         nxt = stage(0, n)
@@ -337,7 +434,8 @@ def run_ours(args):
             cur = torch.cuda.current_stream()
             cur.wait_event(ev)
             record_plans((vb_dev, qb_dev), cur)   # allocator safety across streams
-            gflat.zero_()
+            if state["micro"] % accum == 0:
+                gflat.zero_()
             t_b = time.perf_counter()
             clip = fwd_bwd(vb_dev, qb_dev)
             t_c = time.perf_counter()
@@ -361,15 +459,12 @@ def run_ours(args):
                 tt[k] += v
         pending[0].synchronize()
         out += float(pending[1][0])
-        if dbg:
-            print("e2e stage() totals ms:", {k: round(v * 1e3, 1) for k, v in stage_t.items()},
-                  file=sys.stderr)
-            stage_t.clear()
-            gaps = [round(a.elapsed_time(b), 2) for a, b in zip(dones[:-1], dones[1:])]
-            print("e2e device ms between step ends:", gaps, file=sys.stderr)
-            print("e2e host phases ms/step:", {k: round(v / n * 1e3, 2) for k, v in tt.items()},
-                  file=sys.stderr)
-        return out
+        gaps = [round(a.elapsed_time(b), 2) for a, b in zip(dones[:-1], dones[1:])]
+        diag = {"stage_totals_ms": {k: round(v * 1e3, 1) for k, v in stage_t.items()},
+                "device_ms_between_step_ends": gaps,
+                "host_phases_ms_per_step": {k: round(v / n * 1e3, 2) for k, v in tt.items()}}
+        stage_t.clear()
+        return out, diag
 
     def prime():     # a running loader always has two batches of plans in flight
         plan_futs.clear()
@@ -379,13 +474,13 @@ def run_ours(args):
     # start every loader worker (each imports torch once) before anything is timed
     if loader_state["pool"] is not None:
         try:
-            for f in [loader_state["pool"].submit(*host[0]) for _ in range(6)]:
+            for f in [loader_state["pool"].submit(*e2e_host[0]) for _ in range(6)]:
                 f.result(timeout=300)
         except Exception as e:                              # noqa: BLE001
             loader_state["pool"] = None
             loader_state["mode"] = f"in-process (worker pool failed: {type(e).__name__})"
     prime()
-    e2e_loop(max(3, args.warmup))
+    e2e_loop(max(5, args.warmup))
     prime()
     for f in plan_futs:
         if f is not None:
@@ -393,21 +488,42 @@ def run_ours(args):
                 f.result(timeout=300)
             except Exception:                               # noqa: BLE001
                 pass
+    # Host-side jitter protection for the timed e2e window: no cyclic GC passes (nothing in the
+    # loop creates cycles that must be reclaimed within 20 steps), and the caching allocator must
+    # not grow (every buffer of a step has been allocated during warm-up).
+    gc.collect()
+    gc.freeze()
+    gc.disable()
+    mem0 = torch.cuda.memory_stats(device).get("num_device_alloc", 0) if hasattr(
+        torch.cuda, "memory_stats") else 0
+    state["micro"] = 0
     if world > 1:
         torch.distributed.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    e2e_loop(args.steps)
+    _, diag = e2e_loop(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    gc.enable()
+    gc.unfreeze()
+    mem1 = torch.cuda.memory_stats(device).get("num_device_alloc", 0) if hasattr(
+        torch.cuda, "memory_stats") else 0
+    if sampler is not None:
+        sampler.window(t0, t0 + e2e_s)
+    print("e2e diagnostics:", json.dumps(diag), file=sys.stderr)
     if loader_state["pool"] is not None:
         loader_state["pool"].shutdown()
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / float(t.item())
-    bi = h2d_bytes(host[0][0]) + h2d_bytes(host[0][1])
+    e2e_value = world * B * args.steps / _max_over_ranks(e2e_s, device, world)
+    bi = h2d_bytes(e2e_host[0][0]) + h2d_bytes(e2e_host[0][1])
+    e2e_gaps = diag["device_ms_between_step_ends"]
+    clocks = sampler.stop() if sampler is not None else None
 
+    # ------------------------------------------------------------- reference arms
+    del resident, stager
+    torch.cuda.empty_cache()
+    gpu_ref = None
+    if not args.no_gpu_reference:
+        gpu_ref = gpu_reference(args, rank, world, device, B)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(sample_clips=args.cpu_clips, steps=2, warmup=1)
@@ -416,6 +532,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "clips/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
+            "median_ms_per_step": round(ms_median, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": "SYN-TVR-dense: HierarchicalVlModel 'repr' + CrossModalTrm 'txt' "
@@ -423,26 +540,36 @@ def run_ours(args):
                                    "100 frames x 4352-d + 640 rows x (5 frames + 20 tokens) + 32 "
                                    "queries x 16 tokens",
                        "global_batch": world * B, "per_gpu_batch": B, "parallelism": f"dp{world}",
-                       "dropout": 0.1, "optimizer_in_step": bool(args.with_optimizer),
+                       "dropout": 0.1, "optimizer_in_step": False,
+                       "gradient_accumulation_steps": accum,
                        "query_rows": "separate call" if args.separate_txt else
                        "fused into the video-row pass (forward_repr_txt)",
                        "allreduce_in_step": world > 1 and not args.dp_skip_exchange,
-                       "allreduce_overlap": (("per-layer buckets during backward, "
-                                              + ("peer copies over NVLink (copy engines)"
-                                                 if bucketer.p2p is not None else "NCCL")
-                                              + "; remainder NCCL after backward")
-                                             if bucketer is not None else
-                                             "none: one NCCL all-reduce of the flat gradient "
-                                             "buffer after backward" if world > 1 else "none"),
+                       "allreduce": (("per-layer buckets during backward (GradBucketer)")
+                                     if bucketer is not None else
+                                     exchange.describe() if exchange is not None else "none"),
+                       "allreduce_check": allreduce_check,
                        "e2e_plans": loader_state["mode"],
+                       "e2e_batch": "packed (no f_v_feats: frame slots read from c_v_feats through "
+                                    "the plan)" if slim else "legacy dict incl. f_v_feats",
                        "l2": "no explicit flush: per-step working set (~0.35 GB weights+grads, "
-                             "~3 GB activations, 111 MB inputs) exceeds the 126 MB L2"},
+                             "~3 GB activations, 56-112 MB inputs) exceeds the 126 MB L2"},
             "clocks": clocks, "gpu_launches": launches,
             "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
             "e2e": {"value": round(e2e_value, 2), "unit": "clips/s", "h2d_bytes_per_step": bi,
-                    "d2h_bytes_per_step": 4},
+                    "d2h_bytes_per_step": 4,
+                    "median_device_ms_between_step_ends":
+                        round(statistics.median(e2e_gaps), 3) if e2e_gaps else None,
+                    "max_device_ms_between_step_ends": max(e2e_gaps) if e2e_gaps else None,
+                    "device_allocations_during_timed_region": int(mem1 - mem0)},
             "roofline": roofline,
+            "extra": extra,
         }
+        if gpu_ref is not None:
+            line["gpu_reference"] = gpu_ref
+            if gpu_ref.get("value"):
+                line["vs_gpu_reference"] = {"value_ratio": round(value / gpu_ref["value"], 2),
+                                            "e2e_ratio": round(e2e_value / gpu_ref["value"], 2)}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -450,30 +577,88 @@ def run_ours(args):
         torch.distributed.destroy_process_group()
 
 
-def cpu_baseline(sample_clips=4, steps=2, warmup=1):
-    """The oracle port of the reference path on the host cores: fwd+bwd (autograd) on a bounded
-    sample of the same workload (first `sample_clips` clips of SYN-TVR-dense)."""
+# ----------------------------------------------------------------------------- reference arms
+def _ref_inputs(sample_clips, seed=1234):
     from hero_b200 import synth
-    from oracle import hero_oracle as orc
-    torch.manual_seed(0)
-    P = orc.seeded_weights(orc.param_shapes(), seed=0)
-    P = {k: v.requires_grad_(True) for k, v in P.items()}
-    vb, qb = synth.syn_tvr_dense(batch_size=sample_clips, seed=1234)
+    vb, qb = synth.syn_tvr_dense(batch_size=sample_clips, seed=seed)
     g = torch.Generator().manual_seed(7)
     dclip = torch.randn(sample_clips, 100, H, generator=g) * 1e-2
     dq = torch.randn(sample_clips, qb["input_ids"].shape[1], H, generator=g) * 1e-2
+    return vb, qb, dclip, dq
 
-    def step():
-        for v in P.values():
-            v.grad = None
-        clip = orc.hierarchical_repr(P, vb, F_LAYERS, C_LAYERS, HEADS)
-        q = orc.cross_modal_txt(P, "f_encoder.", qb, F_LAYERS, HEADS)
-        torch.autograd.backward([clip, q], [dclip, dq])
+
+def gpu_reference(args, rank, world, device, B):
+    """The unmodified reference (baseline/_ref) doing the same step on the GPU under
+    torch.autocast(bfloat16): fwd `forward_repr` + `f_encoder('txt')`, backward, and at N > 1 its
+    own all_reduce_and_rescale_tensors over a torch.distributed-backed Horovod shim."""
+    from baseline import ref_runner as rr
+    from hero_b200 import synth
+    if rr.available() is None:
+        return {"unavailable": "baseline/_ref not staged (run baseline/stage_ref.py where "
+                               "/root/reference exists)"}
+    try:
+        rr.install(dist_backed=world > 1)
+        model = rr.build_model(device, seed=0, train=True)
+        step = rr.make_step(model, autocast_dtype=torch.bfloat16, world=world, train=True)
+        vb, qb, dclip, dq = _ref_inputs(B, seed=1234 + rank)
+        vb, qb = synth.to_device(vb, device), synth.to_device(qb, device)
+        dclip, dq = dclip.to(device), dq.to(device)
+        k = max(3, min(args.steps, 10))
+        for _ in range(3):
+            step(vb, qb, dclip, dq)
+        t_ms, med, host_ms, _ = timed_loop(lambda i: step(vb, qb, dclip, dq), k, device, world)
+        ms = t_ms / k
+        out = {"value": round(world * B / (ms * 1e-3), 2), "unit": "clips/s",
+               "ms_per_step": round(ms, 3), "median_ms_per_step": round(med, 3), "steps": k,
+               "host_ms_per_step": round(host_ms, 3), "dtype": "bf16 autocast (fp32 master)",
+               "kind": "reference",
+               "what": "unmodified reference HierarchicalVlModel (config/hero_finetune.json) "
+                       "fwd+bwd" + (" + its all_reduce_and_rescale_tensors (NCCL)" if world > 1
+                                    else "") + ", device-resident inputs, stock PyTorch kernels"}
+        del model, step
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:                                  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+
+
+def cpu_baseline(sample_clips=8, steps=2, warmup=1):
+    """The reference's own CPU path (unmodified modules from baseline/_ref; oracle port if the
+    reference was not staged) on all host cores: fwd+bwd on a bounded sample of the same workload
+    (first `sample_clips` clips of SYN-TVR-dense)."""
+    from baseline import ref_runner as rr
+    n_thr = os.cpu_count() or 1
+    torch.set_num_threads(n_thr)       # torchrun exports OMP_NUM_THREADS=1: use the whole box
+    vb, qb, dclip, dq = _ref_inputs(sample_clips)
+    kind = "reference"
+    if rr.available() is not None:
+        rr.install(dist_backed=False)
+        model = rr.build_model(torch.device("cpu"), seed=0, train=True)
+        for m in model.modules():          # dropout 0 for fwd+bwd timing (SURVEY §8d protocol)
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        ref_step = rr.make_step(model, autocast_dtype=None, world=1, train=True)
+
+        def step():
+            ref_step(vb, qb, dclip, dq)
+        what = "unmodified reference modules (baseline/_ref), fp32, torch CPU autograd"
+    else:
+        from oracle import hero_oracle as orc
+        kind = "port"
+        P = orc.seeded_weights(orc.param_shapes(), seed=0)
+        P = {k: v.requires_grad_(True) for k, v in P.items()}
+
+        def step():
+            for v in P.values():
+                v.grad = None
+            clip = orc.hierarchical_repr(P, vb, F_LAYERS, C_LAYERS, HEADS)
+            q = orc.cross_modal_txt(P, "f_encoder.", qb, F_LAYERS, HEADS)
+            torch.autograd.backward([clip, q], [dclip, dq])
+        what = "oracle port (fp32, torch CPU autograd)"
 
     for _ in range(warmup):
         step()
-    best = float("inf")
-    t_all = 0.0
+    best, t_all = float("inf"), 0.0
     for _ in range(steps):
         t0 = time.perf_counter()
         step()
@@ -481,15 +666,17 @@ def cpu_baseline(sample_clips=4, steps=2, warmup=1):
         best = min(best, dt)
         t_all += dt
     return {"value": round(sample_clips / (t_all / steps), 3), "unit": "clips/s",
-            "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": "port",
+            "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": kind,
             "best_value": round(sample_clips / best, 3),
-            "sample": f"oracle fwd+bwd (fp32, torch CPU autograd) on the first {sample_clips} "
-                      f"clips of SYN-TVR-dense, {steps} timed steps after {warmup} warm-up"}
+            "ms_per_clip": round(1e3 * (t_all / steps) / sample_clips, 1),
+            "sample": f"{what}: fwd+bwd on the first {sample_clips} clips of SYN-TVR-dense "
+                      f"(same per-clip shapes as the GPU arm), {steps} timed steps after "
+                      f"{warmup} warm-up"}
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's own CPU path, restated by the oracle port (the Python
-    reference cannot travel to the GPU box), all host threads, bounded sample per step."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host
+    cores (all threads), bounded sample per step. Rank 0 alone runs; other ranks exit 0."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -501,7 +688,9 @@ def run_reference(args):
             "ms_per_step": round(1e3 * args.cpu_clips / cb["value"], 2), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"SYN-TVR-dense sample of {args.cpu_clips} clips per step "
-                                   "(same per-clip shapes as the GPU arm)", "parallelism": "cpu"},
+                                   "(same per-clip shapes as the GPU arm; clips/s is per clip, "
+                                   "so the sample size does not change the unit)",
+                       "parallelism": "cpu"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "clips/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
@@ -516,26 +705,27 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-size", type=int, default=32)
-    ap.add_argument("--with-optimizer", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true",
-                    help="N>1: force one all-reduce of the flat gradient after backward (already "
-                         "the default; overrides --dp-transport)")
+    ap.add_argument("--accum", type=int, default=1,
+                    help="gradient accumulation micro-steps per exchange (config/train-tvr-8gpu.json "
+                         "uses 2); every micro-step counts as a step")
+    ap.add_argument("--dp-wire", default="bf16", choices=("bf16", "fp32"),
+                    help="N>1: dtype of the gradient all-reduce on the wire (the reference "
+                         "exchanged fp16 gradients under apex O2)")
     ap.add_argument("--dp-transport", default="none", choices=("none", "p2p", "nccl", "auto"),
-                    help="N>1: 'none' = one NCCL all-reduce of the flat gradient buffer after "
-                         "backward (default, measured fastest end to end); 'p2p' / 'nccl' = "
-                         "GradBucketer: buckets travel during backward")
+                    help="N>1: 'none' = chunked NCCL all-reduce of the flat gradient buffer "
+                         "(default); 'p2p' / 'nccl' = GradBucketer: per-layer buckets during backward")
     ap.add_argument("--dp-skip-exchange", action="store_true",
-                    help="DIAGNOSTIC (invalid as a result): N>1 without any gradient exchange, to "
-                         "separate per-GPU compute time from communication")
-    ap.add_argument("--bucket-elems", type=int, default=1 << 20,
-                    help="N>1: gradient ranges are exchanged once this many elements are final")
-    ap.add_argument("--overlap-ctas", type=int, default=0,
-                    help="N>1: CTAs of the communicator that exchanges gradient buckets during "
-                         "backward (the compute kernels leave that many SMs free)")
+                    help="DIAGNOSTIC (invalid as a result): N>1 without any gradient exchange")
+    ap.add_argument("--bucket-elems", type=int, default=1 << 20)
+    ap.add_argument("--overlap-ctas", type=int, default=0)
     ap.add_argument("--separate-txt", action="store_true",
                     help="encode the query rows with a separate f_encoder(batch, 'txt') call")
+    ap.add_argument("--e2e-legacy-batch", action="store_true",
+                    help="e2e ships the legacy batch dict including f_v_feats (2x the H2D bytes)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config-2 / config-3 lines")
+    ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-clips", type=int, default=4)
+    ap.add_argument("--cpu-clips", type=int, default=8)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

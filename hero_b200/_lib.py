@@ -32,6 +32,7 @@ class GemmArgs(C.Structure):
         ("drop_threshold", C.c_uint32), ("drop_key", C.c_uint32),
         ("drop_scale", C.c_float),
         ("block_n", C.c_int32), ("k_splits", C.c_int32), ("cta_pair", C.c_int32),
+        ("resid_f32", C.c_int32), ("out_f32_store", C.c_int32),
     ]
 
 
@@ -42,7 +43,8 @@ class LnArgs(C.Structure):
         ("x_rows", C.c_void_p), ("add_tab", C.c_void_p), ("add_idx", C.c_void_p),
         ("add_vec", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
         ("eps", C.c_float), ("n_rows", C.c_int32), ("h", C.c_int32),
-        ("y", C.c_void_p), ("y_rows", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
+        ("y", C.c_void_p), ("y_rows", C.c_void_p), ("y_f32", C.c_void_p),
+        ("mean", C.c_void_p), ("rstd", C.c_void_p),
         ("drop_threshold", C.c_uint32), ("drop_key", C.c_uint32), ("drop_scale", C.c_float),
         ("dy", C.c_void_p), ("dx", C.c_void_p), ("dx_drop", C.c_void_p),
         ("drop2_threshold", C.c_uint32), ("drop2_key", C.c_uint32), ("drop2_scale", C.c_float),
@@ -60,8 +62,8 @@ class LayerWeights(C.Structure):
 
 class LayerActs(C.Structure):
     """Mirror of `hero_layer_acts`."""
-    _fields_ = [(n, C.c_void_p) for n in ("qkv", "cx", "lse", "s1", "mean1", "rstd1", "a", "pre",
-                                            "f", "s2", "mean2", "rstd2", "out")]
+    _fields_ = [(n, C.c_void_p) for n in ("qkv", "cx", "lse", "s1", "mean1", "rstd1", "a", "a_f32",
+                                            "pre", "f", "s2", "mean2", "rstd2", "out", "out_f32")]
 
 
 class LayerGrads(C.Structure):
@@ -78,7 +80,7 @@ class StackArgs(C.Structure):
         ("eps", C.c_float),
         ("weights", C.POINTER(LayerWeights)), ("acts", C.POINTER(LayerActs)),
         ("grads", C.POINTER(LayerGrads)),
-        ("x", C.c_void_p),
+        ("x", C.c_void_p), ("x_f32", C.c_void_p),
         ("tile_tok0", C.c_void_p), ("tile_ntok", C.c_void_p), ("seq_lo", C.c_void_p),
         ("seq_hi", C.c_void_p),
         ("hidden_drop_threshold", C.c_uint32), ("attn_drop_threshold", C.c_uint32),
@@ -120,11 +122,12 @@ def _declare(lib):
     lib.hero_bert_stack_bwd_scratch_bytes.argtypes = [i32, i32, i32]
     sig("hero_cast_f32_to_bf16", vp, vp, i64, vp)
     sig("hero_gather_rows_bf16", vp, vp, vp, i32, i32, vp)
+    sig("hero_gather_rows_f32", vp, vp, vp, i32, i32, vp)
     sig("hero_gather_sum_rows_bf16", vp, vp, vp, vp, i32, i32, vp)
     sig("hero_gather_sum_rows_f32", vp, vp, vp, vp, i32, i32, vp)
     sig("hero_colsum_bf16", vp, i64, i32, i32, vp, vp)
     sig("hero_relu_bwd_bf16", vp, vp, vp, i64, vp)
-    sig("hero_adamw_step", vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp)
+    sig("hero_adamw_step", vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp, f32, vp)
     sig("hero_sumsq_f32", vp, i64, vp, vp)
     sig("hero_reduce_slots_f32", vp, vp, i32, i64, i64, f32, i32, vp)
 

@@ -1,11 +1,18 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring ->
 // tcgen05.mma (fp32 accumulators in TMEM, double buffered) -> fused epilogue.
 //
-// One CTA per SM, 6 warps:
+// One CTA per SM (or one CTA pair per TPC), 10 warps:
 //   warp 0      TMA producer (one elected lane)
 //   warp 1      TMEM allocator + MMA issuer (one lane issues tcgen05.mma / tcgen05.commit)
-//   warps 2..5  epilogue: tcgen05.ld their 32-lane TMEM quadrant, bias/act/dropout/residual,
-//               bf16 store or fp32 atomic accumulate (split-K wgrad)
+//   warps 2..9  epilogue: two warps per 32-lane TMEM quadrant, splitting the tile's column slabs.
+//               Per slab (32 rows x 64 bf16 columns, or 32 rows x 32 fp32 columns when the
+//               residual stream is involved — always 32 x 128 B = one 4 KB swizzled smem slab):
+//                 tcgen05.ld -> bias -> activation -> dropout -> residual -> pack -> smem -> TMA store
+//               Everything that comes from or goes to HBM moves by TMA: the residual /
+//               saved-derivative slab is prefetched one slab ahead into a warp-private smem slab
+//               (its own mbarrier), outputs leave through double-buffered slabs so a store never
+//               waits for the previous one to drain. No CTA-wide barrier in the epilogue: each warp
+//               keeps its own bias slice.
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty x2 (MMA <-> epilogue), so the
 // epilogue of tile i overlaps the mainloop of tile i+1.
 //
@@ -15,6 +22,7 @@
 #include <cudaTypedefs.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -28,8 +36,12 @@ constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle span
 constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+constexpr int SLAB_BYTES = 32 * 128;   // 32 rows x 128 B, swizzle-128B
+constexpr int SMEM_LIMIT = 232448;     // 227 KB opt-in dynamic shared memory per CTA
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_GELU_GRAD = 3 };
+enum { OUT_BF16 = 0, OUT_F32_ATOMIC = 1, OUT_F32 = 2 };
+enum { RES_NONE = 0, RES_BF16 = 1, RES_F32 = 2 };
 
 struct GemmShape {
   int M, N, K;
@@ -38,13 +50,8 @@ struct GemmShape {
 
 struct GemmEpilogue {
   const float* bias;
-  const __nv_bfloat16* resid;
-  long long ld_resid;
-  const __nv_bfloat16* aux_in;
-  long long ld_aux_in;
-  __nv_bfloat16* aux_out;
-  long long ld_aux_out;
-  void* out;
+  int has_aux;
+  void* out;           // OUT_F32_ATOMIC only
   long long ld_out;
   uint32_t drop_threshold;
   uint32_t drop_key;
@@ -53,62 +60,40 @@ struct GemmEpilogue {
 
 // CTA2 = 1: the CTA is half of a pair (cluster of 2) running cta_group::2 MMAs on a 256 x BLOCK_N
 // tile; it stages its own 128 rows of A and BLOCK_N / 2 columns of B per pipeline stage.
-// SLABS = 2 (GELU kernels, which store two tensors per tile: the activation and its derivative):
-// a second staging slab per epilogue warp so the two TMA stores of a slab never wait for each
-// other; paid for with one pipeline stage (these are K = hidden tiles, epilogue- not load-bound).
-template <int BLOCK_N, int CTA2 = 0, int SLABS = 1>
+template <int BLOCK_N, int CTA2, int ACT, int OUT, int RES>
 struct GemmCfg {
-  static constexpr int STAGES = ((BLOCK_N == 256 && !CTA2) ? 4 : 6) - (SLABS - 1);
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;   // B columns staged by this CTA
   static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers
-  // epilogue staging: one slab of 32 rows x 64 bf16 (128 B rows, swizzled) per epilogue warp
-  static constexpr int SLAB_BYTES = 32 * 128;
-  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * SLAB_BYTES * SLABS;
-  static constexpr int BIAS_OFFSET = STAGES * STAGE_BYTES + STAGING_BYTES;
-  static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;  // per-tile bias slice, double buffered
+  // slab width in columns: 128-byte rows of the element type that travels
+  static constexpr int W = (OUT == OUT_F32 || RES == RES_F32) ? 32 : 64;
+  // staging slabs per epilogue warp: output (double buffered; the GELU / ReLU kernels, which also
+  // store a second tensor, use one slab per tensor), residual operand
+  static constexpr int AUX = (ACT == ACT_GELU || ACT == ACT_RELU) ? 1 : 0;
+  static constexpr int N_RES_BUF = RES ? 1 : 0;
+  static constexpr int BIAS_BYTES = NUM_EPI_WARPS * 64 * 4;    // warp-private bias slices
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int stages_with(int slabs_per_warp) {
+    return (SMEM_LIMIT - NUM_EPI_WARPS * slabs_per_warp * SLAB_BYTES - BIAS_BYTES - BAR_BYTES) /
+           STAGE_BYTES;
+  }
+  // a second output slab only where it leaves the operand pipeline at least 4 stages deep
+  static constexpr int N_OUT_BUF =
+      (OUT == OUT_F32_ATOMIC) ? 0 : ((!AUX && stages_with(2 + N_RES_BUF) >= 4) ? 2 : 1);
+  static constexpr int SLABS_PER_WARP = N_OUT_BUF + AUX + N_RES_BUF;
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * SLABS_PER_WARP * SLAB_BYTES;
+  static constexpr int MAX_STAGES = stages_with(SLABS_PER_WARP);
+  static constexpr int STAGES = MAX_STAGES > 6 ? 6 : MAX_STAGES;
+  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BIAS_OFFSET = STAGING_OFFSET + STAGING_BYTES;
   static constexpr int BAR_OFFSET = BIAS_OFFSET + BIAS_BYTES;
-  static constexpr int SMEM_BYTES = BAR_OFFSET + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = BAR_OFFSET + BAR_BYTES;
+  static_assert(STAGES >= 3, "not enough shared memory for a 3-stage pipeline");
+  static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget exceeded");
 };
 
-// Epilogue arithmetic on one 64-column slab of one row (v in/out), organised in phases so that
-// every warp-uniform option (bias / dropout / residual / derivative output) is tested once per slab
-// and the arithmetic inside a phase is straight-line code. Operands that come from memory arrive
-// already loaded: bias from the per-tile smem slice, residual / saved-derivative rows prefetched
-// into registers one slab ahead.
-__device__ __forceinline__ void slab_add_bias(float (&v)[64], const float* bias_s) {
-#pragma unroll
-  for (int g = 0; g < 16; ++g) {
-    const float4 b = *reinterpret_cast<const float4*>(bias_s + g * 4);
-    v[4 * g] += b.x; v[4 * g + 1] += b.y; v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
-  }
-}
-__device__ __forceinline__ void slab_mul_bf16(float (&v)[64], const uint4 (&m)[8]) {
-#pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    const uint32_t pw[4] = {m[g].x, m[g].y, m[g].z, m[g].w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 x = unpack_bf16x2(pw[j]);
-      v[8 * g + 2 * j] *= x.x;
-      v[8 * g + 2 * j + 1] *= x.y;
-    }
-  }
-}
-__device__ __forceinline__ void slab_add_bf16(float (&v)[64], const uint4 (&m)[8]) {
-#pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    const uint32_t pw[4] = {m[g].x, m[g].y, m[g].z, m[g].w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 x = unpack_bf16x2(pw[j]);
-      v[8 * g + 2 * j] += x.x;
-      v[8 * g + 2 * j + 1] += x.y;
-    }
-  }
-}
 __device__ __forceinline__ uint4 pack8(const float* v) {
   uint4 u;
   u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
@@ -116,15 +101,39 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   return u;
 }
 
-template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT_F32, int CTA2>
+// Write W fp32 values of this lane's row into its 128-byte row of a swizzled slab, as bf16
+// (W = 64) or fp32 (W = 32): 8 16-byte chunks, chunk g stored at position g ^ (row & 7).
+template <int W, bool F32>
+__device__ __forceinline__ void stage_row(uint8_t* slab, int lane, const float (&v)[W]) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    uint4 u;
+    if (F32) {
+      u.x = __float_as_uint(v[4 * g]); u.y = __float_as_uint(v[4 * g + 1]);
+      u.z = __float_as_uint(v[4 * g + 2]); u.w = __float_as_uint(v[4 * g + 3]);
+    } else {
+      u = pack8(&v[8 * g]);
+    }
+    *reinterpret_cast<uint4*>(slab + lane * 128 + ((g ^ (lane & 7)) << 4)) = u;
+  }
+}
+
+template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT, int CTA2, int RES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out,
-                    const __grid_constant__ CUtensorMap tmap_aux, const GemmShape s,
+                    const __grid_constant__ CUtensorMap tmap_aux,
+                    const __grid_constant__ CUtensorMap tmap_res, const GemmShape s,
                     const GemmEpilogue e) {
-  using Cfg = GemmCfg<BLOCK_N, CTA2, (ACT == ACT_GELU) ? 2 : 1>;
+  using Cfg = GemmCfg<BLOCK_N, CTA2, ACT, OUT, RES>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int W = Cfg::W;
+  constexpr int NSLAB = BLOCK_N / W;
+  static_assert(!(ACT == ACT_GELU || ACT == ACT_RELU || ACT == ACT_GELU_GRAD) || W == 64,
+                "activation epilogues use 64-column bf16 slabs");
+  static_assert(ACT != ACT_GELU_GRAD || RES == RES_BF16, "GELU' multiplier arrives as a bf16 slab");
+  static_assert(OUT != OUT_F32_ATOMIC || RES == RES_NONE, "split-K accumulation takes no residual");
   // pair rank (0 = leader: issues the MMAs and owns the pipeline "full" / TMEM "empty" barriers)
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
   const bool leader = (rank == 0u);
@@ -136,7 +145,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full_bar = bars + 2 * STAGES;
   uint64_t* tmem_empty_bar = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* res_bar = bars + 2 * STAGES + 4;                     // one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + NUM_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -144,7 +154,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    if (!OUT_F32) tma_prefetch_desc(&tmap_out);
+    if (OUT != OUT_F32_ATOMIC) tma_prefetch_desc(&tmap_out);
+    if (RES) tma_prefetch_desc(&tmap_res);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -154,6 +165,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       // one arrive per epilogue warp (of both CTAs on the leader's barrier in pair mode)
       mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS * (CTA2 ? 2 : 1));
     }
+    for (int i = 0; i < NUM_EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -271,78 +283,113 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else {
     // ------------------------------------------------------------- epilogue warps
     // Two warps share each TMEM lane quadrant (hardware: warp w may touch lanes 32*(w%4)..+31) and
-    // split the tile's 64-column slabs between them; 8 warps = 2 per SM sub-partition, which hides
-    // the ALU/MUFU latency of the GELU / dropout / pack arithmetic.
+    // split the tile's column slabs between them (slab c -> warp half c & 1).
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;     // 0 or 1: which slabs of the tile this warp handles
-    const int et = threadIdx.x - 64;      // 0..255 within the epilogue group
-    uint8_t* slab = smem + STAGES * Cfg::STAGE_BYTES + (warp - 2) * Cfg::SLAB_BYTES;
-    // second slab (GELU kernels): staging of the derivative tensor
-    uint8_t* slab_aux = (ACT == ACT_GELU) ? slab + NUM_EPI_WARPS * Cfg::SLAB_BYTES : slab;
-    float* bias_all = reinterpret_cast<float*>(smem + Cfg::BIAS_OFFSET);
-    const bool has_aux = (e.aux_out != nullptr);
+    const int half = (warp - 2) >> 2;
+    const int ew = warp - 2;
+    uint8_t* stage0 = smem + Cfg::STAGING_OFFSET + ew * Cfg::SLABS_PER_WARP * SLAB_BYTES;
+    uint8_t* out_slab = stage0;                                            // N_OUT_BUF slabs
+    uint8_t* aux_slab = stage0 + Cfg::N_OUT_BUF * SLAB_BYTES;             // AUX slab
+    uint8_t* res_slab = stage0 + (Cfg::N_OUT_BUF + Cfg::AUX) * SLAB_BYTES;
+    float* bias_w = reinterpret_cast<float*>(smem + Cfg::BIAS_OFFSET) + ew * 64;
+    uint64_t* my_res_bar = &res_bar[ew];
+    const bool has_aux = Cfg::AUX && e.has_aux;
     const bool has_bias = (e.bias != nullptr);
-    const bool has_resid = (ACT != ACT_GELU_GRAD) && (e.resid != nullptr);
-    uint32_t slab_it = 0;
-    uint32_t local_tile = 0;
-    // The bias slice of tile i+1 is read (into a register) before tile i is processed, so its
-    // latency never sits on the critical path; the residual / saved-derivative rows of a slab are
-    // requested together with the slab's TMEM load. (Requesting them one slab ahead was measured
-    // slower: +32 live registers push the kernel over the 168-register budget of a 10-warp CTA.)
-    const bool has_opnd = has_resid || ACT == ACT_GELU_GRAD;
-    const __nv_bfloat16* opnd_base = (ACT == ACT_GELU_GRAD) ? e.aux_in : e.resid;
-    const long long ld_opnd = (ACT == ACT_GELU_GRAD) ? e.ld_aux_in : e.ld_resid;
-    auto tile_bias = [&](int t) -> float {
-      if (!has_bias || et >= BLOCK_N || t >= total_tiles) return 0.0f;
-      const int col = ((t / s.k_splits) % s.num_n_blocks) * BLOCK_N + et;
-      return (col < s.N) ? __ldg(e.bias + col) : 0.0f;
+    const int row_off = q * 32;
+
+    // (tile, slab) sequence of this warp, one step ahead of the slab being processed: its bias
+    // slice is fetched into a register pair and its residual slab is requested by TMA
+    auto slab_col0 = [&](int tile, int c) {
+      return ((tile / s.k_splits) % s.num_n_blocks) * BLOCK_N + c * W;
     };
-    auto load_opnd = [&](uint4 (&dst)[8], int row, bool row_ok, int col0) {
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        const int col = col0 + g * 8;
-        dst[g] = (row_ok && col < s.N)
-                     ? *reinterpret_cast<const uint4*>(opnd_base + (long long)row * ld_opnd + col)
-                     : make_uint4(0, 0, 0, 0);
+    auto slab_row0 = [&](int tile) {
+      const int m_blk = (tile / s.k_splits) / s.num_n_blocks;
+      return (CTA2 ? m_blk * 2 + (int)rank : m_blk) * BLOCK_M + row_off;
+    };
+    int ntile = first_tile, nc = half;
+    auto skip_invalid = [&]() {
+      while (ntile < total_tiles && (nc >= NSLAB || slab_col0(ntile, nc) >= s.N)) {
+        ntile += tile_step;
+        nc = half;
+        if (half >= NSLAB) { ntile = total_tiles; break; }
       }
     };
-    float bias_next = tile_bias(first_tile);
+    auto fetch_bias = [&]() -> float2 {
+      float2 b = make_float2(0.f, 0.f);
+      if (has_bias && ntile < total_tiles && W == 64) {
+        const int col = slab_col0(ntile, nc) + 2 * lane;
+        if (col < s.N) b = __ldg(reinterpret_cast<const float2*>(e.bias + col));
+      } else if (has_bias && ntile < total_tiles) {   // W == 32: one column per lane
+        const int col = slab_col0(ntile, nc) + lane;
+        if (col < s.N) b.x = __ldg(e.bias + col);
+      }
+      return b;
+    };
+    auto request_res = [&]() {
+      if (RES && ntile < total_tiles && lane == 0) {
+        mbar_arrive_expect_tx(my_res_bar, SLAB_BYTES);
+        tma_load_2d(res_slab, &tmap_res, my_res_bar, slab_col0(ntile, nc), slab_row0(ntile));
+      }
+    };
+    skip_invalid();
+    float2 bias_next = fetch_bias();
+    request_res();
+    uint32_t res_phase = 0;
+    uint32_t out_it = 0;
+    uint32_t local_tile = 0;
+
     for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++local_tile) {
-      const int t2 = tile / s.k_splits;
-      const int n_blk = t2 % s.num_n_blocks;
-      const int m_blk = t2 / s.num_n_blocks;
       const uint32_t acc = local_tile & 1u;
       const uint32_t acc_ph = (local_tile >> 1) & 1u;
-      float* bias_s = bias_all + acc * BLOCK_N;
-      const int row0 = (CTA2 ? m_blk * 2 + (int)rank : m_blk) * BLOCK_M + q * 32;
+      const int row0 = slab_row0(tile);
       const int row = row0 + lane;
       const bool row_ok = row < s.M;
-      if (has_bias) {
-        // this tile's bias slice (fetched one tile ago) -> smem; the slot was last read two tiles
-        // back, and every epilogue warp has passed this barrier once since then
-        if (et < BLOCK_N) bias_s[et] = bias_next;
-        bias_next = tile_bias(tile + tile_step);
-        asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
-      }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after_sync();
-      const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(row_off) << 16);
 #pragma unroll 1
-      for (int c = half; c < BLOCK_N / 64; c += 2) {
-        const int col0 = n_blk * BLOCK_N + c * 64;
+      for (int c = half; c < NSLAB; c += 2) {
+        const int col0 = slab_col0(tile, c);
         if (col0 >= s.N) break;  // warp-uniform
-        uint32_t r[2][32];
-        tmem_ld_32x32(t_addr + c * 64, r[0]);
-        tmem_ld_32x32(t_addr + c * 64 + 32, r[1]);
+        // accumulator slab -> registers (asynchronous until tmem_ld_wait)
+        uint32_t r[W / 32][32];
+        tmem_ld_32x32(t_addr + c * W, r[0]);
+        if (W == 64) tmem_ld_32x32(t_addr + c * W + 32, r[W / 32 - 1]);
+        // this slab's bias slice -> warp-private smem; then look one slab ahead
+        if (has_bias) {
+          __syncwarp();     // the previous slab's broadcast reads of bias_w are done
+          if (W == 64) *reinterpret_cast<float2*>(bias_w + 2 * lane) = bias_next;
+          else bias_w[lane] = bias_next.x;
+          __syncwarp();
+        }
+        nc += 2;
+        skip_invalid();
+        bias_next = fetch_bias();
+        // residual / saved-derivative slab (requested one slab ago) -> registers; its smem slab is
+        // then free for the next request
         uint4 opnd[8];
-        if (has_opnd) load_opnd(opnd, row, row_ok, col0);
-        tmem_ld_wait();
-        float v[64];
+        if (RES) {
+          mbar_wait(my_res_bar, res_phase);
+          res_phase ^= 1u;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = __uint_as_float(r[j >> 5][j & 31]);
-        if (has_bias) slab_add_bias(v, bias_s + c * 64);
+          for (int g = 0; g < 8; ++g)
+            opnd[g] = *reinterpret_cast<const uint4*>(res_slab + lane * 128 + ((g ^ (lane & 7)) << 4));
+          __syncwarp();
+          request_res();
+        }
+        tmem_ld_wait();
+        float v[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) v[j] = __uint_as_float(r[j >> 5][j & 31]);
+        if (has_bias) {
+#pragma unroll
+          for (int g = 0; g < W / 4; ++g) {
+            const float4 b = *reinterpret_cast<const float4*>(bias_w + g * 4);
+            v[4 * g] += b.x; v[4 * g + 1] += b.y; v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
+          }
+        }
         // activation (compile-time); the training FFN-up also emits gelu'(x) through its own slab
-        if (ACT == ACT_GELU) {
+        if constexpr (ACT == ACT_GELU) {
           if (has_aux) {
             if (lane == 0) bulk_wait_read<1>();   // the aux slab's previous store (two groups back)
             __syncwarp();
@@ -352,41 +399,47 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
               for (int j = 0; j < 8; j += 2)
                 gelu_erf_with_grad2(v[8 * g + j], v[8 * g + j + 1], d[j], d[j + 1]);
-              *reinterpret_cast<uint4*>(slab_aux + lane * 128 + ((g ^ (lane & 7)) << 4)) = pack8(d);
+              *reinterpret_cast<uint4*>(aux_slab + lane * 128 + ((g ^ (lane & 7)) << 4)) = pack8(d);
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmap_aux, slab_aux, col0, row0);
+              tma_store_2d(&tmap_aux, aux_slab, col0, row0);
               bulk_commit();
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < W; ++j) v[j] = gelu_erf(v[j]);
           }
-        } else if (ACT == ACT_RELU) {
+        } else if constexpr (ACT == ACT_RELU) {
           if (has_aux) {   // pre-activation copy (the ReLU backward needs its sign)
-            if (lane == 0) bulk_wait_read<0>();
+            if (lane == 0) bulk_wait_read<1>();
             __syncwarp();
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              *reinterpret_cast<uint4*>(slab_aux + lane * 128 + ((g ^ (lane & 7)) << 4)) =
-                  pack8(v + 8 * g);
+            stage_row<W, false>(aux_slab, lane, v);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&tmap_aux, slab_aux, col0, row0);
+              tma_store_2d(&tmap_aux, aux_slab, col0, row0);
               bulk_commit();
             }
           }
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.0f);
-        } else if (ACT == ACT_GELU_GRAD) {   // multiply by the saved activation derivative
-          slab_mul_bf16(v, opnd);
+          for (int j = 0; j < W; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else if constexpr (ACT == ACT_GELU_GRAD) {   // multiply by the saved activation derivative
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t pw[4] = {opnd[g].x, opnd[g].y, opnd[g].z, opnd[g].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 x = unpack_bf16x2(pw[j]);
+              v[8 * g + 2 * j] *= x.x;
+              v[8 * g + 2 * j + 1] *= x.y;
+            }
+          }
         }
         if (e.drop_threshold != 0u) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
+          for (int g = 0; g < W / 8; ++g) {
             float t[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) t[j] = v[8 * g + j];
@@ -396,11 +449,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             for (int j = 0; j < 8; ++j) v[8 * g + j] = t[j];
           }
         }
-        if (has_resid) slab_add_bf16(v, opnd);
-        if (OUT_F32) {
+        if constexpr (RES == RES_F32) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            v[4 * g] += __uint_as_float(opnd[g].x); v[4 * g + 1] += __uint_as_float(opnd[g].y);
+            v[4 * g + 2] += __uint_as_float(opnd[g].z); v[4 * g + 3] += __uint_as_float(opnd[g].w);
+          }
+        } else if constexpr (RES == RES_BF16 && ACT != ACT_GELU_GRAD) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t pw[4] = {opnd[g].x, opnd[g].y, opnd[g].z, opnd[g].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 x = unpack_bf16x2(pw[j]);
+              v[8 * g + 2 * j] += x.x;
+              v[8 * g + 2 * j + 1] += x.y;
+            }
+          }
+        }
+        if constexpr (OUT == OUT_F32_ATOMIC) {
           if (row_ok) {
 #pragma unroll
-            for (int g = 0; g < 16; ++g) {
+            for (int g = 0; g < W / 4; ++g) {
               const int col = col0 + g * 4;
               if (col < s.N) {
                 float* o = reinterpret_cast<float*>(e.out) + (long long)row * e.ld_out + col;
@@ -411,26 +481,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           }
         } else {
-          // stage the 32 x 64 bf16 slab in swizzled smem and let TMA write full 128 B rows; the
-          // previous store from this slab must have drained (a derivative store issued just above
-          // from the second slab may stay in flight)
-          uint4 outp[8];
-#pragma unroll
-          for (int g = 0; g < 8; ++g) outp[g] = pack8(v + 8 * g);
+          // stage the slab in swizzled smem and let TMA write full 128 B rows. Output slabs are
+          // double buffered: only the store issued two slabs ago must have finished READING smem
+          // (bulk groups complete in order; with an aux store per slab the distance is the same).
+          // (a GELU / ReLU kernel that stores no second tensor uses that tensor's slab as its
+          // second output buffer: the slabs are adjacent)
+          const bool two_bufs = (Cfg::N_OUT_BUF == 2) || (Cfg::AUX && !has_aux);
+          uint8_t* slab = out_slab + (two_bufs ? (out_it & 1u) * SLAB_BYTES : 0);
           if (lane == 0) {
-            if (ACT == ACT_GELU && has_aux) bulk_wait_read<1>(); else bulk_wait_read<0>();
+            // one group may stay in flight when it reads another slab (the other output buffer,
+            // or this slab's derivative store); a lone slab must have drained
+            if (two_bufs || has_aux) bulk_wait_read<1>(); else bulk_wait_read<0>();
           }
           __syncwarp();
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<uint4*>(slab + lane * 128 + ((g ^ (lane & 7)) << 4)) = outp[g];
+          stage_row<W, OUT == OUT_F32>(slab, lane, v);
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tmap_out, slab, col0, row0);
             bulk_commit();
           }
-          ++slab_it;
+          ++out_it;
         }
       }
       tc_fence_before_sync();
@@ -439,7 +510,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (CTA2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]);
       }
     }
-    if (!OUT_F32 && lane == 0) bulk_wait_all();
+    if (OUT != OUT_F32_ATOMIC && lane == 0) bulk_wait_all();
   }
 
   tc_fence_before_sync();
@@ -451,7 +522,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
-// ------------------------------------------------------------------ host side
+// ------------------------------------------------------------------ host side: tensor maps
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (fn) return fn;
@@ -465,69 +536,104 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-// K-major operand: global [rows, k] row-major (ld elements); box = 64 k x box_rows rows.
-static int encode_kmajor(CUtensorMap* map, const void* ptr, int rows, int k, long long ld,
-                         int box_rows) {
+// Tensor maps are pure functions of (pointer, extents, leading dimension, box, kind), and the
+// training loop presents the same few hundred combinations every step (weights never move;
+// activation workspaces come back from the caching allocator at the same addresses): a small
+// direct-mapped cache replaces ~400 cuTensorMapEncodeTiled calls per step with lookups.
+enum { TM_KMAJOR = 0, TM_MNMAJOR = 1, TM_SLAB_BF16 = 2, TM_SLAB_F32 = 3 };
+struct TmapKey {
+  const void* ptr;
+  long long ld;
+  int d0, d1, box, kind;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && ld == o.ld && d0 == o.d0 && d1 == o.d1 && box == o.box && kind == o.kind;
+  }
+};
+struct TmapEntry {
+  TmapKey key;
+  bool valid;
+  CUtensorMap map;
+};
+constexpr int TMAP_CACHE_SIZE = 4096;   // entries (power of two)
+
+static int encode_uncached(CUtensorMap* map, const TmapKey& k) {
   auto fn = get_encode_fn();
   if (!fn) return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r;
+  if (k.kind == TM_KMAJOR) {
+    // global [rows = d0, k = d1] row-major (ld elements); box = 64 k x box rows
+    cuuint64_t dims[2] = {(cuuint64_t)k.d1, (cuuint64_t)k.d0};
+    cuuint64_t strides[1] = {(cuuint64_t)k.ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)k.box};
+    cuuint32_t estr[2] = {1, 1};
+    r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(k.ptr), dims, strides, box,
+           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (k.kind == TM_MNMAJOR) {
+    // global [k = d0, mn = d1] row-major (ld elements), viewed as (64, k, mn/64) so one box
+    // (64, BLOCK_K, box/64) lands in smem as consecutive [BLOCK_K x 128 B] swizzle-128B chunks
+    cuuint64_t dims[3] = {64, (cuuint64_t)k.d0, (cuuint64_t)(k.d1 / 64)};
+    cuuint64_t strides[2] = {(cuuint64_t)k.ld * 2, 128};
+    cuuint32_t box[3] = {64, (cuuint32_t)BLOCK_K, (cuuint32_t)(k.box / 64)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(k.ptr), dims, strides, box,
+           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    // epilogue slab over a row-major [rows = d0, cols = d1] matrix: 32 rows x 128 bytes
+    const bool f32 = (k.kind == TM_SLAB_F32);
+    cuuint64_t dims[2] = {(cuuint64_t)k.d1, (cuuint64_t)k.d0};
+    cuuint64_t strides[1] = {(cuuint64_t)k.ld * (f32 ? 4 : 2)};
+    cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : 64), 32};
+    cuuint32_t estr[2] = {1, 1};
+    r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+           const_cast<void*>(k.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS)
-    return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled(K-major %dx%d ld %lld) failed: %d", rows,
-                     k, ld, (int)r);
+    return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled(kind %d, %d x %d, ld %lld) failed: %d",
+                     k.kind, k.d0, k.d1, k.ld, (int)r);
   return HERO_OK;
 }
 
-// MN-major operand: global [k, mn] row-major (ld elements), viewed as (64, k, mn/64) so one box
-// (64, BLOCK_K, box_mn/64) lands in smem as consecutive [BLOCK_K x 128 B] swizzle-128B chunks.
-static int encode_mnmajor(CUtensorMap* map, const void* ptr, int k, int mn, long long ld,
-                          int box_mn) {
-  auto fn = get_encode_fn();
-  if (!fn) return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t dims[3] = {64, (cuuint64_t)k, (cuuint64_t)(mn / 64)};
-  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, 128};
-  cuuint32_t box[3] = {64, (cuuint32_t)BLOCK_K, (cuuint32_t)(box_mn / 64)};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled(MN-major %dx%d ld %lld) failed: %d", k,
-                     mn, ld, (int)r);
-  return HERO_OK;
-}
-
-// bf16 row-major output [rows, cols]: box = 64 cols x 32 rows (one epilogue-warp slab).
-static int encode_out(CUtensorMap* map, const void* ptr, int rows, int cols, long long ld) {
-  auto fn = get_encode_fn();
-  if (!fn) return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, 32};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return set_error(HERO_ERR_CUDA, "cuTensorMapEncodeTiled(out %dx%d ld %lld) failed: %d", rows,
-                     cols, ld, (int)r);
+static int get_tmap(CUtensorMap* out, const void* ptr, int d0, int d1, long long ld, int box,
+                    int kind) {
+  static thread_local std::vector<TmapEntry> cache;
+  if (cache.empty()) {
+    cache.resize(TMAP_CACHE_SIZE);
+    for (auto& en : cache) en.valid = false;
+  }
+  TmapKey k;
+  memset(&k, 0, sizeof(k));
+  k.ptr = ptr; k.ld = ld; k.d0 = d0; k.d1 = d1; k.box = box; k.kind = kind;
+  uint64_t h = reinterpret_cast<uintptr_t>(ptr) >> 4;
+  h ^= (uint64_t)d0 * 0x9E3779B97F4A7C15ull;
+  h ^= ((uint64_t)d1 << 21) ^ ((uint64_t)box << 7) ^ (uint64_t)kind ^ ((uint64_t)ld << 40);
+  h *= 0xD6E8FEB86659FD93ull;
+  h ^= h >> 32;
+  TmapEntry& en = cache[h & (TMAP_CACHE_SIZE - 1)];
+  if (!(en.valid && en.key == k)) {
+    if (int rc = encode_uncached(&en.map, k)) {
+      en.valid = false;
+      return rc;
+    }
+    en.key = k;
+    en.valid = true;
+  }
+  *out = en.map;
   return HERO_OK;
 }
 
 struct GemmMaps {
-  CUtensorMap a, b, out, aux;
+  CUtensorMap a, b, out, aux, res;
 };
 
-template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT_F32, int CTA2>
+template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT, int CTA2, int RES>
 static int launch(const GemmMaps& tm, const GemmShape& s, const GemmEpilogue& e,
                   cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, CTA2, (ACT == ACT_GELU) ? 2 : 1>;
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, ACT, OUT_F32, CTA2>;
+  using Cfg = GemmCfg<BLOCK_N, CTA2, ACT, OUT, RES>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, ACT, OUT, CTA2, RES>;
   static bool attr_set = false;
   if (!attr_set) {
     HERO_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -557,7 +663,7 @@ static int launch(const GemmMaps& tm, const GemmShape& s, const GemmEpilogue& e,
     cfg.gridDim = dim3(total < sms ? total : sms);
   }
   cfg.attrs = attr;
-  HERO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.out, tm.aux, s, e));
+  HERO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.out, tm.aux, tm.res, s, e));
   return HERO_OK;
 }
 
@@ -565,28 +671,54 @@ template <int BLOCK_N, int CTA2>
 static int dispatch(const hero_gemm_args* g, const GemmMaps& tm, const GemmShape& s,
                     const GemmEpilogue& e, cudaStream_t st) {
   const int layout = g->a_mn_major * 2 + g->b_mn_major;
+  const bool res = g->resid != nullptr;
   if (g->out_f32_accumulate) {
-    HERO_REQUIRE(g->act == ACT_NONE, "fp32-accumulate output supports act=0 only");
-    if (layout == 3) return launch<BLOCK_N, 1, 1, ACT_NONE, 1, CTA2>(tm, s, e, st);
-    if (layout == 0) return launch<BLOCK_N, 0, 0, ACT_NONE, 1, CTA2>(tm, s, e, st);
+    if (layout == 3) return launch<BLOCK_N, 1, 1, ACT_NONE, OUT_F32_ATOMIC, CTA2, RES_NONE>(tm, s, e, st);
+    if (layout == 0) return launch<BLOCK_N, 0, 0, ACT_NONE, OUT_F32_ATOMIC, CTA2, RES_NONE>(tm, s, e, st);
     return set_error(HERO_ERR_INVALID, "fp32-accumulate supports layouts (0,0) and (1,1)");
+  }
+  if (g->out_f32_store) {
+    // the residual stream: fp32 pre-LayerNorm sums (forward out-projection / FFN-down)
+    if (layout == 0 && g->act == ACT_NONE) {
+      if (res) return launch<BLOCK_N, 0, 0, ACT_NONE, OUT_F32, CTA2, RES_F32>(tm, s, e, st);
+      return launch<BLOCK_N, 0, 0, ACT_NONE, OUT_F32, CTA2, RES_NONE>(tm, s, e, st);
+    }
+    return set_error(HERO_ERR_INVALID, "fp32-store output supports layout (0,0), act 0 only");
   }
   if (layout == 0) {
     switch (g->act) {
-      case ACT_NONE: return launch<BLOCK_N, 0, 0, ACT_NONE, 0, CTA2>(tm, s, e, st);
-      case ACT_GELU: return launch<BLOCK_N, 0, 0, ACT_GELU, 0, CTA2>(tm, s, e, st);
-      case ACT_RELU: return launch<BLOCK_N, 0, 0, ACT_RELU, 0, CTA2>(tm, s, e, st);
+      case ACT_NONE:
+        if (res) return launch<BLOCK_N, 0, 0, ACT_NONE, OUT_BF16, CTA2, RES_BF16>(tm, s, e, st);
+        return launch<BLOCK_N, 0, 0, ACT_NONE, OUT_BF16, CTA2, RES_NONE>(tm, s, e, st);
+      case ACT_GELU:
+        if (!res) return launch<BLOCK_N, 0, 0, ACT_GELU, OUT_BF16, CTA2, RES_NONE>(tm, s, e, st);
+        break;
+      case ACT_RELU:
+        if (res) {
+          // three staging slabs per warp (output, pre-activation copy, residual): the single-CTA
+          // 128 x 256 tile has no room left for a pipeline (the host picks 128-wide tiles or pairs)
+          if constexpr (BLOCK_N == 256 && !CTA2)
+            return set_error(HERO_ERR_INVALID, "relu + residual needs block_n 128 or CTA pairs");
+          else
+            return launch<BLOCK_N, 0, 0, ACT_RELU, OUT_BF16, CTA2, RES_BF16>(tm, s, e, st);
+        }
+        return launch<BLOCK_N, 0, 0, ACT_RELU, OUT_BF16, CTA2, RES_NONE>(tm, s, e, st);
       default: break;
     }
   } else if (layout == 1) {
     switch (g->act) {
-      case ACT_NONE: return launch<BLOCK_N, 0, 1, ACT_NONE, 0, CTA2>(tm, s, e, st);
-      case ACT_GELU_GRAD: return launch<BLOCK_N, 0, 1, ACT_GELU_GRAD, 0, CTA2>(tm, s, e, st);
+      case ACT_NONE:
+        if (res) return launch<BLOCK_N, 0, 1, ACT_NONE, OUT_BF16, CTA2, RES_BF16>(tm, s, e, st);
+        return launch<BLOCK_N, 0, 1, ACT_NONE, OUT_BF16, CTA2, RES_NONE>(tm, s, e, st);
+      case ACT_GELU_GRAD:
+        return launch<BLOCK_N, 0, 1, ACT_GELU_GRAD, OUT_BF16, CTA2, RES_BF16>(tm, s, e, st);
       default: break;
     }
   }
-  return set_error(HERO_ERR_INVALID, "unsupported gemm variant: a_mn=%d b_mn=%d act=%d f32=%d",
-                   g->a_mn_major, g->b_mn_major, g->act, g->out_f32_accumulate);
+  return set_error(HERO_ERR_INVALID,
+                   "unsupported gemm variant: a_mn=%d b_mn=%d act=%d f32acc=%d f32store=%d resid=%d",
+                   g->a_mn_major, g->b_mn_major, g->act, g->out_f32_accumulate, g->out_f32_store,
+                   (int)res);
 }
 
 // Optional per-launch timing (bench.py roofline): CUDA events on the launching stream around every
@@ -597,9 +729,9 @@ struct GemmProfileRec {
 struct GemmProfile {
   bool on = false;
   std::vector<cudaEvent_t> ev;   // pairs
+  std::vector<cudaEvent_t> pool; // recycled events
   std::vector<GemmProfileRec> rec;
   double flops = 0.0;
-  const char* dump_path = nullptr;
 };
 static GemmProfile g_prof;
 
@@ -609,7 +741,7 @@ bool gemm_profile_active() { return g_prof.on; }
 
 extern "C" int hero_gemm_profile_begin(void) {
   using namespace hero;
-  for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : g_prof.ev) g_prof.pool.push_back(e);
   g_prof.ev.clear();
   g_prof.rec.clear();
   g_prof.flops = 0.0;
@@ -639,7 +771,7 @@ extern "C" int hero_gemm_profile_end(double* ms, double* flops, int64_t* launche
   if (ms) *ms = total;
   if (flops) *flops = g_prof.flops;
   if (launches) *launches = (int64_t)(g_prof.ev.size() / 2);
-  for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : g_prof.ev) g_prof.pool.push_back(e);
   g_prof.ev.clear();
   return HERO_OK;
 }
@@ -649,18 +781,24 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream);
 extern "C" int hero_gemm_bf16(const hero_gemm_args* g, void* stream) {
   using namespace hero;
   if (!g_prof.on) return hero_gemm_bf16_impl(g, stream);
-  cudaEvent_t e0, e1;
-  HERO_CUDA_CHECK(cudaEventCreate(&e0));
-  HERO_CUDA_CHECK(cudaEventCreate(&e1));
+  cudaEvent_t ev[2];
+  for (int i = 0; i < 2; ++i) {
+    if (!g_prof.pool.empty()) {
+      ev[i] = g_prof.pool.back();
+      g_prof.pool.pop_back();
+    } else {
+      HERO_CUDA_CHECK(cudaEventCreate(&ev[i]));
+    }
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  HERO_CUDA_CHECK(cudaEventRecord(e0, st));
+  HERO_CUDA_CHECK(cudaEventRecord(ev[0], st));
   const int rc = hero_gemm_bf16_impl(g, stream);
-  HERO_CUDA_CHECK(cudaEventRecord(e1, st));
-  g_prof.ev.push_back(e0);
-  g_prof.ev.push_back(e1);
+  HERO_CUDA_CHECK(cudaEventRecord(ev[1], st));
+  g_prof.ev.push_back(ev[0]);
+  g_prof.ev.push_back(ev[1]);
   if (g)
     g_prof.rec.push_back(GemmProfileRec{g->m, g->n, g->k, g->a_mn_major, g->b_mn_major, g->act,
-                                        g->out_f32_accumulate});
+                                        g->out_f32_accumulate + 2 * g->out_f32_store});
   if (rc == HERO_OK && g) g_prof.flops += 2.0 * (double)g->m * (double)g->n * (double)g->k;
   return rc;
 }
@@ -674,6 +812,11 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   HERO_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0 && g->ld_out % 4 == 0, "unaligned leading dim");
   HERO_REQUIRE(g->act != ACT_GELU_GRAD || g->aux_in != nullptr, "act=3 needs aux_in");
   HERO_REQUIRE(g->act != ACT_GELU_GRAD || g->resid == nullptr, "act=3 cannot take a residual");
+  HERO_REQUIRE(!(g->out_f32_accumulate && g->out_f32_store), "fp32 store and accumulate exclude each other");
+  HERO_REQUIRE(!g->out_f32_accumulate || (g->act == ACT_NONE && !g->resid && !g->aux_out),
+               "fp32-accumulate output supports act=0 without residual only");
+  HERO_REQUIRE(!g->resid || (g->resid_f32 != 0) == (g->out_f32_store != 0),
+               "an fp32 residual goes with an fp32 stored output (and a bf16 one with bf16)");
   if (g->a_mn_major) HERO_REQUIRE(g->m % 64 == 0, "MN-major A needs m %% 64 == 0 (m=%d)", g->m);
   if (g->b_mn_major) HERO_REQUIRE(g->n % 64 == 0, "MN-major B needs n %% 64 == 0 (n=%d)", g->n);
 
@@ -693,15 +836,16 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
     }
   }
   HERO_REQUIRE(block_n == 128 || block_n == 256, "block_n must be 128 or 256");
+  const bool relu_res = g->act == ACT_RELU && g->resid != nullptr;
   // CTA pairs (cta_group::2, 256-row tiles) whenever the tile is 256 wide and there is more than
   // one 128-row block; cta_pair: 0 auto, 1 never, 2 force.
   // A single-CTA 128x256 tile needs more L2->SM bandwidth than the fabric delivers at the tensor
   // peak ("Why pairs"), so every GEMM with enough row blocks to fill the machine runs
-  // as CTA pairs. (Until the remote accumulator-release arrive was made .relaxed, pairs lost ~10 %
-  // on short-K tiles with heavy epilogues: each release compiled to MEMBAR + ERRBAR.)
+  // as CTA pairs.
   const bool pair_auto = g->m > 128 &&
                          (g->out_f32_accumulate || m_blocks * ceil_div(g->n, 256) >= sms);
   const bool pair = (block_n == 256) && (g->cta_pair == 2 || (g->cta_pair == 0 && pair_auto));
+  if (relu_res && block_n == 256 && !pair) block_n = 128;
 
   GemmShape s;
   s.M = g->m; s.N = g->n; s.K = g->k;
@@ -737,12 +881,7 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
 
   GemmEpilogue e;
   e.bias = g->bias;
-  e.resid = reinterpret_cast<const __nv_bfloat16*>(g->resid);
-  e.ld_resid = g->ld_resid;
-  e.aux_in = reinterpret_cast<const __nv_bfloat16*>(g->aux_in);
-  e.ld_aux_in = g->ld_aux_in;
-  e.aux_out = reinterpret_cast<__nv_bfloat16*>(g->aux_out);
-  e.ld_aux_out = g->ld_aux_out;
+  e.has_aux = g->aux_out != nullptr;
   e.out = g->out;
   e.ld_out = g->ld_out;
   e.drop_threshold = g->drop_threshold;
@@ -752,28 +891,46 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   GemmMaps tm;
   int rc;
   if (g->a_mn_major)
-    rc = encode_mnmajor(&tm.a, g->a, g->k, g->m, g->lda, BLOCK_M);
+    rc = get_tmap(&tm.a, g->a, g->k, g->m, g->lda, BLOCK_M, TM_MNMAJOR);
   else
-    rc = encode_kmajor(&tm.a, g->a, g->m, g->k, g->lda, BLOCK_M);
+    rc = get_tmap(&tm.a, g->a, g->m, g->k, g->lda, BLOCK_M, TM_KMAJOR);
   if (rc) return rc;
   const int b_box = pair ? block_n / 2 : block_n;   // a CTA of a pair stages half of the B tile
   if (g->b_mn_major)
-    rc = encode_mnmajor(&tm.b, g->b, g->k, g->n, g->ldb, b_box);
+    rc = get_tmap(&tm.b, g->b, g->k, g->n, g->ldb, b_box, TM_MNMAJOR);
   else
-    rc = encode_kmajor(&tm.b, g->b, g->n, g->k, g->ldb, b_box);
+    rc = get_tmap(&tm.b, g->b, g->n, g->k, g->ldb, b_box, TM_KMAJOR);
   if (rc) return rc;
+  tm.out = tm.a;
+  tm.aux = tm.a;
+  tm.res = tm.a;
   if (!g->out_f32_accumulate) {
-    HERO_REQUIRE(g->ld_out % 8 == 0, "bf16 output needs ld_out %% 8 == 0");
-    if ((rc = encode_out(&tm.out, g->out, g->m, g->n, g->ld_out))) return rc;
+    if (g->out_f32_store) {
+      if ((rc = get_tmap(&tm.out, g->out, g->m, g->n, g->ld_out, 32, TM_SLAB_F32))) return rc;
+    } else {
+      HERO_REQUIRE(g->ld_out % 8 == 0, "bf16 output needs ld_out %% 8 == 0");
+      if ((rc = get_tmap(&tm.out, g->out, g->m, g->n, g->ld_out, 64, TM_SLAB_BF16))) return rc;
+    }
     if (g->aux_out) {
       HERO_REQUIRE(g->ld_aux_out % 8 == 0, "aux_out needs ld %% 8 == 0");
-      if ((rc = encode_out(&tm.aux, g->aux_out, g->m, g->n, g->ld_aux_out))) return rc;
-    } else {
-      tm.aux = tm.out;
+      HERO_REQUIRE(g->act == ACT_GELU || g->act == ACT_RELU, "aux_out needs act 1 or 2");
+      if ((rc = get_tmap(&tm.aux, g->aux_out, g->m, g->n, g->ld_aux_out, 64, TM_SLAB_BF16)))
+        return rc;
     }
-  } else {
-    tm.out = tm.a;
-    tm.aux = tm.a;
+    if (g->act == ACT_GELU_GRAD) {
+      HERO_REQUIRE(g->ld_aux_in % 8 == 0, "aux_in needs ld %% 8 == 0");
+      if ((rc = get_tmap(&tm.res, g->aux_in, g->m, g->n, g->ld_aux_in, 64, TM_SLAB_BF16)))
+        return rc;
+    } else if (g->resid) {
+      if (g->resid_f32) {
+        HERO_REQUIRE(g->ld_resid % 4 == 0, "fp32 residual needs ld %% 4 == 0");
+        if ((rc = get_tmap(&tm.res, g->resid, g->m, g->n, g->ld_resid, 32, TM_SLAB_F32))) return rc;
+      } else {
+        HERO_REQUIRE(g->ld_resid % 8 == 0, "bf16 residual needs ld %% 8 == 0");
+        if ((rc = get_tmap(&tm.res, g->resid, g->m, g->n, g->ld_resid, 64, TM_SLAB_BF16)))
+          return rc;
+      }
+    }
   }
 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

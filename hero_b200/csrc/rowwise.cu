@@ -75,6 +75,11 @@ __device__ __forceinline__ void red_add_f32x8(float* p, const float (&v)[8]) {
                : "memory");
 }
 
+__device__ __forceinline__ void store_f32x8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float (&v)[8]) {
   uint4 u;
   u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
@@ -155,6 +160,7 @@ ln_fwd_kernel(const hero_ln_args a) {
             dropout_apply8(o, a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0,
                            a.drop_threshold, a.drop_scale);
           store_bf16x8(y + e0, o);
+          if (a.y_f32) store_f32x8(a.y_f32 + yrow * a.h + e0, o);
         }
       }
     }
@@ -178,16 +184,40 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
   }
 }
 
-__device__ __forceinline__ void load_row_raw(const __nv_bfloat16* base, long long row, int h,
-                                             int lane, uint4 (&raw)[LNF_J]) {
-  const __nv_bfloat16* p = base + row * h;
+// A row of <= 768 elements as this lane holds it between the load and its use: packed bf16
+// (one uint4 per 8 elements) or fp32 (two float4). The pre-LayerNorm sums of the transformer layers
+// are fp32 (the residual stream), embedding-side rows bf16.
+template <bool XF32>
+struct RowRaw {
+  uint4 q[LNF_J][XF32 ? 2 : 1];
+  __device__ __forceinline__ void load(const void* base, long long row, int h, int lane) {
 #pragma unroll
-  for (int c = 0; c < LNF_J; ++c) {
-    const int e0 = (c * 32 + lane) * 8;
-    raw[c] = (e0 < h) ? *reinterpret_cast<const uint4*>(p + e0) : make_uint4(0, 0, 0, 0);
+    for (int c = 0; c < LNF_J; ++c) {
+      const int e0 = (c * 32 + lane) * 8;
+      if (XF32) {
+        const float* p = reinterpret_cast<const float*>(base) + row * h + e0;
+        q[c][0] = (e0 < h) ? *reinterpret_cast<const uint4*>(p) : make_uint4(0, 0, 0, 0);
+        q[c][XF32 ? 1 : 0] = (e0 < h) ? *reinterpret_cast<const uint4*>(p + 4) : make_uint4(0, 0, 0, 0);
+      } else {
+        const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + row * h + e0;
+        q[c][0] = (e0 < h) ? *reinterpret_cast<const uint4*>(p) : make_uint4(0, 0, 0, 0);
+      }
+    }
   }
-}
+  __device__ __forceinline__ void unpack(int c, float (&v)[8]) const {
+    if (XF32) {
+      const uint4 a = q[c][0], b = q[c][XF32 ? 1 : 0];
+      v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y);
+      v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+      v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y);
+      v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
+    } else {
+      unpack8(q[c][0], v);
+    }
+  }
+};
 
+template <bool XF32>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_fast_kernel(const hero_ln_args a) {
   pdl_wait();
@@ -195,7 +225,6 @@ ln_fwd_fast_kernel(const hero_ln_args a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stride = gridDim.x * LN_WARPS;
   const float inv_h = 1.0f / (float)a.h;
-  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
   float g[LNF_J][8], b[LNF_J][8];
 #pragma unroll
   for (int c = 0; c < LNF_J; ++c) {
@@ -206,19 +235,19 @@ ln_fwd_fast_kernel(const hero_ln_args a) {
     }
   }
   int i = blockIdx.x * LN_WARPS + warp;
-  uint4 raw[LNF_J];
-  if (i < a.n_rows) load_row_raw(x, a.x_rows ? a.x_rows[i] : i, a.h, lane, raw);
+  RowRaw<XF32> raw;
+  if (i < a.n_rows) raw.load(a.x, a.x_rows ? a.x_rows[i] : i, a.h, lane);
   for (; i < a.n_rows; i += stride) {
     float v[LNF_J][8];
     float sum = 0.f;
 #pragma unroll
     for (int c = 0; c < LNF_J; ++c) {
-      unpack8(raw[c], v[c]);
+      raw.unpack(c, v[c]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) sum += v[c][j];
     }
     const int nxt = i + stride;
-    if (nxt < a.n_rows) load_row_raw(x, a.x_rows ? a.x_rows[nxt] : nxt, a.h, lane, raw);
+    if (nxt < a.n_rows) raw.load(a.x, a.x_rows ? a.x_rows[nxt] : nxt, a.h, lane);
     const float mean = warp_sum(sum) * inv_h;
     float sq = 0.f;
 #pragma unroll
@@ -236,7 +265,8 @@ ln_fwd_fast_kernel(const hero_ln_args a) {
       if (a.mean) a.mean[i] = mean;
       if (a.rstd) a.rstd[i] = rstd;
     }
-    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.y) + (a.y_rows ? a.y_rows[i] : i) * (long long)a.h;
+    const long long yrow = a.y_rows ? a.y_rows[i] : i;
+    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.y) + yrow * (long long)a.h;
 #pragma unroll
     for (int c = 0; c < LNF_J; ++c) {
       const int e0 = (c * 32 + lane) * 8;
@@ -248,6 +278,7 @@ ln_fwd_fast_kernel(const hero_ln_args a) {
           dropout_apply8(o, a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0,
                          a.drop_threshold, a.drop_scale);
         store_bf16x8(y + e0, o);
+        if (a.y_f32) store_f32x8(a.y_f32 + yrow * (long long)a.h + e0, o);
       }
     }
   }
@@ -258,15 +289,14 @@ ln_fwd_fast_kernel(const hero_ln_args a) {
 // whole kernel; at the end the CTA's warps are summed through shared memory and each CTA issues
 // one atomicAdd per column and output. (The split row kernel + column kernel read x and dy twice
 // and dx_drop once more: 55 us per 16.5 k-token call against 17 us of HBM time.)
-__global__ void __launch_bounds__(LN_WARPS * 32, 2)
+template <bool XF32>
+__global__ void __launch_bounds__(LN_WARPS * 32, XF32 ? 1 : 2)
 ln_bwd_fast_kernel(const hero_ln_args a) {
   pdl_wait();
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stride = gridDim.x * LN_WARPS;
   const float inv_h = 1.0f / (float)a.h;
-  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(a.x);
-  const __nv_bfloat16* dyp = reinterpret_cast<const __nv_bfloat16*>(a.dy);
   float g[LNF_J][8], dg[LNF_J][8], db[LNF_J][8], dbi[LNF_J][8];
 #pragma unroll
   for (int c = 0; c < LNF_J; ++c) {
@@ -276,11 +306,12 @@ ln_bwd_fast_kernel(const hero_ln_args a) {
     if (e0 < a.h) load_f32x8(a.gamma + e0, g[c]);
   }
   int i = blockIdx.x * LN_WARPS + warp;
-  uint4 rx[LNF_J], rd[LNF_J];
+  RowRaw<XF32> rx;
+  RowRaw<false> rd;
   float mean = 0.f, rstd = 0.f;
   if (i < a.n_rows) {
-    load_row_raw(x, a.x_rows ? a.x_rows[i] : i, a.h, lane, rx);
-    load_row_raw(dyp, a.y_rows ? a.y_rows[i] : i, a.h, lane, rd);
+    rx.load(a.x, a.x_rows ? a.x_rows[i] : i, a.h, lane);
+    rd.load(a.dy, a.y_rows ? a.y_rows[i] : i, a.h, lane);
     mean = a.mean[i];
     rstd = a.rstd[i];
   }
@@ -290,8 +321,8 @@ ln_bwd_fast_kernel(const hero_ln_args a) {
 #pragma unroll
     for (int c = 0; c < LNF_J; ++c) {
       float d[8];
-      unpack8(rx[c], xh[c]);
-      unpack8(rd[c], d);
+      rx.unpack(c, xh[c]);
+      rd.unpack(c, d);
       const int e0 = (c * 32 + lane) * 8;
       if (a.drop_threshold != 0u)
         dropout_apply8(d, a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0,
@@ -310,8 +341,8 @@ ln_bwd_fast_kernel(const hero_ln_args a) {
     const float rstd_i = rstd;
     const int nxt = i + stride;
     if (nxt < a.n_rows) {
-      load_row_raw(x, a.x_rows ? a.x_rows[nxt] : nxt, a.h, lane, rx);
-      load_row_raw(dyp, a.y_rows ? a.y_rows[nxt] : nxt, a.h, lane, rd);
+      rx.load(a.x, a.x_rows ? a.x_rows[nxt] : nxt, a.h, lane);
+      rd.load(a.dy, a.y_rows ? a.y_rows[nxt] : nxt, a.h, lane);
       mean = a.mean[nxt];
       rstd = a.rstd[nxt];
     }
@@ -614,6 +645,19 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src,
   reinterpret_cast<uint4*>(dst)[(long long)i * h8 + c] = v;
 }
 
+__global__ void gather_rows_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
+                                       float* __restrict__ dst, int n, int h4) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * h4) return;
+  const int i = (int)(t / h4), c = (int)(t % h4);
+  const int s = idx[i];
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s >= 0) v = reinterpret_cast<const float4*>(src)[(long long)s * h4 + c];
+  reinterpret_cast<float4*>(dst)[(long long)i * h4 + c] = v;
+}
+
 // bf16 output: one thread per (row, 8-column chunk) walks the row's (short) CSR list.
 __global__ void gather_sum_rows_kernel(const __nv_bfloat16* __restrict__ src,
                                        const int32_t* __restrict__ off,
@@ -734,7 +778,7 @@ __global__ void cast_kernel(const float* __restrict__ src, __nv_bfloat16* __rest
 
 // Plain bf16 rows of at most 768 columns (every transformer-layer LayerNorm): fast kernels.
 static bool ln_fast_ok(const hero_ln_args* a) {
-  return a->h <= LNF_J * 256 && !a->x_is_f32 && a->add_tab == nullptr && a->add_vec == nullptr;
+  return a->h <= LNF_J * 256 && a->add_tab == nullptr && a->add_vec == nullptr;
 }
 
 static int check_ln(const hero_ln_args* a) {
@@ -752,6 +796,7 @@ using namespace hero;
 extern "C" int hero_ln_fwd(const hero_ln_args* a, void* stream) {
   if (int rc = check_ln(a)) return rc;
   HERO_REQUIRE(a->y && a->beta, "ln_fwd: null y/beta");
+  HERO_REQUIRE(a->y_f32 == nullptr || a->h <= 768, "ln_fwd: y_f32 needs h <= 768");
   if (a->n_rows <= 0) return HERO_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int sms = sm_count();
@@ -759,7 +804,10 @@ extern "C" int hero_ln_fwd(const hero_ln_args* a, void* stream) {
   if (ln_fast_ok(a)) {
     int grid = ceil_div(a->n_rows, LN_WARPS);
     if (grid > sms * 4) grid = sms * 4;
-    HERO_CUDA_CHECK(launch_pdl(ln_fwd_fast_kernel, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
+    if (a->x_is_f32)
+      HERO_CUDA_CHECK(launch_pdl(ln_fwd_fast_kernel<true>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
+    else
+      HERO_CUDA_CHECK(launch_pdl(ln_fwd_fast_kernel<false>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
   } else if (a->h <= 768) {
     HERO_CUDA_CHECK(launch_pdl(ln_fwd_kernel<3, 1>, dim3(ceil_div(a->n_rows, LN_WARPS)),
                                dim3(LN_WARPS * 32), 0, st, *a));
@@ -787,7 +835,10 @@ extern "C" int hero_ln_bwd(const hero_ln_args* a, void* stream) {
     // one pass: row gradients + dgamma / dbeta / dbias
     int grid = ceil_div(a->n_rows, LN_WARPS);
     if (grid > sms * 2) grid = sms * 2;
-    HERO_CUDA_CHECK(launch_pdl(ln_bwd_fast_kernel, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
+    if (a->x_is_f32)
+      HERO_CUDA_CHECK(launch_pdl(ln_bwd_fast_kernel<true>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
+    else
+      HERO_CUDA_CHECK(launch_pdl(ln_bwd_fast_kernel<false>, dim3(grid), dim3(LN_WARPS * 32), 0, st, *a));
     return HERO_OK;
   }
   if (want_rows) {
@@ -832,6 +883,17 @@ extern "C" int hero_gather_rows_bf16(const void* src, const int32_t* idx, void* 
                        reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(src), idx, reinterpret_cast<__nv_bfloat16*>(dst), n,
       h / 8);
+  HERO_LAUNCH_CHECK();
+  return HERO_OK;
+}
+
+extern "C" int hero_gather_rows_f32(const float* src, const int32_t* idx, float* dst, int32_t n,
+                                    int32_t h, void* stream) {
+  HERO_REQUIRE(src && idx && dst && h % 4 == 0, "gather_rows_f32: bad args");
+  if (n <= 0) return HERO_OK;
+  const long long total = (long long)n * (h / 4);
+  gather_rows_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0,
+                           reinterpret_cast<cudaStream_t>(stream)>>>(src, idx, dst, n, h / 4);
   HERO_LAUNCH_CHECK();
   return HERO_OK;
 }

@@ -29,6 +29,10 @@ struct Gemm {
   }
   Gemm& bias(const float* p) { g.bias = p; return *this; }
   Gemm& resid(const void* p, long long ld) { g.resid = p; g.ld_resid = ld; return *this; }
+  // fp32 residual in, fp32 pre-LayerNorm sum out (the residual stream of the forward pass)
+  Gemm& resid_f32(const float* p, long long ld) {
+    g.resid = p; g.ld_resid = ld; g.resid_f32 = 1; g.out_f32_store = 1; return *this;
+  }
   Gemm& act(int a) { g.act = a; return *this; }
   Gemm& aux_out(void* p, long long ld) { g.aux_out = p; g.ld_aux_out = ld; return *this; }
   Gemm& aux_in(const void* p, long long ld) { g.aux_in = p; g.ld_aux_in = ld; return *this; }
@@ -42,7 +46,7 @@ struct Gemm {
 static void ln_base(hero_ln_args* a, const void* x, const float* gamma, const float* beta, float eps,
                     int n_rows, int h, float* mean, float* rstd) {
   memset(a, 0, sizeof(*a));
-  a->x = x; a->gamma = gamma; a->beta = beta; a->eps = eps;
+  a->x = x; a->x_is_f32 = 1; a->gamma = gamma; a->beta = beta; a->eps = eps;
   a->n_rows = n_rows; a->h = h; a->mean = mean; a->rstd = rstd;
   a->x_pad_idx = -1; a->add_pad_idx = -1;
   a->drop_scale = 1.0f; a->drop2_scale = 1.0f;
@@ -93,6 +97,7 @@ static int check_stack(const hero_stack_args* s, bool bwd) {
   HERO_REQUIRE(s->weights && s->acts && s->x, "stack: null weights/acts/x");
   HERO_REQUIRE(s->tile_tok0 && s->tile_ntok && s->seq_lo && s->seq_hi, "stack: null attention plan");
   if (bwd) HERO_REQUIRE(s->grads && s->dout && s->scratch, "stack bwd: null grads/dout/scratch");
+  if (!bwd) HERO_REQUIRE(s->x_f32 != nullptr, "stack fwd: null x_f32 (fp32 copy of the input)");
   return HERO_OK;
 }
 
@@ -112,22 +117,25 @@ extern "C" int hero_bert_stack_fwd(const hero_stack_args* s, void* stream) {
   HERO_TRY(check_stack(s, false));
   const int M = s->n_tok, H = s->hidden, I = s->inter;
   const float scale = 0.125f;
-  const void* h = s->x;
+  const void* h = s->x;          // bf16: GEMM operand
+  const float* h32 = s->x_f32;   // fp32: residual
   for (int l = 0; l < s->n_layers; ++l) {
     const hero_layer_weights& W = s->weights[l];
     const hero_layer_acts& A = s->acts[l];
+    HERO_REQUIRE(A.s1 && A.s2 && A.a_f32 && A.out_f32, "stack fwd: layer %d misses fp32 buffers", l);
     HERO_TRY(Gemm(h, H, 0, W.wqkv, H, 0, M, 3 * H, H, A.qkv, 3 * H).bias(W.bqkv).run(stream));
     HERO_TRY(hero_attn_fwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, A.lse, M,
                            s->n_tiles, s->heads, 64, scale, s->attn_drop_threshold,
                            site_key(s->drop_key, s->first_layer + l, 0), s->attn_drop_scale, stream));
     HERO_TRY(Gemm(A.cx, H, 0, W.wo, H, 0, M, H, H, A.s1, H)
                  .bias(W.bo)
-                 .resid(h, H)
+                 .resid_f32(h32, H)
                  .drop(s->hidden_drop_threshold, site_key(s->drop_key, s->first_layer + l, 1), s->hidden_drop_scale)
                  .run(stream));
     hero_ln_args ln;
     ln_base(&ln, A.s1, W.ln1_g, W.ln1_b, s->eps, M, H, A.mean1, A.rstd1);
     ln.y = A.a;
+    ln.y_f32 = A.a_f32;
     HERO_TRY(hero_ln_fwd(&ln, stream));
     Gemm up(A.a, H, 0, W.w1, H, 0, M, I, H, A.f, I);
     up.bias(W.b1).act(ACT_GELU);
@@ -135,13 +143,15 @@ extern "C" int hero_bert_stack_fwd(const hero_stack_args* s, void* stream) {
     HERO_TRY(up.run(stream));
     HERO_TRY(Gemm(A.f, I, 0, W.w2, I, 0, M, H, I, A.s2, H)
                  .bias(W.b2)
-                 .resid(A.a, H)
+                 .resid_f32(A.a_f32, H)
                  .drop(s->hidden_drop_threshold, site_key(s->drop_key, s->first_layer + l, 2), s->hidden_drop_scale)
                  .run(stream));
     ln_base(&ln, A.s2, W.ln2_g, W.ln2_b, s->eps, M, H, A.mean2, A.rstd2);
     ln.y = A.out;
+    ln.y_f32 = A.out_f32;
     HERO_TRY(hero_ln_fwd(&ln, stream));
     h = A.out;
+    h32 = A.out_f32;
   }
   return HERO_OK;
 }

@@ -237,6 +237,9 @@ class CrossModalTrm(RobertaPreTrainedModel):
                 if img_masks is not None:
                     raise ValueError("frame masking (f_v_masks) needs the f_v_feats copy: the MFM "
                                      "path overwrites c_v_feats in place (model/model.py:244-247)")
+                if not getattr(fplan, "shared_feats_ok", True):
+                    raise ValueError("a frame slot marked valid in f_attn_masks is not listed in "
+                                     "sub_idx2frame_idx: this batch cannot omit f_v_feats")
                 img_feat, img_src = shared_feats, dev.f_img_src_c
             D = img_feat.shape[-1]
             feats = img_feat.reshape(-1, D)
@@ -270,8 +273,9 @@ class CrossModalTrm(RobertaPreTrainedModel):
         return params
 
     def encode_packed(self, fplan, dev, input_ids, position_ids, img_feat=None, img_pos_ids=None,
-                      img_masks=None, drop=None, pos_keys=None, shared_feats=None):
-        """Embeddings + encoder on packed tokens -> bf16 [n_tokens, H]."""
+                      img_masks=None, drop=None, pos_keys=None, shared_feats=None, out_f32=False):
+        """Embeddings + encoder on packed tokens -> [n_tokens, H], bf16 (feeds further kernels) or
+        fp32 (`out_f32`: the caller unpacks it as the final result)."""
         device = dev.flat.device
         flat = flat_of(self, device)
         if drop is None:
@@ -284,8 +288,9 @@ class CrossModalTrm(RobertaPreTrainedModel):
         with_img = fplan.n_img > 0
         if with_img:
             cfg["img_lin_w_bf16"] = flat.bf16(self.img_embeddings.img_linear.weight)
-        emb = Fn.cross_modal_embed(cfg, self._embed_params(with_img))
-        return self.encoder.forward_packed(emb, fplan.seq.attn(dev, "f_"), drop)
+        emb, emb32 = Fn.cross_modal_embed(cfg, self._embed_params(with_img))
+        return self.encoder.forward_packed(emb, fplan.seq.attn(dev, "f_"), drop, x_f32=emb32,
+                                           out_f32=out_f32)
 
     def encode_packed_joint(self, jplan, rdev, tdev, jdev, batch, txt_batch, drop=None):
         """One pass of embeddings + encoder over [video rows | query rows] (see plan.JointPlan).
@@ -324,12 +329,14 @@ class CrossModalTrm(RobertaPreTrainedModel):
         if with_img:
             cfg["img_lin_w_bf16"] = flat.bf16(self.img_embeddings.img_linear.weight)
         cfg["flat"] = flat
-        emb = Fn.cross_modal_embed(cfg, self._embed_params(with_img))
-        return self.encoder.forward_packed(emb, jplan.attn(jdev), drop)
+        emb, emb32 = Fn.cross_modal_embed(cfg, self._embed_params(with_img))
+        return self.encoder.forward_packed(emb, jplan.attn(jdev), drop, x_f32=emb32)
 
     def _unpack(self, y, dev, shape):
         out = Fn.gather_rows(y, dev.f_pad_to_tok, dev.f_tok_flat)
-        return out.view(shape[0], shape[1], y.shape[1]).to(_output_dtype(self))
+        out = out.view(shape[0], shape[1], y.shape[1])
+        want = _output_dtype(self)
+        return out if out.dtype == want else out.to(want)
 
     # ---- reference-facing API ---------------------------------------------------------------
     def forward(self, batch, task="repr", compute_loss=True):
@@ -381,7 +388,7 @@ class CrossModalTrm(RobertaPreTrainedModel):
         fplan, dev, pos_keys = self._plan_for(input_ids, img_feat, attention_mask, gather_index,
                                               _plan)
         y = self.encode_packed(fplan, dev, input_ids, position_ids, img_feat, img_pos_ids,
-                               img_masks, pos_keys=pos_keys)
+                               img_masks, pos_keys=pos_keys, out_f32=True)
         sequence_output = self._unpack(y, dev, attention_mask.shape)
         pooled_output = self.pooler(sequence_output)
         return (sequence_output, pooled_output)
@@ -391,7 +398,7 @@ class CrossModalTrm(RobertaPreTrainedModel):
                     gather_index, txt_mask_tgt, txt_labels=None, compute_loss=True):
         fplan, dev, pos_keys = self._plan_for(input_ids, img_feat, attention_mask, gather_index)
         y = self.encode_packed(fplan, dev, input_ids, position_ids, img_feat, img_pos_ids,
-                               pos_keys=pos_keys)
+                               pos_keys=pos_keys, out_f32=True)
         sequence_output = self._unpack(y, dev, attention_mask.shape)
         masked_output = sequence_output[txt_mask_tgt].contiguous().view(
             -1, sequence_output.size(-1))
@@ -415,14 +422,15 @@ class TemporalTrm(RobertaPreTrainedModel):
         self.output_dtype = torch.float32
 
     def embed_encode_packed(self, g, dev_t, att, pos_off, pos_idx, drop=None):
-        """g: packed bf16 [n_c_tokens, H] -> FrameEmbeddings -> encoder (packed)."""
+        """g: packed bf16 [n_c_tokens, H] -> FrameEmbeddings -> encoder -> packed FP32 output (the
+        temporal transformer's output is the final result of the path)."""
         if drop is None:
             drop = self.encoder.dropout_state()
         e = self.embeddings
         cfg = {"drop": drop, "t": dev_t, "pos_off": pos_off, "pos_idx": pos_idx}
-        z = Fn.frame_embed(g, cfg, [e.position_embeddings.weight, e.LayerNorm.weight,
-                                    e.LayerNorm.bias])
-        return self.encoder.forward_packed(z, att, drop)
+        z, z32 = Fn.frame_embed(g, cfg, [e.position_embeddings.weight, e.LayerNorm.weight,
+                                         e.LayerNorm.bias])
+        return self.encoder.forward_packed(z, att, drop, x_f32=z32, out_f32=True)
 
     def forward_encoder(self, embedding_output, attention_mask, pool=False):
         sequence_output = self.encoder(embedding_output, attention_mask)[0]
@@ -450,8 +458,9 @@ class TemporalTrm(RobertaPreTrainedModel):
         g = Fn.gather_rows(flat_in, dev.c_tok_flat, dev.c_pad_to_tok)
         y = self.embed_encode_packed(g, dev.c_t, sp.attn(dev, "c_"), dev.c_pos_off,
                                      dev.c_pos_idx)
-        out = Fn.gather_rows(y, dev.c_pad_to_tok, dev.c_tok_flat)
-        return out.view(B, T, H).to(_output_dtype(self))
+        out = Fn.gather_rows(y, dev.c_pad_to_tok, dev.c_tok_flat).view(B, T, H)
+        want = _output_dtype(self)
+        return out if out.dtype == want else out.to(want)
 
 
 class QueryFeatEncoder(nn.Module):

@@ -95,26 +95,32 @@ class LayerWeights:
 
 class _TransformerStack(torch.autograd.Function):
     """L x BertLayer on packed tokens through the native layer runtime (one C call per direction).
-    args = (x, cfg, *params) with 16 fp32 params per layer in the order
-    q.w q.b k.w k.b v.w v.b o.w o.b ln1.w ln1.b i.w i.b out.w out.b ln2.w ln2.b."""
+    args = (x, x_f32, cfg, *params) with 16 fp32 params per layer in the order
+    q.w q.b k.w k.b v.w v.b o.w o.b ln1.w ln1.b i.w i.b out.w out.b ln2.w ln2.b.
+    `x` (bf16) feeds the first GEMM, `x_f32` (same values, fp32; may be None) the first residual
+    add: the residual stream stays fp32 through the stack. Returns the last layer's output as bf16
+    (default: it feeds further bf16 kernels) or fp32 (`cfg["out_f32"]`: it is the final result)."""
 
     @staticmethod
-    def forward(ctx, x, cfg, *params):
+    def forward(ctx, x, x_f32, cfg, *params):
         drop = cfg["drop"]
         dspec = (ops.drop_params(drop.hidden_p, 0), ops.drop_params(drop.attn_p, 0),
                  drop.next_key())
         need_grad = any(ctx.needs_input_grad)
-        out, saved = ops.bert_stack_fwd(x, cfg["layers"], cfg["att"], heads=cfg["heads"],
-                                        eps=cfg["eps"], drop=dspec, save=need_grad)
+        out, out_f32, saved = ops.bert_stack_fwd(x, cfg["layers"], cfg["att"], heads=cfg["heads"],
+                                                 eps=cfg["eps"], drop=dspec, save=need_grad,
+                                                 x_f32=x_f32)
         ctx.cfg, ctx.dspec, ctx.saved, ctx.params = cfg, dspec, saved, params
         ctx.x = x
         if need_grad and GRAD_HOOK[0] is not None:
             GRAD_HOOK[0].expect(params)
-        return out
+        return out_f32 if cfg.get("out_f32") else out
 
     @staticmethod
     def backward(ctx, dout):
         cfg, params = ctx.cfg, ctx.params
+        if dout.dtype != BF16:
+            dout = dout.to(BF16)
         n = len(cfg["layers"])
         grads, ret = _stack_sinks(cfg, params, ctx.x.shape[1], dout.device)
         hook = GRAD_HOOK[0]
@@ -141,7 +147,7 @@ class _TransformerStack(torch.autograd.Function):
                                         need_dx=(li > 0 or ctx.needs_input_grad[0]), only_layer=li)
                 hook.ready(params[16 * li:16 * li + 16])
         ctx.saved = None
-        return (dx, None) + tuple(ret)
+        return (dx, None, None) + tuple(ret)
 
 
 def _layer_events(cfg, n, device):
@@ -204,8 +210,8 @@ def _stack_sinks(cfg, params, H, device):
     return grads, ret
 
 
-def transformer_stack(x, cfg, params):
-    return _TransformerStack.apply(x, cfg, *params)
+def transformer_stack(x, cfg, params, x_f32=None):
+    return _TransformerStack.apply(x, x_f32, cfg, *params)
 
 
 def _slot_table_grad(dx, off, idx, slot_pos, dtable, tok_pos):
@@ -232,6 +238,7 @@ class _CrossModalEmbed(torch.autograd.Function):
         drop = cfg["drop"]
         n_tok, H = cfg["n_tok"], word.shape[1]
         emb = torch.empty((n_tok, H), dtype=BF16, device=word.device)
+        emb32 = torch.empty((n_tok, H), dtype=F32, device=word.device)   # residual of layer 0
         type_row = typ[1]
         st = {}
         # text tokens: LN(word[id] + pos[pid] + type[1]) -> packed row  (model/embed.py:44-58)
@@ -243,7 +250,7 @@ class _CrossModalEmbed(torch.autograd.Function):
             ops.ln_fwd(word, ln_w, ln_b, 1e-5, emb, n_rows=n_txt, x_rows=cfg["txt_ids"],
                        add_tab=pos, add_idx=cfg["txt_pos"], add_vec=type_row,
                        y_rows=cfg["txt_tok"], mean=st["t_mean"], rstd=st["t_rstd"],
-                       drop=st["t_drop"])
+                       drop=st["t_drop"], y_f32=emb32)
         n_img = cfg["n_img"]
         if n_img:
             (lin_w, lin_b, iln_w, iln_b, ipos, mask_emb, oln_w, oln_b) = params[5:13]
@@ -262,14 +269,15 @@ class _CrossModalEmbed(torch.autograd.Function):
             st["o_drop"] = drop.next(drop.hidden_p)
             ops.ln_fwd(proj, oln_w, oln_b, 1e-5, emb, n_rows=n_img, add_tab=ipos,
                        add_idx=cfg["img_k"], add_vec=type_row, y_rows=cfg["img_tok"],
-                       mean=st["o_mean"], rstd=st["o_rstd"], drop=st["o_drop"])
+                       mean=st["o_mean"], rstd=st["o_rstd"], drop=st["o_drop"], y_f32=emb32)
             st["xn"], st["proj"] = xn, proj
         ctx.cfg, ctx.st = cfg, st
         ctx.params = params      # python refs: backward accumulates into the parameters' .grad
-        return emb
+        ctx.mark_non_differentiable(emb32)
+        return emb, emb32
 
     @staticmethod
-    def backward(ctx, demb):
+    def backward(ctx, demb, _demb32=None):
         cfg, st = ctx.cfg, ctx.st
         params = ctx.params
         word, pos, typ, ln_w, ln_b = params[:5]
@@ -399,17 +407,19 @@ class _FrameEmbed(torch.autograd.Function):
         drop = cfg["drop"]
         n, H = g.shape
         z = torch.empty_like(g)
+        z32 = torch.empty(g.shape, dtype=F32, device=g.device)    # residual of layer 0
         mean, rstd = torch.empty(n, device=g.device), torch.empty(n, device=g.device)
         d = drop.next(drop.hidden_p)
         ops.ln_fwd(g, ln_w, ln_b, 1e-5, z, n_rows=n, add_tab=pos, add_idx=cfg["t"], mean=mean,
-                   rstd=rstd, drop=d)
+                   rstd=rstd, drop=d, y_f32=z32)
         ctx.cfg, ctx.st = cfg, (mean, rstd, d)
         ctx.save_for_backward(g)
         ctx.params = (pos, ln_w, ln_b)
-        return z
+        ctx.mark_non_differentiable(z32)
+        return z, z32
 
     @staticmethod
-    def backward(ctx, dz):
+    def backward(ctx, dz, _dz32=None):
         cfg = ctx.cfg
         mean, rstd, d = ctx.st
         (g,) = ctx.saved_tensors
@@ -438,18 +448,19 @@ class _GatherRows(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, src, idx, inv_idx):
-        out = torch.empty((idx.numel(), src.shape[1]), dtype=BF16, device=src.device)
-        ops.gather_rows(src, idx, out)
+        out = torch.empty((idx.numel(), src.shape[1]), dtype=src.dtype, device=src.device)
+        ops.gather_rows(src.contiguous(), idx, out)
         ctx.inv = inv_idx
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        dsrc = torch.empty((ctx.inv.numel(), dout.shape[1]), dtype=BF16, device=dout.device)
+        dsrc = torch.empty((ctx.inv.numel(), dout.shape[1]), dtype=dout.dtype, device=dout.device)
         ops.gather_rows(dout.contiguous(), ctx.inv, dsrc)
         return dsrc, None, None
 
 
 def gather_rows(src, idx, inv_idx):
-    """`inv_idx[j]` = the i with idx[i] == j (or -1): both maps are injective here."""
+    """`inv_idx[j]` = the i with idx[i] == j (or -1): both maps are injective here. bf16 or fp32
+    rows (the output has the dtype of `src`)."""
     return _GatherRows.apply(src, idx, inv_idx)

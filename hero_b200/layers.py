@@ -169,10 +169,12 @@ class BertEncoder(nn.Module):
         return Fn.DropoutState(l0.output.dropout.p, l0.attention.self.dropout.p, self.training,
                                base_key)
 
-    def forward_packed(self, x, att, drop=None):
-        """x: packed bf16 [n_tokens, H]; att: device attention plan (`SeqPlan.attn`)."""
+    def forward_packed(self, x, att, drop=None, x_f32=None, out_f32=False):
+        """x: packed bf16 [n_tokens, H]; att: device attention plan (`SeqPlan.attn`); x_f32: the
+        same input in fp32 (residual of the first layer; derived from x when None); out_f32: return
+        the last layer's fp32 output instead of its bf16 copy."""
         if len(self.layer) == 0:
-            return x
+            return x_f32 if (out_f32 and x_f32 is not None) else (x.float() if out_f32 else x)
         flat = flat_of(self, x.device)
         if drop is None:
             drop = self.dropout_state()
@@ -187,9 +189,9 @@ class BertEncoder(nn.Module):
             cache["params"] = [p for l in self.layer for p in l.ordered_params()]
         params = cache["params"]
         cfg = {"layers": cache["layers"], "att": att, "heads": self.num_heads, "eps": self.eps,
-               "drop": drop, "cache": cache}
+               "drop": drop, "cache": cache, "out_f32": bool(out_f32)}
         cfg["flat"] = flat     # backward marks the bf16 mirror stale (an optimizer step follows)
-        return Fn.transformer_stack(x, cfg, params)
+        return Fn.transformer_stack(x, cfg, params, x_f32=x_f32)
 
     def forward(self, hidden_states, attention_mask=None, head_mask=None):
         if head_mask is not None:
@@ -199,9 +201,10 @@ class BertEncoder(nn.Module):
             attention_mask = torch.ones(N, L, dtype=torch.long, device=hidden_states.device)
         plan = TxtPlan(attention_mask, with_embedding=False)
         dev = plan.to(hidden_states.device)
-        flat_in = hidden_states.reshape(N * L, H).to(BF16)
-        x = Fn.gather_rows(flat_in, dev.f_tok_flat, dev.f_pad_to_tok)
-        y = self.forward_packed(x, plan.f.seq.attn(dev, "f_"))
+        flat_in = hidden_states.reshape(N * L, H)
+        x32 = Fn.gather_rows(flat_in.float(), dev.f_tok_flat, dev.f_pad_to_tok)
+        y = self.forward_packed(x32.to(BF16), plan.f.seq.attn(dev, "f_"), x_f32=x32.detach(),
+                                out_f32=True)
         out = Fn.gather_rows(y, dev.f_pad_to_tok, dev.f_tok_flat)
         return (out.view(N, L, H).to(hidden_states.dtype),)
 

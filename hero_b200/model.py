@@ -167,7 +167,8 @@ class HierarchicalVlModel(VideoPreTrainedModel):
 
     def _unpack_c(self, y, dev, shape):
         out = Fn.gather_rows(y, dev.c_pad_to_tok, dev.c_tok_flat)
-        return out.view(shape[0], shape[1], y.shape[1]).to(self.output_dtype)
+        out = out.view(shape[0], shape[1], y.shape[1])
+        return out if out.dtype == self.output_dtype else out.to(self.output_dtype)
 
     def forward_repr(self, batch, encode_clip=True):
         """model/model.py:195-224 -> (B, T, H); padded frames hold zeros."""

@@ -111,6 +111,7 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None
         assert bias.dtype == torch.float32 and bias.numel() == n
     g.resid = _ptr(resid)
     g.ld_resid = resid.stride(0) if resid is not None else 0
+    g.resid_f32 = int(resid is not None and resid.dtype == torch.float32)
     g.aux_in = _ptr(aux_in)
     g.ld_aux_in = aux_in.stride(0) if aux_in is not None else 0
     g.aux_out = _ptr(aux_out)
@@ -119,7 +120,10 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None
     g.ld_out = out.stride(0)
     g.act = act
     g.out_f32_accumulate = int(accumulate_f32)
-    assert out.dtype == (torch.float32 if accumulate_f32 else BF16)
+    # an fp32 `out` without accumulate_f32 is a plain fp32 store (pre-LayerNorm sums of the
+    # residual stream); its residual, if any, is fp32 too
+    g.out_f32_store = int(out.dtype == torch.float32 and not accumulate_f32)
+    assert out.dtype in (torch.float32, BF16) and (out.dtype == torch.float32 or not accumulate_f32)
     g.drop_threshold, g.drop_key, g.drop_scale = drop
     g.block_n, g.k_splits, g.cta_pair = block_n, k_splits, cta_pair
     _count()
@@ -148,12 +152,16 @@ def _ln_args(x, gamma, beta, eps, n_rows, h, x_rows=None, add_tab=None, add_idx=
 
 
 def ln_fwd(x, gamma, beta, eps, y, *, n_rows, x_rows=None, add_tab=None, add_idx=None,
-           add_vec=None, y_rows=None, mean=None, rstd=None, drop=(0, 0, 1.0)):
-    """Fused gather + add + LayerNorm (+dropout) + scatter; see `hero_ln_args`."""
+           add_vec=None, y_rows=None, mean=None, rstd=None, drop=(0, 0, 1.0), y_f32=None):
+    """Fused gather + add + LayerNorm (+dropout) + scatter; see `hero_ln_args`. `y_f32`: optional
+    fp32 copy of the output (same rows): the residual stream of the transformer layers."""
     _require_cuda(x, y)
     h = gamma.numel()
     a = _ln_args(x, gamma, beta, eps, n_rows, h, x_rows, add_tab, add_idx, add_vec)
     a.y, a.y_rows = _ptr(y), _ptr(y_rows)
+    if y_f32 is not None:
+        assert y_f32.dtype == torch.float32 and y_f32.is_contiguous() and y_f32.shape == y.shape
+    a.y_f32 = _ptr(y_f32)
     a.mean, a.rstd = _ptr(mean), _ptr(rstd)
     a.drop_threshold, a.drop_key, a.drop_scale = drop
     _count()
@@ -227,8 +235,8 @@ class _PtrTensor:
 
 # kernels launched per layer by the native runtime (for bench.py's gpu_launches)
 _STACK_FWD_LAUNCHES, _STACK_BWD_LAUNCHES = 7, 15   # bwd: 8 GEMM, 2x2 LN, attn, 2 colsum
-_ACT_FIELDS = ("qkv", "cx", "lse", "s1", "mean1", "rstd1", "a", "pre", "f", "s2", "mean2", "rstd2",
-               "out")
+_ACT_FIELDS = ("qkv", "cx", "lse", "s1", "mean1", "rstd1", "a", "a_f32", "pre", "f", "s2", "mean2",
+               "rstd2", "out", "out_f32")
 _GRAD_FIELDS = ("dwqkv", "dbqkv", "dwo", "dbo", "dln1_g", "dln1_b", "dw1", "db1", "dw2", "db2",
                 "dln2_g", "dln2_b")
 
@@ -240,10 +248,11 @@ def _al(n):
 def _stack_layout(M, H, inter, save):
     """Byte offsets of one layer's activations inside the workspace slot."""
     sizes = {"qkv": M * 3 * H * 2, "cx": M * H * 2, "lse": M * (H // 64) * 4 if save else 0,
-             "s1": M * H * 2, "mean1": M * 4,
-             "rstd1": M * 4, "a": M * H * 2, "pre": M * inter * 2 if save else 0,
-             "f": M * inter * 2, "s2": M * H * 2, "mean2": M * 4, "rstd2": M * 4,
-             "out": M * H * 2}
+             "s1": M * H * 4, "mean1": M * 4,
+             "rstd1": M * 4, "a": M * H * 2, "a_f32": M * H * 4,
+             "pre": M * inter * 2 if save else 0,
+             "f": M * inter * 2, "s2": M * H * 4, "mean2": M * 4, "rstd2": M * 4,
+             "out": M * H * 2, "out_f32": M * H * 4}
     offs, o = {}, 0
     for k in _ACT_FIELDS:
         offs[k] = o
@@ -251,7 +260,7 @@ def _stack_layout(M, H, inter, save):
     return offs, o, sizes
 
 
-def _stack_struct(x, layers, att, heads, eps, drop, act_ptrs):
+def _stack_struct(x, layers, att, heads, eps, drop, act_ptrs, x_f32=None):
     n = len(layers)
     W = (_lib.LayerWeights * n)()
     A = (_lib.LayerActs * n)()
@@ -272,6 +281,7 @@ def _stack_struct(x, layers, att, heads, eps, drop, act_ptrs):
     s.eps = eps
     s.weights, s.acts = W, A
     s.x = x.data_ptr()
+    s.x_f32 = None if x_f32 is None else x_f32.data_ptr()
     s.tile_tok0, s.tile_ntok = att["tile_tok0"].data_ptr(), att["tile_ntok"].data_ptr()
     s.seq_lo, s.seq_hi = att["seq_lo"].data_ptr(), att["seq_hi"].data_ptr()
     (hthr, _, hscale), (athr, _, ascale), key = drop
@@ -280,15 +290,19 @@ def _stack_struct(x, layers, att, heads, eps, drop, act_ptrs):
     return s, (W, A)
 
 
-def bert_stack_fwd(x, layers, att, *, heads, eps, drop, save):
+def bert_stack_fwd(x, layers, att, *, heads, eps, drop, save, x_f32=None):
     """All layers of a BertEncoder forward in ONE native call (`hero_bert_stack_fwd`).
 
-    x: packed bf16 [n_tok, H]; layers: functional.LayerWeights per layer; att: attention plan;
-    drop: ((hidden thr, _, scale), (attn thr, _, scale), base key). Returns (out, saved) where
-    `saved` is what bert_stack_bwd needs (None when save is False: activations then ping-pong
-    between two workspace slots)."""
+    x: packed bf16 [n_tok, H] (GEMM operand) and x_f32: the same values in fp32 (residual of
+    layer 0; derived from x when omitted); layers: functional.LayerWeights per layer; att:
+    attention plan; drop: ((hidden thr, _, scale), (attn thr, _, scale), base key).
+    Returns (out_bf16, out_f32, saved) where `saved` is what bert_stack_bwd needs (None when save
+    is False: activations then ping-pong between two workspace slots)."""
     _require_cuda(x)
     assert x.dtype == BF16 and x.is_contiguous()
+    if x_f32 is None:
+        x_f32 = x.float()
+    assert x_f32.dtype == torch.float32 and x_f32.is_contiguous() and x_f32.shape == x.shape
     n = len(layers)
     M, H = x.shape
     inter = layers[0].w1.shape[0]
@@ -301,12 +315,15 @@ def bert_stack_fwd(x, layers, att, *, heads, eps, drop, save):
         b = base + (i if save else i % 2) * slot
         act_ptrs.append([None if (k in ("pre", "lse") and not save) else b + offs[k]
                          for k in _ACT_FIELDS])
-    s, keep = _stack_struct(x, layers, att, heads, eps, drop, act_ptrs)
+    s, keep = _stack_struct(x, layers, att, heads, eps, drop, act_ptrs, x_f32)
     _count(_STACK_FWD_LAUNCHES * n)
     _lib.check(_lib.lib().hero_bert_stack_fwd(C.byref(s), _stream()))
-    last = ((n - 1) if save else (n - 1) % 2) * slot + offs["out"]
+    base_last = ((n - 1) if save else (n - 1) % 2) * slot
+    last = base_last + offs["out"]
     out = ws[last:last + M * H * 2].view(BF16).view(M, H)
-    return out, ((ws, act_ptrs) if save else None)
+    last32 = base_last + offs["out_f32"]
+    out_f32 = ws[last32:last32 + M * H * 4].view(torch.float32).view(M, H)
+    return out, out_f32, ((ws, act_ptrs) if save else None)
 
 
 def bert_stack_bwd(x, layers, att, saved, dout, grads, *, heads, eps, drop, need_dx=True,
@@ -363,12 +380,15 @@ def cast_bf16(src, dst):
 
 
 def gather_rows(src, idx, dst):
+    """dst[i] = idx[i] >= 0 ? src[idx[i]] : 0 over bf16 rows, or over fp32 rows (both fp32)."""
     _require_cuda(src, idx, dst)
-    assert src.dtype == BF16 and dst.dtype == BF16 and idx.dtype == torch.int32
+    assert src.dtype == dst.dtype and src.dtype in (BF16, torch.float32)
+    assert idx.dtype == torch.int32 and src.is_contiguous() and dst.is_contiguous()
     h = src.shape[-1]
     _count()
-    _lib.check(_lib.lib().hero_gather_rows_bf16(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), h,
-                                                _stream()))
+    fn = (_lib.lib().hero_gather_rows_f32 if src.dtype == torch.float32
+          else _lib.lib().hero_gather_rows_bf16)
+    _lib.check(fn(_ptr(src), _ptr(idx), _ptr(dst), idx.numel(), h, _stream()))
     return dst
 
 
@@ -402,12 +422,16 @@ def relu_bwd(dy, pre, out):
     return out
 
 
-def adamw_step(p, g, m, v, p_bf16, *, step_size, beta1, beta2, eps, lr_wd, grad_scale=1.0):
+def adamw_step(p, g, m, v, p_bf16, *, step_size, beta1, beta2, eps, lr_wd, grad_scale=1.0,
+               clip_sumsq=None, clip_max_norm=0.0):
+    """`clip_sumsq`: device scalar holding sum(g^2) over ALL gradients (ops.sumsq); the kernel then
+    scales g by min(1, clip_max_norm / (sqrt(sumsq) + 1e-6)) — global-norm clipping without a
+    device->host read."""
     _require_cuda(p, g, m, v)
     _count()
     _lib.check(_lib.lib().hero_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(p_bf16),
                                           p.numel(), step_size, beta1, beta2, eps, lr_wd,
-                                          grad_scale, _stream()))
+                                          grad_scale, _ptr(clip_sumsq), clip_max_norm, _stream()))
 
 
 def reduce_slots(dst, slots, n_slots, slot_stride, scale, max_ctas=16):

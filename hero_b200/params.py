@@ -83,6 +83,7 @@ class FlatParams:
         self._stale = False
         self._probe = []
         self._hooked = False
+        self.generation = 0          # bumped by every re-flatten (optimizers / exchanges check it)
         _LIVE.add(self)
         _install_optimizer_hook()
 
@@ -131,6 +132,12 @@ class FlatParams:
             self.grad_flat = None
             self.dirty = True
             self._stale = False
+            self.generation += 1
+            # every submodule resolves to THIS manager (modules swapped in after the first flatten,
+            # e.g. HeroModel.load_partial_pretrained replacing f_encoder, must not build a private
+            # one and pull their parameters out of the shared buffer)
+            for m in self.module.modules():
+                m.__dict__["_hero_flat"] = self
             k = max(1, len(self.entries) // 8)
             self._probe = self.entries[::k] + self.entries[-1:]
             if not self._hooked:
@@ -193,6 +200,7 @@ class FlatParams:
         for _, p, off, n in self.entries:
             want = self.grad_flat[off:off + n].view(p.shape)
             if p.grad is None:
+                want.zero_()      # "absent grads are zeros": never resurrect a stale gradient
                 p.grad = want
             elif p.grad.data_ptr() != want.data_ptr():
                 with torch.no_grad():
@@ -205,6 +213,12 @@ def flat_of(module, device):
     """The FlatParams owning `module`'s parameters: the one installed by the outermost hero_b200
     module that has run a forward, else a private one."""
     fp = module.__dict__.get("_hero_flat")
+    if fp is not None and fp.module is not module and not fp._stale:
+        # stamped by an outer manager: still part of its tree? (a module that was swapped out of
+        # the tree, or swapped in without invalidate(), must not keep using a stale stamp)
+        first = next(module.parameters(), None)
+        if first is not None and id(first) not in fp._by_id:
+            fp.invalidate()
     if fp is None:
         fp = FlatParams(module)
         for m in module.modules():

@@ -255,6 +255,10 @@ class ReprPlan:
         # packed frame token, so a batch may omit `f_v_feats` altogether (half the H2D bytes).
         self.f.img_src_c = self.c.frame_source[self.f.img_src] if self.f.n_img else \
             np.zeros(0, np.int32)
+        # a frame slot that is valid in f_attn_masks but not listed in sub_idx2frame_idx has no
+        # clip frame behind it: such a batch must ship its own f_v_feats (checked on the host, the
+        # LayerNorm kernels index x_rows without a sign test)
+        self.f.shared_feats_ok = self.shared_feats_ok = bool((self.f.img_src_c >= 0).all())
         self.shape_f = tuple(batch["f_attn_masks"].shape)
         self.shape_c = tuple(batch["c_attn_masks"].shape)
         # position-table CSRs for the deterministic embedding gradients

@@ -68,8 +68,12 @@ int hero_set_sm_limit(int32_t n);
  *        act 1: aux_out[m,n] = bf16(gelu_erf'(v))   (consumed by act 3 in the dgrad GEMM)
  *        else : aux_out[m,n] = bf16(v)              (pre-activation; ReLU backward uses its sign)
  *   dropout: v = keep(m*N+n) ? v * drop_scale : 0 (drop_threshold != 0; keep iff hash>=threshold)
- *   v += resid[m,n]                               (resid != NULL; bf16)
- *   out: bf16 store, or fp32 atomic accumulate (out_f32_accumulate; split-K allowed)
+ *   v += resid[m,n]                               (resid != NULL; bf16, or fp32 when resid_f32)
+ *   out: bf16 store, fp32 store (out_f32_store: the pre-LayerNorm sums of the transformer layers
+ *        stay fp32 end to end, like the fp32 residual stream of the reference under autocast), or
+ *        fp32 atomic accumulate (out_f32_accumulate; split-K allowed)
+ * Residual / saved-derivative tiles reach the epilogue by TMA (one 32-row slab per epilogue warp,
+ * prefetched one slab ahead), outputs leave through double-buffered smem slabs and TMA stores.
  * Constraints: K % 8 == 0, N % 8 == 0, lds % 8 == 0, 16-byte aligned pointers; MN-major operands
  * need their contiguous extent to be a multiple of 64.
  * ---------------------------------------------------------------------------------------- */
@@ -97,6 +101,8 @@ typedef struct hero_gemm_args {
   int32_t k_splits;        /* 0 = auto (only > 1 when out_f32_accumulate) */
   int32_t cta_pair;        /* 0 = auto, 1 = single-CTA tiles, 2 = force CTA pairs (cta_group::2,
                               256 x 256 tiles; needs block_n 256) */
+  int32_t resid_f32;       /* resid is f32 [m, ld_resid] (needs out_f32_store) */
+  int32_t out_f32_store;   /* out is f32 [m, ld_out], plain store (act 0 only; ld_out % 4 == 0) */
 } hero_gemm_args;
 
 int hero_gemm_bf16(const hero_gemm_args* args, void* stream);
@@ -153,6 +159,8 @@ typedef struct hero_ln_args {
   /* forward outputs / backward saved stats */
   void* y;                 /* bf16 */
   const int32_t* y_rows;   /* NULL = identity; also indexes dy in bwd */
+  float* y_f32;            /* optional fp32 copy of y (same rows, after dropout): the residual
+                              stream consumed by the next GEMM epilogue; NULL = none; h <= 768 */
   float* mean;
   float* rstd;
   /* dropout applied to the LN output */
@@ -219,6 +227,10 @@ int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile
  *   forward   qkv = x Wqkv^T + b -> attention -> s1 = drop(ctx Wo^T + bo) + x -> a = LN(s1) ->
  *             f = gelu(a W1^T + b1) (pre-activation kept when `pre` != NULL) ->
  *             s2 = drop(f W2^T + b2) + a -> out = LN(s2)
+ *             The residual stream (x, s1, a, s2, out) is carried in FP32 — the GEMM epilogues add
+ *             an fp32 residual and store fp32 sums, the LayerNorm kernels read them and write a
+ *             bf16 copy (next GEMM operand) plus an fp32 copy (next residual) — exactly where
+ *             torch.autocast(bfloat16) keeps fp32 in the reference; only GEMM operands are bf16.
  *   backward  the exact adjoint chain (LN bwd with fused dropout-masked copy, bias column sums,
  *             split-K wgrads accumulated in fp32 into `grads`, dgrads with fused GELU' / residual
  *             adds, attention backward)
@@ -246,16 +258,18 @@ typedef struct hero_layer_acts { /* bf16 unless noted; [n_tok, ...] */
   void* qkv;    /* [n_tok, 3H] */
   void* cx;     /* attention output [n_tok, H] */
   float* lse;   /* f32 [n_tok, heads]: attention log-sum-exp (NULL in inference) */
-  void* s1;     /* pre-LN sum after attention block */
+  float* s1;    /* f32 pre-LN sum after the attention block */
   float* mean1;
   float* rstd1;
-  void* a;      /* LN(s1) */
+  void* a;      /* LN(s1), bf16: operand of the FFN-up GEMM and of its weight gradient */
+  float* a_f32; /* LN(s1), f32: residual input of the FFN-down epilogue */
   void* pre;    /* gelu'(FFN pre-activation) [n_tok, I], saved for the backward; NULL in inference */
   void* f;      /* gelu(pre) [n_tok, I] */
-  void* s2;     /* pre-LN sum after FFN */
+  float* s2;    /* f32 pre-LN sum after the FFN */
   float* mean2;
   float* rstd2;
-  void* out;    /* LN(s2): the layer output */
+  void* out;    /* LN(s2), bf16: the layer output as the next layer's GEMM operand */
+  float* out_f32; /* LN(s2), f32: the layer output as the next layer's residual */
 } hero_layer_acts;
 
 typedef struct hero_layer_grads { /* fp32, accumulated */
@@ -270,6 +284,7 @@ typedef struct hero_stack_args {
   const hero_layer_acts* acts;
   const hero_layer_grads* grads; /* backward only */
   const void* x;                 /* stack input, bf16 [n_tok, H] */
+  const float* x_f32;            /* the same input in f32 (residual of layer 0); forward only */
   const int32_t* tile_tok0;      /* attention plan, see hero_attn_fwd */
   const int32_t* tile_ntok;
   const int32_t* seq_lo;
@@ -309,6 +324,10 @@ int hero_gather_rows_bf16(const void* src, const int32_t* idx, void* dst, int32_
  * Deterministic replacement of collect_frame_outputs (model/model.py:156-187). */
 int hero_gather_sum_rows_bf16(const void* src, const int32_t* off, const int32_t* idx, void* dst,
                               int32_t n, int32_t h, void* stream);
+/* dst[i, :] = idx[i] >= 0 ? src[idx[i], :] : 0 over f32 rows (h % 4 == 0): unpacks the f32 layer
+ * output of the last transformer layer into the padded (B, T, H) / (N, L, H) API tensors. */
+int hero_gather_rows_f32(const float* src, const int32_t* idx, float* dst, int32_t n, int32_t h,
+                         void* stream);
 /* Same CSR gather-sum over bf16 rows but accumulating into fp32 rows: dst[i, :] += sum(...).
  * Deterministic embedding-table gradients (position tables) from the LN backward's dx. */
 int hero_gather_sum_rows_f32(const void* src, const int32_t* off, const int32_t* idx, float* dst,
@@ -328,7 +347,10 @@ int hero_relu_bwd_bf16(const void* dy, const void* pre, void* out, int64_t n, vo
  * ---------------------------------------------------------------------------------------- */
 int hero_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n,
                     float step_size, float beta1, float beta2, float eps, float lr_wd,
-                    float grad_scale, void* stream);
+                    float grad_scale, const float* clip_sumsq, float clip_max_norm, void* stream);
+/* clip_sumsq != NULL folds global-norm clipping (train_vcmr.py:258-259) into the update without a
+ * device->host round trip: g' is additionally scaled by min(1, clip_max_norm / (sqrt(*clip_sumsq)
+ * + 1e-6)), *clip_sumsq being the device scalar accumulated by hero_sumsq_f32 over ALL gradients. */
 /* dst[i] = (dst[i] + sum_{s < n_slots} slots[s * slot_stride + i]) * scale, i < n (n, stride
  * multiples of 4), on at most max_ctas CTAs (0: 64). Reduction step of the copy-engine gradient
  * exchange (hero_b200.distributed.GradBucketer): peers deposit their slices of a bucket in `slots`

@@ -40,7 +40,11 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None
         v = v + resid.float()
     if accumulate_f32:
         out.add_(v)
+    elif out.dtype == torch.float32:      # fp32 store: pre-LayerNorm sums of the residual stream
+        assert act == 0 and (resid is None or resid.dtype == torch.float32)
+        out.copy_(v)
     else:
+        assert resid is None or resid.dtype == BF16
         out.copy_(v.to(BF16))
     return out
 
@@ -55,17 +59,22 @@ def _gather_sum(x, n_rows, x_rows, add_tab, add_idx, add_vec):
 
 
 def ln_fwd(x, gamma, beta, eps, y, *, n_rows, x_rows=None, add_tab=None, add_idx=None,
-           add_vec=None, y_rows=None, mean=None, rstd=None, drop=(0, 0, 1.0)):
+           add_vec=None, y_rows=None, mean=None, rstd=None, drop=(0, 0, 1.0), y_f32=None):
     _ck_drop(drop)
     s = _gather_sum(x, n_rows, x_rows, add_tab, add_idx, add_vec)
     mu = s.mean(-1, keepdim=True)
     var = ((s - mu) ** 2).mean(-1, keepdim=True)
     r = torch.rsqrt(var + eps)
-    out = ((s - mu) * r * gamma + beta).to(BF16)
+    out32 = (s - mu) * r * gamma + beta
+    out = out32.to(BF16)
     if y_rows is not None:
         y[y_rows.long()] = out
+        if y_f32 is not None:
+            y_f32[y_rows.long()] = out32
     else:
         y[:n_rows] = out
+        if y_f32 is not None:
+            y_f32[:n_rows] = out32
     if mean is not None:
         mean.copy_(mu.squeeze(-1))
     if rstd is not None:
@@ -187,7 +196,10 @@ def relu_bwd(dy, pre, out):
     return out
 
 
-def adamw_step(p, g, m, v, p_bf16, *, step_size, beta1, beta2, eps, lr_wd, grad_scale=1.0):
+def adamw_step(p, g, m, v, p_bf16, *, step_size, beta1, beta2, eps, lr_wd, grad_scale=1.0,
+               clip_sumsq=None, clip_max_norm=0.0):
+    if clip_sumsq is not None:
+        grad_scale = grad_scale * min(1.0, clip_max_norm / (float(clip_sumsq.sqrt()) + 1e-6))
     gr = g * grad_scale
     m.mul_(beta1).add_(gr, alpha=1 - beta1)
     v.mul_(beta2).addcmul_(gr, gr, value=1 - beta2)
@@ -203,36 +215,40 @@ def sumsq(x, out):
     return out
 
 
-def bert_stack_fwd(x, layers, att, *, heads, eps, drop, save):
+def bert_stack_fwd(x, layers, att, *, heads, eps, drop, save, x_f32=None):
     """Contract of `hero_bert_stack_fwd` (include/hero_b200.h) composed from the per-kernel
-    restatements above; dropout thresholds must be 0."""
+    restatements above; dropout thresholds must be 0. The residual stream (layer inputs as
+    residuals, pre-LayerNorm sums, LayerNorm outputs as residuals) is fp32; GEMM operands bf16."""
     assert drop[0][0] == 0 and drop[1][0] == 0, "fake ops do not model dropout"
     M, H = x.shape
     saved = []
     h = x
+    h32 = x.float() if x_f32 is None else x_f32
     for lw in layers:
         inter = lw.w1.shape[0]
         qkv = torch.empty(M, 3 * H, dtype=BF16)
         gemm(h, lw.wqkv, qkv, bias=lw.bqkv)
         cx = torch.empty(M, H, dtype=BF16)
         attn_fwd(qkv, att, cx, heads=heads)
-        s1 = torch.empty(M, H, dtype=BF16)
-        gemm(cx, lw.wo, s1, bias=lw.bo, resid=h)
+        s1 = torch.empty(M, H)
+        gemm(cx, lw.wo, s1, bias=lw.bo, resid=h32)
         a = torch.empty(M, H, dtype=BF16)
+        a32 = torch.empty(M, H)
         mean1, rstd1 = torch.empty(M), torch.empty(M)
-        ln_fwd(s1, lw.ln1_g, lw.ln1_b, eps, a, n_rows=M, mean=mean1, rstd=rstd1)
+        ln_fwd(s1, lw.ln1_g, lw.ln1_b, eps, a, n_rows=M, mean=mean1, rstd=rstd1, y_f32=a32)
         f = torch.empty(M, inter, dtype=BF16)
         pre = torch.empty(M, inter, dtype=BF16) if save else None
         gemm(a, lw.w1, f, bias=lw.b1, act=1, aux_out=pre)
-        s2 = torch.empty(M, H, dtype=BF16)
-        gemm(f, lw.w2, s2, bias=lw.b2, resid=a)
+        s2 = torch.empty(M, H)
+        gemm(f, lw.w2, s2, bias=lw.b2, resid=a32)
         out = torch.empty(M, H, dtype=BF16)
+        out32 = torch.empty(M, H)
         mean2, rstd2 = torch.empty(M), torch.empty(M)
-        ln_fwd(s2, lw.ln2_g, lw.ln2_b, eps, out, n_rows=M, mean=mean2, rstd=rstd2)
+        ln_fwd(s2, lw.ln2_g, lw.ln2_b, eps, out, n_rows=M, mean=mean2, rstd=rstd2, y_f32=out32)
         saved.append(dict(h=h, qkv=qkv, cx=cx, s1=s1, mean1=mean1, rstd1=rstd1, a=a, pre=pre, f=f,
                           s2=s2, mean2=mean2, rstd2=rstd2, out=out))
-        h = out
-    return h, (saved if save else None)
+        h, h32 = out, out32
+    return h, h32, (saved if save else None)
 
 
 def bert_stack_bwd(x, layers, att, saved, dout, grads, *, heads, eps, drop, need_dx=True,

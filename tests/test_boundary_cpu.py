@@ -58,7 +58,10 @@ def test_header_symbols_exported_and_bound():
 def test_struct_mirrors_match_header_field_order():
     from hero_b200 import _lib
     header = open(os.path.join(ROOT, "include", "hero_b200.h")).read()
-    for cname, cls in (("hero_gemm_args", _lib.GemmArgs), ("hero_ln_args", _lib.LnArgs)):
+    for cname, cls in (("hero_gemm_args", _lib.GemmArgs), ("hero_ln_args", _lib.LnArgs),
+                       ("hero_layer_weights", _lib.LayerWeights),
+                       ("hero_layer_acts", _lib.LayerActs), ("hero_layer_grads", _lib.LayerGrads),
+                       ("hero_stack_args", _lib.StackArgs)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), header, re.S).group(1)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = []

@@ -1,16 +1,14 @@
 """End-to-end parity of the CUDA encoder path against (a) golden fixtures produced by the
 unmodified reference and (b) the CPU oracle on seeded inputs, forward and backward.
 
-Tolerances (bf16 kernels vs fp32 oracle, eval mode, valid positions only):
-  outputs   elementwise |y - y*| <= 4e-2 + 1.6e-2 |y*|  (outputs reach |y*| ~ 6.7 where one bf16
-            ulp is 3.1e-2; measured worst case after 6+3 layers: 6.9e-2 at |y*| ~ 6), mean-abs <= 8e-3, per-token cosine >= 0.999
-  gradients per-parameter relative Frobenius error <= 3e-2, except
-            * frame_transform.* <= 6e-2: these four gradients are ill-conditioned in bf16 — the
-              oracle itself run under torch CPU bf16 autocast shows 4.2e-2 / 4.2e-2 / 3.8e-2 /
-              3.7e-2 on the dense case (tests/parity_report.py; ours: 4.2e-2 / 4.1e-2 / 3.7e-2 /
-              3.7e-2), i.e. the bound is 1.5x the bf16 yardstick as SURVEY.md §8c prescribes;
-            * attention.self.key.bias: the exact gradient is identically zero (softmax is
-              invariant to a per-query constant), so it is checked in absolute terms.
+Tolerances (bf16 GEMM operands + fp32 residual stream vs the fp32 oracle, eval
+mode, valid positions only):
+  outputs   max-abs <= 6e-2, mean-abs <= 8e-3, per-token cosine >= 0.999
+  gradients per-parameter relative Frobenius error <= 3e-2; attention.self.key.bias, whose exact
+            gradient is identically zero (softmax is invariant to a per-query constant), is
+            checked in absolute terms.
+(tests/test_bench_path_gpu.py additionally holds the outputs to 1.5x the error of the oracle under
+torch bf16 autocast, at the benchmark configuration.)
 """
 import json
 
@@ -24,7 +22,7 @@ from tests import golden_util as gu
 
 pytestmark = pytest.mark.gpu
 
-OUT_ATOL, OUT_RTOL, OUT_MEAN, OUT_COS, GRAD_REL, GRAD_REL_FT = 4e-2, 1.6e-2, 8e-3, 0.999, 3e-2, 6e-2
+OUT_ATOL, OUT_RTOL, OUT_MEAN, OUT_COS, GRAD_REL, GRAD_REL_FT = 6e-2, 0.0, 8e-3, 0.999, 3e-2, 3e-2
 
 
 def _json(tmp_path, d):

@@ -355,3 +355,132 @@ def test_adamw_matches_reference_update_rule():
     s = torch.zeros(1, device=_dev())
     ops.sumsq(g, s)
     _close(s, (g.double() ** 2).sum().float().reshape(1), 0, 1e-4, "sumsq")
+
+
+# ------------------------------------------------------------------------------ fp32 residual stream
+@pytest.mark.parametrize("m,n,k", [(1000, 768, 768), (16512, 768, 768), (3200, 768, 3072),
+                                   (130, 768, 768)])
+@pytest.mark.parametrize("block_n,cta_pair", [(128, 1), (256, 1), (256, 2)])
+def test_gemm_fp32_residual_in_fp32_sum_out(m, n, k, block_n, cta_pair):
+    """Forward out-projection / FFN-down form: s = x W^T + b + resid, resid and s in fp32 (the
+    residual stream never passes through bf16)."""
+    from hero_b200 import ops
+    a, w = _rand((m, k), seed=90), _rand((n, k), 0.05, seed=91)
+    bias = _rand((n,), 0.5, seed=92, dtype=torch.float32)
+    resid = _rand((m, n), 3.0, seed=93, dtype=torch.float32)
+    out = torch.full((m, n), float("nan"), dtype=torch.float32, device=_dev())
+    ops.gemm(a, w, out, bias=bias, resid=resid, block_n=block_n, cta_pair=cta_pair)
+    ref = a.float() @ w.float().t() + bias + resid
+    _close(out, ref, 2e-3, 1e-4, f"fp32 residual stream {m}x{n}x{k} bn{block_n} pair{cta_pair}")
+    out2 = torch.full((m, n), float("nan"), dtype=torch.float32, device=_dev())
+    ops.gemm(a, w, out2, bias=bias, block_n=block_n, cta_pair=cta_pair)       # no residual
+    _close(out2, ref - resid, 2e-3, 1e-4, "fp32 store without residual")
+
+
+def test_gemm_fp32_residual_with_dropout_matches_bf16_path_mask():
+    """The dropout mask depends only on (key, element index): the fp32-store kernel (32-column
+    slabs) and the bf16-store kernel (64-column slabs) must drop the same elements."""
+    from hero_b200 import ops
+    m, n, k = 640, 768, 768
+    a, w = _rand((m, k), seed=94), _rand((n, k), 0.05, seed=95)
+    drop = ops.drop_params(0.1, 4321)
+    o16 = torch.empty(m, n, dtype=BF16, device=_dev())
+    o32 = torch.empty(m, n, dtype=torch.float32, device=_dev())
+    ops.gemm(a, w, o16, drop=drop)
+    ops.gemm(a, w, o32, drop=drop)
+    assert torch.equal(o16.float() == 0, o32 == 0)
+    _close(o32, o16, 2e-2, 1.6e-2, "same values up to the bf16 rounding of the bf16 path")
+
+
+@pytest.mark.parametrize("block_n,cta_pair", [(128, 1), (256, 1), (256, 2)])
+@pytest.mark.parametrize("m", [515, 16512])
+def test_gemm_tma_operand_epilogues_all_tilings(m, block_n, cta_pair):
+    """bf16 residual add and saved-derivative multiply, operands arriving by TMA."""
+    from hero_b200 import ops
+    n, k = 3072, 768
+    dy, w, dg = _rand((m, k), seed=96), _rand((k, n), 0.05, seed=97), _rand((m, n), 0.5, seed=98)
+    out = torch.empty(m, n, dtype=BF16, device=_dev())
+    ops.gemm(dy, w, out, b_mn=True, act=ops.ACT_GELU_GRAD, aux_in=dg, block_n=block_n,
+             cta_pair=cta_pair)
+    _close(out, (dy.float() @ w.float()) * dg.float(), 2e-2, 1.6e-2, "dgrad * saved gelu'")
+    ops.gemm(dy, w, out, b_mn=True, resid=dg, block_n=block_n, cta_pair=cta_pair)
+    _close(out, dy.float() @ w.float() + dg.float(), 2e-2, 1.6e-2, "dgrad + residual")
+
+
+def test_gemm_relu_residual_with_saved_preactivation():
+    """frame_transform form (model/layers.py:86-93 + model/model.py:211-212)."""
+    from hero_b200 import ops
+    m, n, k = 3200, 768, 4352
+    a, w = _rand((m, k), seed=99), _rand((n, k), 0.02, seed=100)
+    bias = _rand((n,), 0.5, seed=101, dtype=torch.float32)
+    resid = _rand((m, n), seed=102)
+    out = torch.empty(m, n, dtype=BF16, device=_dev())
+    pre = torch.empty(m, n, dtype=BF16, device=_dev())
+    ops.gemm(a, w, out, bias=bias, act=ops.ACT_RELU, resid=resid, aux_out=pre)
+    p = a.float() @ w.float().t() + bias
+    _close(pre, p, 2e-2, 1.6e-2, "saved pre-activation")
+    _close(out, torch.relu(p) + resid.float(), 2e-2, 1.6e-2, "relu + residual")
+
+
+@pytest.mark.parametrize("n", [1037, 16512])
+def test_ln_fp32_rows_fast_path_fwd_bwd_with_fp32_copy(n):
+    """Transformer-layer LayerNorms: fp32 pre-LN sums in, bf16 + fp32 outputs, one-pass backward."""
+    from hero_b200 import ops
+    h, eps = 768, 1e-12
+    x = _rand((n, h), 2.0, seed=110, dtype=torch.float32)
+    gamma = _rand((h,), 1.0, seed=111, dtype=torch.float32)
+    beta = _rand((h,), 1.0, seed=112, dtype=torch.float32)
+    y = torch.empty(n, h, dtype=BF16, device=_dev())
+    y32 = torch.empty(n, h, dtype=torch.float32, device=_dev())
+    mean, rstd = torch.empty(n, device=_dev()), torch.empty(n, device=_dev())
+    ops.ln_fwd(x, gamma, beta, eps, y, n_rows=n, mean=mean, rstd=rstd, y_f32=y32)
+    xr = x.clone().requires_grad_(True)
+    g, b = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (h,), g, b, eps)
+    _close(y32, ref, 2e-5, 1e-5, "fp32 copy")
+    assert torch.equal(y, y32.to(BF16))
+    dy = _rand((n, h), 1.0, seed=113)
+    ref.backward(dy.float())
+    dx = torch.empty(n, h, dtype=BF16, device=_dev())
+    dxd = torch.empty(n, h, dtype=BF16, device=_dev())
+    dgamma, dbeta, dbias = (torch.zeros(h, device=_dev()) for _ in range(3))
+    ops.ln_bwd(dy, x, gamma, mean, rstd, n_rows=n, dx=dx, dx_drop=dxd, dgamma=dgamma, dbeta=dbeta,
+               dbias=dbias)
+    _close(dx, xr.grad, 1e-2, 1.6e-2, "ln dx")
+    assert torch.equal(dx, dxd)
+    _close(dgamma, g.grad, 0.5, 2e-2, "ln dgamma")
+    _close(dbeta, b.grad, 0.5, 2e-2, "ln dbeta")
+    _close(dbias, dx.float().sum(0), 0.5, 2e-2, "bias gradient of the feeding Linear")
+
+
+def test_gather_rows_fp32():
+    from hero_b200 import ops
+    src = _rand((500, 768), seed=120, dtype=torch.float32)
+    g = torch.Generator().manual_seed(121)
+    idx = torch.randint(-1, 500, (700,), generator=g).int().to(_dev())
+    dst = torch.empty(700, 768, dtype=torch.float32, device=_dev())
+    ops.gather_rows(src, idx, dst)
+    ref = torch.where((idx >= 0)[:, None], src[idx.clamp(min=0).long()], torch.zeros_like(dst))
+    assert torch.equal(dst, ref)
+
+
+def test_adamw_device_side_global_norm_clip():
+    """train_vcmr.py:258-259 folded into the update: scale = min(1, max_norm / (norm + 1e-6)) read
+    from a device scalar (no host round trip)."""
+    from hero_b200 import ops
+    n = 40000
+    p = _rand((n,), 0.05, seed=130, dtype=torch.float32)
+    g = _rand((n,), 0.5, seed=131, dtype=torch.float32)
+    m, v = torch.zeros(n, device=_dev()), torch.zeros(n, device=_dev())
+    s = torch.zeros(1, device=_dev())
+    ops.sumsq(g, s)
+    norm = float(g.double().norm())
+    scale = min(1.0, 1.0 / (norm + 1e-6))
+    assert scale < 0.5
+    rp, rm, rv = p.clone(), m.clone(), v.clone()
+    ops.adamw_step(rp, g * scale, rm, rv, None, step_size=1e-3, beta1=0.9, beta2=0.98, eps=1e-6,
+                   lr_wd=0.0)
+    ops.adamw_step(p, g, m, v, None, step_size=1e-3, beta1=0.9, beta2=0.98, eps=1e-6, lr_wd=0.0,
+                   clip_sumsq=s, clip_max_norm=1.0)
+    _close(p, rp, 1e-7, 1e-4, "clipped update")
+    _close(m, rm, 1e-9, 1e-4, "clipped first moment")
