@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ("drop_scale", C.c_float),
         ("block_n", C.c_int32), ("k_splits", C.c_int32), ("cta_pair", C.c_int32),
         ("resid_f32", C.c_int32), ("out_f32_store", C.c_int32),
+        ("a_lo", C.c_void_p), ("b_lo", C.c_void_p),
     ]
 
 
@@ -43,7 +44,7 @@ class LnArgs(C.Structure):
         ("x_rows", C.c_void_p), ("add_tab", C.c_void_p), ("add_idx", C.c_void_p),
         ("add_vec", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
         ("eps", C.c_float), ("n_rows", C.c_int32), ("h", C.c_int32),
-        ("y", C.c_void_p), ("y_rows", C.c_void_p), ("y_f32", C.c_void_p),
+        ("y", C.c_void_p), ("y_lo", C.c_void_p), ("y_rows", C.c_void_p), ("y_f32", C.c_void_p),
         ("mean", C.c_void_p), ("rstd", C.c_void_p),
         ("drop_threshold", C.c_uint32), ("drop_key", C.c_uint32), ("drop_scale", C.c_float),
         ("dy", C.c_void_p), ("dx", C.c_void_p), ("dx_drop", C.c_void_p),
@@ -77,6 +78,7 @@ class StackArgs(C.Structure):
     _fields_ = [
         ("n_layers", C.c_int32), ("n_tok", C.c_int32), ("hidden", C.c_int32),
         ("inter", C.c_int32), ("heads", C.c_int32), ("n_tiles", C.c_int32),
+        ("n_long", C.c_int32), ("max_long", C.c_int32),
         ("eps", C.c_float),
         ("weights", C.POINTER(LayerWeights)), ("acts", C.POINTER(LayerActs)),
         ("grads", C.POINTER(LayerGrads)),
@@ -110,9 +112,10 @@ def _declare(lib):
 
     sig("hero_ln_fwd", C.POINTER(LnArgs), vp)
     sig("hero_ln_bwd", C.POINTER(LnArgs), vp)
-    sig("hero_attn_fwd", vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u32, u32, f32, vp)
-    sig("hero_attn_bwd", vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, u32, u32,
+    sig("hero_attn_fwd", vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, u32, u32,
         f32, vp)
+    sig("hero_attn_bwd", vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, u32,
+        u32, f32, vp)
     sig("hero_gemm_profile_begin")
     sig("hero_gemm_profile_end", C.POINTER(C.c_double), C.POINTER(C.c_double),
         C.POINTER(C.c_int64))

@@ -472,6 +472,255 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   }
 }
 
+
+// ------------------------------------------------------------------------------------ long rows
+// Sequences longer than one 128-token tile (reference limit: max_position_embeddings = 514;
+// cross-modal rows of max_txt_len subtitle tokens + matched frames, model/embed.py:33-41,
+// config/train-tv*.json) are rare in HERO batches. They are handled by plain fp32 CUDA-core
+// kernels, one CTA per (sequence, head), K / V (forward, dQ) or Q / dO (dK, dV) of the whole
+// sequence staged in shared memory as bf16: exact same arithmetic contract as the tile kernels
+// (softmax over the row's own sequence, the same dropout words, log2-domain LSE), ~20x slower per
+// token, which is irrelevant at their frequency.
+constexpr int AL_MAX = 768;            // tokens per long sequence (2 x 768 x 128 B = 192 KB smem)
+constexpr int AL_THREADS = 256;
+
+__device__ __forceinline__ void al_load_rows(uint8_t* dst, const __nv_bfloat16* src, long long ld,
+                                             int n) {
+  // n rows of 64 bf16 (128 B) -> dense [n][128 B] smem, 16-byte units
+  for (int idx = threadIdx.x; idx < n * 8; idx += blockDim.x) {
+    const int r = idx >> 3, u = idx & 7;
+    *reinterpret_cast<uint4*>(dst + r * 128 + u * 16) =
+        *reinterpret_cast<const uint4*>(src + (long long)r * ld + u * 8);
+  }
+}
+
+__device__ __forceinline__ void al_row_f32(const uint8_t* row, float (&v)[64]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint4 q = *reinterpret_cast<const uint4*>(row + u * 16);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      v[u * 8 + 2 * j] = f.x;
+      v[u * 8 + 2 * j + 1] = f.y;
+    }
+  }
+}
+
+__device__ __forceinline__ void al_global_row_f32(const __nv_bfloat16* p, float (&v)[64]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p + u * 8);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      v[u * 8 + 2 * j] = f.x;
+      v[u * 8 + 2 * j + 1] = f.y;
+    }
+  }
+}
+
+__device__ __forceinline__ float al_dot_row(const float (&q)[64], const uint8_t* row) {
+  float s = 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint4 k = *reinterpret_cast<const uint4*>(row + u * 16);   // broadcast read
+    const uint32_t w[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      s = fmaf(q[u * 8 + 2 * j], f.x, s);
+      s = fmaf(q[u * 8 + 2 * j + 1], f.y, s);
+    }
+  }
+  return s;
+}
+
+__device__ __forceinline__ void al_axpy_row(float (&acc)[64], float a, const uint8_t* row) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const uint4 k = *reinterpret_cast<const uint4*>(row + u * 16);
+    const uint32_t w[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      acc[u * 8 + 2 * j] = fmaf(a, f.x, acc[u * 8 + 2 * j]);
+      acc[u * 8 + 2 * j + 1] = fmaf(a, f.y, acc[u * 8 + 2 * j + 1]);
+    }
+  }
+}
+
+__device__ __forceinline__ void al_store_row(__nv_bfloat16* p, const float (&v)[64], float scale) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    uint4 q;
+    q.x = pack_bf16x2(v[u * 8] * scale, v[u * 8 + 1] * scale);
+    q.y = pack_bf16x2(v[u * 8 + 2] * scale, v[u * 8 + 3] * scale);
+    q.z = pack_bf16x2(v[u * 8 + 4] * scale, v[u * 8 + 5] * scale);
+    q.w = pack_bf16x2(v[u * 8 + 6] * scale, v[u * 8 + 7] * scale);
+    *reinterpret_cast<uint4*>(p + u * 8) = q;
+  }
+}
+
+// dropout keep factor of probability (query token tok, head, key column j RELATIVE to the tile
+// start = the sequence start for a long tile): the same word layout as the tile kernels
+__device__ __forceinline__ float al_keep(const AttnTcArgs& a, int tok, int head, int j) {
+  if (a.drop_thr == 0u) return 1.0f;
+  const uint32_t h = attn_drop_word(a.drop_key, tok, a.heads, head, j >> 1);
+  const uint32_t bits = (j & 1) ? (h >> 16) : (h & 0xFFFFu);
+  return (bits >= (a.drop_thr >> 16)) ? a.drop_scale : 0.f;
+}
+
+// forward (MODE 0): ctx, lse.   dQ (MODE 1): K, V in smem, thread per query row.
+template <int MODE>
+__global__ void __launch_bounds__(AL_THREADS)
+attn_long_q_kernel(const AttnTcArgs a, int first_tile, const __nv_bfloat16* __restrict__ qkv,
+                   __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
+                   const __nv_bfloat16* __restrict__ dctx, __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int tile = first_tile + blockIdx.x, head = blockIdx.y;
+  const int tok0 = a.tile_tok0[tile], n = a.tile_ntok[tile];
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + (size_t)n * 128;
+  const long long ld = 3LL * a.H;
+  al_load_rows(sK, qkv + (long long)tok0 * ld + a.H + head * AT_D, ld, n);
+  al_load_rows(sV, qkv + (long long)tok0 * ld + 2 * a.H + head * AT_D, ld, n);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float q[64];
+    al_global_row_f32(qkv + (long long)(tok0 + i) * ld + head * AT_D, q);
+    if (MODE == 0) {
+      float mx = -INFINITY;
+      for (int j = 0; j < n; ++j) mx = fmaxf(mx, al_dot_row(q, sK + j * 128));
+      float sum = 0.f, o[64];
+#pragma unroll
+      for (int d = 0; d < 64; ++d) o[d] = 0.f;
+      for (int j = 0; j < n; ++j) {
+        const float p = ex2((al_dot_row(q, sK + j * 128) - mx) * a.scale_log2);
+        sum += p;
+        al_axpy_row(o, p * al_keep(a, tok0 + i, head, j), sV + j * 128);
+      }
+      if (lse != nullptr) lse[(long long)(tok0 + i) * a.heads + head] = mx * a.scale_log2 + log2f(sum);
+      al_store_row(ctx + (long long)(tok0 + i) * a.H + head * AT_D, o, 1.0f / sum);
+    } else {
+      float dO[64], O[64], dq[64];
+      al_global_row_f32(dctx + (long long)(tok0 + i) * a.H + head * AT_D, dO);
+      al_global_row_f32(ctx + (long long)(tok0 + i) * a.H + head * AT_D, O);
+      float Di = 0.f;
+#pragma unroll
+      for (int d = 0; d < 64; ++d) {
+        Di = fmaf(dO[d], O[d], Di);
+        dq[d] = 0.f;
+      }
+      const float row_lse = lse[(long long)(tok0 + i) * a.heads + head];
+      for (int j = 0; j < n; ++j) {
+        const float p = ex2(fmaf(al_dot_row(q, sK + j * 128), a.scale_log2, -row_lse));
+        const float dp = al_dot_row(dO, sV + j * 128);
+        const float ds = p * (dp * al_keep(a, tok0 + i, head, j) - Di) * a.scale;
+        al_axpy_row(dq, ds, sK + j * 128);
+      }
+      al_store_row(dqkv + (long long)(tok0 + i) * ld + head * AT_D, dq, 1.0f);
+    }
+  }
+}
+
+// dK, dV: Q, dO of the sequence in smem (+ per-query LSE and D); a PAIR of threads owns one key
+// row, each half of the 64 features (partial dot products are summed with one shuffle).
+__global__ void __launch_bounds__(AL_THREADS)
+attn_long_kv_kernel(const AttnTcArgs a, int first_tile, const __nv_bfloat16* __restrict__ qkv,
+                    const __nv_bfloat16* __restrict__ ctx, const float* __restrict__ lse,
+                    const __nv_bfloat16* __restrict__ dctx, __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int tile = first_tile + blockIdx.x, head = blockIdx.y;
+  const int tok0 = a.tile_tok0[tile], n = a.tile_ntok[tile];
+  uint8_t* sQ = smem;
+  uint8_t* sdO = smem + (size_t)n * 128;
+  float* sL = reinterpret_cast<float*>(smem + (size_t)n * 256);
+  float* sD = sL + n;
+  const long long ld = 3LL * a.H;
+  al_load_rows(sQ, qkv + (long long)tok0 * ld + head * AT_D, ld, n);
+  al_load_rows(sdO, dctx + (long long)tok0 * a.H + head * AT_D, a.H, n);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float dO[64], O[64];
+    al_row_f32(sdO + i * 128, dO);
+    al_global_row_f32(ctx + (long long)(tok0 + i) * a.H + head * AT_D, O);
+    float Di = 0.f;
+#pragma unroll
+    for (int d = 0; d < 64; ++d) Di = fmaf(dO[d], O[d], Di);
+    sD[i] = Di;
+    sL[i] = lse[(long long)(tok0 + i) * a.heads + head];
+  }
+  __syncthreads();
+  const int half = threadIdx.x & 1;
+  for (int j0 = 0; j0 < n; j0 += AL_THREADS / 2) {
+    const int j = j0 + (threadIdx.x >> 1);
+    const bool ok = j < n;          // pairs stay together: the shuffle below needs both lanes
+    float k[32], v[32], dk[32], dv[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) k[d] = v[d] = dk[d] = dv[d] = 0.f;
+    if (ok) {
+      const __nv_bfloat16* kp = qkv + (long long)(tok0 + j) * ld + a.H + head * AT_D + half * 32;
+      const __nv_bfloat16* vp = kp + a.H;
+#pragma unroll
+      for (int d = 0; d < 32; d += 2) {
+        const float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(kp + d));
+        const float2 y = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vp + d));
+        k[d] = x.x; k[d + 1] = x.y; v[d] = y.x; v[d + 1] = y.y;
+      }
+    }
+    for (int i = 0; i < n; ++i) {
+      const uint8_t* qrow = sQ + i * 128 + half * 64;
+      const uint8_t* drow = sdO + i * 128 + half * 64;
+      float q[32], dO[32];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint4 a4 = *reinterpret_cast<const uint4*>(qrow + u * 16);
+        const uint4 b4 = *reinterpret_cast<const uint4*>(drow + u * 16);
+        const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w}, bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 x = unpack_bf16x2(aw[t]), y = unpack_bf16x2(bw[t]);
+          q[u * 8 + 2 * t] = x.x; q[u * 8 + 2 * t + 1] = x.y;
+          dO[u * 8 + 2 * t] = y.x; dO[u * 8 + 2 * t + 1] = y.y;
+        }
+      }
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) {
+        s = fmaf(q[d], k[d], s);
+        dp = fmaf(dO[d], v[d], dp);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      dp += __shfl_xor_sync(0xffffffffu, dp, 1);
+      const float p = ex2(fmaf(s, a.scale_log2, -sL[i]));
+      const float keep = al_keep(a, tok0 + i, head, j);
+      const float pd = p * keep;
+      const float ds = p * (dp * keep - sD[i]) * a.scale;
+#pragma unroll
+      for (int d = 0; d < 32; ++d) {
+        dv[d] = fmaf(pd, dO[d], dv[d]);
+        dk[d] = fmaf(ds, q[d], dk[d]);
+      }
+    }
+    if (ok) {
+      __nv_bfloat16* dkp = dqkv + (long long)(tok0 + j) * ld + a.H + head * AT_D + half * 32;
+      __nv_bfloat16* dvp = dkp + a.H;
+#pragma unroll
+      for (int d = 0; d < 32; d += 2) {
+        *reinterpret_cast<uint32_t*>(dkp + d) = pack_bf16x2(dk[d], dk[d + 1]);
+        *reinterpret_cast<uint32_t*>(dvp + d) = pack_bf16x2(dv[d], dv[d + 1]);
+      }
+    }
+  }
+}
+
 static int fill_args(AttnTcArgs* a, const int32_t* tile_tok0, const int32_t* tile_ntok,
                      const int32_t* seq_lo, const int32_t* seq_hi, int heads, int head_dim,
                      float scale, uint32_t thr, uint32_t key, float dscale) {
@@ -496,13 +745,20 @@ static int fill_args(AttnTcArgs* a, const int32_t* tile_tok0, const int32_t* til
 
 using namespace hero;
 
+static int long_smem_bytes(int max_long) { return max_long * 256 + max_long * 8 + 64; }
+
 extern "C" int hero_attn_fwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
                                 const int32_t* seq_lo, const int32_t* seq_hi, void* ctx, float* lse,
-                                int32_t n_tok, int32_t n_tiles, int32_t heads, int32_t head_dim,
+                                int32_t n_tok, int32_t n_tiles, int32_t n_long, int32_t max_long,
+                                int32_t heads, int32_t head_dim,
                                 float scale, uint32_t drop_threshold, uint32_t drop_key,
                                 float drop_scale, void* stream) {
   HERO_REQUIRE(qkv && ctx, "attn_fwd: null pointer");
+  HERO_REQUIRE(n_long >= 0 && n_long <= n_tiles && (n_long == 0 || (max_long > AT_ROWS && max_long <= AL_MAX)),
+               "attn_fwd: bad long-sequence tiles (n_long %d, max_long %d; limit %d tokens)", n_long,
+               max_long, AL_MAX);
   if (n_tiles <= 0 || n_tok <= 0) return HERO_OK;
+  const int n_short = n_tiles - n_long;
   AttnTcArgs a;
   if (int rc = fill_args(&a, tile_tok0, tile_ntok, seq_lo, seq_hi, heads, head_dim, scale,
                          drop_threshold, drop_key, drop_scale))
@@ -516,22 +772,39 @@ extern "C" int hero_attn_fwd(const void* qkv, const int32_t* tile_tok0, const in
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid(n_tiles, heads);
-  HERO_CUDA_CHECK(launch_pdl(attn_tc_fwd_kernel, grid, dim3(128), smem,
-                             reinterpret_cast<cudaStream_t>(stream), tm, a,
-                             reinterpret_cast<__nv_bfloat16*>(ctx), lse));
+  if (n_short > 0) {
+    dim3 grid(n_short, heads);
+    HERO_CUDA_CHECK(launch_pdl(attn_tc_fwd_kernel, grid, dim3(128), smem,
+                               reinterpret_cast<cudaStream_t>(stream), tm, a,
+                               reinterpret_cast<__nv_bfloat16*>(ctx), lse));
+  }
+  if (n_long > 0) {
+    const int lsm = long_smem_bytes(max_long);
+    HERO_CUDA_CHECK(cudaFuncSetAttribute(attn_long_q_kernel<0>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, lsm));
+    HERO_CUDA_CHECK(launch_pdl(attn_long_q_kernel<0>, dim3(n_long, heads), dim3(AL_THREADS), lsm,
+                               reinterpret_cast<cudaStream_t>(stream), a, n_short,
+                               reinterpret_cast<const __nv_bfloat16*>(qkv),
+                               reinterpret_cast<__nv_bfloat16*>(ctx), lse,
+                               static_cast<const __nv_bfloat16*>(nullptr),
+                               static_cast<__nv_bfloat16*>(nullptr)));
+  }
   return HERO_OK;
 }
 
 extern "C" int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
                                 const int32_t* seq_lo, const int32_t* seq_hi, const void* ctx,
                                 const void* dctx, const float* lse, void* dqkv, int32_t n_tok,
-                                int32_t n_tiles,
+                                int32_t n_tiles, int32_t n_long, int32_t max_long,
                                 int32_t heads, int32_t head_dim, float scale,
                                 uint32_t drop_threshold, uint32_t drop_key, float drop_scale,
                                 void* stream) {
   HERO_REQUIRE(qkv && ctx && dctx && dqkv && lse, "attn_bwd: null pointer");
+  HERO_REQUIRE(n_long >= 0 && n_long <= n_tiles && (n_long == 0 || (max_long > AT_ROWS && max_long <= AL_MAX)),
+               "attn_bwd: bad long-sequence tiles (n_long %d, max_long %d; limit %d tokens)", n_long,
+               max_long, AL_MAX);
   if (n_tiles <= 0 || n_tok <= 0) return HERO_OK;
+  const int n_short = n_tiles - n_long;
   AttnTcArgs a;
   if (int rc = fill_args(&a, tile_tok0, tile_ntok, seq_lo, seq_hi, heads, head_dim, scale,
                          drop_threshold, drop_key, drop_scale))
@@ -547,9 +820,30 @@ extern "C" int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const in
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid(n_tiles, heads);
-  HERO_CUDA_CHECK(launch_pdl(attn_tc_bwd_kernel, grid, dim3(128), smem,
-                             reinterpret_cast<cudaStream_t>(stream), tq, td, to, a, lse,
-                             reinterpret_cast<__nv_bfloat16*>(dqkv)));
+  if (n_short > 0) {
+    dim3 grid(n_short, heads);
+    HERO_CUDA_CHECK(launch_pdl(attn_tc_bwd_kernel, grid, dim3(128), smem,
+                               reinterpret_cast<cudaStream_t>(stream), tq, td, to, a, lse,
+                               reinterpret_cast<__nv_bfloat16*>(dqkv)));
+  }
+  if (n_long > 0) {
+    const int lsm = long_smem_bytes(max_long);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    HERO_CUDA_CHECK(cudaFuncSetAttribute(attn_long_q_kernel<1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, lsm));
+    HERO_CUDA_CHECK(cudaFuncSetAttribute(attn_long_kv_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, lsm));
+    HERO_CUDA_CHECK(launch_pdl(attn_long_q_kernel<1>, dim3(n_long, heads), dim3(AL_THREADS), lsm, st,
+                               a, n_short, reinterpret_cast<const __nv_bfloat16*>(qkv),
+                               const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(ctx)),
+                               const_cast<float*>(lse),
+                               reinterpret_cast<const __nv_bfloat16*>(dctx),
+                               reinterpret_cast<__nv_bfloat16*>(dqkv)));
+    HERO_CUDA_CHECK(launch_pdl(attn_long_kv_kernel, dim3(n_long, heads), dim3(AL_THREADS), lsm, st, a,
+                               n_short, reinterpret_cast<const __nv_bfloat16*>(qkv),
+                               reinterpret_cast<const __nv_bfloat16*>(ctx), lse,
+                               reinterpret_cast<const __nv_bfloat16*>(dctx),
+                               reinterpret_cast<__nv_bfloat16*>(dqkv)));
+  }
   return HERO_OK;
 }

@@ -46,6 +46,10 @@ enum { RES_NONE = 0, RES_BF16 = 1, RES_F32 = 2 };
 struct GemmShape {
   int M, N, K;
   int num_m_blocks, num_n_blocks, k_splits, k_blocks;
+  // 1, or 3 = split-bf16 operands: A = A_hi + A_lo, B = B_hi + B_lo, accumulate A_hi B_hi +
+  // A_lo B_hi + A_hi B_lo into the same fp32 accumulator (~16 mantissa bits per operand): the
+  // frame_transform pre-activation, whose ReLU gate flips on bf16 operand rounding
+  int k_passes;
 };
 
 struct GemmEpilogue {
@@ -124,7 +128,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out,
                     const __grid_constant__ CUtensorMap tmap_aux,
-                    const __grid_constant__ CUtensorMap tmap_res, const GemmShape s,
+                    const __grid_constant__ CUtensorMap tmap_res,
+                    const __grid_constant__ CUtensorMap tmap_a_lo,
+                    const __grid_constant__ CUtensorMap tmap_b_lo, const GemmShape s,
                     const GemmEpilogue e) {
   using Cfg = GemmCfg<BLOCK_N, CTA2, ACT, OUT, RES>;
   constexpr int STAGES = Cfg::STAGES;
@@ -203,35 +209,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int m_blk = t2 / s.num_n_blocks;
         const int kb0 = (int)(((long long)ks * s.k_blocks) / s.k_splits);
         const int kb1 = (int)(((long long)(ks + 1) * s.k_blocks) / s.k_splits);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const uint32_t stage = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(&empty_bar[stage], ph ^ 1u);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
-          if (CTA2) {
-            // both CTAs' loads complete on the LEADER's barrier, which expects the pair's bytes
-            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-            const int m128 = m_blk * 2 + (int)rank;                       // this CTA's A rows
-            const int n0 = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);   // this CTA's B columns
-            if (A_MN)
-              tma_load_3d_2sm(sa, &tmap_a, &full_bar[stage], 0, kb * BLOCK_K, m128 * (BLOCK_M / 64));
-            else
-              tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m128 * BLOCK_M);
-            if (B_MN)
-              tma_load_3d_2sm(sb, &tmap_b, &full_bar[stage], 0, kb * BLOCK_K, n0 / 64);
-            else
-              tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n0);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            if (A_MN)
-              tma_load_3d(sa, &tmap_a, &full_bar[stage], 0, kb * BLOCK_K, m_blk * (BLOCK_M / 64));
-            else
-              tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-            if (B_MN)
-              tma_load_3d(sb, &tmap_b, &full_bar[stage], 0, kb * BLOCK_K, n_blk * (BLOCK_N / 64));
-            else
-              tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+        for (int pass = 0; pass < s.k_passes; ++pass) {
+          // split-bf16 passes: (A_hi, B_hi), (A_lo, B_hi), (A_hi, B_lo)
+          const CUtensorMap* ma = (pass == 1) ? &tmap_a_lo : &tmap_a;
+          const CUtensorMap* mb = (pass == 2) ? &tmap_b_lo : &tmap_b;
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const uint32_t stage = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            mbar_wait(&empty_bar[stage], ph ^ 1u);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            if (CTA2) {
+              // both CTAs' loads complete on the LEADER's barrier, which expects the pair's bytes
+              if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+              const int m128 = m_blk * 2 + (int)rank;                       // this CTA's A rows
+              const int n0 = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);   // this CTA's B columns
+              if (A_MN)
+                tma_load_3d_2sm(sa, ma, &full_bar[stage], 0, kb * BLOCK_K, m128 * (BLOCK_M / 64));
+              else
+                tma_load_2d_2sm(sa, ma, &full_bar[stage], kb * BLOCK_K, m128 * BLOCK_M);
+              if (B_MN)
+                tma_load_3d_2sm(sb, mb, &full_bar[stage], 0, kb * BLOCK_K, n0 / 64);
+              else
+                tma_load_2d_2sm(sb, mb, &full_bar[stage], kb * BLOCK_K, n0);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              if (A_MN)
+                tma_load_3d(sa, ma, &full_bar[stage], 0, kb * BLOCK_K, m_blk * (BLOCK_M / 64));
+              else
+                tma_load_2d(sa, ma, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+              if (B_MN)
+                tma_load_3d(sb, mb, &full_bar[stage], 0, kb * BLOCK_K, n_blk * (BLOCK_N / 64));
+              else
+                tma_load_2d(sb, mb, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+            }
           }
         }
       }
@@ -257,7 +268,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int n_kb = (kb1 - kb0) * s.k_passes;
+        for (int kbi = 0; kbi < n_kb; ++kbi, ++it) {
           const uint32_t stage = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(&full_bar[stage], ph);
@@ -269,9 +281,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             const uint64_t adesc = make_sw128_desc(sa + k * A_KSTEP, A_LBO, 1024);
             const uint64_t bdesc = make_sw128_desc(sb + k * B_KSTEP, B_LBO, 1024);
             if (CTA2)
-              umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_f16_2sm(d_tmem, adesc, bdesc, idesc, (kbi > 0 || k > 0) ? 1u : 0u);
             else
-              umma_f16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_f16(d_tmem, adesc, bdesc, idesc, (kbi > 0 || k > 0) ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs retire
           if (CTA2) umma_commit_2sm(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -510,7 +522,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         if (CTA2) mbar_arrive_leader(&tmem_empty_bar[acc]); else mbar_arrive(&tmem_empty_bar[acc]);
       }
     }
-    if (OUT != OUT_F32_ATOMIC && lane == 0) bulk_wait_all();
+    // the slabs must not go away under stores still reading them; their global writes are
+    // complete when the grid is (a dependent kernel's griddepcontrol.wait covers them)
+    if (OUT != OUT_F32_ATOMIC && lane == 0) bulk_wait_read<0>();
   }
 
   tc_fence_before_sync();
@@ -626,7 +640,7 @@ static int get_tmap(CUtensorMap* out, const void* ptr, int d0, int d1, long long
 }
 
 struct GemmMaps {
-  CUtensorMap a, b, out, aux, res;
+  CUtensorMap a, b, out, aux, res, a_lo, b_lo;
 };
 
 template <int BLOCK_N, int A_MN, int B_MN, int ACT, int OUT, int CTA2, int RES>
@@ -663,7 +677,7 @@ static int launch(const GemmMaps& tm, const GemmShape& s, const GemmEpilogue& e,
     cfg.gridDim = dim3(total < sms ? total : sms);
   }
   cfg.attrs = attr;
-  HERO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.out, tm.aux, tm.res, s, e));
+  HERO_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b, tm.out, tm.aux, tm.res, tm.a_lo, tm.b_lo, s, e));
   return HERO_OK;
 }
 
@@ -799,6 +813,7 @@ extern "C" int hero_gemm_bf16(const hero_gemm_args* g, void* stream) {
   if (g)
     g_prof.rec.push_back(GemmProfileRec{g->m, g->n, g->k, g->a_mn_major, g->b_mn_major, g->act,
                                         g->out_f32_accumulate + 2 * g->out_f32_store});
+  // (a split-bf16 GEMM issues 3x the MMAs; the profile counts its algorithmic 2MNK once)
   if (rc == HERO_OK && g) g_prof.flops += 2.0 * (double)g->m * (double)g->n * (double)g->k;
   return rc;
 }
@@ -878,6 +893,8 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   }
   if (k_splits > s.k_blocks) k_splits = s.k_blocks;
   s.k_splits = k_splits;
+  HERO_REQUIRE((g->a_lo == nullptr) == (g->b_lo == nullptr), "a_lo and b_lo go together");
+  s.k_passes = g->a_lo ? 3 : 1;
 
   GemmEpilogue e;
   e.bias = g->bias;
@@ -901,6 +918,20 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   else
     rc = get_tmap(&tm.b, g->b, g->n, g->k, g->ldb, b_box, TM_KMAJOR);
   if (rc) return rc;
+  tm.a_lo = tm.a;
+  tm.b_lo = tm.b;
+  if (g->a_lo) {     // same shapes / leading dimensions as the hi parts
+    if (g->a_mn_major)
+      rc = get_tmap(&tm.a_lo, g->a_lo, g->k, g->m, g->lda, BLOCK_M, TM_MNMAJOR);
+    else
+      rc = get_tmap(&tm.a_lo, g->a_lo, g->m, g->k, g->lda, BLOCK_M, TM_KMAJOR);
+    if (rc) return rc;
+    if (g->b_mn_major)
+      rc = get_tmap(&tm.b_lo, g->b_lo, g->k, g->n, g->ldb, b_box, TM_MNMAJOR);
+    else
+      rc = get_tmap(&tm.b_lo, g->b_lo, g->n, g->k, g->ldb, b_box, TM_KMAJOR);
+    if (rc) return rc;
+  }
   tm.out = tm.a;
   tm.aux = tm.a;
   tm.res = tm.a;

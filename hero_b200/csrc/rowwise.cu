@@ -80,6 +80,20 @@ __device__ __forceinline__ void store_f32x8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
 
+// bf16(v) to `hi` and the bf16 of what that rounding lost to `lo`: v ~ hi + lo to ~16 mantissa bits
+__device__ __forceinline__ void store_bf16x8_split(__nv_bfloat16* hi, __nv_bfloat16* lo,
+                                                   const float (&v)[8]) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    const float2 back = unpack_bf16x2(h[j]);
+    l[j] = pack_bf16x2(v[2 * j] - back.x, v[2 * j + 1] - back.y);
+  }
+  *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 __device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const float (&v)[8]) {
   uint4 u;
   u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
@@ -159,7 +173,10 @@ ln_fwd_kernel(const hero_ln_args a) {
           if (a.drop_threshold != 0u)
             dropout_apply8(o, a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0,
                            a.drop_threshold, a.drop_scale);
-          store_bf16x8(y + e0, o);
+          if (a.y_lo)
+            store_bf16x8_split(y + e0, reinterpret_cast<__nv_bfloat16*>(a.y_lo) + yrow * a.h + e0, o);
+          else
+            store_bf16x8(y + e0, o);
           if (a.y_f32) store_f32x8(a.y_f32 + yrow * a.h + e0, o);
         }
       }
@@ -459,8 +476,9 @@ ln_fwd_wide_kernel(const hero_ln_args a) {
       if (a.mean) a.mean[i] = mean;
       if (a.rstd) a.rstd[i] = rstd;
     }
-    __nv_bfloat16* y =
-        reinterpret_cast<__nv_bfloat16*>(a.y) + (a.y_rows ? a.y_rows[i] : i) * (long long)a.h;
+    const long long yoff = (a.y_rows ? a.y_rows[i] : i) * (long long)a.h;
+    __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(a.y) + yoff;
+    __nv_bfloat16* ylo = a.y_lo ? reinterpret_cast<__nv_bfloat16*>(a.y_lo) + yoff : nullptr;
 #pragma unroll
     for (int c = 0; c < LNW_C; ++c) {
       const int e0 = (c * LNW_THREADS + threadIdx.x) * 8;
@@ -471,7 +489,7 @@ ln_fwd_wide_kernel(const hero_ln_args a) {
         if (a.drop_threshold != 0u)
           dropout_apply8(o, a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0,
                          a.drop_threshold, a.drop_scale);
-        store_bf16x8(y + e0, o);
+        if (ylo) store_bf16x8_split(y + e0, ylo + e0, o); else store_bf16x8(y + e0, o);
       }
     }
   }
@@ -778,7 +796,8 @@ __global__ void cast_kernel(const float* __restrict__ src, __nv_bfloat16* __rest
 
 // Plain bf16 rows of at most 768 columns (every transformer-layer LayerNorm): fast kernels.
 static bool ln_fast_ok(const hero_ln_args* a) {
-  return a->h <= LNF_J * 256 && a->add_tab == nullptr && a->add_vec == nullptr;
+  return a->h <= LNF_J * 256 && a->add_tab == nullptr && a->add_vec == nullptr &&
+         a->y_lo == nullptr;
 }
 
 static int check_ln(const hero_ln_args* a) {

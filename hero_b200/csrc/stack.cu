@@ -125,7 +125,8 @@ extern "C" int hero_bert_stack_fwd(const hero_stack_args* s, void* stream) {
     HERO_REQUIRE(A.s1 && A.s2 && A.a_f32 && A.out_f32, "stack fwd: layer %d misses fp32 buffers", l);
     HERO_TRY(Gemm(h, H, 0, W.wqkv, H, 0, M, 3 * H, H, A.qkv, 3 * H).bias(W.bqkv).run(stream));
     HERO_TRY(hero_attn_fwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, A.lse, M,
-                           s->n_tiles, s->heads, 64, scale, s->attn_drop_threshold,
+                           s->n_tiles, s->n_long, s->max_long, s->heads, 64, scale,
+                           s->attn_drop_threshold,
                            site_key(s->drop_key, s->first_layer + l, 0), s->attn_drop_scale, stream));
     HERO_TRY(Gemm(A.cx, H, 0, W.wo, H, 0, M, H, H, A.s1, H)
                  .bias(W.bo)
@@ -254,7 +255,8 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
     HERO_TRY(Gemm(g1, H, 0, W.wo, H, 1, M, H, H, dcx, H).run(stream));
     // attention core
     HERO_TRY(hero_attn_bwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, dcx, A.lse,
-                           dqkv, M, s->n_tiles, s->heads, 64, scale, s->attn_drop_threshold,
+                           dqkv, M, s->n_tiles, s->n_long, s->max_long, s->heads, 64, scale,
+                           s->attn_drop_threshold,
                            site_key(s->drop_key, s->first_layer + l, 0), s->attn_drop_scale, stream));
     HERO_TRY(publish());
     // QKV projection

@@ -88,7 +88,7 @@ def drop_params(p, key):
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None, resid=None,
          aux_in=None, aux_out=None, act=ACT_NONE, accumulate_f32=False, drop=(0, 0, 1.0),
-         block_n=0, k_splits=0, cta_pair=0):
+         block_n=0, k_splits=0, cta_pair=0, a_lo=None, b_lo=None):
     """out = epilogue(A·B) with the operand conventions of `hero_gemm_args`.
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True) bf16; b: [N,K] (b_mn=False) or [K,N] (b_mn=True).
@@ -126,6 +126,12 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None
     assert out.dtype in (torch.float32, BF16) and (out.dtype == torch.float32 or not accumulate_f32)
     g.drop_threshold, g.drop_key, g.drop_scale = drop
     g.block_n, g.k_splits, g.cta_pair = block_n, k_splits, cta_pair
+    if a_lo is not None or b_lo is not None:     # split-bf16 operands: a*b + a_lo*b + a*b_lo
+        assert a_lo is not None and b_lo is not None
+        assert a_lo.dtype == BF16 and b_lo.dtype == BF16
+        assert a_lo.shape == a.shape and a_lo.stride() == a.stride()
+        assert b_lo.shape == b.shape and b_lo.stride() == b.stride()
+        g.a_lo, g.b_lo = _ptr(a_lo), _ptr(b_lo)
     _count()
     _lib.check(_lib.lib().hero_gemm_bf16(C.byref(g), _stream()))
     return out
@@ -152,7 +158,8 @@ def _ln_args(x, gamma, beta, eps, n_rows, h, x_rows=None, add_tab=None, add_idx=
 
 
 def ln_fwd(x, gamma, beta, eps, y, *, n_rows, x_rows=None, add_tab=None, add_idx=None,
-           add_vec=None, y_rows=None, mean=None, rstd=None, drop=(0, 0, 1.0), y_f32=None):
+           add_vec=None, y_rows=None, mean=None, rstd=None, drop=(0, 0, 1.0), y_f32=None,
+           y_lo=None):
     """Fused gather + add + LayerNorm (+dropout) + scatter; see `hero_ln_args`. `y_f32`: optional
     fp32 copy of the output (same rows): the residual stream of the transformer layers."""
     _require_cuda(x, y)
@@ -162,6 +169,9 @@ def ln_fwd(x, gamma, beta, eps, y, *, n_rows, x_rows=None, add_tab=None, add_idx
     if y_f32 is not None:
         assert y_f32.dtype == torch.float32 and y_f32.is_contiguous() and y_f32.shape == y.shape
     a.y_f32 = _ptr(y_f32)
+    if y_lo is not None:      # low half of a split-bf16 operand: bf16(y_f32 - float(bf16(y)))
+        assert y_lo.dtype == BF16 and y_lo.is_contiguous() and y_lo.shape == y.shape
+    a.y_lo = _ptr(y_lo)
     a.mean, a.rstd = _ptr(mean), _ptr(rstd)
     a.drop_threshold, a.drop_key, a.drop_scale = drop
     _count()
@@ -201,7 +211,8 @@ def attn_fwd(qkv, att, ctx, *, heads, head_dim=64, drop=(0, 0, 1.0), lse=None):
     _count()
     _lib.check(_lib.lib().hero_attn_fwd(
         _ptr(qkv), _ptr(att["tile_tok0"]), _ptr(att["tile_ntok"]), _ptr(att["seq_lo"]),
-        _ptr(att["seq_hi"]), _ptr(ctx), _ptr(lse), att["n_tok"], att["n_tiles"], heads, head_dim,
+        _ptr(att["seq_hi"]), _ptr(ctx), _ptr(lse), att["n_tok"], att["n_tiles"],
+        att.get("n_long", 0), att.get("max_long", 0), heads, head_dim,
         1.0 / (head_dim ** 0.5), drop[0], drop[1], drop[2], _stream()))
     return ctx
 
@@ -213,7 +224,7 @@ def attn_bwd(qkv, att, ctx, dctx, lse, dqkv, *, heads, head_dim=64, drop=(0, 0, 
     _lib.check(_lib.lib().hero_attn_bwd(
         _ptr(qkv), _ptr(att["tile_tok0"]), _ptr(att["tile_ntok"]), _ptr(att["seq_lo"]),
         _ptr(att["seq_hi"]), _ptr(ctx), _ptr(dctx), _ptr(lse), _ptr(dqkv), att["n_tok"],
-        att["n_tiles"],
+        att["n_tiles"], att.get("n_long", 0), att.get("max_long", 0),
         heads, head_dim, 1.0 / (head_dim ** 0.5), drop[0], drop[1], drop[2], _stream()))
     return dqkv
 
@@ -278,6 +289,7 @@ def _stack_struct(x, layers, att, heads, eps, drop, act_ptrs, x_f32=None):
     s = _lib.StackArgs()
     s.n_layers, s.n_tok, s.hidden = n, x.shape[0], x.shape[1]
     s.inter, s.heads, s.n_tiles = layers[0].w1.shape[0], heads, att["n_tiles"]
+    s.n_long, s.max_long = att.get("n_long", 0), att.get("max_long", 0)
     s.eps = eps
     s.weights, s.acts = W, A
     s.x = x.data_ptr()

@@ -20,7 +20,8 @@ import numpy as np
 import torch
 
 
-ATTN_TILE = 128
+ATTN_TILE = 128        # tokens per tensor-core attention tile
+ATTN_LONG_MAX = 768    # longest sequence the long-sequence kernels take (hero_attn_fwd)
 
 
 def _np(t):
@@ -102,29 +103,47 @@ class SeqPlan:
         p2t[self.tok_flat] = np.arange(self.n_tok, dtype=np.int32)
         self.pad_to_tok = p2t                                                    # padded -> packed
         # attention tiling: consecutive sequences packed into tiles of <= 128 tokens (a sequence
-        # never straddles tiles); per token the [lo, hi) range of its own sequence
-        if self.max_len > ATTN_TILE:
-            raise ValueError(f"sequence of {self.max_len} tokens exceeds the attention tile "
-                             f"({ATTN_TILE}); HERO rows are bounded by max_clip_len=100 / short "
-                             "subtitle rows")
+        # never straddles tiles); per token the [lo, hi) range of its own sequence. Sequences
+        # longer than one tile (up to ATTN_LONG_MAX tokens; the reference's position table allows
+        # 514, model/encoder.py:50) become tiles of their own at the END of the list: the library
+        # runs those `n_long` tiles on its long-sequence kernels (hero_attn_fwd).
+        if self.max_len > ATTN_LONG_MAX:
+            row = int(np.argmax(lens))
+            raise ValueError(f"row {row} has {self.max_len} valid tokens; the attention kernels "
+                             f"support sequences of up to {ATTN_LONG_MAX} tokens")
         self.seq_lo = np.repeat(self.cu[:-1], lens).astype(np.int32)
         self.seq_hi = np.repeat(self.cu[1:], lens).astype(np.int32)
-        t0, tn = [], []
+        t0, tn, l0, ln = [], [], [], []
         start, cur = 0, 0
+        pos = 0
         for n in lens.tolist():
             if n == 0:
+                continue
+            if n > ATTN_TILE:
+                if cur:
+                    t0.append(start)
+                    tn.append(cur)
+                l0.append(pos)
+                ln.append(n)
+                pos += n
+                start, cur = pos, 0
                 continue
             if cur + n > ATTN_TILE:
                 t0.append(start)
                 tn.append(cur)
                 start, cur = start + cur, 0
             cur += n
+            pos += n
         if cur:
             t0.append(start)
             tn.append(cur)
-        self.tile_tok0 = np.asarray(t0, np.int32)
-        self.tile_ntok = np.asarray(tn, np.int32)
-        self.n_tiles = len(t0)
+        self.n_long = len(l0)
+        self.max_long = max(ln) if ln else 0
+        self.short_tok0, self.short_ntok = np.asarray(t0, np.int32), np.asarray(tn, np.int32)
+        self.long_tok0, self.long_ntok = np.asarray(l0, np.int32), np.asarray(ln, np.int32)
+        self.tile_tok0 = np.concatenate([self.short_tok0, self.long_tok0]).astype(np.int32)
+        self.tile_ntok = np.concatenate([self.short_ntok, self.long_ntok]).astype(np.int32)
+        self.n_tiles = len(t0) + len(l0)
 
     def arrays(self, prefix):
         return {prefix + "cu": self.cu, prefix + "tok_flat": self.tok_flat,
@@ -138,6 +157,7 @@ class SeqPlan:
                 "seq_hi": getattr(dev, prefix + "seq_hi"),
                 "tile_tok0": getattr(dev, prefix + "tile_tok0"),
                 "tile_ntok": getattr(dev, prefix + "tile_ntok"), "n_tiles": self.n_tiles,
+                "n_long": self.n_long, "max_long": self.max_long,
                 "n_tok": self.n_tok, "n_seq": self.n_seq, "max_len": self.max_len}
 
 
@@ -322,12 +342,17 @@ class JointPlan:
         self.n_seq = sv.n_seq + sq.n_seq
         self.max_len = max(sv.max_len, sq.max_len)
         self.n_tiles = sv.n_tiles + sq.n_tiles
+        # long-sequence tiles (rare) of both row kinds go last, after every 128-token tile
+        self.n_long = sv.n_long + sq.n_long
+        self.max_long = max(sv.max_long, sq.max_long)
         self.arr = {
             "j_cu": np.concatenate([sv.cu, sq.cu[1:] + a]).astype(np.int32),
             "j_seq_lo": np.concatenate([sv.seq_lo, sq.seq_lo + a]).astype(np.int32),
             "j_seq_hi": np.concatenate([sv.seq_hi, sq.seq_hi + a]).astype(np.int32),
-            "j_tile_tok0": np.concatenate([sv.tile_tok0, sq.tile_tok0 + a]).astype(np.int32),
-            "j_tile_ntok": np.concatenate([sv.tile_ntok, sq.tile_ntok]).astype(np.int32),
+            "j_tile_tok0": np.concatenate([sv.short_tok0, sq.short_tok0 + a, sv.long_tok0,
+                                           sq.long_tok0 + a]).astype(np.int32),
+            "j_tile_ntok": np.concatenate([sv.short_ntok, sq.short_ntok, sv.long_ntok,
+                                           sq.long_ntok]).astype(np.int32),
             "j_txt_tok": np.concatenate([fv.txt_tok, fq.txt_tok + a]).astype(np.int32),
             "j_txt_j": np.concatenate([fv.txt_j, fq.txt_j]).astype(np.int32),
         }
@@ -352,8 +377,8 @@ class JointPlan:
     def attn(self, dev):
         return {"cu": dev.j_cu, "seq_lo": dev.j_seq_lo, "seq_hi": dev.j_seq_hi,
                 "tile_tok0": dev.j_tile_tok0, "tile_ntok": dev.j_tile_ntok,
-                "n_tiles": self.n_tiles, "n_tok": self.n_tok, "n_seq": self.n_seq,
-                "max_len": self.max_len}
+                "n_tiles": self.n_tiles, "n_long": self.n_long, "max_long": self.max_long,
+                "n_tok": self.n_tok, "n_seq": self.n_seq, "max_len": self.max_len}
 
 
 PLAN_KEY = "_hero_plan"

@@ -103,6 +103,13 @@ typedef struct hero_gemm_args {
                               256 x 256 tiles; needs block_n 256) */
   int32_t resid_f32;       /* resid is f32 [m, ld_resid] (needs out_f32_store) */
   int32_t out_f32_store;   /* out is f32 [m, ld_out], plain store (act 0 only; ld_out % 4 == 0) */
+  /* Split-bf16 operands (both or neither; same layout / leading dims as a, b): the contraction
+   * becomes a*b + a_lo*b + a*b_lo in ONE accumulator, i.e. operands with ~16 mantissa bits
+   * (x_lo = bf16(x - float(bf16(x)))). Used for the frame_transform Linear (model/layers.py:86-93):
+   * its ReLU gate flips on ~0.08 % of the units when the pre-activation is computed from plain
+   * bf16 operands, which alone costs 4e-2 relative error in that layer's gradients. */
+  const void* a_lo;
+  const void* b_lo;
 } hero_gemm_args;
 
 int hero_gemm_bf16(const hero_gemm_args* args, void* stream);
@@ -158,6 +165,8 @@ typedef struct hero_ln_args {
   int32_t n_rows, h;
   /* forward outputs / backward saved stats */
   void* y;                 /* bf16 */
+  void* y_lo;              /* optional bf16 remainder bf16(y_f32 - float(bf16 y)) at the same rows: the
+                              low half of a split-bf16 GEMM operand (see hero_gemm_args.a_lo) */
   const int32_t* y_rows;   /* NULL = identity; also indexes dy in bwd */
   float* y_f32;            /* optional fp32 copy of y (same rows, after dropout): the residual
                               stream consumed by the next GEMM epilogue; NULL = none; h <= 768 */
@@ -207,17 +216,22 @@ int hero_ln_bwd(const hero_ln_args* args, void* stream);
  * per probability, word index ((i*heads + h)*64 + u); forward and backward regenerate the same
  * words from the same plan.
  * The backward takes the saved forward output (D_i = dO_i . O_i).
- * Constraints: head_dim == 64, sequences <= 128 tokens.
+ * Sequences of more than 128 tokens (up to 768; the reference's position table allows 514) take
+ * the LAST n_long tiles of the plan, one whole sequence per tile (tile_ntok = its length,
+ * max_long = the longest): they run on fp32 CUDA-core kernels with the same arithmetic contract
+ * (one CTA per (sequence, head), K / V or Q / dO staged in shared memory).
+ * Constraints: head_dim == 64, sequences <= 768 tokens.
  * ---------------------------------------------------------------------------------------- */
 int hero_attn_fwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
                   const int32_t* seq_lo, const int32_t* seq_hi, void* ctx, float* lse,
-                  int32_t n_tok, int32_t n_tiles, int32_t heads, int32_t head_dim, float scale,
-                  uint32_t drop_threshold, uint32_t drop_key, float drop_scale, void* stream);
-int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
-                  const int32_t* seq_lo, const int32_t* seq_hi, const void* ctx, const void* dctx,
-                  const float* lse, void* dqkv, int32_t n_tok, int32_t n_tiles, int32_t heads,
+                  int32_t n_tok, int32_t n_tiles, int32_t n_long, int32_t max_long, int32_t heads,
                   int32_t head_dim, float scale, uint32_t drop_threshold, uint32_t drop_key,
                   float drop_scale, void* stream);
+int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
+                  const int32_t* seq_lo, const int32_t* seq_hi, const void* ctx, const void* dctx,
+                  const float* lse, void* dqkv, int32_t n_tok, int32_t n_tiles, int32_t n_long,
+                  int32_t max_long, int32_t heads, int32_t head_dim, float scale,
+                  uint32_t drop_threshold, uint32_t drop_key, float drop_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Native layer runtime: a whole stack of BertLayers (model/layers.py:257-327) forward / backward
@@ -279,6 +293,7 @@ typedef struct hero_layer_grads { /* fp32, accumulated */
 
 typedef struct hero_stack_args {
   int32_t n_layers, n_tok, hidden, inter, heads, n_tiles;
+  int32_t n_long, max_long;      /* long-sequence tiles of the attention plan (see hero_attn_fwd) */
   float eps;
   const hero_layer_weights* weights;
   const hero_layer_acts* acts;

@@ -16,11 +16,15 @@ def _ck_drop(drop):
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None, resid=None,
          aux_in=None, aux_out=None, act=0, accumulate_f32=False, drop=(0, 0, 1.0), block_n=0,
-         k_splits=0, cta_pair=0):
+         k_splits=0, cta_pair=0, a_lo=None, b_lo=None):
     _ck_drop(drop)
     A = a.float().t() if a_mn else a.float()
     B = b.float() if b_mn else b.float().t()
     v = A @ B
+    if a_lo is not None:      # split-bf16 operands: a*b + a_lo*b + a*b_lo
+        A_lo = a_lo.float().t() if a_mn else a_lo.float()
+        B_lo = b_lo.float() if b_mn else b_lo.float().t()
+        v = v + A_lo @ B + A @ B_lo
     if bias is not None:
         v = v + bias
     if aux_out is not None:
@@ -59,7 +63,8 @@ def _gather_sum(x, n_rows, x_rows, add_tab, add_idx, add_vec):
 
 
 def ln_fwd(x, gamma, beta, eps, y, *, n_rows, x_rows=None, add_tab=None, add_idx=None,
-           add_vec=None, y_rows=None, mean=None, rstd=None, drop=(0, 0, 1.0), y_f32=None):
+           add_vec=None, y_rows=None, mean=None, rstd=None, drop=(0, 0, 1.0), y_f32=None,
+           y_lo=None):
     _ck_drop(drop)
     s = _gather_sum(x, n_rows, x_rows, add_tab, add_idx, add_vec)
     mu = s.mean(-1, keepdim=True)
@@ -67,14 +72,19 @@ def ln_fwd(x, gamma, beta, eps, y, *, n_rows, x_rows=None, add_tab=None, add_idx
     r = torch.rsqrt(var + eps)
     out32 = (s - mu) * r * gamma + beta
     out = out32.to(BF16)
+    lo = (out32 - out.float()).to(BF16)
     if y_rows is not None:
         y[y_rows.long()] = out
         if y_f32 is not None:
             y_f32[y_rows.long()] = out32
+        if y_lo is not None:
+            y_lo[y_rows.long()] = lo
     else:
         y[:n_rows] = out
         if y_f32 is not None:
             y_f32[:n_rows] = out32
+        if y_lo is not None:
+            y_lo[:n_rows] = lo
     if mean is not None:
         mean.copy_(mu.squeeze(-1))
     if rstd is not None:
@@ -129,15 +139,23 @@ def _attn_core(qkv, cu, heads):
 
 
 def _check_att(att):
-    """The tiling must cover the token stream with whole sequences, <= 128 tokens per tile."""
+    """The tiling must cover the token stream with whole sequences: <= 128 tokens per tile, then
+    (the last n_long tiles) one whole sequence of 129..768 tokens per tile."""
     t0, tn = att["tile_tok0"].tolist(), att["tile_ntok"].tolist()
     assert len(t0) == att["n_tiles"] and sum(tn) == att["n_tok"]
     cu = att["cu"].tolist()
     bounds = set(cu)
+    n_long = att.get("n_long", 0)
+    n_short = len(t0) - n_long
+    covered = sorted(zip(t0, tn))
     pos = 0
-    for a, n in zip(t0, tn):
-        assert a == pos and 0 < n <= 128 and a in bounds and (a + n) in bounds
+    for a, n in covered:
+        assert a == pos and a in bounds and (a + n) in bounds
         pos += n
+    for a, n in zip(t0[:n_short], tn[:n_short]):
+        assert 0 < n <= 128
+    for a, n in zip(t0[n_short:], tn[n_short:]):
+        assert 128 < n <= att.get("max_long", 0) <= 768 and cu[cu.index(a) + 1] == a + n
     lo, hi = att["seq_lo"].tolist(), att["seq_hi"].tolist()
     for s in range(len(cu) - 1):
         for t in range(cu[s], cu[s + 1]):
@@ -146,7 +164,7 @@ def _check_att(att):
 
 def attn_fwd(qkv, att, ctx, *, heads, head_dim=64, drop=(0, 0, 1.0), lse=None):
     _ck_drop(drop)
-    assert head_dim == 64 and att["max_len"] <= 128
+    assert head_dim == 64 and att["max_len"] <= 768
     _check_att(att)
     ctx.copy_(_attn_core(qkv.float(), att["cu"], heads).to(BF16))
     return ctx

@@ -231,14 +231,19 @@ def _att_plan(lens):
 
 
 @pytest.mark.parametrize("lens", [[25] * 40, [1, 7, 33, 64, 100, 128, 2, 90], [100] * 8,
-                                  [16] * 32, [3, 0, 5, 120, 9]])
+                                  [16] * 32, [3, 0, 5, 120, 9],
+                                  # rows longer than one tile (max_txt_len + matched frames can
+                                  # exceed 128; the position table allows 514): long-sequence path
+                                  [20, 200, 31, 129, 64], [514], [300, 7, 768]])
 def test_attention_fwd_bwd(lens):
     from hero_b200 import ops
-    heads = 12
+    heads = 12 if max(lens) <= 200 else 3
     ntok = sum(lens)
     qkv = _rand((ntok, 3 * heads * 64), 1.0, seed=50)
     sp, att = _att_plan(lens)
-    assert all(n <= 128 for n in sp.tile_ntok) and int(sp.tile_ntok.sum()) == ntok
+    n_short = sp.n_tiles - sp.n_long
+    assert all(n <= 128 for n in sp.tile_ntok[:n_short]) and int(sp.tile_ntok.sum()) == ntok
+    assert sp.n_long == sum(n > 128 for n in lens)
     ctx = torch.empty(ntok, heads * 64, dtype=BF16, device=_dev())
     lse = torch.empty(ntok, heads, device=_dev())
     ops.attn_fwd(qkv, att, ctx, heads=heads, lse=lse)
@@ -282,11 +287,29 @@ def test_attention_dropout_consistent_between_fwd_and_bwd():
     assert abs(lhs - rhs) <= 2e-2 * max(abs(lhs), 1.0), (lhs, rhs)
 
 
-def test_attention_rejects_long_sequences():
+def test_attention_long_rows_share_the_dropout_words_of_the_tile_kernels():
+    """Forward / backward of a long row regenerate the same mask (adjoint identity), and the plan
+    refuses rows beyond the long-sequence limit with the offending row in the message."""
     import numpy as np
+    from hero_b200 import ops
     from hero_b200.plan import SeqPlan
-    with pytest.raises(ValueError):
-        SeqPlan(np.ones((1, 200), np.int64))
+    with pytest.raises(ValueError, match="row 0 has 900"):
+        SeqPlan(np.ones((1, 900), np.int64))
+    heads, lens = 2, [150, 40]
+    ntok = sum(lens)
+    qkv = _rand((ntok, 3 * heads * 64), 1.0, seed=55)
+    _, att = _att_plan(lens)
+    drop = ops.drop_params(0.1, 777)
+    c1 = torch.empty(ntok, heads * 64, dtype=BF16, device=_dev())
+    lse = torch.empty(ntok, heads, device=_dev())
+    ops.attn_fwd(qkv, att, c1, heads=heads, drop=drop, lse=lse)
+    dctx = _rand((ntok, heads * 64), 1.0, seed=56)
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(qkv, att, c1, dctx, lse, dqkv, heads=heads, drop=drop)
+    H = heads * 64
+    lhs = (c1.float() * dctx.float()).sum().item()
+    rhs = (qkv[:, 2 * H:].float() * dqkv[:, 2 * H:].float()).sum().item()
+    assert abs(lhs - rhs) <= 2e-2 * max(abs(lhs), 1.0), (lhs, rhs)
 
 
 # ------------------------------------------------------------------------------ row utilities
@@ -484,3 +507,37 @@ def test_adamw_device_side_global_norm_clip():
                    clip_sumsq=s, clip_max_norm=1.0)
     _close(p, rp, 1e-7, 1e-4, "clipped update")
     _close(m, rm, 1e-9, 1e-4, "clipped first moment")
+
+
+def test_split_bf16_gemm_and_ln_low_half():
+    """frame_transform form: the LayerNorm emits hi + lo bf16 halves of its fp32 output, the GEMM
+    contracts hi*hi + lo*hi + hi*lo in one accumulator: the pre-activation (and therefore the ReLU
+    gate) agrees with fp32 arithmetic to ~1e-4 instead of ~1e-2."""
+    from hero_b200 import ops
+    n, d, h = 3200, 4352, 768
+    x = _rand((n, d), 1.0, seed=140, dtype=torch.float32)
+    gamma = (1.0 + 0.1 * _rand((d,), 1.0, seed=141, dtype=torch.float32))
+    beta = _rand((d,), 0.05, seed=142, dtype=torch.float32)
+    w = _rand((h, d), 0.02, seed=143, dtype=torch.float32)
+    bias = _rand((h,), 0.05, seed=144, dtype=torch.float32)
+    hi = torch.empty(n, d, dtype=BF16, device=_dev())
+    lo = torch.empty(n, d, dtype=BF16, device=_dev())
+    ops.ln_fwd(x, gamma, beta, 1e-5, hi, n_rows=n, y_lo=lo)
+    ref_xn = torch.nn.functional.layer_norm(x, (d,), gamma, beta, 1e-5)
+    _close(hi.float() + lo.float(), ref_xn, 1e-4, 1e-4, "hi + lo reproduces the fp32 LayerNorm output")
+    w_hi = w.to(BF16)
+    w_lo = (w - w_hi.float()).to(BF16)
+    resid = _rand((n, h), seed=145)
+    out = torch.empty(n, h, dtype=BF16, device=_dev())
+    pre = torch.empty(n, h, dtype=BF16, device=_dev())
+    ops.gemm(hi, w_hi, out, bias=bias, act=ops.ACT_RELU, resid=resid, aux_out=pre, a_lo=lo, b_lo=w_lo)
+    ref_pre = ref_xn.double() @ w.double().t() + bias.double()
+    flips = ((pre.float() > 0) != (ref_pre > 0)).float().mean().item()
+    assert flips < 5e-5, f"ReLU gate differs from fp64 arithmetic on {flips:.2e} of the units"
+    _close(pre, ref_pre.float(), 1e-2, 1e-2, "split-bf16 pre-activation")
+    _close(out, torch.relu(ref_pre.float()) + resid.float(), 2e-2, 1.6e-2, "relu + residual")
+    # the plain bf16 GEMM flips far more gates: this is what the split exists for
+    pre1 = torch.empty_like(pre)
+    ops.gemm(hi, w_hi, out, bias=bias, act=ops.ACT_RELU, resid=resid, aux_out=pre1)
+    flips1 = ((pre1.float() > 0) != (ref_pre > 0)).float().mean().item()
+    assert flips1 > 5 * max(flips, 1e-6), (flips1, flips)

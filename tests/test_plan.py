@@ -211,3 +211,34 @@ def test_plan_invariants_on_random_batches():
         assert jp.same_slot_pos in (True, False)
 
     check()
+
+
+def test_long_rows_become_trailing_tiles_and_joint_plans_keep_them_last():
+    """Rows of more than 128 valid tokens (max_txt_len + matched frames; the position table allows
+    514) are single-sequence tiles at the END of the tile list — also after concatenating the
+    video rows' and the query rows' plans."""
+    import numpy as np
+    from hero_b200.plan import ATTN_LONG_MAX, SeqPlan
+
+    def mask_of(lens):
+        m = np.zeros((len(lens), max(lens)), np.int64)
+        for r, n in enumerate(lens):
+            m[r, :n] = 1
+        return m
+
+    lens = [30, 200, 5, 128, 129, 60, 70]
+    sp = SeqPlan(mask_of(lens))
+    assert sp.n_long == 2 and sp.max_long == 200
+    n_short = sp.n_tiles - sp.n_long
+    assert sp.tile_ntok[n_short:].tolist() == [200, 129]
+    assert all(n <= 128 for n in sp.tile_ntok[:n_short])
+    # every token is covered exactly once and no tile splits a sequence
+    cover = np.zeros(sp.n_tok, np.int64)
+    for a, n in zip(sp.tile_tok0, sp.tile_ntok):
+        cover[a:a + n] += 1
+        assert a in set(sp.cu.tolist()) and a + n in set(sp.cu.tolist())
+    assert (cover == 1).all()
+    assert sp.tile_tok0[n_short:].tolist() == [30, 30 + 200 + 5 + 128]
+    import pytest
+    with pytest.raises(ValueError, match="row 1"):
+        SeqPlan(mask_of([3, ATTN_LONG_MAX + 1]))
