@@ -200,7 +200,7 @@ def run_ours(args):
     gflat = flat.ensure_flat_grads()
     exchange = None
     if world > 1 and bucketer is None and not args.dp_skip_exchange:
-        exchange = hdist.FlatGradExchange(flat, wire=args.dp_wire)
+        exchange = hdist.FlatGradExchange(flat, wire=args.dp_wire, overlap=not args.no_dp_overlap)
 
     B = args.batch_size
     n_host = 3
@@ -222,6 +222,8 @@ def run_ours(args):
     def fwd_bwd(vb_dev, qb_dev, opt=None, clip_norm=None):
         if bucketer is not None:   # per-layer gradient exchange overlapped with backward
             bucketer.__enter__()
+        if exchange is not None and (state["micro"] + 1) % accum == 0:
+            exchange.prepare()     # this step's gradients are exchanged: overlap what is final early
         if args.separate_txt:      # the reference's two calls (model/pretrain.py:65-70)
             clip = model(vb_dev, "repr")
             q = model.f_encoder(qb_dev, "txt")[0]
@@ -260,6 +262,15 @@ def run_ours(args):
     allreduce_check = None
     if world > 1 and exchange is not None:
         allreduce_check = exchange.self_check()
+        # and on real gradients through the overlapped path: per-rank batches differ, so the ranks
+        # can only agree bit for bit afterwards if every range of the buffer was reduced
+        state["micro"] = accum - 1
+        gflat.zero_()
+        fwd_bwd(*resident[0])
+        if not exchange.ranks_agree():
+            raise RuntimeError("ranks disagree on the exchanged gradients of a training step")
+        allreduce_check += "; ranks bit-identical after an exchanged training step"
+        state["micro"] = 0
     for i in range(args.warmup):
         resident_step(i)
     ops.reset_launch_count()
@@ -741,6 +752,9 @@ def main():
     ap.add_argument("--dp-transport", default="none", choices=("none", "p2p", "nccl", "auto"),
                     help="N>1: 'none' = chunked NCCL all-reduce of the flat gradient buffer "
                          "(default); 'p2p' / 'nccl' = GradBucketer: per-layer buckets during backward")
+    ap.add_argument("--no-dp-overlap", action="store_true",
+                    help="N>1: one all-reduce after backward instead of reducing the stack gradients "
+                         "during the embedding backward")
     ap.add_argument("--dp-skip-exchange", action="store_true",
                     help="DIAGNOSTIC (invalid as a result): N>1 without any gradient exchange")
     ap.add_argument("--bucket-elems", type=int, default=1 << 20)

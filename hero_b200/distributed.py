@@ -72,34 +72,106 @@ class FlatGradExchange:
     """The gradient exchange of `all_reduce_and_rescale_tensors` (utils/distributed.py:19-46) on the
     flat gradient buffer of a FlatParams: mean over ranks, in place, no pack / unpack.
 
-    wire="bf16" (default): the buffer is cast into a persistent bf16 staging buffer, all-reduced
-    there and cast back — half the NVLink bytes of an fp32 exchange (the reference exchanged fp16
+    wire="bf16" (default): ranges are cast into a persistent bf16 staging buffer, all-reduced there
+    and cast back — half the NVLink bytes of an fp32 exchange (the reference exchanged fp16
     gradients under apex O2, train_vcmr.py:234-239); every rank ends with bit-identical fp32
-    values (they are the same bf16 numbers). wire="fp32": one in-place ncclAllReduce(AVG)."""
+    values (they are the same bf16 numbers). wire="fp32": in-place ncclAllReduce(AVG).
 
-    def __init__(self, flat, wire="bf16"):
+    overlap=True: the flat buffer keeps the cross-modal embedding tables (41 % of the bytes, final
+    only when backward ends) at the end of each parameter group (params.is_late_grad). Call
+    `prepare()` before the forward of a step that will be exchanged: when the embedding backward —
+    the last node of the graph — begins, the exchange of everything else is enqueued on a side
+    stream and runs beside it; `all_reduce()` after backward then reduces only the embedding
+    ranges and joins. Without `prepare()` (or if the graph differentiates the stacks in an unusual
+    order) `all_reduce()` reduces the whole buffer, as before."""
+
+    def __init__(self, flat, wire="bf16", overlap=True):
         assert wire in ("bf16", "fp32")
-        self.flat, self.wire = flat, wire
+        self.flat, self.wire, self.overlap = flat, wire, overlap
         g = flat.ensure_flat_grads()
         self.stage = (torch.empty(g.numel(), dtype=torch.bfloat16, device=g.device)
                       if wire == "bf16" else None)
+        self.comm_stream = torch.cuda.Stream(g.device) if (overlap and g.is_cuda) else None
+        self._armed = False
+        self._early_done = None
+        self._n_fwd = self._n_bwd = 0
 
     def describe(self):
-        return (f"one NCCL all-reduce(AVG) of the flat gradient buffer after backward, "
-                f"{self.wire} on the wire")
+        how = ("stack / head gradients all-reduced on a side stream during the embedding "
+               "backward, embedding tables after backward" if self.overlap and self.comm_stream
+               else "one all-reduce of the flat gradient buffer after backward")
+        return f"NCCL all-reduce(AVG), {self.wire} on the wire; {how}"
+
+    # ---- reduction of flat ranges on the current stream ----------------------------------------
+    def _reduce_ranges(self, g, ranges):
+        for a, b in ranges:
+            if b <= a:
+                continue
+            if self.stage is None:
+                _avg_inplace(g[a:b])
+            else:
+                self.stage[a:b].copy_(g[a:b])
+                _avg_inplace(self.stage[a:b])
+                g[a:b].copy_(self.stage[a:b])
+
+    # ---- hook protocol (functional.EXCHANGE_HOOK) ------------------------------------------------
+    def prepare(self):
+        """The gradients of the forward/backward that follows will be exchanged."""
+        from . import functional
+        self._armed = bool(self.overlap and self.comm_stream is not None and size() > 1)
+        self._early_done = None
+        self._n_fwd = self._n_bwd = 0
+        functional.EXCHANGE_HOOK[0] = self if self._armed else None
+
+    def stack_forward(self):
+        self._n_fwd += 1
+
+    def stack_backward(self):
+        self._n_bwd += 1
+
+    def embedding_backward_begins(self):
+        if not self._armed or self._early_done is not None:
+            return
+        if self._n_fwd == 0 or self._n_bwd != self._n_fwd:
+            return          # some stack is still to be differentiated: leave it to all_reduce()
+        g = self.flat.grad_flat
+        cur = torch.cuda.current_stream(g.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.comm_stream.wait_event(ready)
+        with torch.cuda.stream(self.comm_stream):
+            self._reduce_ranges(g, self.flat.early_ranges())
+            done = torch.cuda.Event()
+            done.record(self.comm_stream)
+        self._early_done = done
 
     def all_reduce(self, rescale_denom=1.0):
+        from . import functional
         g = self.flat.ensure_flat_grads()
         if size() > 1:
-            if self.stage is None:
-                _avg_inplace(g)
+            if self._early_done is not None:
+                self._reduce_ranges(g, self.flat.late_ranges())
+                torch.cuda.current_stream(g.device).wait_event(self._early_done)
             else:
-                self.stage.copy_(g)
-                _avg_inplace(self.stage)
-                g.copy_(self.stage)
+                self._reduce_ranges(g, [(0, g.numel())])
+        self._early_done = None
+        self._armed = False
+        functional.EXCHANGE_HOOK[0] = None
         if rescale_denom != 1.0:
             g.div_(rescale_denom)
         return g
+
+    def ranks_agree(self):
+        """True iff every rank holds a bit-identical gradient buffer (collective call)."""
+        g = self.flat.ensure_flat_grads()
+        bits = g.view(torch.int32).to(torch.int64)
+        digest = torch.stack([bits.sum(), (bits * (torch.arange(bits.numel(), device=g.device) % 8191
+                                                   + 1)).sum()])
+        if size() == 1:
+            return True
+        all_d = [torch.empty_like(digest) for _ in range(size())]
+        dist.all_gather(all_d, digest)
+        return all(bool((d == all_d[0]).all()) for d in all_d)
 
     def self_check(self):
         """Known-answer test of the exchange on this job's ranks and transport: rank r fills the
@@ -114,15 +186,7 @@ class FlatGradExchange:
         want = base * ((W + 1) / 2.0)
         tol = (2.0 ** -7 if self.stage is not None else 2.0 ** -20)
         err = float(((g - want).abs() - tol * want.abs()).max().item())
-        bits = g.view(torch.int32).to(torch.int64)
-        digest = torch.stack([bits.sum(), (bits * (torch.arange(bits.numel(), device=g.device) % 8191
-                                                   + 1)).sum()])
-        if W > 1:
-            all_d = [torch.empty_like(digest) for _ in range(W)]
-            dist.all_gather(all_d, digest)
-            same = all(bool((d == all_d[0]).all()) for d in all_d)
-        else:
-            same = True
+        same = self.ranks_agree()
         g.zero_()
         if err > 1e-6 or not same:
             raise RuntimeError(f"gradient all-reduce self-check failed on rank {r}: max excess "

@@ -23,6 +23,11 @@ F32 = torch.float32
 # they use (`expect`), backward passes report parameters whose gradient contribution is complete
 # (`ready`), so the exchange of a layer's gradients overlaps the backward of the layers below.
 GRAD_HOOK = [None]
+# Lighter protocol of distributed.FlatGradExchange(overlap=True): it counts transformer-stack
+# forwards / backwards and is told when the cross-modal embedding backward (the last node of the
+# graph) begins — at that point every gradient outside the embedding tables is final and their
+# all-reduce can run beside the embedding backward.
+EXCHANGE_HOOK = [None]
 
 
 class DropoutState:
@@ -114,6 +119,8 @@ class _TransformerStack(torch.autograd.Function):
         ctx.x = x
         if need_grad and GRAD_HOOK[0] is not None:
             GRAD_HOOK[0].expect(params)
+        if need_grad and EXCHANGE_HOOK[0] is not None:
+            EXCHANGE_HOOK[0].stack_forward()
         return out_f32 if cfg.get("out_f32") else out
 
     @staticmethod
@@ -147,6 +154,8 @@ class _TransformerStack(torch.autograd.Function):
                                         need_dx=(li > 0 or ctx.needs_input_grad[0]), only_layer=li)
                 hook.ready(params[16 * li:16 * li + 16])
         ctx.saved = None
+        if EXCHANGE_HOOK[0] is not None:
+            EXCHANGE_HOOK[0].stack_backward()
         return (dx, None, None) + tuple(ret)
 
 
@@ -278,6 +287,8 @@ class _CrossModalEmbed(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, demb, _demb32=None):
+        if EXCHANGE_HOOK[0] is not None:
+            EXCHANGE_HOOK[0].embedding_backward_begins()
         cfg, st = ctx.cfg, ctx.st
         params = ctx.params
         word, pos, typ, ln_w, ln_b = params[:5]

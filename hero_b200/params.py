@@ -40,8 +40,12 @@ def _ordered_named_params(module):
         placed.add(name)
     # decayed parameters first, then the no-decay set of optim/misc.py:22 (names containing
     # 'bias' / 'LayerNorm.bias' / 'LayerNorm.weight'): the fused AdamW then needs two launches.
-    # Stable sort keeps q/k/v weights (and q/k/v biases) adjacent.
-    out.sort(key=lambda np_: is_no_decay(np_[0]))
+    # Inside each group, the parameters whose gradients only become final at the very end of
+    # backward (the cross-modal embeddings: word / position / type tables, frame projection) go
+    # last, so "everything that is final once the transformer stacks are differentiated" is one
+    # contiguous range per group (distributed.FlatGradExchange reduces it during the embedding
+    # backward). Stable sort keeps q/k/v weights (and q/k/v biases) adjacent.
+    out.sort(key=lambda np_: (is_no_decay(np_[0]), is_late_grad(np_[0])))
     return out
 
 
@@ -50,6 +54,14 @@ NO_DECAY = ("bias", "LayerNorm.bias", "LayerNorm.weight")
 
 def is_no_decay(name):
     return any(nd in name for nd in NO_DECAY)
+
+
+LATE_GRAD = ("f_encoder.embeddings.", "f_encoder.img_embeddings.")
+
+
+def is_late_grad(name):
+    """Parameters differentiated by the LAST backward node (functional._CrossModalEmbed)."""
+    return any(t in name for t in LATE_GRAD)
 
 
 # Every live FlatParams; any torch optimizer step marks their bf16 mirrors stale (global post-step
@@ -128,6 +140,13 @@ class FlatParams:
             # first element of the no-decay block (== total when every parameter decays)
             self.no_decay_start = next((off for (name, _), off in zip(named, offs)
                                         if is_no_decay(name)), total)
+            # [early, late) split of each group: gradients in the "early" ranges are final when
+            # the last transformer stack has been differentiated
+            self.late_start_decay = next((off for (name, _), off in zip(named, offs)
+                                          if not is_no_decay(name) and is_late_grad(name)),
+                                         self.no_decay_start)
+            self.late_start_no_decay = next((off for (name, _), off in zip(named, offs)
+                                             if is_no_decay(name) and is_late_grad(name)), total)
             self.mirror = torch.empty(total, dtype=torch.bfloat16, device=device)
             self.grad_flat = None
             self.dirty = True
@@ -158,6 +177,14 @@ class FlatParams:
         automatically after every `torch.optim.Optimizer.step()` and `load_state_dict`; call it by
         hand after editing weights through `p.data` outside an optimizer."""
         self.dirty = True
+
+    def early_ranges(self):
+        """Flat ranges whose gradients are final before the cross-modal embedding backward."""
+        return [(0, self.late_start_decay), (self.no_decay_start, self.late_start_no_decay)]
+
+    def late_ranges(self):
+        return [(self.late_start_decay, self.no_decay_start),
+                (self.late_start_no_decay, self.total)]
 
     # ------------------------------------------------------------------ views
     def bf16(self, p):

@@ -251,3 +251,54 @@ def test_vsm_video_level_scores_gather_all_ranks():
         got, want = out[r]
         assert torch.allclose(torch.tensor(got), torch.tensor(want), atol=1e-6)
         assert len(got) == 4 and len(got[0]) == 4
+
+
+class _TinyModel(torch.nn.Module):
+    """Parameter names shaped like the encoder's: early (stack) and late (embedding) tensors in
+    both the decay and the no-decay group."""
+
+    def __init__(self):
+        super().__init__()
+        self.f_encoder = torch.nn.Module()
+        self.f_encoder.embeddings = torch.nn.Module()
+        self.f_encoder.embeddings.word_embeddings = torch.nn.Embedding(50, 16)
+        self.f_encoder.embeddings.LayerNorm = torch.nn.LayerNorm(16)
+        self.f_encoder.encoder = torch.nn.Linear(16, 16)
+        self.c_encoder = torch.nn.Linear(16, 8)
+
+
+def _flat_exchange_case(rank, world, hd):
+    from tests import fake_ops
+    from hero_b200 import ops
+    from hero_b200.params import flat_of, is_late_grad
+    ops.cast_bf16 = fake_ops.cast_bf16          # CPU process: no CUDA library
+    torch.manual_seed(0)
+    model = _TinyModel()
+    flat = flat_of(model, torch.device("cpu"))
+    out = {}
+    # layout: the embedding tensors close each group; early + late ranges tile the buffer
+    ranges = sorted(flat.early_ranges() + flat.late_ranges())
+    out["tiles"] = ranges[0][0] == 0 and ranges[-1][1] == flat.total and all(
+        a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    late = [(off, off + n) for name, _, off, n in flat.entries if is_late_grad(name)]
+    out["late_inside"] = all(any(a <= lo and hi <= b for a, b in flat.late_ranges())
+                             for lo, hi in late)
+    early = [(off, off + n) for name, _, off, n in flat.entries if not is_late_grad(name)]
+    out["early_inside"] = all(any(a <= lo and hi <= b for a, b in flat.early_ranges())
+                              for lo, hi in early)
+    for wire in ("fp32", "bf16"):
+        ex = hd.FlatGradExchange(flat, wire=wire, overlap=True)   # CPU: no side stream, plain path
+        g = flat.ensure_flat_grads()
+        base = ((torch.arange(g.numel()) % 31) - 15).float() / 16.0
+        g.copy_(base * (rank + 1))
+        ex.prepare()
+        ex.all_reduce()
+        out[wire] = bool(torch.equal(g, base * 1.5)) and ex.ranks_agree()
+        out[wire + "_check"] = ex.self_check().startswith("ok")
+    return out
+
+
+def test_flat_grad_exchange_layout_and_mean_on_both_wires():
+    out = _run("_flat_exchange_case")
+    for r in (0, 1):
+        assert all(out[r].values()), out[r]

@@ -9,7 +9,7 @@ import torch
 from hero_b200 import ops
 
 dev = torch.device("cuda:0")
-REPS = int(os.environ.get("REPS", "2"))
+REPS = int(os.environ.get("REPS", "1"))
 
 
 def bf(*shape, s=1.0):

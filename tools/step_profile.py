@@ -53,3 +53,22 @@ print(f"| kernel | launches/step | us/step | avg us | share of busy |\n|---|---|
 for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"| `{name}` | {n / steps:.1f} | {us / steps:.1f} | {us / n:.1f} | {100 * us / total:.1f} % |")
 print(f"\nbusy {total / steps:.0f} us/step, wall span {span:.0f} us/step over {steps} steps")
+
+# timeline of the LAST step: kernel start (us since the step's first kernel), duration, gap to the
+# previous kernel's end on the device (idle time if positive and no other stream is busy)
+evs = sorted((ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA),
+             key=lambda ev: ev.time_range.start)
+per = len(evs) // steps
+last = evs[-per:]
+t0 = last[0].time_range.start
+out = os.environ.get("STEP_TIMELINE", "gpurun_out/step_timeline.csv")
+busy_until, idle = t0, 0.0
+with open(out, "w") as f:
+    f.write("start_us,dur_us,idle_before_us,name\n")
+    for ev in last:
+        s, e = ev.time_range.start, ev.time_range.end
+        gap = max(0.0, s - busy_until)
+        idle += gap
+        busy_until = max(busy_until, e)
+        f.write(f"{s - t0:.1f},{e - s:.1f},{gap:.1f},{ev.name.split('(')[0][:80]}\n")
+print(f"last step: {len(last)} kernels, device idle {idle:.0f} us of {busy_until - t0:.0f} us")
