@@ -34,6 +34,8 @@ class GemmArgs(C.Structure):
         ("block_n", C.c_int32), ("k_splits", C.c_int32), ("cta_pair", C.c_int32),
         ("resid_f32", C.c_int32), ("out_f32_store", C.c_int32),
         ("a_lo", C.c_void_p), ("b_lo", C.c_void_p),
+        ("resid_ln_mean", C.c_void_p), ("resid_ln_rstd", C.c_void_p),
+        ("resid_ln_gamma", C.c_void_p), ("resid_ln_beta", C.c_void_p),
     ]
 
 

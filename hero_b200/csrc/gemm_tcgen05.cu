@@ -41,7 +41,10 @@ constexpr int SMEM_LIMIT = 232448;     // 227 KB opt-in dynamic shared memory pe
 
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_GELU_GRAD = 3 };
 enum { OUT_BF16 = 0, OUT_F32_ATOMIC = 1, OUT_F32 = 2 };
-enum { RES_NONE = 0, RES_BF16 = 1, RES_F32 = 2 };
+// RES_F32_LN: the fp32 residual is given in its pre-LayerNorm form — the epilogue applies
+// (r - mean[row]) * rstd[row] * gamma[col] + beta[col] itself, so the LayerNorm kernel that feeds the
+// next GEMM never has to write an fp32 copy of its output
+enum { RES_NONE = 0, RES_BF16 = 1, RES_F32 = 2, RES_F32_LN = 3 };
 
 struct GemmShape {
   int M, N, K;
@@ -54,6 +57,10 @@ struct GemmShape {
 
 struct GemmEpilogue {
   const float* bias;
+  const float* ln_mean;    // RES_F32_LN: per-row statistics and per-column affine of the residual
+  const float* ln_rstd;
+  const float* ln_gamma;
+  const float* ln_beta;
   int has_aux;
   void* out;           // OUT_F32_ATOMIC only
   long long ld_out;
@@ -72,12 +79,13 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers
   // slab width in columns: 128-byte rows of the element type that travels
-  static constexpr int W = (OUT == OUT_F32 || RES == RES_F32) ? 32 : 64;
+  static constexpr int W = (OUT == OUT_F32 || RES == RES_F32 || RES == RES_F32_LN) ? 32 : 64;
   // staging slabs per epilogue warp: output (double buffered; the GELU / ReLU kernels, which also
   // store a second tensor, use one slab per tensor), residual operand
   static constexpr int AUX = (ACT == ACT_GELU || ACT == ACT_RELU) ? 1 : 0;
   static constexpr int N_RES_BUF = RES ? 1 : 0;
-  static constexpr int BIAS_BYTES = NUM_EPI_WARPS * 64 * 4;    // warp-private bias slices
+  // warp-private per-column slices: bias (64 floats) + residual-LayerNorm gamma, beta (32 + 32)
+  static constexpr int BIAS_BYTES = NUM_EPI_WARPS * 128 * 4;
   static constexpr int BAR_BYTES = 512;
   static constexpr int stages_with(int slabs_per_warp) {
     return (SMEM_LIMIT - NUM_EPI_WARPS * slabs_per_warp * SLAB_BYTES - BIAS_BYTES - BAR_BYTES) /
@@ -303,7 +311,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint8_t* out_slab = stage0;                                            // N_OUT_BUF slabs
     uint8_t* aux_slab = stage0 + Cfg::N_OUT_BUF * SLAB_BYTES;             // AUX slab
     uint8_t* res_slab = stage0 + (Cfg::N_OUT_BUF + Cfg::AUX) * SLAB_BYTES;
-    float* bias_w = reinterpret_cast<float*>(smem + Cfg::BIAS_OFFSET) + ew * 64;
+    float* bias_w = reinterpret_cast<float*>(smem + Cfg::BIAS_OFFSET) + ew * 128;
+    float* gamma_w = bias_w + 64;
+    float* beta_w = bias_w + 96;
     uint64_t* my_res_bar = &res_bar[ew];
     const bool has_aux = Cfg::AUX && e.has_aux;
     const bool has_bias = (e.bias != nullptr);
@@ -343,8 +353,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tma_load_2d(res_slab, &tmap_res, my_res_bar, slab_col0(ntile, nc), slab_row0(ntile));
       }
     };
+    auto fetch_affine = [&]() -> float2 {      // (gamma, beta) of this lane's column of the next slab
+      float2 gb = make_float2(0.f, 0.f);
+      if (RES == RES_F32_LN && ntile < total_tiles) {
+        const int col = slab_col0(ntile, nc) + lane;
+        if (col < s.N) gb = make_float2(__ldg(e.ln_gamma + col), __ldg(e.ln_beta + col));
+      }
+      return gb;
+    };
     skip_invalid();
     float2 bias_next = fetch_bias();
+    float2 affine_next = fetch_affine();
     request_res();
     uint32_t res_phase = 0;
     uint32_t out_it = 0;
@@ -356,6 +375,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int row0 = slab_row0(tile);
       const int row = row0 + lane;
       const bool row_ok = row < s.M;
+      float ln_scale = 0.f, ln_shift = 0.f;      // (r - mean) * rstd = r * rstd - mean * rstd
+      if (RES == RES_F32_LN && row_ok) {
+        ln_scale = __ldg(e.ln_rstd + row);
+        ln_shift = -__ldg(e.ln_mean + row) * ln_scale;
+      }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(row_off) << 16);
@@ -368,15 +392,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tmem_ld_32x32(t_addr + c * W, r[0]);
         if (W == 64) tmem_ld_32x32(t_addr + c * W + 32, r[W / 32 - 1]);
         // this slab's bias slice -> warp-private smem; then look one slab ahead
-        if (has_bias) {
-          __syncwarp();     // the previous slab's broadcast reads of bias_w are done
+        if (has_bias || RES == RES_F32_LN) {
+          __syncwarp();     // the previous slab's broadcast reads of the slices are done
           if (W == 64) *reinterpret_cast<float2*>(bias_w + 2 * lane) = bias_next;
           else bias_w[lane] = bias_next.x;
+          if (RES == RES_F32_LN) {
+            gamma_w[lane] = affine_next.x;
+            beta_w[lane] = affine_next.y;
+          }
           __syncwarp();
         }
         nc += 2;
         skip_invalid();
         bias_next = fetch_bias();
+        affine_next = fetch_affine();
         // residual / saved-derivative slab (requested one slab ago) -> registers; its smem slab is
         // then free for the next request
         uint4 opnd[8];
@@ -466,6 +495,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int g = 0; g < 8; ++g) {
             v[4 * g] += __uint_as_float(opnd[g].x); v[4 * g + 1] += __uint_as_float(opnd[g].y);
             v[4 * g + 2] += __uint_as_float(opnd[g].z); v[4 * g + 3] += __uint_as_float(opnd[g].w);
+          }
+        } else if constexpr (RES == RES_F32_LN) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 ga = *reinterpret_cast<const float4*>(gamma_w + g * 4);
+            const float4 be = *reinterpret_cast<const float4*>(beta_w + g * 4);
+            v[4 * g] += fmaf(fmaf(__uint_as_float(opnd[g].x), ln_scale, ln_shift), ga.x, be.x);
+            v[4 * g + 1] += fmaf(fmaf(__uint_as_float(opnd[g].y), ln_scale, ln_shift), ga.y, be.y);
+            v[4 * g + 2] += fmaf(fmaf(__uint_as_float(opnd[g].z), ln_scale, ln_shift), ga.z, be.z);
+            v[4 * g + 3] += fmaf(fmaf(__uint_as_float(opnd[g].w), ln_scale, ln_shift), ga.w, be.w);
           }
         } else if constexpr (RES == RES_BF16 && ACT != ACT_GELU_GRAD) {
 #pragma unroll
@@ -694,6 +733,8 @@ static int dispatch(const hero_gemm_args* g, const GemmMaps& tm, const GemmShape
   if (g->out_f32_store) {
     // the residual stream: fp32 pre-LayerNorm sums (forward out-projection / FFN-down)
     if (layout == 0 && g->act == ACT_NONE) {
+      if (res && g->resid_ln_mean)
+        return launch<BLOCK_N, 0, 0, ACT_NONE, OUT_F32, CTA2, RES_F32_LN>(tm, s, e, st);
       if (res) return launch<BLOCK_N, 0, 0, ACT_NONE, OUT_F32, CTA2, RES_F32>(tm, s, e, st);
       return launch<BLOCK_N, 0, 0, ACT_NONE, OUT_F32, CTA2, RES_NONE>(tm, s, e, st);
     }
@@ -859,8 +900,13 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   // as CTA pairs.
   const bool pair_auto = g->m > 128 &&
                          (g->out_f32_accumulate || m_blocks * ceil_div(g->n, 256) >= sms);
-  const bool pair = (block_n == 256) && (g->cta_pair == 2 || (g->cta_pair == 0 && pair_auto));
-  if (relu_res && block_n == 256 && !pair) block_n = 128;
+  bool pair = (block_n == 256) && (g->cta_pair == 2 || (g->cta_pair == 0 && pair_auto));
+  // relu + residual + saved pre-activation stages three slabs per warp: no room for a pipeline in
+  // the single-CTA 128 x 256 configuration -> CTA pairs (32 KB stages) when there are two row
+  // blocks to pair and pairs were not ruled out, else 128-wide tiles
+  if (relu_res && block_n == 256 && !pair) {
+    if (g->m > 128 && g->cta_pair != 1) pair = true; else block_n = 128;
+  }
 
   GemmShape s;
   s.M = g->m; s.N = g->n; s.K = g->k;
@@ -898,6 +944,14 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
 
   GemmEpilogue e;
   e.bias = g->bias;
+  e.ln_mean = g->resid_ln_mean;
+  e.ln_rstd = g->resid_ln_rstd;
+  e.ln_gamma = g->resid_ln_gamma;
+  e.ln_beta = g->resid_ln_beta;
+  if (g->resid_ln_mean || g->resid_ln_rstd || g->resid_ln_gamma || g->resid_ln_beta)
+    HERO_REQUIRE(g->resid && g->resid_f32 && g->resid_ln_mean && g->resid_ln_rstd &&
+                     g->resid_ln_gamma && g->resid_ln_beta,
+                 "a LayerNorm-form residual needs an fp32 resid and all four of mean/rstd/gamma/beta");
   e.has_aux = g->aux_out != nullptr;
   e.out = g->out;
   e.ld_out = g->ld_out;

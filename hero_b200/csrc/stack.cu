@@ -33,6 +33,13 @@ struct Gemm {
   Gemm& resid_f32(const float* p, long long ld) {
     g.resid = p; g.ld_resid = ld; g.resid_f32 = 1; g.out_f32_store = 1; return *this;
   }
+  // ... with the residual given as a pre-LayerNorm sum + its statistics and affine parameters
+  Gemm& resid_ln(const float* sum, long long ld, const float* mean, const float* rstd,
+                 const float* gamma, const float* beta) {
+    resid_f32(sum, ld);
+    g.resid_ln_mean = mean; g.resid_ln_rstd = rstd; g.resid_ln_gamma = gamma; g.resid_ln_beta = beta;
+    return *this;
+  }
   Gemm& act(int a) { g.act = a; return *this; }
   Gemm& aux_out(void* p, long long ld) { g.aux_out = p; g.ld_aux_out = ld; return *this; }
   Gemm& aux_in(const void* p, long long ld) { g.aux_in = p; g.ld_aux_in = ld; return *this; }
@@ -118,25 +125,31 @@ extern "C" int hero_bert_stack_fwd(const hero_stack_args* s, void* stream) {
   const int M = s->n_tok, H = s->hidden, I = s->inter;
   const float scale = 0.125f;
   const void* h = s->x;          // bf16: GEMM operand
-  const float* h32 = s->x_f32;   // fp32: residual
   for (int l = 0; l < s->n_layers; ++l) {
     const hero_layer_weights& W = s->weights[l];
     const hero_layer_acts& A = s->acts[l];
-    HERO_REQUIRE(A.s1 && A.s2 && A.a_f32 && A.out_f32, "stack fwd: layer %d misses fp32 buffers", l);
+    HERO_REQUIRE(A.s1 && A.s2, "stack fwd: layer %d misses its fp32 pre-LayerNorm buffers", l);
     HERO_TRY(Gemm(h, H, 0, W.wqkv, H, 0, M, 3 * H, H, A.qkv, 3 * H).bias(W.bqkv).run(stream));
     HERO_TRY(hero_attn_fwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, A.lse, M,
                            s->n_tiles, s->n_long, s->max_long, s->heads, 64, scale,
                            s->attn_drop_threshold,
                            site_key(s->drop_key, s->first_layer + l, 0), s->attn_drop_scale, stream));
-    HERO_TRY(Gemm(A.cx, H, 0, W.wo, H, 0, M, H, H, A.s1, H)
-                 .bias(W.bo)
-                 .resid_f32(h32, H)
-                 .drop(s->hidden_drop_threshold, site_key(s->drop_key, s->first_layer + l, 1), s->hidden_drop_scale)
-                 .run(stream));
+    // residual of the attention block = this layer's input in fp32: the caller's fp32 copy for
+    // layer 0, LayerNorm(previous layer's s2) recomputed in the epilogue afterwards
+    Gemm outp(A.cx, H, 0, W.wo, H, 0, M, H, H, A.s1, H);
+    outp.bias(W.bo).drop(s->hidden_drop_threshold, site_key(s->drop_key, s->first_layer + l, 1),
+                         s->hidden_drop_scale);
+    if (l == 0) {
+      outp.resid_f32(s->x_f32, H);
+    } else {
+      const hero_layer_acts& P = s->acts[l - 1];
+      const hero_layer_weights& PW = s->weights[l - 1];
+      outp.resid_ln(P.s2, H, P.mean2, P.rstd2, PW.ln2_g, PW.ln2_b);
+    }
+    HERO_TRY(outp.run(stream));
     hero_ln_args ln;
     ln_base(&ln, A.s1, W.ln1_g, W.ln1_b, s->eps, M, H, A.mean1, A.rstd1);
     ln.y = A.a;
-    ln.y_f32 = A.a_f32;
     HERO_TRY(hero_ln_fwd(&ln, stream));
     Gemm up(A.a, H, 0, W.w1, H, 0, M, I, H, A.f, I);
     up.bias(W.b1).act(ACT_GELU);
@@ -144,15 +157,14 @@ extern "C" int hero_bert_stack_fwd(const hero_stack_args* s, void* stream) {
     HERO_TRY(up.run(stream));
     HERO_TRY(Gemm(A.f, I, 0, W.w2, I, 0, M, H, I, A.s2, H)
                  .bias(W.b2)
-                 .resid_f32(A.a_f32, H)
+                 .resid_ln(A.s1, H, A.mean1, A.rstd1, W.ln1_g, W.ln1_b)
                  .drop(s->hidden_drop_threshold, site_key(s->drop_key, s->first_layer + l, 2), s->hidden_drop_scale)
                  .run(stream));
     ln_base(&ln, A.s2, W.ln2_g, W.ln2_b, s->eps, M, H, A.mean2, A.rstd2);
     ln.y = A.out;
-    ln.y_f32 = A.out_f32;
+    ln.y_f32 = A.out_f32;      // NULL except where the caller wants the fp32 result (last layer)
     HERO_TRY(hero_ln_fwd(&ln, stream));
     h = A.out;
-    h32 = A.out_f32;
   }
   return HERO_OK;
 }

@@ -88,7 +88,7 @@ def drop_params(p, key):
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None, resid=None,
          aux_in=None, aux_out=None, act=ACT_NONE, accumulate_f32=False, drop=(0, 0, 1.0),
-         block_n=0, k_splits=0, cta_pair=0, a_lo=None, b_lo=None):
+         block_n=0, k_splits=0, cta_pair=0, a_lo=None, b_lo=None, resid_ln=None):
     """out = epilogue(A·B) with the operand conventions of `hero_gemm_args`.
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True) bf16; b: [N,K] (b_mn=False) or [K,N] (b_mn=True).
@@ -132,6 +132,12 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None
         assert a_lo.shape == a.shape and a_lo.stride() == a.stride()
         assert b_lo.shape == b.shape and b_lo.stride() == b.stride()
         g.a_lo, g.b_lo = _ptr(a_lo), _ptr(b_lo)
+    if resid_ln is not None:     # (mean[m], rstd[m], gamma[n], beta[n]): resid is a pre-LN fp32 sum
+        assert resid is not None and resid.dtype == torch.float32
+        for t in resid_ln:
+            assert t.dtype == torch.float32 and t.is_contiguous()
+        (g.resid_ln_mean, g.resid_ln_rstd, g.resid_ln_gamma,
+         g.resid_ln_beta) = (_ptr(t) for t in resid_ln)
     _count()
     _lib.check(_lib.lib().hero_gemm_bf16(C.byref(g), _stream()))
     return out
@@ -260,7 +266,7 @@ def _stack_layout(M, H, inter, save):
     """Byte offsets of one layer's activations inside the workspace slot."""
     sizes = {"qkv": M * 3 * H * 2, "cx": M * H * 2, "lse": M * (H // 64) * 4 if save else 0,
              "s1": M * H * 4, "mean1": M * 4,
-             "rstd1": M * 4, "a": M * H * 2, "a_f32": M * H * 4,
+             "rstd1": M * 4, "a": M * H * 2, "a_f32": 0,
              "pre": M * inter * 2 if save else 0,
              "f": M * inter * 2, "s2": M * H * 4, "mean2": M * 4, "rstd2": M * 4,
              "out": M * H * 2, "out_f32": M * H * 4}
@@ -325,7 +331,10 @@ def bert_stack_fwd(x, layers, att, *, heads, eps, drop, save, x_f32=None):
     act_ptrs = []
     for i in range(n):
         b = base + (i if save else i % 2) * slot
-        act_ptrs.append([None if (k in ("pre", "lse") and not save) else b + offs[k]
+        # a_f32 is never materialised (the FFN-down epilogue recomputes LayerNorm(s1) in fp32);
+        # out_f32 only for the last layer (the stack's fp32 result)
+        act_ptrs.append([None if ((k in ("pre", "lse") and not save) or k == "a_f32" or
+                                  (k == "out_f32" and i != n - 1)) else b + offs[k]
                          for k in _ACT_FIELDS])
     s, keep = _stack_struct(x, layers, att, heads, eps, drop, act_ptrs, x_f32)
     _count(_STACK_FWD_LAUNCHES * n)

@@ -110,6 +110,14 @@ typedef struct hero_gemm_args {
    * bf16 operands, which alone costs 4e-2 relative error in that layer's gradients. */
   const void* a_lo;
   const void* b_lo;
+  /* LayerNorm-form residual (all four or none; needs resid_f32): the value added is
+   *   (resid[m,n] - resid_ln_mean[m]) * resid_ln_rstd[m] * resid_ln_gamma[n] + resid_ln_beta[n],
+   * i.e. LayerNorm(resid) in fp32, recomputed here from the pre-LayerNorm sum and the statistics
+   * the LayerNorm kernel saved — the residual stream then needs no fp32 copy of LayerNorm outputs. */
+  const float* resid_ln_mean;
+  const float* resid_ln_rstd;
+  const float* resid_ln_gamma;
+  const float* resid_ln_beta;
 } hero_gemm_args;
 
 int hero_gemm_bf16(const hero_gemm_args* args, void* stream);
@@ -276,14 +284,16 @@ typedef struct hero_layer_acts { /* bf16 unless noted; [n_tok, ...] */
   float* mean1;
   float* rstd1;
   void* a;      /* LN(s1), bf16: operand of the FFN-up GEMM and of its weight gradient */
-  float* a_f32; /* LN(s1), f32: residual input of the FFN-down epilogue */
+  float* a_f32; /* unused (NULL): the FFN-down epilogue recomputes LN(s1) in fp32 from s1, mean1,
+                   rstd1 and the LayerNorm parameters (hero_gemm_args.resid_ln_*) */
   void* pre;    /* gelu'(FFN pre-activation) [n_tok, I], saved for the backward; NULL in inference */
   void* f;      /* gelu(pre) [n_tok, I] */
   float* s2;    /* f32 pre-LN sum after the FFN */
   float* mean2;
   float* rstd2;
   void* out;    /* LN(s2), bf16: the layer output as the next layer's GEMM operand */
-  float* out_f32; /* LN(s2), f32: the layer output as the next layer's residual */
+  float* out_f32; /* LN(s2), f32: written only when non-NULL (the caller wants the stack's result in
+                     fp32: last layer); the next layer's residual is recomputed from s2 */
 } hero_layer_acts;
 
 typedef struct hero_layer_grads { /* fp32, accumulated */

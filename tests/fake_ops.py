@@ -16,7 +16,7 @@ def _ck_drop(drop):
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None, resid=None,
          aux_in=None, aux_out=None, act=0, accumulate_f32=False, drop=(0, 0, 1.0), block_n=0,
-         k_splits=0, cta_pair=0, a_lo=None, b_lo=None):
+         k_splits=0, cta_pair=0, a_lo=None, b_lo=None, resid_ln=None):
     _ck_drop(drop)
     A = a.float().t() if a_mn else a.float()
     B = b.float() if b_mn else b.float().t()
@@ -40,7 +40,10 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None
         v = torch.relu(v)
     elif act == 3:
         v = v * aux_in.float()
-    if resid is not None:
+    if resid is not None and resid_ln is not None:
+        mu, rs, ga, be = resid_ln
+        v = v + (resid - mu[:, None]) * rs[:, None] * ga + be
+    elif resid is not None:
         v = v + resid.float()
     if accumulate_f32:
         out.add_(v)

@@ -541,3 +541,25 @@ def test_split_bf16_gemm_and_ln_low_half():
     ops.gemm(hi, w_hi, out, bias=bias, act=ops.ACT_RELU, resid=resid, aux_out=pre1)
     flips1 = ((pre1.float() > 0) != (ref_pre > 0)).float().mean().item()
     assert flips1 > 5 * max(flips, 1e-6), (flips1, flips)
+
+
+@pytest.mark.parametrize("block_n,cta_pair", [(128, 1), (256, 1), (256, 2)])
+def test_gemm_layernorm_form_residual(block_n, cta_pair):
+    """The residual handed over as a pre-LayerNorm fp32 sum + (mean, rstd, gamma, beta): the
+    epilogue adds LayerNorm(resid) computed in fp32 — what the separate fp32 LayerNorm output
+    would have been, without that tensor ever existing."""
+    from hero_b200 import ops, _lib
+    import ctypes as C
+    m, n, k = 3333, 768, 3072
+    a, w = _rand((m, k), seed=150), _rand((n, k), 0.03, seed=151)
+    bias = _rand((n,), 0.5, seed=152, dtype=torch.float32)
+    pre = _rand((m, n), 2.0, seed=153, dtype=torch.float32)
+    gamma = 1.0 + 0.1 * _rand((n,), 1.0, seed=154, dtype=torch.float32)
+    beta = _rand((n,), 0.2, seed=155, dtype=torch.float32)
+    mean = pre.mean(-1)
+    rstd = torch.rsqrt(pre.var(-1, unbiased=False) + 1e-12)
+    out = torch.full((m, n), float("nan"), dtype=torch.float32, device=_dev())
+    ops.gemm(a, w, out, bias=bias, resid=pre, resid_ln=(mean, rstd, gamma, beta), block_n=block_n,
+             cta_pair=cta_pair)
+    ref = a.float() @ w.float().t() + bias + torch.nn.functional.layer_norm(pre, (n,), gamma, beta, 1e-12)
+    _close(out, ref, 2e-3, 1e-4, f"LayerNorm-form residual bn{block_n} pair{cta_pair}")

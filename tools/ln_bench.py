@@ -47,3 +47,17 @@ for M in (16512, 3200):
     print(f"M={M}: ln_fwd {t_f:.1f} us ({2 * by / t_f:.2f} TB/s)  ln_bwd rows {t_b:.1f} us "
           f"({4 * by / t_b:.2f} TB/s)  rows+params {t_p:.1f} us  colsum {t_c:.1f} us "
           f"({by / t_c:.2f} TB/s)")
+
+    # fp32 pre-LayerNorm sums (the residual stream of the transformer layers)
+    xs32 = [x.float() for x in xs[:6]]
+    y32 = torch.empty(M, H, device=dev)
+    R2 = len(xs32)
+    t_f = timeit(lambda i: ops.ln_fwd(xs32[i % R2], g, b, 1e-12, ys[i % R], n_rows=M, mean=mean,
+                                      rstd=rstd))
+    t_f2 = timeit(lambda i: ops.ln_fwd(xs32[i % R2], g, b, 1e-12, ys[i % R], n_rows=M, mean=mean,
+                                       rstd=rstd, y_f32=y32))
+    t_p = timeit(lambda i: ops.ln_bwd(dys[i % R], xs32[i % R2], g, mean, rstd, n_rows=M,
+                                      dx=dxs[i % R], dx_drop=dxd[i % R], drop2=drop, dgamma=dg,
+                                      dbeta=db, dbias=dbias))
+    print(f"M={M} fp32 rows: ln_fwd {t_f:.1f} us ({3 * by / t_f:.2f} TB/s)  +fp32 copy {t_f2:.1f} us "
+          f"({5 * by / t_f2:.2f} TB/s)  ln_bwd rows+params {t_p:.1f} us ({5 * by / t_p:.2f} TB/s)")
