@@ -135,6 +135,11 @@ def _declare(lib):
     sig("hero_adamw_step", vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp, f32, vp)
     sig("hero_sumsq_f32", vp, i64, vp, vp)
     sig("hero_reduce_slots_f32", vp, vp, i32, i64, i64, f32, i32, vp)
+    sig("hero_l2norm_split_f32", vp, i64, i32, f32, vp, vp, vp, vp)
+    sig("hero_vsm_masked_max", vp, i64, vp, i32, i32, i32, vp, vp, vp)
+    sig("hero_vsm_scores_bwd", vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp)
+    sig("hero_vsm_span_fwd", vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp)
+    sig("hero_vsm_span_bwd", vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp)
 
 
 def lib():

@@ -606,11 +606,20 @@ class VsmAllgather(torch.autograd.Function):
     gradient that corresponds to its own rows (no reduction)."""
 
     @staticmethod
-    def forward(ctx, tensor, name=None):
+    def forward(ctx, tensor, name=None, equal_counts=False):
         ctx.span = (0, tensor.shape[0])
         if size() == 1:
             return tensor
         tensor = tensor.contiguous()
+        if equal_counts:
+            # every rank contributes tensor.shape[0] rows (stated by the caller): one collective
+            # into a preallocated block, nothing read back to the host
+            n0 = tensor.shape[0]
+            out = torch.empty((n0 * size(),) + tuple(tensor.shape[1:]), dtype=tensor.dtype,
+                              device=tensor.device)
+            dist.all_gather_into_tensor(out, tensor)
+            ctx.span = (rank() * n0, (rank() + 1) * n0)
+            return out
         n = torch.tensor([tensor.shape[0]], dtype=torch.int64, device=tensor.device)
         counts = [torch.zeros_like(n) for _ in range(size())]
         dist.all_gather(counts, n)
@@ -633,7 +642,7 @@ class VsmAllgather(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_output):
         a, b = ctx.span
-        return grad_output[a:b], None
+        return grad_output[a:b], None, None
 
 
 vsm_allgather = VsmAllgather.apply

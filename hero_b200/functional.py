@@ -484,3 +484,82 @@ def gather_rows(src, idx, inv_idx):
     """`inv_idx[j]` = the i with idx[i] == j (or -1): both maps are injective here. bf16 or fp32
     rows (the output has the dtype of `src`)."""
     return _GatherRows.apply(src, idx, inv_idx)
+
+
+# ---------------------------------------------------------------------------------------------
+class _VsmVideoScores(torch.autograd.Function):
+    """(Nq, Nv) = max over a clip's valid frames of the cosine of every query with every frame
+    (model/pretrain.py:364-413 after the cross-rank gather): l2norm (split-bf16) -> tcgen05 GEMM
+    q^ . c^ with split-bf16 operands -> masked max; backward through the arg-max frames."""
+
+    @staticmethod
+    def forward(ctx_, q, frames, mask):
+        nq, d = q.shape
+        nv, length, _ = frames.shape
+        dev = q.device
+        q = q.float().contiguous()
+        c = frames.float().contiguous().view(nv * length, d)
+        rows_c = (nv * length + 7) // 8 * 8          # GEMM N must be a multiple of 8
+        q_hi, q_lo = _empty((nq, d), q), _empty((nq, d), q)
+        c_hi = torch.zeros((rows_c, d), dtype=BF16, device=dev)
+        c_lo = torch.zeros((rows_c, d), dtype=BF16, device=dev)
+        q_inv = torch.empty(nq, dtype=F32, device=dev)
+        c_inv = torch.empty(nv * length, dtype=F32, device=dev)
+        ops.l2norm_split(q, q_hi, q_lo, q_inv)
+        ops.l2norm_split(c, c_hi, c_lo, c_inv)
+        s = torch.empty((nq, rows_c), dtype=F32, device=dev)
+        ops.gemm(q_hi, c_hi, s, a_lo=q_lo, b_lo=c_lo)
+        mask_u8 = (mask != 0).to(torch.uint8).contiguous()
+        scores = torch.empty((nq, nv), dtype=F32, device=dev)
+        argmax = torch.empty((nq, nv), dtype=torch.int32, device=dev)
+        ops.vsm_masked_max(s, mask_u8, nq, nv, length, scores, argmax)
+        ctx_.st = (q_hi, q_lo, q_inv, c_hi, c_lo, c_inv, mask_u8, argmax, (nq, nv, length, d))
+        ctx_.in_dtypes = (q.dtype, frames.dtype)
+        return scores
+
+    @staticmethod
+    def backward(ctx_, g):
+        q_hi, q_lo, q_inv, c_hi, c_lo, c_inv, mask_u8, argmax, (nq, nv, length, d) = ctx_.st
+        need_q, need_c = ctx_.needs_input_grad[0], ctx_.needs_input_grad[1]
+        dq = torch.empty((nq, d), dtype=F32, device=g.device) if need_q else None
+        dc = torch.empty((nv, length, d), dtype=F32, device=g.device) if need_c else None
+        ops.vsm_scores_bwd(g.float().contiguous(), argmax, mask_u8, q_hi, q_lo, q_inv, c_hi, c_lo,
+                           c_inv, nq, nv, length, d, dq, dc)
+        return dq, dc, None
+
+
+def vsm_video_scores(q, frames, mask):
+    return _VsmVideoScores.apply(q, frames, mask)
+
+
+class _VsmSpanLogits(torch.autograd.Function):
+    """Start / end logits of each query against its own clip (model/pretrain.py:128-166, non-cross
+    form): per-frame similarity + two width-K convolutions + mask_logits, one kernel each way."""
+
+    @staticmethod
+    def forward(ctx_, query, frames, mask, w_st, w_ed):
+        n, length, d = frames.shape
+        dev = frames.device
+        query = query.float().contiguous()
+        frames = frames.float().contiguous()
+        ws, we = w_st.float().reshape(-1).contiguous(), w_ed.float().reshape(-1).contiguous()
+        mask_u8 = (mask != 0).to(torch.uint8).contiguous()
+        sim = torch.empty((n, length), dtype=F32, device=dev)
+        st, ed = torch.empty_like(sim), torch.empty_like(sim)
+        ops.vsm_span_fwd(query, frames, mask_u8, ws, we, sim, st, ed)
+        ctx_.st = (query, frames, mask_u8, ws, we, sim)
+        ctx_.w_shape = tuple(w_st.shape)
+        return st, ed
+
+    @staticmethod
+    def backward(ctx_, dst, ded):
+        query, frames, mask_u8, ws, we, sim = ctx_.st
+        dquery, dframes = torch.empty_like(query), torch.empty_like(frames)
+        dws, dwe = torch.zeros_like(ws), torch.zeros_like(we)
+        ops.vsm_span_bwd(dst.float().contiguous(), ded.float().contiguous(), mask_u8, ws, we, sim,
+                         query, frames, dquery, dframes, dws, dwe)
+        return dquery, dframes, None, dws.view(ctx_.w_shape), dwe.view(ctx_.w_shape)
+
+
+def vsm_span_logits(query, frames, mask, w_st, w_ed):
+    return _VsmSpanLogits.apply(query, frames, mask, w_st, w_ed)

@@ -93,6 +93,7 @@ class HierarchicalVlModel(VideoPreTrainedModel):
         self.c_encoder = TemporalTrm(config.c_config)
         self.feat_regress = FrameFeatureRegression(config.f_config.hidden_size, vfeat_dim)
         self.nce_temp = nce_temp
+        self.max_clip_len = max_clip_len
         self.mask_embedding = nn.Embedding(2, vfeat_dim, padding_idx=0)
         self.fom_output = MLPLayer(config.c_config.hidden_size, max_clip_len)
         self.register_buffer("pad", torch.zeros(8, config.c_config.hidden_size))

@@ -470,3 +470,58 @@ def sumsq(x, out):
     _count()
     _lib.check(_lib.lib().hero_sumsq_f32(_ptr(x), x.numel(), _ptr(out), _stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# VSM / moment-retrieval head (hero_b200/csrc/vsm.cu)
+def l2norm_split(x, hi, lo, inv, eps=1e-5):
+    """Rows of x (fp32 [R, d]) L2-normalised (F.normalize, eps clamp) into split-bf16 halves;
+    inv[r] = 1 / max(|x_r|, eps) (negative where clamped). hi / lo may have more rows than x."""
+    _require_cuda(x, hi, lo, inv)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    assert hi.dtype == BF16 and lo.dtype == BF16 and hi.shape[1] == x.shape[1]
+    _count()
+    _lib.check(_lib.lib().hero_l2norm_split_f32(_ptr(x), x.shape[0], x.shape[1], eps, _ptr(hi),
+                                                _ptr(lo), _ptr(inv), _stream()))
+
+
+def vsm_masked_max(s, mask_u8, nq, nv, length, scores, argmax):
+    _require_cuda(s, mask_u8, scores, argmax)
+    assert s.dtype == torch.float32 and mask_u8.dtype == torch.uint8 and argmax.dtype == torch.int32
+    _count()
+    _lib.check(_lib.lib().hero_vsm_masked_max(_ptr(s), s.stride(0), _ptr(mask_u8), nq, nv, length,
+                                              _ptr(scores), _ptr(argmax), _stream()))
+
+
+def vsm_scores_bwd(g, argmax, mask_u8, q_hi, q_lo, q_inv, c_hi, c_lo, c_inv, nq, nv, length, d,
+                   dq, dctx):
+    _require_cuda(g, argmax, mask_u8)
+    assert g.dtype == torch.float32 and g.is_contiguous()
+    _count(2)
+    _lib.check(_lib.lib().hero_vsm_scores_bwd(_ptr(g), _ptr(argmax), _ptr(mask_u8), _ptr(q_hi),
+                                              _ptr(q_lo), _ptr(q_inv), _ptr(c_hi), _ptr(c_lo),
+                                              _ptr(c_inv), nq, nv, length, d, _ptr(dq), _ptr(dctx),
+                                              _stream()))
+
+
+def vsm_span_fwd(query, ctx, mask_u8, w_st, w_ed, sim, st, ed):
+    _require_cuda(query, ctx, mask_u8, sim, st, ed)
+    n, length, d = ctx.shape
+    for t in (query, ctx, w_st, w_ed):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    _count()
+    _lib.check(_lib.lib().hero_vsm_span_fwd(_ptr(query), _ptr(ctx), _ptr(mask_u8), _ptr(w_st),
+                                            _ptr(w_ed), n, length, d, w_st.numel(), _ptr(sim),
+                                            _ptr(st), _ptr(ed), _stream()))
+
+
+def vsm_span_bwd(dst, ded, mask_u8, w_st, w_ed, sim, query, ctx, dquery, dctx, dw_st, dw_ed):
+    _require_cuda(dst, ded, query, ctx)
+    n, length, d = ctx.shape
+    for t in (dst, ded, sim, query, ctx, w_st, w_ed):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    _count()
+    _lib.check(_lib.lib().hero_vsm_span_bwd(_ptr(dst), _ptr(ded), _ptr(mask_u8), _ptr(w_st),
+                                            _ptr(w_ed), _ptr(sim), _ptr(query), _ptr(ctx), n, length,
+                                            d, w_st.numel(), _ptr(dquery), _ptr(dctx), _ptr(dw_st),
+                                            _ptr(dw_ed), _stream()))

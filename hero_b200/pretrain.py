@@ -10,8 +10,12 @@ classes, so `train_vcmr.py` / `pretrain.py` and their checkpoints keep working. 
 * the cross-rank gather of queries / clips for in-batch negatives uses torch.distributed
   (`distributed.vsm_allgather`, same forward/backward contract as the Horovod-based
   `VsmAllgather`, model/pretrain.py:427-451);
-* the head itself (query pooling, span convolutions, masked max, ranking losses) is small —
-  32 queries x 32 clips x 100 frames per step — and stays in torch on the encoder's device.
+* the head's device work after the query pooling is fused (hero_b200/csrc/vsm.cu): the
+  video-level scores are l2norm -> split-bf16 tcgen05 GEMM -> masked max (3 launches forward, 2
+  backward, instead of ~15 + ~25 torch kernels), the span logits one kernel each way; nothing in
+  the training-mode forward reads a value back to the host (clips are padded to `max_clip_len`
+  for the cross-rank gather instead of exchanging lengths; equal per-rank query / clip counts are
+  a stated requirement, `gather_equal_counts`). The ranking losses (two small sorts) stay torch.
 
 Known deviation: hero_b200 returns ZEROS at padded frame positions (packed layout), the reference
 returns what its transformer computed there. The width-5 span convolutions reach two frames past
@@ -27,6 +31,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from . import distributed as hdist
+from . import functional as Fn
 from .encoder import QueryFeatEncoder
 from .layers import mask_logits
 from .model import HeroModel
@@ -48,6 +53,10 @@ class HeroForPretraining(HeroModel):
         self.use_all_neg = use_all_neg
         self.drop_svmr_prob = drop_svmr_prob
         self.gather_gpus = True       # in-batch negatives from every rank while training
+        # every rank contributes the same number of queries / clips per step (drop_last loaders):
+        # the cross-rank gather then needs no count exchange and no host sync. Set False for
+        # ragged last batches (falls back to the reference's count exchange, one sync per gather).
+        self.gather_equal_counts = True
         self.video_query_linear = nn.Linear(config.q_config.hidden_size,
                                             config.c_config.hidden_size)
         conv = dict(in_channels=1, out_channels=1, kernel_size=conv_kernel_size,
@@ -115,19 +124,17 @@ class HeroForPretraining(HeroModel):
         smoothed by a width-5 convolution each (model/pretrain.py:128-166). cross=True scores
         every query against every clip (Nq, Nv, L)."""
         query = self.video_query_linear(modularized_query.to(self.video_query_linear.weight.dtype))
+        if not cross:
+            # one fused kernel each way: per-frame similarity, both convolutions, mask_logits
+            return Fn.vsm_span_logits(query, context_feat2, context_mask,
+                                      self.video_st_predictor.weight, self.video_ed_predictor.weight)
         ctx = context_feat2.to(query.dtype)
-        if cross:
-            sim = torch.einsum("md,nld->mnl", query, ctx)
-            n_q, n_c, length = sim.shape
-            flat = sim.reshape(n_q * n_c, 1, length)
-            st = self.video_st_predictor(flat).view(n_q, n_c, length)
-            ed = self.video_ed_predictor(flat).view(n_q, n_c, length)
-            context_mask = context_mask.unsqueeze(0)
-        else:
-            sim = torch.einsum("bd,bld->bl", query, ctx).unsqueeze(1)
-            st = self.video_st_predictor(sim).squeeze()
-            ed = self.video_ed_predictor(sim).squeeze()
-        mask = context_mask.to(st.dtype)
+        sim = torch.einsum("md,nld->mnl", query, ctx)
+        n_q, n_c, length = sim.shape
+        flat = sim.reshape(n_q * n_c, 1, length)
+        st = self.video_st_predictor(flat).view(n_q, n_c, length)
+        ed = self.video_ed_predictor(flat).view(n_q, n_c, length)
+        mask = context_mask.unsqueeze(0).to(st.dtype)
         return mask_logits(st, mask), mask_logits(ed, mask)
 
     def get_pred_from_mod_query(self, frame_embeddings, c_attn_masks, modularized_query,
@@ -141,23 +148,28 @@ class HeroForPretraining(HeroModel):
         """(Nq, Nv) cosine score of every query against every clip = max over the clip's valid
         frames (model/pretrain.py:364-413). Queries / clips of all ranks are gathered first
         (clips padded to the longest) so every rank sees the same in-batch negatives."""
-        q = F.normalize(modularized_query.float(), dim=-1, eps=1e-5)
-        ctx = F.normalize(context_feat1.float(), dim=-1, eps=1e-5)
+        q, ctx = modularized_query.float(), context_feat1.float()
         gather = (self.training and self.gather_gpus) or (not self.training and val_gather_gpus)
         if gather and hdist.size() > 1:
-            lens = torch.tensor([ctx.shape[1]], device=ctx.device)
-            all_lens = [torch.zeros_like(lens) for _ in range(hdist.size())]
-            torch.distributed.all_gather(all_lens, lens)
-            pad = int(max(int(x) for x in all_lens)) - ctx.shape[1]
+            # every rank pads its clips to the model's max_clip_len: the gathered block has a
+            # known shape and no length exchange (and no device->host read) is needed
+            cap = getattr(self.v_encoder, "max_clip_len", ctx.shape[1])
+            equal = self.gather_equal_counts and ctx.shape[1] <= cap
+            if equal:
+                pad = cap - ctx.shape[1]
+            else:
+                lens = torch.tensor([ctx.shape[1]], device=ctx.device)
+                all_lens = [torch.zeros_like(lens) for _ in range(hdist.size())]
+                torch.distributed.all_gather(all_lens, lens)
+                pad = int(max(int(x) for x in all_lens)) - ctx.shape[1]
             if pad:
                 ctx = F.pad(ctx, (0, 0, 0, pad))
                 context_mask = F.pad(context_mask, (0, pad))
-            q = hdist.vsm_allgather(q).contiguous()
-            ctx = hdist.vsm_allgather(ctx).contiguous()
-            context_mask = hdist.vsm_allgather(context_mask).contiguous()
-        scores = torch.einsum("md,nld->mln", q, ctx)                       # (Nq, L, Nv)
-        mask = context_mask.transpose(0, 1).unsqueeze(0).to(scores.dtype)   # (1, L, Nv)
-        return mask_logits(scores, mask).max(dim=1).values
+            q = hdist.vsm_allgather(q, None, equal).contiguous()
+            ctx = hdist.vsm_allgather(ctx, None, equal).contiguous()
+            context_mask = hdist.vsm_allgather(context_mask, None, equal).contiguous()
+        # normalise (F.normalize, eps 1e-5) + einsum("md,nld->mln") + mask_logits + max over frames
+        return Fn.vsm_video_scores(q, ctx, context_mask)
 
     def get_video_level_loss(self, query_context_scores, reduction="mean"):
         """Ranking losses of the positive (query, clip) pairs against negative clips and negative

@@ -386,6 +386,42 @@ int hero_reduce_slots_f32(float* dst, const float* slots, int32_t n_slots, int64
 /* out[0] += sum x^2 (global-norm clipping, train_vcmr.py:258-259). */
 int hero_sumsq_f32(const float* x, int64_t n, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Video-subtitle matching / moment-retrieval head: the ops that follow the
+ * encoder in HeroForPretraining / HeroForVcmr.
+ *   model/pretrain.py:364-413  get_video_level_scores: F.normalize (eps 1e-5) of queries and
+ *       frames, einsum("md,nld->mln"), mask_logits, max over frames
+ *   model/pretrain.py:128-166  _get_st_ed_prob (non-cross form): einsum("bd,bld->bl"), two
+ *       Conv1d(1, 1, k, padding k/2, bias=False), mask_logits
+ * ---------------------------------------------------------------------------------------- */
+/* x^[r] = x[r] / max(|x[r]|_2, eps) written as split-bf16 halves hi + lo (operands of a split-bf16
+ * hero_gemm_bf16, ~16 mantissa bits); inv_norm[r] = 1 / max(|x[r]|, eps), NEGATED where the clamp
+ * was active. d % 4 == 0. */
+int hero_l2norm_split_f32(const float* x, int64_t rows, int32_t d, float eps, void* hi, void* lo,
+                          float* inv_norm, void* stream);
+/* scores[m, n] = max_l (mask[n, l] ? s[m, n * len + l] : -1e4), argmax[m, n] = its (lowest) l;
+ * s is the [nq, ld_s] fp32 output of the q^ . c^ GEMM, mask [nv, len] bytes. */
+int hero_vsm_masked_max(const float* s, int64_t ld_s, const uint8_t* mask, int32_t nq, int32_t nv,
+                        int32_t len, float* scores, int32_t* argmax, void* stream);
+/* Backward of the three steps above given g = d loss / d scores [nq, nv]: dq [nq, d] and
+ * dctx [nv * len, d] (fp32, OVERWRITTEN; either may be NULL), through the max (gradient to the
+ * arg-max frame only, none through masked frames) and the normalisations. d <= 1024. */
+int hero_vsm_scores_bwd(const float* g, const int32_t* argmax, const uint8_t* mask, const void* q_hi,
+                        const void* q_lo, const float* q_inv, const void* c_hi, const void* c_lo,
+                        const float* c_inv, int32_t nq, int32_t nv, int32_t len, int32_t d,
+                        float* dq, float* dctx, void* stream);
+/* Span logits of n (query, clip) pairs: sim[b, l] = query[b] . ctx[b, l];
+ * st / ed[b, l] = mask ? sum_k w[k] * sim[b, l + k - K/2] : -1e4 (zero padding). len <= 512,
+ * odd K <= 15, d % 4 == 0. The backward OVERWRITES dquery [n, d], dctx [n, len, d] and
+ * ACCUMULATES (+=) dw_st / dw_ed [K]. */
+int hero_vsm_span_fwd(const float* query, const float* ctx, const uint8_t* mask, const float* w_st,
+                      const float* w_ed, int32_t n, int32_t len, int32_t d, int32_t k, float* sim,
+                      float* st, float* ed, void* stream);
+int hero_vsm_span_bwd(const float* dst, const float* ded, const uint8_t* mask, const float* w_st,
+                      const float* w_ed, const float* sim, const float* query, const float* ctx,
+                      int32_t n, int32_t len, int32_t d, int32_t k, float* dquery, float* dctx,
+                      float* dw_st, float* dw_ed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

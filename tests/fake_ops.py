@@ -310,10 +310,78 @@ def bert_stack_bwd(x, layers, att, saved, dout, grads, *, heads, eps, drop, need
     return dy if need_dx else None
 
 
+def l2norm_split(x, hi, lo, inv, eps=1e-5):
+    nrm = x.norm(dim=-1)
+    s = 1.0 / nrm.clamp(min=eps)
+    xh = x * s[:, None]
+    h = xh.to(BF16)
+    hi[:x.shape[0]] = h
+    lo[:x.shape[0]] = (xh - h.float()).to(BF16)
+    inv.copy_(torch.where(nrm < eps, -s, s))
+
+
+def vsm_masked_max(s, mask_u8, nq, nv, length, scores, argmax):
+    v = s[:, :nv * length].reshape(nq, nv, length)
+    v = torch.where(mask_u8.bool()[None], v, torch.full_like(v, -1e4))
+    best, arg = v.max(dim=2)
+    scores.copy_(best)
+    argmax.copy_(arg.int())
+
+
+def _normalize_bwd(acc, xh, inv):
+    s = inv.abs()[:, None]
+    proj = acc - xh * (xh * acc).sum(-1, keepdim=True)
+    return torch.where((inv < 0)[:, None], acc, proj) * s
+
+
+def vsm_scores_bwd(g, argmax, mask_u8, q_hi, q_lo, q_inv, c_hi, c_lo, c_inv, nq, nv, length, d,
+                   dq, dctx):
+    qh = q_hi.float() + q_lo.float()
+    ch = (c_hi.float() + c_lo.float())[:nv * length]
+    am = argmax.long()
+    rows = torch.arange(nv)[None, :] * length + am                 # (nq, nv) frame rows
+    live = mask_u8.reshape(-1)[rows].float() * g
+    if dq is not None:
+        dq.copy_(_normalize_bwd((live[:, :, None] * ch[rows]).sum(1), qh, q_inv))
+    if dctx is not None:
+        acc = torch.zeros(nv * length, d)
+        acc.index_add_(0, rows.reshape(-1), (live[:, :, None] * qh[:, None, :]).reshape(-1, d))
+        dctx.copy_(_normalize_bwd(acc, ch, c_inv).view_as(dctx))
+
+
+def _conv_same(sim, w):
+    k = w.numel()
+    return torch.nn.functional.conv1d(sim[:, None, :], w.view(1, 1, k), padding=k // 2)[:, 0]
+
+
+def vsm_span_fwd(query, ctx, mask_u8, w_st, w_ed, sim, st, ed):
+    s = torch.einsum("bd,bld->bl", query, ctx)
+    on = mask_u8.bool()
+    sim.copy_(s)
+    st.copy_(torch.where(on, _conv_same(s, w_st), torch.full_like(s, -1e4)))
+    ed.copy_(torch.where(on, _conv_same(s, w_ed), torch.full_like(s, -1e4)))
+
+
+def vsm_span_bwd(dst, ded, mask_u8, w_st, w_ed, sim, query, ctx, dquery, dctx, dw_st, dw_ed):
+    with torch.enable_grad():
+        q = query.detach().requires_grad_(True)
+        c = ctx.detach().requires_grad_(True)
+        ws, we = w_st.detach().requires_grad_(True), w_ed.detach().requires_grad_(True)
+        s = torch.einsum("bd,bld->bl", q, c)
+        on = mask_u8.bool().float()
+        loss = (_conv_same(s, ws) * on * dst).sum() + (_conv_same(s, we) * on * ded).sum()
+        gq, gc, gws, gwe = torch.autograd.grad(loss, (q, c, ws, we))
+    dquery.copy_(gq)
+    dctx.copy_(gc)
+    dw_st.add_(gws)
+    dw_ed.add_(gwe)
+
+
 def install(monkeypatch):
     """Route hero_b200.ops through the torch restatements for the duration of a test."""
     from hero_b200 import ops
     for name in ("gemm", "ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd", "cast_bf16", "gather_rows",
                  "gather_sum_rows", "colsum", "relu_bwd", "adamw_step", "sumsq", "bert_stack_fwd",
-                 "bert_stack_bwd"):
+                 "bert_stack_bwd", "l2norm_split", "vsm_masked_max", "vsm_scores_bwd",
+                 "vsm_span_fwd", "vsm_span_bwd"):
         monkeypatch.setattr(ops, name, globals()[name])
