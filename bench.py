@@ -133,6 +133,88 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def build_pretrain_model(device, seed=0):
+    """HeroForPretraining (pretrain.py task heads on the encoder) with the hero_pretrain.json
+    architecture: 6 + 3 layers, q_config with 0 layers (config/hero_pretrain.json), loss weights of
+    config/pretrain-tv-16gpu.json."""
+    from hero_b200.model import VideoModelConfig
+    from hero_b200.pretrain import HeroForPretraining
+    torch.manual_seed(seed)
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "hero_pretrain.json")
+        model_json(p)
+        cfg = json.load(open(p))
+        q = dict(cfg["c_config"], num_hidden_layers=0, vocab_size=50272)
+        cfg["q_config"] = q
+        json.dump(cfg, open(p, "w"))
+        model = HeroForPretraining(VideoModelConfig(p), vfeat_dim=D, max_frm_seq_len=100,
+                                   lw_neg_ctx=8.0, lw_neg_q=8.0, lw_st_ed=0.01, margin=0.1)
+    return model.to(device).train()
+
+
+def pretrain_mix(args, rank, world, device, B):
+    """BASELINE config 5: the pretrain.py task mix (mlm : mfm-nce : fom : vsm = 2 : 2 : 1 : 2,
+    config/pretrain-tv-16gpu.json) on synthetic HowTo100M-shape clips (30 frames, 6 subtitles of
+    5 frames + 20 tokens), fwd + bwd + gradient exchange + global-norm clip + fused AdamW per step,
+    device-resident batches; clips/s over one cycle of 7 steps."""
+    from hero_b200 import distributed as hdist
+    from hero_b200 import synth
+    from hero_b200.optim import FusedAdamW
+    from hero_b200.params import flat_of
+    from hero_b200.plan import attach_plan
+    model = build_pretrain_model(device, seed=0)
+    flat = flat_of(model, device)
+    hdist.broadcast_tensors([flat.flat], 0)
+    flat.mark_dirty()
+    gflat = flat.ensure_flat_grads()
+    exchange = hdist.FlatGradExchange(flat, wire=args.dp_wire, overlap=False) if world > 1 else None
+    opt = FusedAdamW(flat, lr=1e-5)
+    vb, qb = synth.syn_ht100m_dense(batch_size=B, seed=2345 + rank)
+    tasks = {
+        "mlm": synth.syn_mlm_batch(vb, seed=1),
+        "mfm-nce": synth.syn_mfm_batch(vb, seed=2),
+        "fom": attach_plan(synth.syn_fom_batch(vb, seed=3)),
+        "vsm": attach_plan(synth.syn_vsm_batch(vb, qb, seed=4), kind="vsm"),
+    }
+    tasks["mfm-nce"] = attach_plan(tasks["mfm-nce"])
+    tasks = {k: synth.to_device(v, device) for k, v in tasks.items()}
+    cycle = ["mlm", "mfm-nce", "vsm", "fom", "mlm", "mfm-nce", "vsm"]
+
+    def step(i):
+        task = cycle[i % len(cycle)]
+        gflat.zero_()
+        batch = dict(tasks[task])
+        if task == "mfm-nce":      # forward_mfm overwrites c_v_feats in place (model/model.py:244)
+            batch["c_v_feats"] = batch["c_v_feats"].clone()
+        loss = model(batch, task, compute_loss=True)
+        if isinstance(loss, tuple):
+            loss = sum(l.sum() for l in loss)
+        loss.float().mean().backward()
+        if exchange is not None:
+            exchange.all_reduce()
+        opt.clip_grad_norm_device_(1.0)
+        opt.step()
+
+    for i in range(len(cycle)):
+        step(i)
+    n = 2 * len(cycle)
+    t_ms, med, host_ms, gaps = timed_loop(step, n, device, world)
+    per_task = collections.defaultdict(list)
+    for i, gms in enumerate(gaps):
+        per_task[cycle[i % len(cycle)]].append(gms)
+    del model, opt
+    torch.cuda.empty_cache()
+    return {"value": round(world * B / (t_ms / n * 1e-3), 2), "unit": "clips/s",
+            "ms_per_step": round(t_ms / n, 4), "steps": n,
+            "ms_per_task_step": {k: round(statistics.median(v), 3) for k, v in per_task.items()},
+            "host_enqueue_ms_per_step": round(host_ms, 3),
+            "what": "BASELINE config 5: pretrain.py task mix mlm:mfm-nce:fom:vsm = 2:2:1:2 on "
+                    "synthetic HowTo100M-shape batches (32 clips x 30 frames, 6 subtitles of 5 "
+                    "frames + 20 tokens per clip), fwd+bwd"
+                    + (" + gradient all-reduce" if world > 1 else "")
+                    + " + clip + fused AdamW per step"}
+
+
 def build_model(device, seed=0):
     from hero_b200.model import HierarchicalVlModel, VideoModelConfig
     torch.manual_seed(seed)
@@ -451,7 +533,9 @@ def run_ours(args):
             clip = fwd_bwd(vb_dev, qb_dev)
             t_c = time.perf_counter()
             slot = result_host[i % 2:i % 2 + 1]
-            slot.copy_(clip[0, 0, :8].float().sum().reshape(1), non_blocking=True)   # D2H
+            # (detach: the pinned result buffer must not become part of — and keep alive — the
+            # step's autograd graph and its ~3 GB of saved activations)
+            slot.copy_(clip.detach()[0, 0, :8].float().sum().reshape(1), non_blocking=True)   # D2H
             done = torch.cuda.Event(enable_timing=True)
             done.record(cur)
             dones.append(done)
@@ -532,6 +616,11 @@ def run_ours(args):
     # ------------------------------------------------------------- reference arms
     del resident, stager
     torch.cuda.empty_cache()
+    if not args.no_extra and not args.no_pretrain_mix:
+        try:
+            extra["pretrain_mix"] = pretrain_mix(args, rank, world, device, B)
+        except Exception as e:                              # noqa: BLE001
+            extra["pretrain_mix"] = {"unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
     gpu_ref = None
     if not args.no_gpu_reference:
         gpu_ref = gpu_reference(args, rank, world, device, B)
@@ -764,6 +853,7 @@ def main():
     ap.add_argument("--e2e-legacy-batch", action="store_true",
                     help="e2e ships the legacy batch dict including f_v_feats (2x the H2D bytes)")
     ap.add_argument("--no-extra", action="store_true", help="skip the config-2 / config-3 lines")
+    ap.add_argument("--no-pretrain-mix", action="store_true", help="skip the config-5 line")
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-clips", type=int, default=8)

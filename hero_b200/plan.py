@@ -439,9 +439,21 @@ class PlanPool:
         self._ex.shutdown(wait=False, cancel_futures=True)
 
 
+QUERY_PLAN_KEY = "_hero_query_plan"
+
+
 def attach_plan(batch, kind="repr"):
     """Collate-side hook: build the plan from HOST tensors (no device sync later) and stash it in
-    the batch dict; `move_to_cuda`-style helpers leave non-tensor values alone."""
+    the batch dict; `move_to_cuda`-style helpers leave non-tensor values alone.
+    kind: 'repr' (video batch), 'txt' (query batch), or 'vsm' — a VSM / VCMR training batch that
+    carries its queries as `query_input_ids / query_pos_ids / query_attn_masks` (data/vcmr.py):
+    attaches the video plan, the query plan (QUERY_PLAN_KEY) and their joint plan."""
+    if kind == "vsm":
+        rplan = ReprPlan(batch)
+        tplan = TxtPlan(batch["query_attn_masks"], pos_ids=batch.get("query_pos_ids"))
+        rplan.__dict__["_joint"] = JointPlan(rplan, tplan)
+        batch[PLAN_KEY], batch[QUERY_PLAN_KEY] = rplan, tplan
+        return batch
     if kind == "repr":
         batch[PLAN_KEY] = ReprPlan(batch)
     else:

@@ -35,6 +35,7 @@ from . import functional as Fn
 from .encoder import QueryFeatEncoder
 from .layers import mask_logits
 from .model import HeroModel
+from .plan import PLAN_KEY, QUERY_PLAN_KEY
 
 
 class HeroForPretraining(HeroModel):
@@ -75,6 +76,8 @@ class HeroForPretraining(HeroModel):
             raise ValueError(f"Unrecognized task {task}")
         query_batch = {"input_ids": batch["query_input_ids"], "pos_ids": batch["query_pos_ids"],
                        "attn_masks": batch["query_attn_masks"]}
+        if batch[QUERY_PLAN_KEY] is not None:     # collate-side plan (plan.attach_plan(b, 'vsm'))
+            query_batch[PLAN_KEY] = batch[QUERY_PLAN_KEY]
         # one cross-modal pass for the clip rows and the query rows
         frame_embeddings, query_tokens = self.v_encoder.forward_repr_txt(batch, query_batch)
         modularized_query = self.q_feat_attn(query_tokens, batch["query_attn_masks"])

@@ -151,3 +151,109 @@ def to_device(batch, device, non_blocking=True):
     for k, v in batch.items():
         out[k] = v.to(device, non_blocking=non_blocking) if torch.is_tensor(v) else v
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# Pretraining task batches (BASELINE config 5: pretrain.py task mix on HowTo100M-shape clips).
+# Each generator restates the masking / collate logic of the reference's task dataset on top of a
+# SYN-HT100M-dense video batch (T = 30 frames, 6 subtitles of 5 frames + 20 tokens).
+MASK_ID = 50264            # <mask> of the RoBERTa vocabulary (data/data.py:60-63)
+
+
+def syn_ht100m_dense(batch_size=32, seed=2345, n_frames=30, n_subs=6, frames_per_sub=5, sub_len=20,
+                     query_len=16, vfeat_dim=VFEAT_DIM):
+    return syn_tvr_dense(batch_size=batch_size, seed=seed, n_frames=n_frames, n_subs=n_subs,
+                         frames_per_sub=frames_per_sub, sub_len=sub_len, query_len=query_len,
+                         vfeat_dim=vfeat_dim)
+
+
+def syn_mlm_batch(vb, seed=0, mask_prob=0.15, vocab=50265):
+    """data/mlm.py:21-58,132-175 (random_word + mlm_collate) on the subtitle rows of `vb`: 15 % of
+    the subtitle tokens are selected, 80 % -> <mask>, 10 % -> random id, 10 % kept; `txt_mask_tgt`
+    marks them in the [frames, text] row layout, `txt_labels` are their original ids."""
+    rnd = random.Random(seed)
+    ids = vb["f_sub_input_ids"].clone()
+    R, L = ids.shape
+    n_frames = vb["f_attn_masks"].sum(1) - (ids != PAD).sum(1)       # valid frame slots per row
+    tgt = torch.zeros(vb["f_attn_masks"].shape, dtype=torch.bool)
+    labels = []
+    for r in range(R):
+        toks = ids[r].tolist()
+        valid = [j for j in range(1, L) if toks[j] != PAD]             # position 0 is [SEP]/[CLS]
+        picked = [j for j in valid if rnd.random() < mask_prob] or valid[:1]
+        nf = max(int(n_frames[r]), 1 if int(vb["f_attn_masks"][r, 0]) == 0 else int(n_frames[r]))
+        for j in picked:
+            labels.append(toks[j])
+            p = rnd.random()
+            if p < 0.8:
+                ids[r, j] = MASK_ID
+            elif p < 0.9:
+                ids[r, j] = rnd.randrange(3, vocab)
+            tgt[r, nf + j] = True
+    return {"input_ids": ids, "position_ids": vb["f_sub_pos_ids"], "v_feat": vb["f_v_feats"],
+            "attn_masks": vb["f_attn_masks"], "gather_index": vb["f_gather_index"],
+            "txt_mask_tgt": tgt, "txt_labels": torch.tensor(labels, dtype=torch.long)}
+
+
+def syn_mfm_batch(vb, seed=0, mask_prob=0.15):
+    """data/mfm.py:19-97: 15 % of each clip's frames masked (>= 1); masked features zeroed in the
+    clip-level AND the subtitle-level tensors, originals kept as regression / NCE targets."""
+    rnd = random.Random(seed)
+    b = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in vb.items()}
+    B, T, D = b["c_v_feats"].shape
+    c_mask = torch.zeros(B, T, dtype=torch.bool)
+    for i in range(B):
+        n = int(b["c_attn_masks"][i].sum())
+        m = [rnd.random() < mask_prob for _ in range(n)]
+        if not any(m):
+            m[rnd.randrange(n)] = True
+        c_mask[i, :n] = torch.tensor(m)
+    f_mask = torch.zeros(b["f_v_feats"].shape[:2], dtype=torch.bool)
+    row = 0
+    for i, clip in enumerate(b["sub_idx2frame_idx"]):
+        for _, frames in clip:
+            frames = [f for f in frames if 0 <= f < T]
+            if frames:
+                f_mask[row, :len(frames)] = c_mask[i, torch.tensor(frames)]
+            row += 1
+    b["feat_targets"] = b["c_v_feats"][c_mask].contiguous()
+    b["c_v_feats"] = b["c_v_feats"].masked_fill(c_mask.unsqueeze(-1), 0)
+    b["f_v_feats"] = b["f_v_feats"].masked_fill(f_mask.unsqueeze(-1), 0)
+    b["c_v_masks"], b["f_v_masks"] = c_mask, f_mask
+    return b
+
+
+def syn_fom_batch(vb, seed=0, reorder_p=0.15):
+    """data/fom.py:50-115 (random_reorder + fom_collate): 15 % of each clip's frame positions are
+    shuffled among themselves; `targets` holds, at each shuffled slot, the original position
+    (-1 elsewhere)."""
+    rnd = random.Random(seed)
+    b = dict(vb)
+    B, T = vb["c_attn_masks"].shape
+    orders = torch.arange(T).unsqueeze(0).repeat(B, 1)
+    targets = torch.full((B, T), -1, dtype=torch.long)
+    for i in range(B):
+        n = int(vb["c_attn_masks"][i].sum())
+        sel = [t for t in range(n) if rnd.random() < reorder_p]
+        shuf = sel[:]
+        rnd.shuffle(shuf)
+        for pos, new in zip(sel, shuf):
+            orders[i, pos] = new
+            targets[i, new] = pos
+    b["shuffled_orders"], b["targets"] = orders, targets
+    return b
+
+
+def syn_vsm_batch(vb, qb, seed=0):
+    """data/vsm.py / data/vcmr.py: one query per clip with a (start, end) frame target."""
+    rnd = random.Random(seed)
+    b = dict(vb)
+    B = vb["c_attn_masks"].shape[0]
+    tg = []
+    for i in range(B):
+        n = int(vb["c_attn_masks"][i].sum())
+        st = rnd.randrange(0, max(n - 1, 1))
+        tg.append((st, min(n - 1, st + rnd.randrange(1, 5))))
+    b.update(query_input_ids=qb["input_ids"], query_pos_ids=qb["pos_ids"],
+             query_attn_masks=qb["attn_masks"], targets=torch.tensor(tg, dtype=torch.long))
+    return b
