@@ -36,6 +36,9 @@ class GemmArgs(C.Structure):
         ("a_lo", C.c_void_p), ("b_lo", C.c_void_p),
         ("resid_ln_mean", C.c_void_p), ("resid_ln_rstd", C.c_void_p),
         ("resid_ln_gamma", C.c_void_p), ("resid_ln_beta", C.c_void_p),
+        ("ce_label", C.c_void_p), ("ce_partial", C.c_void_p), ("ce_label_logit", C.c_void_p),
+        ("ce_lse", C.c_void_p), ("ce_grad", C.c_void_p), ("ce_ld_partial", C.c_int64),
+        ("ce_n_valid", C.c_int32),
     ]
 
 
@@ -134,6 +137,7 @@ def _declare(lib):
     sig("hero_relu_bwd_bf16", vp, vp, vp, i64, vp)
     sig("hero_adamw_step", vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp, f32, vp)
     sig("hero_sumsq_f32", vp, i64, vp, vp)
+    sig("hero_ce_finish", vp, i64, i32, vp, i32, vp, vp, vp)
     sig("hero_reduce_slots_f32", vp, vp, i32, i64, i64, f32, i32, vp)
     sig("hero_l2norm_split_f32", vp, i64, i32, f32, vp, vp, vp, vp)
     sig("hero_vsm_masked_max", vp, i64, vp, i32, i32, i32, vp, vp, vp)

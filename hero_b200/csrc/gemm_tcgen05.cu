@@ -39,8 +39,12 @@ constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int SLAB_BYTES = 32 * 128;   // 32 rows x 128 B, swizzle-128B
 constexpr int SMEM_LIMIT = 232448;     // 227 KB opt-in dynamic shared memory per CTA
 
-enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_GELU_GRAD = 3 };
-enum { OUT_BF16 = 0, OUT_F32_ATOMIC = 1, OUT_F32 = 2 };
+// ACT_CE / ACT_CE_GRAD: the LM-head of the MLM task (model/layers.py:330-354 + the cross entropy of
+// model/encoder.py:370-372) without materialising fp32 logits: the forward epilogue reduces every
+// 64-column slab of a row to (max, sum exp) partials + the label's logit, the backward epilogue
+// turns the recomputed logits into g * (softmax - onehot) in bf16.
+enum { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_GELU_GRAD = 3, ACT_CE = 4, ACT_CE_GRAD = 5 };
+enum { OUT_BF16 = 0, OUT_F32_ATOMIC = 1, OUT_F32 = 2, OUT_NONE = 3 };
 // RES_F32_LN: the fp32 residual is given in its pre-LayerNorm form — the epilogue applies
 // (r - mean[row]) * rstd[row] * gamma[col] + beta[col] itself, so the LayerNorm kernel that feeds the
 // next GEMM never has to write an fp32 copy of its output
@@ -61,6 +65,14 @@ struct GemmEpilogue {
   const float* ln_rstd;
   const float* ln_gamma;
   const float* ln_beta;
+  // ACT_CE / ACT_CE_GRAD
+  const int32_t* ce_label;   // [M] target column of each row
+  float2* ce_partial;        // [ceil(N / 64)][ce_ld] (max, sum exp) per (slab, row)
+  float* ce_lab;             // [M] logit of the label column
+  const float* ce_lse;       // [M] log-sum-exp of the row (backward)
+  const float* ce_g;         // [M] upstream gradient of the row's loss (backward)
+  long long ce_ld;
+  int ce_n_valid;            // columns >= this are vocabulary padding: excluded / zero gradient
   int has_aux;
   void* out;           // OUT_F32_ATOMIC only
   long long ld_out;
@@ -93,7 +105,8 @@ struct GemmCfg {
   }
   // a second output slab only where it leaves the operand pipeline at least 4 stages deep
   static constexpr int N_OUT_BUF =
-      (OUT == OUT_F32_ATOMIC) ? 0 : ((!AUX && stages_with(2 + N_RES_BUF) >= 4) ? 2 : 1);
+      (OUT == OUT_F32_ATOMIC || OUT == OUT_NONE) ? 0
+                                                 : ((!AUX && stages_with(2 + N_RES_BUF) >= 4) ? 2 : 1);
   static constexpr int SLABS_PER_WARP = N_OUT_BUF + AUX + N_RES_BUF;
   static constexpr int STAGING_BYTES = NUM_EPI_WARPS * SLABS_PER_WARP * SLAB_BYTES;
   static constexpr int MAX_STAGES = stages_with(SLABS_PER_WARP);
@@ -148,6 +161,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 "activation epilogues use 64-column bf16 slabs");
   static_assert(ACT != ACT_GELU_GRAD || RES == RES_BF16, "GELU' multiplier arrives as a bf16 slab");
   static_assert(OUT != OUT_F32_ATOMIC || RES == RES_NONE, "split-K accumulation takes no residual");
+  static_assert((ACT == ACT_CE) == (OUT == OUT_NONE), "the CE forward epilogue stores no tile");
   // pair rank (0 = leader: issues the MMAs and owns the pipeline "full" / TMEM "empty" barriers)
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
   const bool leader = (rank == 0u);
@@ -168,7 +182,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    if (OUT != OUT_F32_ATOMIC) tma_prefetch_desc(&tmap_out);
+    if (OUT != OUT_F32_ATOMIC && OUT != OUT_NONE) tma_prefetch_desc(&tmap_out);
     if (RES) tma_prefetch_desc(&tmap_res);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
@@ -375,6 +389,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int row0 = slab_row0(tile);
       const int row = row0 + lane;
       const bool row_ok = row < s.M;
+      int ce_label = -1;
+      float ce_lse = 0.f, ce_g = 0.f;
+      if ((ACT == ACT_CE || ACT == ACT_CE_GRAD) && row_ok) {
+        ce_label = __ldg(e.ce_label + row);
+        if (ACT == ACT_CE_GRAD) {
+          ce_lse = __ldg(e.ce_lse + row);
+          ce_g = __ldg(e.ce_g + row);
+        }
+      }
       float ln_scale = 0.f, ln_shift = 0.f;      // (r - mean) * rstd = r * rstd - mean * rstd
       if (RES == RES_F32_LN && row_ok) {
         ln_scale = __ldg(e.ln_rstd + row);
@@ -466,6 +489,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
 #pragma unroll
           for (int j = 0; j < W; ++j) v[j] = fmaxf(v[j], 0.0f);
+        } else if constexpr (ACT == ACT_CE) {
+          // online-softmax partials of this row over the slab's valid columns
+          float m = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < W; ++j)
+            if (col0 + j < e.ce_n_valid) m = fmaxf(m, v[j]);
+          float ssum = 0.f;
+#pragma unroll
+          for (int j = 0; j < W; ++j)
+            if (col0 + j < e.ce_n_valid) ssum += fast_ex2((v[j] - m) * 1.4426950408889634f);
+          if (row_ok) {
+            e.ce_partial[(long long)(col0 / W) * e.ce_ld + row] = make_float2(m, ssum);
+            const int rel = ce_label - col0;
+            if (rel >= 0 && rel < W) {
+              float lab = 0.f;
+#pragma unroll
+              for (int j = 0; j < W; ++j) lab = (j == rel) ? v[j] : lab;
+              e.ce_lab[row] = lab;
+            }
+          }
+        } else if constexpr (ACT == ACT_CE_GRAD) {
+          const int rel = ce_label - col0;
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            float p = fast_ex2((v[j] - ce_lse) * 1.4426950408889634f);
+            p = (j == rel) ? p - 1.0f : p;
+            v[j] = (col0 + j < e.ce_n_valid) ? p * ce_g : 0.f;
+          }
         } else if constexpr (ACT == ACT_GELU_GRAD) {   // multiply by the saved activation derivative
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -518,7 +569,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           }
         }
-        if constexpr (OUT == OUT_F32_ATOMIC) {
+        if constexpr (OUT == OUT_NONE) {
+          // nothing to store
+        } else if constexpr (OUT == OUT_F32_ATOMIC) {
           if (row_ok) {
 #pragma unroll
             for (int g = 0; g < W / 4; ++g) {
@@ -563,7 +616,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     // the slabs must not go away under stores still reading them; their global writes are
     // complete when the grid is (a dependent kernel's griddepcontrol.wait covers them)
-    if (OUT != OUT_F32_ATOMIC && lane == 0) bulk_wait_read<0>();
+    if (OUT != OUT_F32_ATOMIC && OUT != OUT_NONE && lane == 0) bulk_wait_read<0>();
   }
 
   tc_fence_before_sync();
@@ -742,6 +795,12 @@ static int dispatch(const hero_gemm_args* g, const GemmMaps& tm, const GemmShape
   }
   if (layout == 0) {
     switch (g->act) {
+      case ACT_CE:
+        if (!res) return launch<BLOCK_N, 0, 0, ACT_CE, OUT_NONE, CTA2, RES_NONE>(tm, s, e, st);
+        break;
+      case ACT_CE_GRAD:
+        if (!res) return launch<BLOCK_N, 0, 0, ACT_CE_GRAD, OUT_BF16, CTA2, RES_NONE>(tm, s, e, st);
+        break;
       case ACT_NONE:
         if (res) return launch<BLOCK_N, 0, 0, ACT_NONE, OUT_BF16, CTA2, RES_BF16>(tm, s, e, st);
         return launch<BLOCK_N, 0, 0, ACT_NONE, OUT_BF16, CTA2, RES_NONE>(tm, s, e, st);
@@ -862,7 +921,7 @@ extern "C" int hero_gemm_bf16(const hero_gemm_args* g, void* stream) {
 static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   using namespace hero;
   HERO_REQUIRE(g != nullptr, "null args");
-  HERO_REQUIRE(g->a && g->b && g->out, "null operand pointer");
+  HERO_REQUIRE(g->a && g->b && (g->out || g->act == ACT_CE), "null operand pointer");
   HERO_REQUIRE(g->m > 0 && g->n > 0 && g->k > 0, "empty gemm %dx%dx%d", g->m, g->n, g->k);
   HERO_REQUIRE(g->n % 8 == 0, "n must be a multiple of 8 (n=%d)", g->n);
   HERO_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0 && g->ld_out % 4 == 0, "unaligned leading dim");
@@ -873,7 +932,12 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
                "fp32-accumulate output supports act=0 without residual only");
   HERO_REQUIRE(!g->resid || (g->resid_f32 != 0) == (g->out_f32_store != 0),
                "an fp32 residual goes with an fp32 stored output (and a bf16 one with bf16)");
-  if (g->a_mn_major) HERO_REQUIRE(g->m % 64 == 0, "MN-major A needs m %% 64 == 0 (m=%d)", g->m);
+  // (an MN-major A whose row count is not a multiple of 64 is accepted when its storage is: the
+  // tail chunk then reads the zero padding, and rows >= m are never written)
+  if (g->a_mn_major)
+    HERO_REQUIRE(g->m % 64 == 0 || g->lda >= (g->m + 63) / 64 * 64,
+                 "MN-major A needs m %% 64 == 0 or lda >= round_up(m, 64) (m=%d lda=%lld)", g->m,
+                 (long long)g->lda);
   if (g->b_mn_major) HERO_REQUIRE(g->n % 64 == 0, "MN-major B needs n %% 64 == 0 (n=%d)", g->n);
 
   int block_n = g->block_n;
@@ -948,6 +1012,20 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   e.ln_rstd = g->resid_ln_rstd;
   e.ln_gamma = g->resid_ln_gamma;
   e.ln_beta = g->resid_ln_beta;
+  e.ce_label = g->ce_label;
+  e.ce_partial = reinterpret_cast<float2*>(g->ce_partial);
+  e.ce_lab = g->ce_label_logit;
+  e.ce_lse = g->ce_lse;
+  e.ce_g = g->ce_grad;
+  e.ce_ld = g->ce_ld_partial;
+  e.ce_n_valid = g->ce_n_valid > 0 ? g->ce_n_valid : g->n;
+  if (g->act == ACT_CE)
+    HERO_REQUIRE(g->ce_label && g->ce_partial && g->ce_label_logit && g->ce_ld_partial >= g->m &&
+                     !g->out_f32_accumulate && !g->out_f32_store,
+                 "act 4 (cross-entropy partials) needs ce_label, ce_partial, ce_label_logit");
+  if (g->act == ACT_CE_GRAD)
+    HERO_REQUIRE(g->ce_label && g->ce_lse && g->ce_grad && !g->out_f32_accumulate && !g->out_f32_store,
+                 "act 5 (cross-entropy gradient) needs ce_label, ce_lse, ce_grad");
   if (g->resid_ln_mean || g->resid_ln_rstd || g->resid_ln_gamma || g->resid_ln_beta)
     HERO_REQUIRE(g->resid && g->resid_f32 && g->resid_ln_mean && g->resid_ln_rstd &&
                      g->resid_ln_gamma && g->resid_ln_beta,
@@ -962,7 +1040,7 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   GemmMaps tm;
   int rc;
   if (g->a_mn_major)
-    rc = get_tmap(&tm.a, g->a, g->k, g->m, g->lda, BLOCK_M, TM_MNMAJOR);
+    rc = get_tmap(&tm.a, g->a, g->k, (g->m + 63) / 64 * 64, g->lda, BLOCK_M, TM_MNMAJOR);
   else
     rc = get_tmap(&tm.a, g->a, g->m, g->k, g->lda, BLOCK_M, TM_KMAJOR);
   if (rc) return rc;
@@ -989,7 +1067,7 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   tm.out = tm.a;
   tm.aux = tm.a;
   tm.res = tm.a;
-  if (!g->out_f32_accumulate) {
+  if (!g->out_f32_accumulate && g->act != ACT_CE) {
     if (g->out_f32_store) {
       if ((rc = get_tmap(&tm.out, g->out, g->m, g->n, g->ld_out, 32, TM_SLAB_F32))) return rc;
     } else {

@@ -86,6 +86,25 @@ sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) 
   }
 }
 
+// Finish of the fused LM-head cross entropy: combine the (max, sum exp) partials of a row.
+__global__ void __launch_bounds__(128)
+ce_finish_kernel(const float2* __restrict__ part, long long ld, int n_slabs,
+                 const float* __restrict__ lab, int m, float* __restrict__ loss,
+                 float* __restrict__ lse) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  float mx = -INFINITY;
+  for (int t = 0; t < n_slabs; ++t) mx = fmaxf(mx, part[(long long)t * ld + r].x);   // coalesced in r
+  float s = 0.f;
+  for (int t = 0; t < n_slabs; ++t) {
+    const float2 p = part[(long long)t * ld + r];
+    s += p.y * __expf(p.x - mx);
+  }
+  const float l = mx + __logf(s);
+  lse[r] = l;
+  loss[r] = l - lab[r];
+}
+
 // dst[i] = (dst[i] + sum_s slots[s * stride + i]) * scale: the reduction step of the copy-engine
 // gradient exchange (peers have written their contributions into `slots`).
 __global__ void reduce_slots_kernel(float* __restrict__ dst, const float* __restrict__ slots,
@@ -139,6 +158,18 @@ extern "C" int hero_adamw_step(float* p, const float* g, float* m, float* v, voi
   adamw_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, step_size, beta1, beta2, eps, lr_wd,
       grad_scale, clip_sumsq, clip_max_norm);
+  HERO_LAUNCH_CHECK();
+  return HERO_OK;
+}
+
+extern "C" int hero_ce_finish(const void* ce_partial, int64_t ld_partial, int32_t n_slabs,
+                              const float* label_logit, int32_t m, float* loss, float* lse,
+                              void* stream) {
+  HERO_REQUIRE(ce_partial && label_logit && loss && lse && n_slabs > 0 && ld_partial >= m,
+               "ce_finish: bad args");
+  if (m <= 0) return HERO_OK;
+  ce_finish_kernel<<<(m + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(ce_partial), ld_partial, n_slabs, label_logit, m, loss, lse);
   HERO_LAUNCH_CHECK();
   return HERO_OK;
 }

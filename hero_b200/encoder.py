@@ -18,7 +18,7 @@ from torch.nn import functional as F
 from . import functional as Fn
 from .embed import FrameEmbeddings, ImageEmbeddings, QueryFeatEmbeddings, SubEmbeddings
 from .layers import (BertAttention, BertEncoder, BertLayerNorm, BertLMPredictionHead, BertPooler,
-                     LinearLayer, mask_logits)
+                     LinearLayer, gelu, mask_logits)
 from .params import flat_of
 from .plan import PLAN_KEY, TxtPlan
 
@@ -396,17 +396,33 @@ class CrossModalTrm(RobertaPreTrainedModel):
     # ---- MLM (model/encoder.py:355-389); head stays torch ('next' row) ------
     def forward_mlm(self, input_ids, position_ids, img_feat, img_pos_ids, attention_mask,
                     gather_index, txt_mask_tgt, txt_labels=None, compute_loss=True):
+        """model/encoder.py:355-374. The masked tokens are picked straight out of the PACKED encoder
+        output (no padded tensor, no boolean-mask compaction: their count is `txt_labels.shape[0]`,
+        host-known), pass the LM-head transform (dense + gelu + LayerNorm, model/layers.py:336-346)
+        and — when the loss is wanted — the fused vocabulary GEMM + cross entropy
+        (functional.lm_head_cross_entropy): no (n_masked, 50272) logits tensor exists."""
         fplan, dev, pos_keys = self._plan_for(input_ids, img_feat, attention_mask, gather_index)
         y = self.encode_packed(fplan, dev, input_ids, position_ids, img_feat, img_pos_ids,
                                pos_keys=pos_keys, out_f32=True)
-        sequence_output = self._unpack(y, dev, attention_mask.shape)
-        masked_output = sequence_output[txt_mask_tgt].contiguous().view(
-            -1, sequence_output.size(-1))
-        prediction_scores = self.lm_head(masked_output.to(self.lm_head.dense.weight.dtype))
+        if txt_labels is not None:
+            n_masked = int(txt_labels.shape[0])
+            flat_idx = torch.nonzero_static(txt_mask_tgt.reshape(-1), size=n_masked).reshape(-1)
+        else:
+            flat_idx = torch.nonzero(txt_mask_tgt.reshape(-1)).reshape(-1)
+        tok = dev.f_pad_to_tok.long()[flat_idx]               # packed row of every masked token
+        masked_output = y[tok]
+        head = self.lm_head
+        wdt = head.dense.weight.dtype
+        h = head.LayerNorm(gelu(head.dense(masked_output.to(wdt))))
+        if compute_loss:
+            flat = flat_of(self, h.device)
+            emb = self.embeddings.word_embeddings.weight
+            cfg = {"labels": txt_labels, "n_valid": emb.shape[0] - self.vocab_pad,
+                   "emb_bf16": flat.bf16(emb)}
+            return Fn.lm_head_cross_entropy(h, emb, head.bias, cfg)
+        prediction_scores = head.decoder(h) + head.bias       # the caller asked for the logits
         if self.vocab_pad:
             prediction_scores = prediction_scores[:, :-self.vocab_pad]
-        if compute_loss:
-            return F.cross_entropy(prediction_scores, txt_labels, reduction="none")
         return prediction_scores
 
 

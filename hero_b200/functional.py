@@ -563,3 +563,50 @@ class _VsmSpanLogits(torch.autograd.Function):
 
 def vsm_span_logits(query, frames, mask, w_st, w_ed):
     return _VsmSpanLogits.apply(query, frames, mask, w_st, w_ed)
+
+
+# ---------------------------------------------------------------------------------------------
+class _LmHeadCrossEntropy(torch.autograd.Function):
+    """loss[r] = cross_entropy(h[r] @ E^T + bias, label[r]) over the first n_valid vocabulary
+    entries (model/layers.py:347-354 decoder + model/encoder.py:366-372), as ONE tcgen05 GEMM whose
+    epilogue keeps only online-softmax partials; the backward recomputes the logits tile by tile
+    and emits d logits in bf16, which feeds the tied-embedding weight gradient (fp32 accumulate
+    into the embedding table's gradient), the bias gradient and d h.
+    args: h (fp32/bf16 [n, H]), emb (fp32 master [V, H], tied), bias (fp32 [V]), cfg."""
+
+    @staticmethod
+    def forward(ctx, h, emb, bias, cfg):
+        hb = h.to(BF16).contiguous()
+        labels = cfg["labels"].to(torch.int32).contiguous()
+        loss, lse = ops.lm_head_ce_fwd(hb, cfg["emb_bf16"], bias.detach(), labels, cfg["n_valid"])
+        ctx.st = (hb, labels, lse)
+        ctx.cfg = cfg
+        ctx.params = (emb, bias)
+        ctx.h_dtype = h.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        hb, labels, lse = ctx.st
+        cfg = ctx.cfg
+        emb, bias = ctx.params
+        n, Hd = hb.shape
+        V = emb.shape[0]
+        ld = (V + 63) // 64 * 64
+        dl_full = torch.empty((n, ld), dtype=BF16, device=hb.device)
+        if ld > V:
+            dl_full[:, V:].zero_()
+        dl = dl_full[:, :V]
+        ops.lm_head_ce_dlogits(hb, cfg["emb_bf16"], bias.detach(), labels, lse,
+                               g.float().contiguous(), cfg["n_valid"], dl_full)
+        demb, r_emb = _sink(emb)
+        ops.gemm(dl, hb, demb, a_mn=True, b_mn=True, accumulate_f32=True)      # dE += dl^T h
+        dbias, r_bias = _sink(bias)
+        ops.colsum(dl, dbias)
+        dh = torch.empty((n, Hd), dtype=BF16, device=hb.device)
+        ops.gemm(dl, cfg["emb_bf16"], dh, b_mn=True)                             # dh = dl E
+        return dh.to(ctx.h_dtype), r_emb, r_bias, None
+
+
+def lm_head_cross_entropy(h, emb, bias, cfg):
+    return _LmHeadCrossEntropy.apply(h, emb, bias, cfg)

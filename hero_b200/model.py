@@ -238,12 +238,24 @@ class HierarchicalVlModel(VideoPreTrainedModel):
         batch["c_v_feats"] = c_v_feats + self.mask_embedding(c_v_mask.long())
         clip_outputs = self.forward_repr(batch)
         head_dtype = self.feat_regress.net[0].weight.dtype
-        masked_output = clip_outputs[c_v_mask].contiguous().view(-1, clip_outputs.size(-1))
+        # masked / unmasked frame rows by index (their counts are host-known from the targets'
+        # shape, so no boolean-mask compaction and no device->host read: model/model.py:249-257)
+        flat_out = clip_outputs.reshape(-1, clip_outputs.size(-1))
+        flat_mask = c_v_mask.reshape(-1)
+        n_masked = batch["feat_targets"].shape[0] if batch["feat_targets"] is not None else None
+        if n_masked is not None:
+            idx = torch.nonzero_static(flat_mask, size=n_masked).reshape(-1)
+        else:
+            idx = torch.nonzero(flat_mask).reshape(-1)
+        masked_output = flat_out[idx]
         prediction_feat = self.feat_regress(masked_output.to(head_dtype))
         neg_pred_feat = None
         if loss == "nce":
-            neg_output = clip_outputs[~c_v_mask].contiguous().view(-1, clip_outputs.size(-1))
-            neg_pred_feat = self.feat_regress(neg_output.to(head_dtype))
+            if n_masked is not None:
+                nidx = torch.nonzero_static(~flat_mask, size=flat_mask.numel() - n_masked).reshape(-1)
+            else:
+                nidx = torch.nonzero(~flat_mask).reshape(-1)
+            neg_pred_feat = self.feat_regress(flat_out[nidx].to(head_dtype))
         if compute_loss:
             feat_targets = batch["feat_targets"]
             if loss == "regression":

@@ -10,7 +10,7 @@ import torch
 
 from . import _lib
 
-ACT_NONE, ACT_GELU, ACT_RELU, ACT_GELU_GRAD = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_GELU_GRAD, ACT_CE, ACT_CE_GRAD = 0, 1, 2, 3, 4, 5
 
 BF16 = torch.bfloat16
 
@@ -525,3 +525,54 @@ def vsm_span_bwd(dst, ded, mask_u8, w_st, w_ed, sim, query, ctx, dquery, dctx, d
                                             _ptr(w_ed), _ptr(sim), _ptr(query), _ptr(ctx), n, length,
                                             d, w_st.numel(), _ptr(dquery), _ptr(dctx), _ptr(dw_st),
                                             _ptr(dw_ed), _stream()))
+
+
+# ---------------------------------------------------------------------------------------------
+# Fused LM-head cross entropy (MLM): vocabulary logits are never materialised in fp32.
+def lm_head_ce_fwd(h, emb, bias, labels, n_valid):
+    """h: bf16 [n, H] (LM-head transform of the masked tokens), emb: bf16 [V, H] (tied word
+    embedding), bias: fp32 [V], labels: int32 [n]. Returns (loss fp32 [n], lse fp32 [n]) of
+    F.cross_entropy(h @ emb.T + bias, labels, reduction='none') over the first n_valid columns."""
+    _require_cuda(h, emb, bias, labels)
+    assert h.dtype == BF16 and emb.dtype == BF16 and labels.dtype == torch.int32
+    n, V = h.shape[0], emb.shape[0]
+    n_slabs = (V + 63) // 64
+    ld = (n + 7) // 8 * 8
+    partial = torch.empty((n_slabs, ld, 2), dtype=torch.float32, device=h.device)
+    lab = torch.empty(n, dtype=torch.float32, device=h.device)
+    g = _lib.GemmArgs()
+    g.a, g.b = _ptr(h), _ptr(emb)
+    g.lda, g.ldb = h.stride(0), emb.stride(0)
+    g.m, g.n, g.k = n, V, h.shape[1]
+    g.bias = _ptr(bias)
+    g.act = ACT_CE
+    g.drop_scale = 1.0
+    g.ce_label, g.ce_partial, g.ce_label_logit = _ptr(labels), _ptr(partial), _ptr(lab)
+    g.ce_ld_partial, g.ce_n_valid = ld, n_valid
+    _count(2)
+    _lib.check(_lib.lib().hero_gemm_bf16(C.byref(g), _stream()))
+    loss = torch.empty(n, dtype=torch.float32, device=h.device)
+    lse = torch.empty(n, dtype=torch.float32, device=h.device)
+    _lib.check(_lib.lib().hero_ce_finish(_ptr(partial), ld, n_slabs, _ptr(lab), n, _ptr(loss),
+                                         _ptr(lse), _stream()))
+    return loss, lse
+
+
+def lm_head_ce_dlogits(h, emb, bias, labels, lse, grad, n_valid, out):
+    """out[:, :V] (bf16, row stride a multiple of 64) = grad[r] * (softmax(logits)[r] - onehot)."""
+    _require_cuda(h, emb, out)
+    n, V = h.shape[0], emb.shape[0]
+    assert out.dtype == BF16 and out.stride(0) % 64 == 0 and out.shape[1] >= V
+    assert lse.dtype == torch.float32 and grad.dtype == torch.float32 and grad.is_contiguous()
+    g = _lib.GemmArgs()
+    g.a, g.b = _ptr(h), _ptr(emb)
+    g.lda, g.ldb = h.stride(0), emb.stride(0)
+    g.m, g.n, g.k = n, V, h.shape[1]
+    g.bias = _ptr(bias)
+    g.act = ACT_CE_GRAD
+    g.drop_scale = 1.0
+    g.out, g.ld_out = _ptr(out), out.stride(0)
+    g.ce_label, g.ce_lse, g.ce_grad, g.ce_n_valid = _ptr(labels), _ptr(lse), _ptr(grad), n_valid
+    _count()
+    _lib.check(_lib.lib().hero_gemm_bf16(C.byref(g), _stream()))
+    return out

@@ -180,7 +180,7 @@ class HeroForPretraining(HeroModel):
         [i * k, (i + 1) * k) belong to clip i, k = Nq / Nv."""
         n_q, n_v = query_context_scores.shape
         k = n_q // n_v
-        zero = torch.tensor(0).to(query_context_scores.device)
+        zero = query_context_scores.new_zeros(())          # (no host->device copy: sync-free)
         if n_v == 1:
             return zero, zero
         rows = torch.arange(n_q, device=query_context_scores.device)
@@ -225,7 +225,7 @@ class HeroForPretraining(HeroModel):
         assert width > sample_min_idx, "Unable to sample negative when bsz==sample_min_idx"
         order = torch.sort(scores_masked, descending=True, dim=1).indices
         hi = min(sample_min_idx + self.hard_pool_size, width) if self.use_hard_negative else width
-        pick = torch.randint(sample_min_idx, hi, size=(n,)).to(scores_masked.device)
+        pick = torch.randint(sample_min_idx, hi, size=(n,), device=scores_masked.device)
         rows = torch.arange(n, device=scores_masked.device)
         return scores_masked[rows, order[rows, pick]]
 

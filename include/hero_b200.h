@@ -63,7 +63,8 @@ int hero_set_sm_limit(int32_t n);
  *   wgrad    dW = dYᵀ·X    : A = dY (1), B = X  (1), out_f32_accumulate = 1
  * Epilogue, applied in this order on v = acc:
  *   v += bias[n]                                  (bias != NULL; fp32)
- *   act: 0 none | 1 gelu_erf(v) | 2 relu(v) | 3 v * aux_in[m,n]
+ *   act: 0 none | 1 gelu_erf(v) | 2 relu(v) | 3 v * aux_in[m,n] | 4, 5 fused LM-head cross entropy
+ *        (see the ce_* fields)
  *   if aux_out (what the backward needs of the activation):
  *        act 1: aux_out[m,n] = bf16(gelu_erf'(v))   (consumed by act 3 in the dgrad GEMM)
  *        else : aux_out[m,n] = bf16(v)              (pre-activation; ReLU backward uses its sign)
@@ -118,6 +119,21 @@ typedef struct hero_gemm_args {
   const float* resid_ln_rstd;
   const float* resid_ln_gamma;
   const float* resid_ln_beta;
+  /* Fused LM-head cross entropy (act 4 forward, act 5 backward; MLM task, model/layers.py:330-354
+   * + model/encoder.py:370-372). v = a . b^T + bias are the vocabulary logits of m masked tokens;
+   * columns >= ce_n_valid (vocabulary padding, model/encoder.py:226-235) are excluded.
+   *   act 4: no tile is stored (out may be NULL). For every 64-column slab t of row r:
+   *          ce_partial[t * ce_ld_partial + r] = (max_j v_j, sum_j exp(v_j - max)) as float2 and
+   *          ce_label_logit[r] = v[ce_label[r]]. hero_ce_finish turns them into loss + lse.
+   *   act 5: out[r, c] = bf16( ce_grad[r] * (exp(v - ce_lse[r]) - [c == ce_label[r]]) ), 0 in the
+   *          padding columns: d loss / d logits, ready for the dgrad / wgrad GEMMs. */
+  const int32_t* ce_label;
+  void* ce_partial;
+  float* ce_label_logit;
+  const float* ce_lse;
+  const float* ce_grad;
+  int64_t ce_ld_partial;
+  int32_t ce_n_valid;
 } hero_gemm_args;
 
 int hero_gemm_bf16(const hero_gemm_args* args, void* stream);
@@ -383,6 +399,10 @@ int hero_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, 
  * (replaces the Horovod allreduce of utils/distributed.py:19-46 for the overlapped buckets). */
 int hero_reduce_slots_f32(float* dst, const float* slots, int32_t n_slots, int64_t slot_stride,
                           int64_t n, float scale, int32_t max_ctas, void* stream);
+/* Combines the per-slab partials of an act-4 GEMM: lse[r] = log sum_c exp(v[r, c]) and
+ * loss[r] = lse[r] - label_logit[r] (F.cross_entropy, reduction='none'), r < m. */
+int hero_ce_finish(const void* ce_partial, int64_t ld_partial, int32_t n_slabs,
+                   const float* label_logit, int32_t m, float* loss, float* lse, void* stream);
 /* out[0] += sum x^2 (global-norm clipping, train_vcmr.py:258-259). */
 int hero_sumsq_f32(const float* x, int64_t n, float* out, void* stream);
 

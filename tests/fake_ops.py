@@ -377,11 +377,26 @@ def vsm_span_bwd(dst, ded, mask_u8, w_st, w_ed, sim, query, ctx, dquery, dctx, d
     dw_ed.add_(gwe)
 
 
+def lm_head_ce_fwd(h, emb, bias, labels, n_valid):
+    logits = (h.float() @ emb.float().t() + bias)[:, :n_valid]
+    lse = torch.logsumexp(logits, dim=-1)
+    return lse - logits.gather(1, labels.long()[:, None])[:, 0], lse
+
+
+def lm_head_ce_dlogits(h, emb, bias, labels, lse, grad, n_valid, out):
+    logits = h.float() @ emb.float().t() + bias
+    p = torch.exp(logits - lse[:, None])
+    p[torch.arange(h.shape[0]), labels.long()] -= 1.0
+    p[:, n_valid:] = 0.0
+    out[:, :emb.shape[0]] = (p * grad[:, None]).to(BF16)
+    return out
+
+
 def install(monkeypatch):
     """Route hero_b200.ops through the torch restatements for the duration of a test."""
     from hero_b200 import ops
     for name in ("gemm", "ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd", "cast_bf16", "gather_rows",
                  "gather_sum_rows", "colsum", "relu_bwd", "adamw_step", "sumsq", "bert_stack_fwd",
                  "bert_stack_bwd", "l2norm_split", "vsm_masked_max", "vsm_scores_bwd",
-                 "vsm_span_fwd", "vsm_span_bwd"):
+                 "vsm_span_fwd", "vsm_span_bwd", "lm_head_ce_fwd", "lm_head_ce_dlogits"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -211,3 +211,71 @@ def test_vsm_span_logits_kernels_forward_backward_vs_torch():
     assert (st - st_r).abs().max().item() < 1e-3 and (ed - ed_r).abs().max().item() < 1e-3
     for gt, t in zip(got, (q, c, w_st, w_ed)):
         assert (gt - t.grad).abs().max().item() < 2e-3 * max(1.0, t.grad.abs().max().item())
+
+
+def test_video_corpus_embedding_pass_matches_per_batch_forward(tmp_path):
+    """eval_vcmr.py:161-203: the forward-only corpus pass fills the same
+    (n_videos, max_clip_len, H) tensor as calling the encoder batch by batch, with ragged clip
+    lengths across batches and an explicit video order."""
+    from hero_b200.evalpass import embed_video_corpus
+    from tests.test_bench_path_gpu import DIMS, _build
+    from oracle import hero_oracle as orc
+    d = dict(DIMS, f_layers=2, c_layers=1)
+    P = orc.seeded_weights(orc.param_shapes(f_layers=2, c_layers=1), seed=21)
+    model = _build(tmp_path, d, P, train=False)
+    batches, order, n = [], [], 0
+    for i, (lo, hi) in enumerate([(20, 40), (10, 16), (30, 60)]):
+        vb, _ = synth.syn_tvr_ragged(batch_size=3, seed=50 + i, t_range=(lo, hi), s_range=(3, 6),
+                                     l_range=(4, 12))
+        batches.append(vb)
+        order.append([8 - n - j for j in range(3)])           # corpus rows in reverse order
+        n += 3
+    emb, masks = embed_video_corpus(model, batches, n_videos=9, max_clip_len=100,
+                                    video_indices=order)
+    longest = max(b["c_v_feats"].shape[1] for b in batches)
+    assert emb.shape == (9, longest, 768) and masks.shape == (9, longest)
+    with torch.no_grad():
+        for vb, idx in zip(batches, order):
+            want = model(synth.to_device(vb, "cuda"), "repr")
+            T = want.shape[1]
+            assert torch.equal(emb[torch.tensor(idx), :T], want)
+            assert float(emb[torch.tensor(idx), T:].abs().max()) == 0.0
+            assert torch.equal(masks[torch.tensor(idx), :T].cpu(), vb["c_attn_masks"])
+    assert model.training is False
+
+
+@pytest.mark.parametrize("n,vocab_pad", [(77, 7), (2400, 7), (300, 0)])
+def test_fused_lm_head_cross_entropy_forward_backward_vs_torch(n, vocab_pad):
+    """Vocabulary GEMM + online-softmax cross entropy (no logits tensor) against torch on
+    materialised fp32 logits from the same bf16 operands: loss, d h, d E (tied embedding), d bias.
+    V = 50272 is not a multiple of 64 (MN-major wgrad operand with a padded row stride) and the
+    last `vocab_pad` columns are vocabulary padding (excluded from the softmax, zero gradient)."""
+    from hero_b200 import functional as Fn
+    g = torch.Generator().manual_seed(9)
+    V, H = 50272, 768
+    emb = (0.02 * torch.randn(V, H, generator=g)).cuda().requires_grad_(True)
+    bias = (0.1 * torch.randn(V, generator=g)).cuda().requires_grad_(True)
+    h = torch.randn(n, H, generator=g).cuda().requires_grad_(True)
+    labels = torch.randint(0, V - vocab_pad, (n,), generator=g).cuda()
+    w = torch.rand(n, generator=g).cuda()
+    emb.grad = torch.zeros_like(emb)        # in-place sinks, like the flat gradient buffer
+    bias.grad = torch.zeros_like(bias)
+    cfg = {"labels": labels, "n_valid": V - vocab_pad, "emb_bf16": emb.detach().to(torch.bfloat16)}
+    loss = Fn.lm_head_cross_entropy(h, emb, bias, cfg)
+    (loss * w).sum().backward()
+    got = (loss.detach().clone(), h.grad.clone(), emb.grad.clone(), bias.grad.clone())
+    h.grad = None
+    emb.grad = None
+    bias.grad = None
+    hb = h.to(torch.bfloat16).float()
+    eb = emb.to(torch.bfloat16).float()
+    logits = (hb @ eb.t() + bias)[:, :V - vocab_pad]
+    ref = torch.nn.functional.cross_entropy(logits, labels, reduction="none")
+    (ref * w).sum().backward()
+    assert (got[0] - ref).abs().max().item() < 2e-3
+    for name, a, b in (("dh", got[1], h.grad), ("dE", got[2], emb.grad), ("dbias", got[3], bias.grad)):
+        rel = ((a - b).norm() / b.norm().clamp(min=1e-12)).item()
+        assert rel < 2e-2, (name, rel)
+    if vocab_pad:
+        assert float(got[2][V - vocab_pad:].abs().max()) == 0.0
+        assert float(got[3][V - vocab_pad:].abs().max()) == 0.0

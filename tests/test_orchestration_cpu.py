@@ -352,3 +352,66 @@ def test_fused_adamw_host_logic_groups_clipping_and_state_dict(monkeypatch):
     opt2.step()
     for (k, a), (_, b) in zip(m2.named_parameters(), m.named_parameters()):
         assert (a.detach() - b.detach()).abs().max() < 1e-7, k
+
+
+def test_model_saver_and_training_restorer_round_trip(tmp_path, monkeypatch):
+    """hero_b200.evalpass.ModelSaver / TrainingRestorer write the reference's
+    file layout (utils/save.py:112-181): `model_step_<n>.pt` with a `vocab_padded` flag (fp16
+    tensors on request), `train_state_<n>.pt`, rotating `restore.pt`; a fresh model + optimizer
+    resume from them bit for bit (fp32) and keep training."""
+    fake_ops.install(monkeypatch)
+    from hero_b200.evalpass import ModelSaver, TrainingRestorer, load_checkpoint
+    from hero_b200.optim import FusedAdamW
+    from hero_b200.params import flat_of
+    fx = gu.load("hier_tiny.npz")
+    vb, _ = gu.stored_batches(fx)
+    out_dir = tmp_path / "ckpt"
+    out_dir.mkdir()
+
+    def train_steps(model, opt, n):
+        for _ in range(n):
+            opt.zero_grad()
+            model(vb, "repr").square().mean().backward()
+            opt.step()
+
+    src = _model(tmp_path, fx).train()
+    for m in src.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    opt = FusedAdamW(flat_of(src, torch.device("cpu")), lr=1e-3)
+    rest = TrainingRestorer(str(out_dir), src, opt, save_steps=2)
+    train_steps(src, opt, 2)
+    rest.step(); rest.step()                     # global_step 2 -> restore.pt written
+    assert (out_dir / "restore.pt").exists()
+    path = ModelSaver(str(out_dir), half=True).save(src, 2, opt)
+    sd = torch.load(path)
+    assert sd["vocab_padded"] is True
+    assert all(v.dtype == torch.float16 for k, v in sd.items()
+               if isinstance(v, torch.Tensor) and v.is_floating_point())
+    assert set(k for k in sd if k != "vocab_padded") == set(src.state_dict())
+    assert (out_dir / "train_state_2.pt").exists()
+
+    # resume in a fresh model + optimizer: same weights, same moments, same next step
+    dst = _model(tmp_path, fx).train()
+    for m in dst.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    with torch.no_grad():
+        for p in dst.parameters():
+            p.add_(0.1)
+    dst(vb, "repr")                              # flat buffers exist before the restore
+    opt2 = FusedAdamW(flat_of(dst, torch.device("cpu")), lr=1e-3)
+    rest2 = TrainingRestorer(str(out_dir), dst, opt2, save_steps=2)
+    assert rest2.global_step == 2 and opt2.step_count == opt.step_count
+    for (k, a), (_, b) in zip(dst.state_dict().items(), src.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert torch.equal(opt2.exp_avg, opt.exp_avg) and torch.equal(opt2.exp_avg_sq, opt.exp_avg_sq)
+    train_steps(src, opt, 1)
+    train_steps(dst, opt2, 1)
+    for (k, a), (_, b) in zip(dst.state_dict().items(), src.state_dict().items()):
+        assert torch.allclose(a, b, atol=1e-6), k
+    # fp16 model file loads into a model that has run
+    load_checkpoint(dst, path)
+    for (k, a), (_, b) in zip(dst.state_dict().items(), sd.items()):
+        if isinstance(b, torch.Tensor):
+            assert torch.equal(a, b.float().to(a.dtype)), k
