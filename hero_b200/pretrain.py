@@ -186,8 +186,8 @@ class HeroForPretraining(HeroModel):
         rows = torch.arange(n_q, device=query_context_scores.device)
         own = rows // k                                        # the clip of every query
         pos = query_context_scores[rows, own]                  # (Nq,)
-        masked = query_context_scores.clone()
-        masked[rows, own] = 999                                # sorts first, then skipped
+        own_mask = own[:, None] == torch.arange(n_v, device=own.device)[None, :]
+        masked = query_context_scores.masked_fill(own_mask, 999.0)   # sorts first, then skipped
         pos_by_video = pos.view(n_v, k)                        # (Nv, k)
         video_major = masked.transpose(0, 1)                   # (Nv, Nq)
         if self.use_all_neg:

@@ -239,7 +239,8 @@ def test_video_corpus_embedding_pass_matches_per_batch_forward(tmp_path):
             want = model(synth.to_device(vb, "cuda"), "repr")
             T = want.shape[1]
             assert torch.equal(emb[torch.tensor(idx), :T], want)
-            assert float(emb[torch.tensor(idx), T:].abs().max()) == 0.0
+            if T < emb.shape[1]:
+                assert float(emb[torch.tensor(idx), T:].abs().max()) == 0.0
             assert torch.equal(masks[torch.tensor(idx), :T].cpu(), vb["c_attn_masks"])
     assert model.training is False
 
