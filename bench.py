@@ -372,6 +372,8 @@ def run_ours(args):
     # durations do not overlap). Runs for >= ~2 s so clocks settle where a long job runs, which is
     # what the "sustained" peak in MEASURED_PEAKS.json was measured under; both fractions reported.
     prof_steps = max(5, min(int(2000.0 / max(ms_per_step * 1.15, 1e-3)), 400))
+    if args.roofline_steps > 0:      # profiler runs (ncu launch lists): a short pass is enough
+        prof_steps = args.roofline_steps
     ops.start_gemm_profile()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tp0 = time.perf_counter()
@@ -853,6 +855,8 @@ def main():
     ap.add_argument("--e2e-legacy-batch", action="store_true",
                     help="e2e ships the legacy batch dict including f_v_feats (2x the H2D bytes)")
     ap.add_argument("--no-extra", action="store_true", help="skip the config-2 / config-3 lines")
+    ap.add_argument("--roofline-steps", type=int, default=0,
+                    help="steps of the per-launch GEMM timing pass (0 = as many as fill ~2 s)")
     ap.add_argument("--no-pretrain-mix", action="store_true", help="skip the config-5 line")
     ap.add_argument("--no-gpu-reference", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
