@@ -7,7 +7,9 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libhero_b200.so")
+# HERO_B200_LIB: load another build of the same C-ABI (tools/ablate.sh uses it for its timing
+# variant); the default is the in-tree library
+LIB_PATH = os.environ.get("HERO_B200_LIB") or os.path.join(_PKG, "libhero_b200.so")
 
 _lib = None
 
@@ -39,6 +41,7 @@ class GemmArgs(C.Structure):
         ("ce_label", C.c_void_p), ("ce_partial", C.c_void_p), ("ce_label_logit", C.c_void_p),
         ("ce_lse", C.c_void_p), ("ce_grad", C.c_void_p), ("ce_ld_partial", C.c_int64),
         ("ce_n_valid", C.c_int32),
+        ("out_colsum", C.c_void_p),
     ]
 
 
@@ -119,8 +122,8 @@ def _declare(lib):
     sig("hero_ln_bwd", C.POINTER(LnArgs), vp)
     sig("hero_attn_fwd", vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, u32, u32,
         f32, vp)
-    sig("hero_attn_bwd", vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, u32,
-        u32, f32, vp)
+    sig("hero_attn_bwd", vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32,
+        u32, u32, f32, vp)
     sig("hero_gemm_profile_begin")
     sig("hero_gemm_profile_end", C.POINTER(C.c_double), C.POINTER(C.c_double),
         C.POINTER(C.c_int64))

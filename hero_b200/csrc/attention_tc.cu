@@ -29,6 +29,46 @@ constexpr int AT_D = 64;               // head dim
 constexpr int AT_TILE_BYTES = AT_ROWS * AT_D * 2;   // 16 KB: one [128 x 64] bf16 operand tile
 constexpr int AT_P_BYTES = AT_ROWS * AT_ROWS * 2;   // 32 KB: one [128 x 128] bf16 tile (2 chunks)
 
+// Block-diagonal mask on the tensor core. A fifth K = 16 step of the S = Q K^T MMA multiplies the
+// tile's sequence-membership matrix E [128 tokens x 16 sequence ordinals] (128.0 at a token's own
+// sequence, else 0) with itself: S'_ij = S_ij + 16384 * [seq(i) == seq(j)]. Softmax is
+// shift-invariant per row, so the row's own sequence sees its plain softmax while every other
+// column (other sequences of the tile, rows past the tile's end) sits 16384 raw = 2955 log2 units
+// lower and its exp2 is exactly 0: the softmax loops need no compares, selects or predicates.
+// 16384 is exact in fp32 next to |S| < 2^10 up to an absolute error of 2^-9 (2.4e-4 relative in
+// p, an eighth of P's bf16 rounding). The reference adds -10000 to the scaled scores
+// (model/layers.py:299-302), i.e. 80000 raw: equally finite. The host plan keeps <= AT_MAX_SEQS
+// sequences per tile.
+constexpr int AT_MAX_SEQS = 16;
+constexpr int AT_MASK_BYTES = 2 * AT_MAX_SEQS * 128;   // [k = ordinal][mn = token], 2 chunks of 64 tokens
+constexpr float AT_MASK_BIG = 16384.0f;
+
+// Column i of the membership operand (MN-major: one 128-byte row per ordinal, tokens contiguous,
+// two 64-token chunks of 2 KB): thread i owns its token's 16 entries.
+__device__ __forceinline__ void write_membership(uint8_t* sE, int i, int ord) {
+  uint8_t* base = sE + (i >> 6) * (AT_MAX_SEQS * 128) + ((i & 7) << 1);
+  const int u = (i & 63) >> 3;
+#pragma unroll
+  for (int k = 0; k < AT_MAX_SEQS; ++k)
+    *reinterpret_cast<uint16_t*>(base + k * 128 + ((u ^ (k & 7)) << 4)) =
+        (k == ord) ? static_cast<uint16_t>(0x4300) : static_cast<uint16_t>(0);   // bf16 128.0
+}
+
+// Ordinal (0-based) of thread i's sequence within the tile, -1 for rows past the tile's end:
+// the number of sequence starts at rows <= i, minus one. `warp_starts` is 4 ints of smem; the
+// caller synchronises the CTA between the two halves.
+__device__ __forceinline__ uint32_t seq_starts_ballot(bool valid, int lo, int i, int* warp_starts) {
+  const uint32_t bal = __ballot_sync(0xffffffffu, valid && lo == i);
+  if ((threadIdx.x & 31) == 0) warp_starts[threadIdx.x >> 5] = __popc(bal);
+  return bal;
+}
+__device__ __forceinline__ int seq_ordinal(bool valid, uint32_t bal, const int* warp_starts) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int ord = __popc(bal & (0xffffffffu >> (31 - lane))) - 1;
+  for (int w = 0; w < warp; ++w) ord += warp_starts[w];
+  return valid ? ord : -1;
+}
+
 // element (row i, col j) of a [128 x 128] bf16 tile stored as two 64-column chunks of
 // [128 rows x 128 B] with the 128-byte swizzle: byte offset of the 16-byte unit holding cols
 // [8u', 8u'+8) where j = 64*chunk + 8u + (j % 8).
@@ -50,15 +90,6 @@ struct AttnTcArgs {
   uint32_t drop_thr, drop_key;
   float drop_scale;
 };
-
-// Dropout: ONE 32-bit hash decides the two probabilities (query token, head, tile columns 2u and
-// 2u + 1), 16 bits each; forward and backward regenerate the same words from the same plan.
-// (One hash per element was ~40 % of the softmax instruction count.)
-__device__ __forceinline__ uint32_t attn_drop_word(uint32_t key, int tok, int heads, int head,
-                                                   int col_pair) {
-  return hash_u32(key, ((uint32_t)tok * (uint32_t)heads + (uint32_t)head) * 64u +
-                           (uint32_t)col_pair);
-}
 
 // Each thread parks its 64-feature row (two 32-column TMEM fragments, optionally scaled) in a
 // swizzled [128 x 128 B] smem tile ...
@@ -104,15 +135,26 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
   uint8_t* sK = smem + AT_TILE_BYTES;
   uint8_t* sV = smem + 2 * AT_TILE_BYTES;
   uint8_t* sP = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * AT_TILE_BYTES);
+  uint8_t* sE = smem + 3 * AT_TILE_BYTES;           // sequence-membership operand (4 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + AT_MASK_BYTES);
   uint64_t* tma_bar = bars;
   uint64_t* mma_bar = bars + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  int* warp_starts = reinterpret_cast<int*>(bars + 3);
 
   const int tile = blockIdx.x, head = blockIdx.y;
   const int warp = threadIdx.x >> 5;
   const int tok0 = a.tile_tok0[tile];
   const int ntok = a.tile_ntok[tile];
+  // (the plan arrays were uploaded long before the previous kernel started: safe before pdl_wait)
+  const int i = threadIdx.x;
+  const bool valid = i < ntok;
+  int lo = 0, hi = 0;
+  if (valid) {
+    lo = a.seq_lo[tok0 + i] - tok0;
+    hi = a.seq_hi[tok0 + i] - tok0;
+  }
+  const uint32_t starts = seq_starts_ballot(valid, lo, i, warp_starts);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_qkv);
@@ -137,6 +179,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
     tma_load_2d(sK, &tmap_qkv, tma_bar, a.H + head * AT_D, tok0);
     tma_load_2d(sV, &tmap_qkv, tma_bar, 2 * a.H + head * AT_D, tok0);
   }
+  {
+    const int ord = seq_ordinal(valid, starts, warp_starts);
+    if (ord >= AT_MAX_SEQS) __trap();     // the plan packs <= AT_MAX_SEQS sequences per tile
+    write_membership(sE, i, ord);
+    fence_proxy_async();
+  }
+  __syncthreads();
   mbar_wait(tma_bar, 0);
 
   if (threadIdx.x == 0) {
@@ -148,19 +197,15 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
       const uint64_t bd = make_sw128_desc(smem_u32(sK) + k * 32, 16, 1024);
       umma_f16(tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
     }
+    // + 16384 where query and key token belong to the same sequence (E E^T, both MN-major)
+    const uint64_t ed = make_sw128_desc(smem_u32(sE), AT_MAX_SEQS * 128, 1024);
+    umma_f16(tmem, ed, ed, make_idesc_bf16(128, 128, 1, 1), 1u);
     umma_commit(mma_bar);
   }
   mbar_wait(mma_bar, 0);
   tc_fence_after_sync();
 
-  // ---- softmax on this thread's row, restricted to the row's own sequence ----
-  const int i = threadIdx.x;
-  const bool valid = i < ntok;
-  int lo = 0, hi = 0;
-  if (valid) {
-    lo = a.seq_lo[tok0 + i] - tok0;
-    hi = a.seq_hi[tok0 + i] - tok0;
-  }
+  // ---- softmax on this thread's row: the other sequences' columns underflow to exactly 0 ----
   // warp-uniform column range (tcgen05.ld is warp-collective)
   int wlo = valid ? lo : AT_ROWS, whi = hi;
 #pragma unroll
@@ -176,13 +221,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
     tmem_ld_32x32(t_row + c * 32, r);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = c * 32 + j;
-      if (col >= lo && col < hi) mx = fmaxf(mx, __uint_as_float(r[j]));
-    }
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
   }
-  float sum = 0.f;
-  const uint32_t t16 = a.drop_thr >> 16;
+  const float nmx = -mx * a.scale_log2;
+  float sum0 = 0.f, sum1 = 0.f;
+  const uint32_t k2 = attn_drop_k2(a.drop_thr);
   for (int c = 0; c < 4; ++c) {
     uint32_t pk[16];
     const bool touch = !(c * 32 >= whi || c * 32 + 32 <= wlo);   // warp-uniform
@@ -192,17 +235,19 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; j += 2) {
-        float p0 = 0.f, p1 = 0.f;
-        const int col = c * 32 + j;
-        if (col >= lo && col < hi) p0 = ex2((__uint_as_float(r[j]) - mx) * a.scale_log2);
-        if (col + 1 >= lo && col + 1 < hi) p1 = ex2((__uint_as_float(r[j + 1]) - mx) * a.scale_log2);
-        sum += p0 + p1;
-        if (a.drop_thr != 0u) {
-          const uint32_t h = attn_drop_word(a.drop_key, tok0 + i, a.heads, head, col >> 1);
-          p0 = ((h & 0xFFFFu) >= t16) ? p0 * a.drop_scale : 0.f;
-          p1 = ((h >> 16) >= t16) ? p1 * a.drop_scale : 0.f;
-        }
+        const float p0 = ex2(fmaf(__uint_as_float(r[j]), a.scale_log2, nmx));
+        const float p1 = ex2(fmaf(__uint_as_float(r[j + 1]), a.scale_log2, nmx));
+        sum0 += p0;
+        sum1 += p1;
         pk[j >> 1] = pack_bf16x2(p0, p1);
+      }
+      if (a.drop_thr != 0u) {     // the 1 / (1 - p) scale is folded into the output row scale
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t h0 = attn_drop_group(a.drop_key, tok0 + i, a.heads, head, c * 4 + g);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pk[g * 4 + k] &= attn_keep_mask2(attn_drop_pair(h0, k), k2);
+        }
       }
     } else {
 #pragma unroll
@@ -215,6 +260,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
       *reinterpret_cast<uint4*>(sP + p_unit_offset(i, c >> 1, (c & 1) * 4 + g)) = v;
     }
   }
+  const float sum = sum0 + sum1;
   fence_proxy_async();
   tc_fence_before_sync();
   __syncthreads();
@@ -235,13 +281,13 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
   tc_fence_after_sync();
 
   {
-    const float inv = sum > 0.f ? 1.0f / sum : 0.f;
+    const float inv = (sum > 0.f ? 1.0f / sum : 0.f) * (a.drop_thr != 0u ? a.drop_scale : 1.0f);
     uint32_t r0[32], r1[32];
     tmem_ld_32x32(t_row, r0);
     tmem_ld_32x32(t_row + 32, r1);
     tmem_ld_wait();
     if (valid && lse != nullptr)   // log2-domain log-sum-exp of the scaled scores, for the backward
-      lse[(long long)(tok0 + i) * a.heads + head] = mx * a.scale_log2 + log2f(sum);
+      lse[(long long)(tok0 + i) * a.heads + head] = (mx - AT_MASK_BIG) * a.scale_log2 + log2f(sum);
     stage_row(sQ, i, r0, r1, inv);   // Q's tile is dead: P.V has retired
   }
   __syncthreads();
@@ -264,7 +310,8 @@ __global__ void __launch_bounds__(128)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                    const __grid_constant__ CUtensorMap tmap_do,
                    const __grid_constant__ CUtensorMap tmap_o, const AttnTcArgs a,
-                   const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv) {
+                   const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
+                   float* __restrict__ dbias) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t* sQ = smem;
@@ -279,11 +326,21 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   uint64_t* tma_bar = bars;
   uint64_t* mma_bar = bars + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  int* warp_starts = reinterpret_cast<int*>(bars + 3);
+  uint8_t* sE = sdS;     // membership operand of the S MMA; dS is written after that MMA retired
 
   const int tile = blockIdx.x, head = blockIdx.y;
   const int warp = threadIdx.x >> 5;
   const int tok0 = a.tile_tok0[tile];
   const int ntok = a.tile_ntok[tile];
+  const int i = threadIdx.x;
+  const bool valid = i < ntok;
+  int lo = 0, hi = 0;
+  if (valid) {
+    lo = a.seq_lo[tok0 + i] - tok0;
+    hi = a.seq_hi[tok0 + i] - tok0;
+  }
+  const uint32_t starts = seq_starts_ballot(valid, lo, i, warp_starts);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_qkv);
@@ -315,13 +372,13 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     tma_load_2d(sP + P_CHUNK, &tmap_o, tma_bar, head * AT_D, tok0);
   }
 
-  const int i = threadIdx.x;
-  const bool valid = i < ntok;
-  int lo = 0, hi = 0;
-  if (valid) {
-    lo = a.seq_lo[tok0 + i] - tok0;
-    hi = a.seq_hi[tok0 + i] - tok0;
+  {
+    const int ord = seq_ordinal(valid, starts, warp_starts);
+    if (ord >= AT_MAX_SEQS) __trap();
+    write_membership(sE, i, ord);
+    fence_proxy_async();
   }
+  __syncthreads();
   mbar_wait(tma_bar, 0);
   // D_i = dO_i . O_i from the swizzled smem tiles (conflict-free 16-byte reads)
   float Di = 0.f;
@@ -350,6 +407,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       const uint64_t bd = make_sw128_desc(smem_u32(sK) + k * 32, 16, 1024);
       umma_f16(tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
     }
+    {   // + 16384 on same-sequence pairs (see AT_MASK_BIG)
+      const uint64_t ed = make_sw128_desc(smem_u32(sE), AT_MAX_SEQS * 128, 1024);
+      umma_f16(tmem, ed, ed, make_idesc_bf16(128, 128, 1, 1), 1u);
+    }
 #pragma unroll
     for (int k = 0; k < AT_D / 16; ++k) {   // dP = dO V^T
       const uint64_t ad = make_sw128_desc(smem_u32(sdO) + k * 32, 16, 1024);
@@ -368,10 +429,17 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, o));
   }
   const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-  const float row_lse = valid ? lse[(long long)(tok0 + i) * a.heads + head] : 0.f;
-  const uint32_t t16 = a.drop_thr >> 16;
-  const float keep_scale = a.drop_thr != 0u ? a.drop_scale : 1.0f;
-  const unsigned seq_len = valid ? static_cast<unsigned>(hi - lo) : 0u;
+  // exponent offset of this row: its log-sum-exp plus the membership shift; rows past the tile's
+  // end get +inf so that their P and dS rows (which the transposed products sum over) are 0
+  const float row_c = valid ? fmaf(AT_MASK_BIG, a.scale_log2,
+                                   lse[(long long)(tok0 + i) * a.heads + head])
+                            : INFINITY;
+  const bool drop = a.drop_thr != 0u;
+  const float keep_scale = drop ? a.drop_scale : 1.0f;
+  const uint32_t ks_bits = __float_as_uint(keep_scale);
+  const uint32_t k2 = attn_drop_k2(a.drop_thr);
+  // Stored tiles: P = bf16(p) on kept lanes (dV = keep_scale * P^T dO, scaled when dV is staged),
+  // dS = p * (dP * keep - D) (dQ, dK scaled by 1 / sqrt(d) when staged; a power of two).
   for (int c = 0; c < 4; ++c) {
     uint32_t pk[16], dk[16];
     const bool touch = !(c * 32 >= whi || c * 32 + 32 <= wlo);
@@ -381,27 +449,27 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
       tmem_ld_32x32(t_row + 128 + c * 32, d);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float pp[2], ds[2];
-        uint32_t h = 0xFFFFFFFFu;   // both halves >= any threshold: keep
-        if (a.drop_thr != 0u)
-          h = attn_drop_word(a.drop_key, tok0 + i, a.heads, head, (c * 32 + j) >> 1);
+      for (int g = 0; g < 4; ++g) {
+        uint32_t h0 = 0u;
+        if (drop) h0 = attn_drop_group(a.drop_key, tok0 + i, a.heads, head, c * 4 + g);
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          // branch-free: evaluate every column, then select (the per-element branches of the
-          // first version cost ~20 % of the kernel's samples in reconvergence / fetch stalls)
-          const int col = c * 32 + j + t;
-          const bool in_seq = static_cast<unsigned>(col - lo) < seq_len;
-          float p = ex2(fmaf(__uint_as_float(r[j + t]), a.scale_log2, -row_lse));
-          p = in_seq ? p : 0.f;
-          const float dp = __uint_as_float(d[j + t]);
-          const uint32_t bits = t ? (h >> 16) : (h & 0xFFFFu);
-          const float keep = (bits >= t16) ? keep_scale : 0.f;
-          pp[t] = p * keep;                          // dropped probability (for dV)
-          ds[t] = p * (dp * keep - Di) * a.scale;    // d(raw QK^T score)
+        for (int k = 0; k < 4; ++k) {
+          const int j = g * 8 + k * 2;
+          uint32_t m2 = 0xFFFFFFFFu;
+          float keep0 = 1.0f, keep1 = 1.0f;
+          if (drop) {
+            const uint32_t sg = attn_keep_sum(attn_drop_pair(h0, k), k2);
+            m2 = prmt(sg, 0u, 0xBB99u);
+            keep0 = __uint_as_float(prmt(sg, 0u, 0x9999u) & ks_bits);
+            keep1 = __uint_as_float(prmt(sg, 0u, 0xBBBBu) & ks_bits);
+          }
+          const float p0 = ex2(fmaf(__uint_as_float(r[j]), a.scale_log2, -row_c));
+          const float p1 = ex2(fmaf(__uint_as_float(r[j + 1]), a.scale_log2, -row_c));
+          const float ds0 = p0 * fmaf(__uint_as_float(d[j]), keep0, -Di);
+          const float ds1 = p1 * fmaf(__uint_as_float(d[j + 1]), keep1, -Di);
+          pk[j >> 1] = pack_bf16x2(p0, p1) & m2;
+          dk[j >> 1] = pack_bf16x2(ds0, ds1);
         }
-        pk[j >> 1] = pack_bf16x2(pp[0], pp[1]);
-        dk[j >> 1] = pack_bf16x2(ds[0], ds[1]);
       }
     } else {
 #pragma unroll
@@ -460,10 +528,61 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     tmem_ld_32x32(t_row + part * 64, r0);
     tmem_ld_32x32(t_row + part * 64 + 32, r1);
     tmem_ld_wait();
-    stage_row(smem + part * AT_TILE_BYTES, i, r0, r1, 1.0f);
+    stage_row(smem + part * AT_TILE_BYTES, i, r0, r1, part == 2 ? keep_scale : a.scale);
   }
+  // Bias gradient of the QKV projection = column sums of dqkv over the tile's tokens: one more
+  // MMA over the staged tiles. A = [dQ | dK] (then [dV | -]) read MN-major (m = feature,
+  // k = token), B = 16 identical rows of the token-validity vector (K-major) -> every column of
+  // D holds the column sums, feature m in TMEM lane m: one fp32 atomic per thread replaces the
+  // separate pass over dqkv (hero_colsum_bf16: 76 MB per layer).
+  uint8_t* sB = sdS;
+  if (dbias != nullptr) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int idx = threadIdx.x + t * 128;               // unit (n, chunk, u)
+      const int n = idx >> 4, ch = (idx >> 3) & 1, u = idx & 7;
+      const int k0 = ch * 64 + u * 8;
+      uint32_t w[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        w[e] = ((k0 + 2 * e < ntok) ? 0x3F80u : 0u) | ((k0 + 2 * e + 1 < ntok) ? 0x3F800000u : 0u);
+      *reinterpret_cast<uint4*>(sB + ch * 2048 + n * 128 + ((u ^ (n & 7)) << 4)) =
+          make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before_sync();
   __syncthreads();
+  if (dbias != nullptr && threadIdx.x == 0) {
+    tc_fence_after_sync();
+    constexpr uint32_t id_c = make_idesc_bf16(128, 16, 1, 0);
+#pragma unroll
+    for (int grp = 0; grp < 2; ++grp) {
+#pragma unroll
+      for (int k = 0; k < AT_ROWS / 16; ++k) {
+        const uint64_t ad = make_sw128_desc(smem_u32(smem) + grp * 2 * AT_TILE_BYTES + k * 2048,
+                                            AT_TILE_BYTES, 1024);
+        const uint64_t bd = make_sw128_desc(smem_u32(sB) + (k >> 2) * 2048 + (k & 3) * 32, 16, 1024);
+        umma_f16(tmem + 192 + grp * 16, ad, bd, id_c, k > 0 ? 1u : 0u);
+      }
+    }
+    umma_commit(mma_bar);
+  }
   store_tiles(smem, 3, dqkv + (long long)tok0 * (3 * a.H) + head * AT_D, 3LL * a.H, a.H, ntok);
+  if (dbias != nullptr) {
+    mbar_wait(mma_bar, 0);       // third phase of this barrier
+    tc_fence_after_sync();
+    const float qk = __uint_as_float(tmem_ld_32x1(t_row + 192));
+    const float vv = __uint_as_float(tmem_ld_32x1(t_row + 208));
+    tmem_ld_wait();
+    float* db = dbias + head * AT_D;
+    if (i < AT_D) {
+      atomicAdd(db + i, qk);                    // dQ feature i
+      atomicAdd(db + 2 * a.H + i, vv);          // dV feature i
+    } else {
+      atomicAdd(db + a.H + (i - AT_D), qk);     // dK feature i - 64
+    }
+  }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 0) {
@@ -564,13 +683,18 @@ __device__ __forceinline__ void al_store_row(__nv_bfloat16* p, const float (&v)[
   }
 }
 
+// bias-gradient contribution of one stored row (the bf16-rounded values, like the tile kernels)
+template <int N>
+__device__ __forceinline__ void al_add_row(float* dst, const float (&v)[N]) {
+#pragma unroll
+  for (int d = 0; d < N; ++d) atomicAdd(dst + d, __bfloat162float(__float2bfloat16(v[d])));
+}
+
 // dropout keep factor of probability (query token tok, head, key column j RELATIVE to the tile
 // start = the sequence start for a long tile): the same word layout as the tile kernels
 __device__ __forceinline__ float al_keep(const AttnTcArgs& a, int tok, int head, int j) {
   if (a.drop_thr == 0u) return 1.0f;
-  const uint32_t h = attn_drop_word(a.drop_key, tok, a.heads, head, j >> 1);
-  const uint32_t bits = (j & 1) ? (h >> 16) : (h & 0xFFFFu);
-  return (bits >= (a.drop_thr >> 16)) ? a.drop_scale : 0.f;
+  return attn_drop_keep(a.drop_key, a.drop_thr, tok, a.heads, head, j) ? a.drop_scale : 0.f;
 }
 
 // forward (MODE 0): ctx, lse.   dQ (MODE 1): K, V in smem, thread per query row.
@@ -578,7 +702,8 @@ template <int MODE>
 __global__ void __launch_bounds__(AL_THREADS)
 attn_long_q_kernel(const AttnTcArgs a, int first_tile, const __nv_bfloat16* __restrict__ qkv,
                    __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse,
-                   const __nv_bfloat16* __restrict__ dctx, __nv_bfloat16* __restrict__ dqkv) {
+                   const __nv_bfloat16* __restrict__ dctx, __nv_bfloat16* __restrict__ dqkv,
+                   float* __restrict__ dbias) {
   extern __shared__ __align__(16) uint8_t smem[];
   pdl_wait();
   pdl_launch_dependents();
@@ -624,6 +749,7 @@ attn_long_q_kernel(const AttnTcArgs a, int first_tile, const __nv_bfloat16* __re
         al_axpy_row(dq, ds, sK + j * 128);
       }
       al_store_row(dqkv + (long long)(tok0 + i) * ld + head * AT_D, dq, 1.0f);
+      if (dbias != nullptr) al_add_row(dbias + head * AT_D, dq);
     }
   }
 }
@@ -633,7 +759,8 @@ attn_long_q_kernel(const AttnTcArgs a, int first_tile, const __nv_bfloat16* __re
 __global__ void __launch_bounds__(AL_THREADS)
 attn_long_kv_kernel(const AttnTcArgs a, int first_tile, const __nv_bfloat16* __restrict__ qkv,
                     const __nv_bfloat16* __restrict__ ctx, const float* __restrict__ lse,
-                    const __nv_bfloat16* __restrict__ dctx, __nv_bfloat16* __restrict__ dqkv) {
+                    const __nv_bfloat16* __restrict__ dctx, __nv_bfloat16* __restrict__ dqkv,
+                    float* __restrict__ dbias) {
   extern __shared__ __align__(16) uint8_t smem[];
   pdl_wait();
   pdl_launch_dependents();
@@ -717,6 +844,10 @@ attn_long_kv_kernel(const AttnTcArgs a, int first_tile, const __nv_bfloat16* __r
         *reinterpret_cast<uint32_t*>(dkp + d) = pack_bf16x2(dk[d], dk[d + 1]);
         *reinterpret_cast<uint32_t*>(dvp + d) = pack_bf16x2(dv[d], dv[d + 1]);
       }
+      if (dbias != nullptr) {
+        al_add_row(dbias + a.H + head * AT_D + half * 32, dk);
+        al_add_row(dbias + 2 * a.H + head * AT_D + half * 32, dv);
+      }
     }
   }
 }
@@ -765,7 +896,7 @@ extern "C" int hero_attn_fwd(const void* qkv, const int32_t* tile_tok0, const in
     return rc;
   CUtensorMap tm;
   if (int rc = encode_tmap_2d_bf16(&tm, qkv, 3LL * a.H, n_tok, 3LL * a.H, AT_D, AT_ROWS)) return rc;
-  const int smem = 3 * AT_TILE_BYTES + 64;
+  const int smem = 3 * AT_TILE_BYTES + AT_MASK_BYTES + 64;
   static bool configured = false;
   if (!configured) {
     HERO_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_fwd_kernel,
@@ -787,14 +918,15 @@ extern "C" int hero_attn_fwd(const void* qkv, const int32_t* tile_tok0, const in
                                reinterpret_cast<const __nv_bfloat16*>(qkv),
                                reinterpret_cast<__nv_bfloat16*>(ctx), lse,
                                static_cast<const __nv_bfloat16*>(nullptr),
-                               static_cast<__nv_bfloat16*>(nullptr)));
+                               static_cast<__nv_bfloat16*>(nullptr), static_cast<float*>(nullptr)));
   }
   return HERO_OK;
 }
 
 extern "C" int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
                                 const int32_t* seq_lo, const int32_t* seq_hi, const void* ctx,
-                                const void* dctx, const float* lse, void* dqkv, int32_t n_tok,
+                                const void* dctx, const float* lse, void* dqkv, float* dbias,
+                                int32_t n_tok,
                                 int32_t n_tiles, int32_t n_long, int32_t max_long,
                                 int32_t heads, int32_t head_dim, float scale,
                                 uint32_t drop_threshold, uint32_t drop_key, float drop_scale,
@@ -824,7 +956,7 @@ extern "C" int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const in
     dim3 grid(n_short, heads);
     HERO_CUDA_CHECK(launch_pdl(attn_tc_bwd_kernel, grid, dim3(128), smem,
                                reinterpret_cast<cudaStream_t>(stream), tq, td, to, a, lse,
-                               reinterpret_cast<__nv_bfloat16*>(dqkv)));
+                               reinterpret_cast<__nv_bfloat16*>(dqkv), dbias));
   }
   if (n_long > 0) {
     const int lsm = long_smem_bytes(max_long);
@@ -838,12 +970,12 @@ extern "C" int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const in
                                const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(ctx)),
                                const_cast<float*>(lse),
                                reinterpret_cast<const __nv_bfloat16*>(dctx),
-                               reinterpret_cast<__nv_bfloat16*>(dqkv)));
+                               reinterpret_cast<__nv_bfloat16*>(dqkv), dbias));
     HERO_CUDA_CHECK(launch_pdl(attn_long_kv_kernel, dim3(n_long, heads), dim3(AL_THREADS), lsm, st, a,
                                n_short, reinterpret_cast<const __nv_bfloat16*>(qkv),
                                reinterpret_cast<const __nv_bfloat16*>(ctx), lse,
                                reinterpret_cast<const __nv_bfloat16*>(dctx),
-                               reinterpret_cast<__nv_bfloat16*>(dqkv)));
+                               reinterpret_cast<__nv_bfloat16*>(dqkv), dbias));
   }
   return HERO_OK;
 }

@@ -74,6 +74,7 @@ struct GemmEpilogue {
   long long ce_ld;
   int ce_n_valid;            // columns >= this are vocabulary padding: excluded / zero gradient
   int has_aux;
+  float* colsum;       // OUT_BF16: column sums of the stored rows accumulate here (may be NULL)
   void* out;           // OUT_F32_ATOMIC only
   long long ld_out;
   uint32_t drop_threshold;
@@ -605,6 +606,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             tma_store_2d(&tmap_out, slab, col0, row0);
             bulk_commit();
           }
+          if constexpr (OUT == OUT_BF16 && W == 64) {
+            // column sums of the slab just staged (bf16, as stored): lane l owns columns
+            // 2l, 2l + 1 = word l of every 128-byte row (conflict-free), rows past M excluded
+            if (e.colsum != nullptr) {
+              const int rmax = min(32, s.M - row0);       // warp-uniform
+              float sx = 0.f, sy = 0.f;
+              const int u = lane >> 2, w4 = (lane & 3) * 4;
+#pragma unroll 8
+              for (int r = 0; r < rmax; ++r) {
+                const float2 x = unpack_bf16x2(
+                    *reinterpret_cast<const uint32_t*>(slab + r * 128 + ((u ^ (r & 7)) << 4) + w4));
+                sx += x.x;
+                sy += x.y;
+              }
+              const int col = col0 + 2 * lane;
+              if (col < s.N)
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(e.colsum + col), "f"(sx),
+                             "f"(sy)
+                             : "memory");
+            }
+          }
           ++out_it;
         }
       }
@@ -1017,6 +1039,11 @@ static int hero_gemm_bf16_impl(const hero_gemm_args* g, void* stream) {
   e.ce_lab = g->ce_label_logit;
   e.ce_lse = g->ce_lse;
   e.ce_g = g->ce_grad;
+  e.colsum = g->out_colsum;
+  if (g->out_colsum != nullptr)
+    HERO_REQUIRE(!g->out_f32_accumulate && !g->out_f32_store && !g->resid_f32 && g->out != nullptr &&
+                     g->n % 2 == 0 && g->act != ACT_CE,
+                 "out_colsum goes with a stored bf16 output of even width");
   e.ce_ld = g->ce_ld_partial;
   e.ce_n_valid = g->ce_n_valid > 0 ? g->ce_n_valid : g->n;
   if (g->act == ACT_CE)

@@ -147,6 +147,12 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "r"(taddr)
       : "memory");
 }
+// one fp32 column: thread (lane) <- its own row
+__device__ __forceinline__ uint32_t tmem_ld_32x1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -315,6 +321,47 @@ __device__ __forceinline__ void dropout_apply8(float (&v)[8], uint32_t key, uint
     v[2 * j] = ((h & 0xFFFFu) >= t16) ? v[2 * j] * scale : 0.0f;
     v[2 * j + 1] = ((h >> 16) >= t16) ? v[2 * j + 1] * scale : 0.0f;
   }
+}
+
+// ---- attention dropout words. One hash per (query token, head, group of 8 key columns); the
+// four pair-words of the group (two 15-bit lanes each, bits [0,15) and [16,31)) are the hash and
+// three multiply-xorshift derivations of it (3 instructions instead of 10 per pair: the hash was
+// the largest single item of the softmax loops). A lane keeps its probability iff lane15 >= t15,
+// t15 = p * 2^15 (p = 0.1 -> 3276 / 32768).
+__device__ __forceinline__ uint32_t attn_drop_group(uint32_t key, int tok, int heads, int head,
+                                                    int col_group) {
+  return hash_u32(key, ((uint32_t)tok * (uint32_t)heads + (uint32_t)head) * 128u +
+                           (uint32_t)col_group);
+}
+__device__ __forceinline__ uint32_t attn_drop_pair(uint32_t h0, int k) {   // k = pair in group
+  if (k == 0) return h0;
+  uint32_t w = h0 * (k == 1 ? 0x9E3779B1u : (k == 2 ? 0x85EBCA6Bu : 0xC2B2AE35u));
+  return w ^ (w >> 15);
+}
+// both lanes at once: 0xFFFF in each 16-bit half whose lane is kept. `k2` = (0x8000 - t15) in
+// both halves: bit 15 of (lane15 + 0x8000 - t15) is set iff lane15 >= t15; PRMT then replicates
+// the sign bits of bytes 1 and 3 over their halves.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ uint32_t attn_keep_sum(uint32_t w, uint32_t k2) {
+  return (w & 0x7FFF7FFFu) + k2;
+}
+__device__ __forceinline__ uint32_t attn_keep_mask2(uint32_t w, uint32_t k2) {
+  return prmt(attn_keep_sum(w, k2), 0u, 0xBB99u);
+}
+__device__ __forceinline__ uint32_t attn_drop_k2(uint32_t threshold) {   // threshold = p * 2^32
+  const uint32_t k = 0x8000u - (threshold >> 17);
+  return k | (k << 16);
+}
+// scalar form (long-row kernels): is key column j of this query kept?
+__device__ __forceinline__ bool attn_drop_keep(uint32_t key, uint32_t threshold, int tok, int heads,
+                                               int head, int j) {
+  const uint32_t w = attn_drop_pair(attn_drop_group(key, tok, heads, head, j >> 3), (j >> 1) & 3);
+  const uint32_t lane = (j & 1) ? ((w >> 16) & 0x7FFFu) : (w & 0x7FFFu);
+  return lane >= (threshold >> 17);
 }
 
 // exp2 on the MUFU unit (one op per element is the epilogue's throughput budget on sm_100).

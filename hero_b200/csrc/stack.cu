@@ -2,6 +2,7 @@
 // (forward and backward) from C++, so the host cost per step is a handful of calls instead of
 // hundreds of Python->ctypes round trips. Pure orchestration: every arithmetic step is one of the
 // kernels behind the C-ABI (gemm_tcgen05, attention_tc, rowwise).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.h"
@@ -47,6 +48,8 @@ struct Gemm {
     g.drop_threshold = thr; g.drop_key = key; g.drop_scale = scale; return *this;
   }
   Gemm& f32_accumulate() { g.out_f32_accumulate = 1; return *this; }
+  // column sums of the stored output accumulate into p (bias gradient of the producing Linear)
+  Gemm& colsum(float* p) { g.out_colsum = p; return *this; }
   int run(void* stream) { return hero_gemm_bf16(&g, stream); }
 };
 
@@ -96,6 +99,25 @@ static int side_stream(SideStream** out) {
     if (_rc) return _rc;      \
   } while (0)
 
+// Timing ablations (tools/ablate.sh builds a second library with -DHERO_ABLATE; never defined in
+// the product build): HERO_ABLATE=<bit mask> skips whole kernel families inside the stack so a
+// bench run shows what each family really costs in the overlapped step. Results are garbage.
+#ifdef HERO_ABLATE
+static int ablate(int bit) {
+  static int mask = -1;
+  if (mask < 0) {
+    const char* e = getenv("HERO_ABLATE");
+    mask = e ? atoi(e) : 0;
+  }
+  return (mask >> bit) & 1;
+}
+#define HERO_STEP(bit, expr) do { if (!ablate(bit)) HERO_TRY(expr); } while (0)
+#else
+#define HERO_STEP(bit, expr) HERO_TRY(expr)
+#endif
+enum { ABL_COLSUM = 0, ABL_ATTN_FWD, ABL_ATTN_BWD, ABL_LN_FWD, ABL_LN_BWD, ABL_WGRAD, ABL_DGRAD,
+       ABL_FWD_GEMM };
+
 static int check_stack(const hero_stack_args* s, bool bwd) {
   HERO_REQUIRE(s != nullptr, "null stack args");
   HERO_REQUIRE(s->n_layers >= 0 && s->n_tok > 0 && s->hidden > 0 && s->inter > 0 && s->heads > 0,
@@ -129,8 +151,8 @@ extern "C" int hero_bert_stack_fwd(const hero_stack_args* s, void* stream) {
     const hero_layer_weights& W = s->weights[l];
     const hero_layer_acts& A = s->acts[l];
     HERO_REQUIRE(A.s1 && A.s2, "stack fwd: layer %d misses its fp32 pre-LayerNorm buffers", l);
-    HERO_TRY(Gemm(h, H, 0, W.wqkv, H, 0, M, 3 * H, H, A.qkv, 3 * H).bias(W.bqkv).run(stream));
-    HERO_TRY(hero_attn_fwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, A.lse, M,
+    HERO_STEP(ABL_FWD_GEMM, Gemm(h, H, 0, W.wqkv, H, 0, M, 3 * H, H, A.qkv, 3 * H).bias(W.bqkv).run(stream));
+    HERO_STEP(ABL_ATTN_FWD, hero_attn_fwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, A.lse, M,
                            s->n_tiles, s->n_long, s->max_long, s->heads, 64, scale,
                            s->attn_drop_threshold,
                            site_key(s->drop_key, s->first_layer + l, 0), s->attn_drop_scale, stream));
@@ -146,16 +168,16 @@ extern "C" int hero_bert_stack_fwd(const hero_stack_args* s, void* stream) {
       const hero_layer_weights& PW = s->weights[l - 1];
       outp.resid_ln(P.s2, H, P.mean2, P.rstd2, PW.ln2_g, PW.ln2_b);
     }
-    HERO_TRY(outp.run(stream));
+    HERO_STEP(ABL_FWD_GEMM, outp.run(stream));
     hero_ln_args ln;
     ln_base(&ln, A.s1, W.ln1_g, W.ln1_b, s->eps, M, H, A.mean1, A.rstd1);
     ln.y = A.a;
-    HERO_TRY(hero_ln_fwd(&ln, stream));
+    HERO_STEP(ABL_LN_FWD, hero_ln_fwd(&ln, stream));
     Gemm up(A.a, H, 0, W.w1, H, 0, M, I, H, A.f, I);
     up.bias(W.b1).act(ACT_GELU);
     if (A.pre) up.aux_out(A.pre, I);
-    HERO_TRY(up.run(stream));
-    HERO_TRY(Gemm(A.f, I, 0, W.w2, I, 0, M, H, I, A.s2, H)
+    HERO_STEP(ABL_FWD_GEMM, up.run(stream));
+    HERO_STEP(ABL_FWD_GEMM, Gemm(A.f, I, 0, W.w2, I, 0, M, H, I, A.s2, H)
                  .bias(W.b2)
                  .resid_ln(A.s1, H, A.mean1, A.rstd1, W.ln1_g, W.ln1_b)
                  .drop(s->hidden_drop_threshold, site_key(s->drop_key, s->first_layer + l, 2), s->hidden_drop_scale)
@@ -163,7 +185,7 @@ extern "C" int hero_bert_stack_fwd(const hero_stack_args* s, void* stream) {
     ln_base(&ln, A.s2, W.ln2_g, W.ln2_b, s->eps, M, H, A.mean2, A.rstd2);
     ln.y = A.out;
     ln.y_f32 = A.out_f32;      // NULL except where the caller wants the fp32 result (last layer)
-    HERO_TRY(hero_ln_fwd(&ln, stream));
+    HERO_STEP(ABL_LN_FWD, hero_ln_fwd(&ln, stream));
     h = A.out;
   }
   return HERO_OK;
@@ -238,16 +260,16 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
       ln.drop2_scale = s->hidden_drop_scale;
       g2 = ds2_d;
     }
-    HERO_TRY(hero_ln_bwd(&ln, stream));
+    HERO_STEP(ABL_LN_BWD, hero_ln_bwd(&ln, stream));
     HERO_TRY(publish());
     // FFN down
-    HERO_TRY(Gemm(g2, H, 1, A.f, I, 1, H, I, M, G.dw2, I).f32_accumulate().run(wstream));
-    HERO_TRY(Gemm(g2, H, 0, W.w2, I, 1, M, I, H, dpre, I).act(ACT_GELU_GRAD).aux_in(A.pre, I).run(stream));
+    HERO_STEP(ABL_WGRAD, Gemm(g2, H, 1, A.f, I, 1, H, I, M, G.dw2, I).f32_accumulate().run(wstream));
+    // (its epilogue also accumulates the column sums of dpre = the FFN-up bias gradient)
+    HERO_STEP(ABL_DGRAD, Gemm(g2, H, 0, W.w2, I, 1, M, I, H, dpre, I).act(ACT_GELU_GRAD).aux_in(A.pre, I).colsum(G.db1).run(stream));
     HERO_TRY(publish());
     // FFN up
-    HERO_TRY(hero_colsum_bf16(dpre, I, M, I, G.db1, wstream));
-    HERO_TRY(Gemm(dpre, I, 1, A.a, H, 1, I, H, M, G.dw1, H).f32_accumulate().run(wstream));
-    HERO_TRY(Gemm(dpre, I, 0, W.w1, H, 1, M, H, I, da, H).resid(ds2, H).run(stream));
+    HERO_STEP(ABL_WGRAD, Gemm(dpre, I, 1, A.a, H, 1, I, H, M, G.dw1, H).f32_accumulate().run(wstream));
+    HERO_STEP(ABL_DGRAD, Gemm(dpre, I, 0, W.w1, H, 1, M, H, I, da, H).resid(ds2, H).run(stream));
     // LN1 backward
     ln_base(&ln, A.s1, W.ln1_g, nullptr, s->eps, M, H, A.mean1, A.rstd1);
     ln.dy = da; ln.dx = ds1; ln.dgamma = G.dln1_g; ln.dbeta = G.dln1_b;
@@ -260,20 +282,19 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
       ln.drop2_scale = s->hidden_drop_scale;
       g1 = ds1_d;
     }
-    HERO_TRY(hero_ln_bwd(&ln, stream));
+    HERO_STEP(ABL_LN_BWD, hero_ln_bwd(&ln, stream));
     HERO_TRY(publish());
     // attention output projection
-    HERO_TRY(Gemm(g1, H, 1, A.cx, H, 1, H, H, M, G.dwo, H).f32_accumulate().run(wstream));
-    HERO_TRY(Gemm(g1, H, 0, W.wo, H, 1, M, H, H, dcx, H).run(stream));
+    HERO_STEP(ABL_WGRAD, Gemm(g1, H, 1, A.cx, H, 1, H, H, M, G.dwo, H).f32_accumulate().run(wstream));
+    HERO_STEP(ABL_DGRAD, Gemm(g1, H, 0, W.wo, H, 1, M, H, H, dcx, H).run(stream));
     // attention core
-    HERO_TRY(hero_attn_bwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, dcx, A.lse,
-                           dqkv, M, s->n_tiles, s->n_long, s->max_long, s->heads, 64, scale,
+    HERO_STEP(ABL_ATTN_BWD, hero_attn_bwd(A.qkv, s->tile_tok0, s->tile_ntok, s->seq_lo, s->seq_hi, A.cx, dcx, A.lse,
+                           dqkv, G.dbqkv, M, s->n_tiles, s->n_long, s->max_long, s->heads, 64, scale,
                            s->attn_drop_threshold,
                            site_key(s->drop_key, s->first_layer + l, 0), s->attn_drop_scale, stream));
     HERO_TRY(publish());
     // QKV projection
-    HERO_TRY(hero_colsum_bf16(dqkv, 3 * H, M, 3 * H, G.dbqkv, wstream));
-    HERO_TRY(Gemm(dqkv, 3 * H, 1, h_in, H, 1, 3 * H, H, M, G.dwqkv, H).f32_accumulate().run(wstream));
+    HERO_STEP(ABL_WGRAD, Gemm(dqkv, 3 * H, 1, h_in, H, 1, 3 * H, H, M, G.dwqkv, H).f32_accumulate().run(wstream));
     if (two_streams) {
       HERO_CUDA_CHECK(cudaEventRecord(side->done[par], side->stream));
       done_recorded[par] = true;
@@ -285,7 +306,7 @@ extern "C" int hero_bert_stack_bwd(const hero_stack_args* s, void* stream) {
                                       two_streams ? side->stream : chain));
     void* dx = (l == 0 && s->dx) ? s->dx : ((l & 1) ? dxa : dxb);
     if (l > 0 || s->dx)
-      HERO_TRY(Gemm(dqkv, 3 * H, 0, W.wqkv, H, 1, M, H, 3 * H, dx, H).resid(ds1, H).run(stream));
+      HERO_STEP(ABL_DGRAD, Gemm(dqkv, 3 * H, 0, W.wqkv, H, 1, M, H, 3 * H, dx, H).resid(ds1, H).run(stream));
     dy = dx;
   }
   if (two_streams && s->n_layers > 0) {   // every gradient is complete in `stream` order on return

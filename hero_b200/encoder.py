@@ -215,16 +215,32 @@ class CrossModalTrm(RobertaPreTrainedModel):
         cfg = {"drop": drop, "n_tok": fplan.seq.n_tok, "n_txt": fplan.n_txt,
                "n_img": fplan.n_img, "pad_idx": self.embeddings.padding_idx, "img_mask": None}
         if fplan.n_txt:
-            src = dev.f_txt_src.long()
-            cfg["txt_ids"] = input_ids.reshape(-1)[src].int()
+            # token / position ids per packed text token: gathered by the plan on the host when
+            # it saw the id tensors (collate side), else here with a few index kernels
+            pre_ids = getattr(dev, "f_txt_ids", None) if getattr(fplan, "txt_ids", None) \
+                is not None else None
+            pre_pos = getattr(dev, "f_txt_pos", None) if getattr(fplan, "txt_pos", None) \
+                is not None else None
+            src = None
+            if pre_ids is not None:
+                cfg["txt_ids"] = pre_ids
+            else:
+                src = dev.f_txt_src.long()
+                cfg["txt_ids"] = input_ids.reshape(-1)[src].int()
             if position_ids is None:
                 position_ids = self.embeddings.create_position_ids_from_input_ids(input_ids)
+                pre_pos = None
             if position_ids.shape[0] == 1 and input_ids.shape[0] != 1:
                 slot_pos = position_ids.reshape(-1)
-                cfg["txt_pos"] = slot_pos[dev.f_txt_j.long()].int()
+                cfg["txt_pos"] = pre_pos if pre_pos is not None else \
+                    slot_pos[dev.f_txt_j.long()].int()
                 cfg["txt_slot_pos"] = slot_pos
             else:
-                cfg["txt_pos"] = position_ids.expand_as(input_ids).reshape(-1)[src].int()
+                if pre_pos is not None:
+                    cfg["txt_pos"] = pre_pos
+                else:
+                    src = dev.f_txt_src.long() if src is None else src
+                    cfg["txt_pos"] = position_ids.expand_as(input_ids).reshape(-1)[src].int()
                 cfg["txt_slot_pos"] = None       # per-row position ids: atomic table gradient
             cfg["txt_tok"] = dev.f_txt_tok
             cfg["txtpos_off"] = getattr(dev, pos_keys[0])
@@ -253,7 +269,9 @@ class CrossModalTrm(RobertaPreTrainedModel):
                 cfg["img_slot_pos"] = torch.arange(fplan.max_vl, device=device)
             else:
                 slot_pos = img_pos_ids.reshape(-1)[:fplan.max_vl]
-                cfg["img_k"] = slot_pos[dev.f_img_k.long()].int()
+                pre = getattr(dev, "f_img_kpos", None) if getattr(fplan, "img_kpos", None) \
+                    is not None else None
+                cfg["img_k"] = pre if pre is not None else slot_pos[dev.f_img_k.long()].int()
                 cfg["img_slot_pos"] = slot_pos
             if img_masks is not None:
                 cfg["img_mask"] = img_masks.reshape(-1)[dev.f_img_src.long()].int()
@@ -310,10 +328,13 @@ class CrossModalTrm(RobertaPreTrainedModel):
                                 pos_keys=("pos_off", "pos_idx", None, None))
         cfg = dict(cfg_v)
         cfg["n_tok"], cfg["n_txt"] = jplan.n_tok, jplan.n_txt
-        cfg["txt_ids"] = torch.cat([cfg_v["txt_ids"], cfg_q["txt_ids"]]) if fv.n_txt else \
-            cfg_q["txt_ids"]
-        cfg["txt_pos"] = torch.cat([cfg_v["txt_pos"], cfg_q["txt_pos"]]) if fv.n_txt else \
-            cfg_q["txt_pos"]
+        if "j_txt_ids" in jplan.arr and "j_txt_pos" in jplan.arr:
+            cfg["txt_ids"], cfg["txt_pos"] = jdev.j_txt_ids, jdev.j_txt_pos    # host-gathered
+        else:
+            cfg["txt_ids"] = torch.cat([cfg_v["txt_ids"], cfg_q["txt_ids"]]) if fv.n_txt else \
+                cfg_q["txt_ids"]
+            cfg["txt_pos"] = torch.cat([cfg_v["txt_pos"], cfg_q["txt_pos"]]) if fv.n_txt else \
+                cfg_q["txt_pos"]
         cfg["txt_tok"] = jdev.j_txt_tok
         cfg["txtpos_off"], cfg["txtpos_idx"] = jdev.j_txtpos_off, jdev.j_txtpos_idx
         sv, sq = cfg_v.get("txt_slot_pos"), cfg_q.get("txt_slot_pos")

@@ -88,7 +88,8 @@ def drop_params(p, key):
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None, resid=None,
          aux_in=None, aux_out=None, act=ACT_NONE, accumulate_f32=False, drop=(0, 0, 1.0),
-         block_n=0, k_splits=0, cta_pair=0, a_lo=None, b_lo=None, resid_ln=None):
+         block_n=0, k_splits=0, cta_pair=0, a_lo=None, b_lo=None, resid_ln=None,
+         out_colsum=None):
     """out = epilogue(A·B) with the operand conventions of `hero_gemm_args`.
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True) bf16; b: [N,K] (b_mn=False) or [K,N] (b_mn=True).
@@ -138,6 +139,9 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None
             assert t.dtype == torch.float32 and t.is_contiguous()
         (g.resid_ln_mean, g.resid_ln_rstd, g.resid_ln_gamma,
          g.resid_ln_beta) = (_ptr(t) for t in resid_ln)
+    if out_colsum is not None:   # f32 [n] += column sums of the stored bf16 rows
+        assert out_colsum.dtype == torch.float32 and out_colsum.numel() == n and out.dtype == BF16
+        g.out_colsum = _ptr(out_colsum)
     _count()
     _lib.check(_lib.lib().hero_gemm_bf16(C.byref(g), _stream()))
     return out
@@ -223,13 +227,18 @@ def attn_fwd(qkv, att, ctx, *, heads, head_dim=64, drop=(0, 0, 1.0), lse=None):
     return ctx
 
 
-def attn_bwd(qkv, att, ctx, dctx, lse, dqkv, *, heads, head_dim=64, drop=(0, 0, 1.0)):
+def attn_bwd(qkv, att, ctx, dctx, lse, dqkv, *, heads, head_dim=64, drop=(0, 0, 1.0), dbias=None):
+    """`dbias` (f32 [3 * heads * head_dim], optional): the column sums of dqkv are ACCUMULATED
+    into it (bias gradient of the QKV projection)."""
     _require_cuda(qkv, ctx, dctx, dqkv)
     assert dctx.is_contiguous() and dqkv.is_contiguous() and ctx.is_contiguous()
+    if dbias is not None:
+        assert dbias.dtype == torch.float32 and dbias.numel() == dqkv.shape[1]
     _count()
     _lib.check(_lib.lib().hero_attn_bwd(
         _ptr(qkv), _ptr(att["tile_tok0"]), _ptr(att["tile_ntok"]), _ptr(att["seq_lo"]),
-        _ptr(att["seq_hi"]), _ptr(ctx), _ptr(dctx), _ptr(lse), _ptr(dqkv), att["n_tok"],
+        _ptr(att["seq_hi"]), _ptr(ctx), _ptr(dctx), _ptr(lse), _ptr(dqkv),
+        _ptr(dbias), att["n_tok"],
         att["n_tiles"], att.get("n_long", 0), att.get("max_long", 0),
         heads, head_dim, 1.0 / (head_dim ** 0.5), drop[0], drop[1], drop[2], _stream()))
     return dqkv

@@ -21,6 +21,7 @@ import torch
 
 
 ATTN_TILE = 128        # tokens per tensor-core attention tile
+ATTN_TILE_SEQS = 16    # sequences per tile (one K = 16 membership step of the S MMA, csrc/attention_tc.cu)
 ATTN_LONG_MAX = 768    # longest sequence the long-sequence kernels take (hero_attn_fwd)
 
 
@@ -102,8 +103,9 @@ class SeqPlan:
         p2t = np.full(self.rows * self.length, -1, np.int32)
         p2t[self.tok_flat] = np.arange(self.n_tok, dtype=np.int32)
         self.pad_to_tok = p2t                                                    # padded -> packed
-        # attention tiling: consecutive sequences packed into tiles of <= 128 tokens (a sequence
-        # never straddles tiles); per token the [lo, hi) range of its own sequence. Sequences
+        # attention tiling: consecutive sequences packed into tiles of <= 128 tokens and <= 16
+        # sequences (a sequence never straddles tiles); per token the [lo, hi) range of its own
+        # sequence. Sequences
         # longer than one tile (up to ATTN_LONG_MAX tokens; the reference's position table allows
         # 514, model/encoder.py:50) become tiles of their own at the END of the list: the library
         # runs those `n_long` tiles on its long-sequence kernels (hero_attn_fwd).
@@ -114,7 +116,7 @@ class SeqPlan:
         self.seq_lo = np.repeat(self.cu[:-1], lens).astype(np.int32)
         self.seq_hi = np.repeat(self.cu[1:], lens).astype(np.int32)
         t0, tn, l0, ln = [], [], [], []
-        start, cur = 0, 0
+        start, cur, nseq = 0, 0, 0
         pos = 0
         for n in lens.tolist():
             if n == 0:
@@ -126,13 +128,14 @@ class SeqPlan:
                 l0.append(pos)
                 ln.append(n)
                 pos += n
-                start, cur = pos, 0
+                start, cur, nseq = pos, 0, 0
                 continue
-            if cur + n > ATTN_TILE:
+            if cur + n > ATTN_TILE or nseq == ATTN_TILE_SEQS:
                 t0.append(start)
                 tn.append(cur)
-                start, cur = start + cur, 0
+                start, cur, nseq = start + cur, 0, 0
             cur += n
+            nseq += 1
             pos += n
         if cur:
             t0.append(start)
@@ -204,7 +207,28 @@ class FPlan:
         a.update({prefix + "img_tok": self.img_tok, prefix + "img_k": self.img_k,
                   prefix + "img_src": self.img_src, prefix + "txt_tok": self.txt_tok,
                   prefix + "txt_j": self.txt_j, prefix + "txt_src": self.txt_src})
+        for name in ("txt_ids", "txt_pos", "img_kpos"):
+            v = getattr(self, name, None)
+            if v is not None:
+                a[prefix + name] = v
         return a
+
+    def gather_ids(self, input_ids=None, pos_ids=None, img_pos_ids=None):
+        """Per packed token: its vocabulary id, text position id and frame position id, gathered
+        HERE on the host (collate side) when the id tensors are host tensors, so the forward
+        does not spend ~15 small index kernels on them. All optional: what is missing is gathered
+        on the device as before."""
+        ids, pos, ipos = _host_ids(input_ids), _host_ids(pos_ids), _host_ids(img_pos_ids)
+        self.txt_ids = self.txt_pos = self.img_kpos = None
+        if ids is not None and self.n_txt:
+            self.txt_ids = ids.reshape(-1)[self.txt_src].astype(np.int32)
+        if pos is not None and self.n_txt:
+            if pos.shape[0] == 1:
+                self.txt_pos = pos[0][self.txt_j].astype(np.int32)
+            elif ids is not None and pos.shape == ids.shape:
+                self.txt_pos = pos.reshape(-1)[self.txt_src].astype(np.int32)
+        if ipos is not None and self.n_img:
+            self.img_kpos = ipos.reshape(-1)[self.img_k].astype(np.int32)
 
 
 class CPlan:
@@ -287,7 +311,9 @@ class ReprPlan:
         self.c_pos_off, self.c_pos_idx = table_csr(self.c.c_t, max(self.shape_c[1], 1))
         # subtitle position ids as the collate made them (lets JointPlan decide on the host
         # whether video and query rows share one slot -> position table)
-        self.sub_pos = _host_ids(batch.get("f_sub_pos_ids") if hasattr(batch, "get") else None)
+        get = batch.get if hasattr(batch, "get") else (lambda k: None)
+        self.sub_pos = _host_ids(get("f_sub_pos_ids"))
+        self.f.gather_ids(get("f_sub_input_ids"), get("f_sub_pos_ids"), get("f_v_pos_ids"))
         self.dev = None
 
     def to(self, device, staging=None):
@@ -305,11 +331,13 @@ class ReprPlan:
 class TxtPlan:
     """Text-only rows (CrossModalTrm 'txt' task, and the generic BertEncoder API)."""
 
-    def __init__(self, attn_mask, with_embedding=True, pos_ids=None):
+    def __init__(self, attn_mask, with_embedding=True, pos_ids=None, input_ids=None):
         self.f = FPlan(attn_mask)
         self.shape = tuple(_np(attn_mask).shape)
         self.with_embedding = with_embedding
         self.pos = _host_ids(pos_ids)
+        if with_embedding:
+            self.f.gather_ids(input_ids, pos_ids)
         if with_embedding:
             self.pos_off, self.pos_idx = table_csr(self.f.txt_j, max(self.shape[1], 1))
         self.dev = None
@@ -358,6 +386,11 @@ class JointPlan:
         }
         n_slot = max(fv.max_sl, fq.max_sl, 1)
         self.arr["j_txtpos_off"], self.arr["j_txtpos_idx"] = table_csr(self.arr["j_txt_j"], n_slot)
+        for name in ("txt_ids", "txt_pos"):      # host-gathered ids of both row kinds, if known
+            a_v, a_q = getattr(fv, name, None), getattr(fq, name, None)
+            if (a_v is not None or fv.n_txt == 0) and a_q is not None:
+                parts = ([a_v] if fv.n_txt else []) + [a_q]
+                self.arr["j_" + name] = np.concatenate(parts).astype(np.int32)
         # Do both row kinds use the same slot -> position map (the collate's arange)? Decided here
         # on the host when the plans saw the position ids; None = unknown (the encoder then has
         # to compare the device tensors, which costs a device sync per step).
@@ -393,9 +426,12 @@ def plan_inputs(batch, kind="repr"):
         return None if v is None else _np(v)
 
     if kind != "repr":
-        return {"attn_masks": _np(batch["attn_masks"]), "pos_ids": opt("pos_ids")}
+        return {"attn_masks": _np(batch["attn_masks"]), "pos_ids": opt("pos_ids"),
+                "input_ids": opt("input_ids")}
     d = {k: (_np(batch[k]) if torch.is_tensor(batch[k]) else batch[k]) for k in _REPR_KEYS}
     d["f_sub_pos_ids"] = opt("f_sub_pos_ids")
+    d["f_sub_input_ids"] = opt("f_sub_input_ids")
+    d["f_v_pos_ids"] = opt("f_v_pos_ids")
     d["_max_vl"] = _max_vl_of(batch)
     d["_max_sl"] = int(batch["f_sub_input_ids"].shape[1])
     return d
@@ -407,7 +443,8 @@ def build_plans(repr_in, txt_in=None):
     rplan = ReprPlan(repr_in)
     if txt_in is None:
         return rplan, None
-    tplan = TxtPlan(txt_in["attn_masks"], pos_ids=txt_in.get("pos_ids"))
+    tplan = TxtPlan(txt_in["attn_masks"], pos_ids=txt_in.get("pos_ids"),
+                    input_ids=txt_in.get("input_ids"))
     rplan.__dict__["_joint"] = JointPlan(rplan, tplan)
     return rplan, tplan
 
@@ -450,13 +487,15 @@ def attach_plan(batch, kind="repr"):
     attaches the video plan, the query plan (QUERY_PLAN_KEY) and their joint plan."""
     if kind == "vsm":
         rplan = ReprPlan(batch)
-        tplan = TxtPlan(batch["query_attn_masks"], pos_ids=batch.get("query_pos_ids"))
+        tplan = TxtPlan(batch["query_attn_masks"], pos_ids=batch.get("query_pos_ids"),
+                        input_ids=batch.get("query_input_ids"))
         rplan.__dict__["_joint"] = JointPlan(rplan, tplan)
         batch[PLAN_KEY], batch[QUERY_PLAN_KEY] = rplan, tplan
         return batch
     if kind == "repr":
         batch[PLAN_KEY] = ReprPlan(batch)
     else:
-        batch[PLAN_KEY] = TxtPlan(batch["attn_masks"],
-                                  pos_ids=batch.get("pos_ids") if hasattr(batch, "get") else None)
+        get = batch.get if hasattr(batch, "get") else (lambda k: None)
+        batch[PLAN_KEY] = TxtPlan(batch["attn_masks"], pos_ids=get("pos_ids"),
+                                  input_ids=get("input_ids"))
     return batch

@@ -134,6 +134,11 @@ typedef struct hero_gemm_args {
   const float* ce_grad;
   int64_t ce_ld_partial;
   int32_t ce_n_valid;
+  /* Optional, bf16 stores only: f32 [n]; the column sums of the (bf16-rounded) output rows < m
+   * are ACCUMULATED into it from the epilogue's staged slabs. With `out` = the gradient of a
+   * Linear's output this is that Linear's bias gradient, for free instead of a second pass over
+   * `out` (the FFN-up bias gradient of model/layers.py:210-225 comes from the x gelu' dgrad). */
+  float* out_colsum;
 } hero_gemm_args;
 
 int hero_gemm_bf16(const hero_gemm_args* args, void* stream);
@@ -232,14 +237,22 @@ int hero_ln_bwd(const hero_ln_args* args, void* stream);
  *                              backward, which rebuilds the probabilities in one pass
  * Host-built plan (int32, device memory; hero_b200/plan.py SeqPlan):
  *   tile_tok0[n_tiles], tile_ntok[n_tiles]  consecutive sequences grouped into tiles of <= 128
- *                                           tokens; a sequence never straddles two tiles
+ *                                           tokens and <= 16 sequences; a sequence never
+ *                                           straddles two tiles
  *   seq_lo[n_tok], seq_hi[n_tok]            [lo, hi) packed-token range of each token's sequence
  * One CTA per (tile, head): S = QK^T and O = PV (forward), S, dP, dQ, dK, dV (backward) are
  * tcgen05.mma contractions with fp32 accumulators in TMEM; probabilities never reach HBM.
- * Dropout: one 32-bit counter hash per (token i, head h, pair of tile columns 2u, 2u+1), 16 bits
- * per probability, word index ((i*heads + h)*64 + u); forward and backward regenerate the same
- * words from the same plan.
- * The backward takes the saved forward output (D_i = dO_i . O_i).
+ * The "own sequence only" mask is itself a tensor-core product: one extra K = 16 step adds 16384
+ * to every same-sequence (query, key) score (membership matrix x its transpose), which leaves the
+ * row's softmax unchanged and sends every other column's exp2 to exactly 0 - no per-element
+ * compares in the softmax loops (hence the 16-sequence limit per tile).
+ * Dropout: one 32-bit counter hash per (token i, head h, group of 8 tile columns), index
+ * ((i*heads + h)*128 + group); its four pair-words (the hash and three multiply-xorshift
+ * derivations) give 15 bits per probability; forward and backward regenerate the same words
+ * from the same plan.
+ * The backward takes the saved forward output (D_i = dO_i . O_i). With `dbias` != NULL it also
+ * ACCUMULATES the column sums of dqkv (= the bias gradient of the QKV projection, f32 [3*H])
+ * into it, through one more MMA over the staged dQ/dK/dV tiles.
  * Sequences of more than 128 tokens (up to 768; the reference's position table allows 514) take
  * the LAST n_long tiles of the plan, one whole sequence per tile (tile_ntok = its length,
  * max_long = the longest): they run on fp32 CUDA-core kernels with the same arithmetic contract
@@ -253,8 +266,8 @@ int hero_attn_fwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile
                   float drop_scale, void* stream);
 int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const int32_t* tile_ntok,
                   const int32_t* seq_lo, const int32_t* seq_hi, const void* ctx, const void* dctx,
-                  const float* lse, void* dqkv, int32_t n_tok, int32_t n_tiles, int32_t n_long,
-                  int32_t max_long, int32_t heads, int32_t head_dim, float scale,
+                  const float* lse, void* dqkv, float* dbias, int32_t n_tok, int32_t n_tiles,
+                  int32_t n_long, int32_t max_long, int32_t heads, int32_t head_dim, float scale,
                   uint32_t drop_threshold, uint32_t drop_key, float drop_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------

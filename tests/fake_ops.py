@@ -16,7 +16,7 @@ def _ck_drop(drop):
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None, resid=None,
          aux_in=None, aux_out=None, act=0, accumulate_f32=False, drop=(0, 0, 1.0), block_n=0,
-         k_splits=0, cta_pair=0, a_lo=None, b_lo=None, resid_ln=None):
+         k_splits=0, cta_pair=0, a_lo=None, b_lo=None, resid_ln=None, out_colsum=None):
     _ck_drop(drop)
     A = a.float().t() if a_mn else a.float()
     B = b.float() if b_mn else b.float().t()
@@ -53,6 +53,8 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, m=None, n=None, k=None, bias=None
     else:
         assert resid is None or resid.dtype == BF16
         out.copy_(v.to(BF16))
+        if out_colsum is not None:
+            out_colsum.add_(out.float().sum(0))
     return out
 
 
@@ -142,7 +144,7 @@ def _attn_core(qkv, cu, heads):
 
 
 def _check_att(att):
-    """The tiling must cover the token stream with whole sequences: <= 128 tokens per tile, then
+    """The tiling must cover the token stream with whole sequences: <= 128 tokens and <= 16 sequences per tile, then
     (the last n_long tiles) one whole sequence of 129..768 tokens per tile."""
     t0, tn = att["tile_tok0"].tolist(), att["tile_ntok"].tolist()
     assert len(t0) == att["n_tiles"] and sum(tn) == att["n_tok"]
@@ -155,8 +157,10 @@ def _check_att(att):
     for a, n in covered:
         assert a == pos and a in bounds and (a + n) in bounds
         pos += n
+    starts = sorted(b for b in bounds if b < att["n_tok"])
     for a, n in zip(t0[:n_short], tn[:n_short]):
         assert 0 < n <= 128
+        assert sum(1 for b in starts if a <= b < a + n) <= 16     # sequences per tile
     for a, n in zip(t0[n_short:], tn[n_short:]):
         assert 128 < n <= att.get("max_long", 0) <= 768 and cu[cu.index(a) + 1] == a + n
     lo, hi = att["seq_lo"].tolist(), att["seq_hi"].tolist()
@@ -173,13 +177,15 @@ def attn_fwd(qkv, att, ctx, *, heads, head_dim=64, drop=(0, 0, 1.0), lse=None):
     return ctx
 
 
-def attn_bwd(qkv, att, ctx, dctx, lse, dqkv, *, heads, head_dim=64, drop=(0, 0, 1.0)):
+def attn_bwd(qkv, att, ctx, dctx, lse, dqkv, *, heads, head_dim=64, drop=(0, 0, 1.0), dbias=None):
     _ck_drop(drop)
     with torch.enable_grad():
         q = qkv.float().detach().requires_grad_(True)
         out = _attn_core(q, att["cu"], heads)
         out.backward(dctx.float())
     dqkv.copy_(q.grad.to(BF16))
+    if dbias is not None:
+        dbias.add_(dqkv.float().sum(0))
     return dqkv
 
 

@@ -2,6 +2,8 @@
 restatement of the same op on the same (bf16-rounded) inputs."""
 import math
 
+import numpy as np
+
 import pytest
 import torch
 
@@ -253,8 +255,74 @@ def test_attention_fwd_bwd(lens):
     dctx = _rand((ntok, heads * 64), 1.0, seed=51)
     ref.backward(dctx.float())
     dqkv = torch.empty_like(qkv)
-    ops.attn_bwd(qkv, att, ctx, dctx, lse, dqkv, heads=heads)
+    dbias = torch.full((3 * heads * 64,), 0.5, device=_dev())
+    ops.attn_bwd(qkv, att, ctx, dctx, lse, dqkv, heads=heads, dbias=dbias)
     _close(dqkv, qr.grad, 4e-2, 3e-2, "attention bwd")
+    # the bias gradient of the QKV projection is ACCUMULATED: column sums of the stored dqkv
+    want = 0.5 + dqkv.float().sum(0)
+    tol = 2e-3 * dqkv.float().abs().sum(0).max().item() + 1e-3
+    assert (dbias - want).abs().max().item() <= tol, ((dbias - want).abs().max().item(), tol)
+    # and without the bias pointer the stored gradients are the same
+    dq2 = torch.empty_like(qkv)
+    ops.attn_bwd(qkv, att, ctx, dctx, lse, dq2, heads=heads)
+    assert torch.equal(dq2, dqkv)
+
+
+def test_attention_tiles_hold_at_most_16_sequences_and_mask_out_their_neighbours():
+    """The block-diagonal mask is a K = 16 membership MMA: the plan closes a tile after 16
+    sequences, and scores of the neighbouring sequences must not leak even when they are far
+    larger than the row's own (here by ~60 in scaled units)."""
+    from hero_b200 import ops
+    lens = [2] * 40 + [5, 1, 1, 7] * 6
+    heads, ntok = 2, sum(lens)
+    sp, att = _att_plan(lens)
+    cu = np.concatenate([[0], np.cumsum(lens)])
+    for a, n in zip(sp.tile_tok0.tolist(), sp.tile_ntok.tolist()):
+        assert ((cu[:-1] >= a) & (cu[:-1] < a + n)).sum() <= 16
+    qkv = _rand((ntok, 3 * heads * 64), 1.0, seed=58)
+    seq_of = np.repeat(np.arange(len(lens)), lens)
+    # keys of odd sequences are large: a leak would swamp the even sequences' rows
+    big = torch.from_numpy((seq_of % 2 == 1)).to(_dev())
+    H = heads * 64
+    qkv[:, H:2 * H] = torch.where(big[:, None], qkv[:, H:2 * H] * 8, qkv[:, H:2 * H])
+    qkv[:, :H] = qkv[:, :H] * 3
+    ctx = torch.empty(ntok, H, dtype=BF16, device=_dev())
+    lse = torch.empty(ntok, heads, device=_dev())
+    ops.attn_fwd(qkv, att, ctx, heads=heads, lse=lse)
+    qr = qkv.float().requires_grad_(True)
+    ref = _attn_ref(qr, lens, heads)
+    _close(ctx, ref, 2e-2, 1.6e-2, "attention fwd, 16-sequence tiles")
+    dctx = _rand((ntok, H), 1.0, seed=59)
+    ref.backward(dctx.float())
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(qkv, att, ctx, dctx, lse, dqkv, heads=heads)
+    _close(dqkv, qr.grad, 4e-2, 3e-2, "attention bwd, 16-sequence tiles")
+
+
+def test_attention_dropout_rate_and_pair_independence():
+    """V = identity block makes ctx row i = its dropped probability row: the drop rate is p and
+    neighbouring columns (which share one hash through the derived pair words) are independent."""
+    from hero_b200 import ops
+    heads, lens = 1, [64] * 24
+    ntok = sum(lens)
+    qkv = torch.zeros(ntok, 3 * 64, dtype=BF16, device=_dev())      # Q = K = 0: uniform P = 1/64
+    eye = torch.eye(64, dtype=BF16, device=_dev()).repeat(len(lens), 1)
+    qkv[:, 128:] = eye
+    _, att = _att_plan(lens)
+    ctx = torch.empty(ntok, 64, dtype=BF16, device=_dev())
+    ops.attn_fwd(qkv, att, ctx, heads=heads, drop=ops.drop_params(0.1, 31337))
+    kept = (ctx.float() > 0)
+    vals = ctx.float()[kept]
+    assert torch.allclose(vals, torch.full_like(vals, 1 / 64 / 0.9), rtol=1e-2)
+    rate = 1.0 - kept.float().mean().item()
+    assert abs(rate - 0.1) < 6e-3, rate                    # 98k samples: sigma ~ 1e-3
+    k = kept.float()
+    for shift in (1, 2, 3, 4, 8):                          # pair partner, same group, next group
+        a, b = k[:, :-shift].reshape(-1), k[:, shift:].reshape(-1)
+        corr = ((a - a.mean()) * (b - b.mean())).mean().item() / (a.std() * b.std()).item()
+        assert abs(corr) < 2e-2, (shift, corr)
+    rows = torch.stack([k[:-1].reshape(-1), k[1:].reshape(-1)])      # neighbouring query rows
+    assert abs(torch.corrcoef(rows)[0, 1].item()) < 2e-2
 
 
 def test_attention_dropout_consistent_between_fwd_and_bwd():
@@ -398,6 +466,25 @@ def test_gemm_fp32_residual_in_fp32_sum_out(m, n, k, block_n, cta_pair):
     out2 = torch.full((m, n), float("nan"), dtype=torch.float32, device=_dev())
     ops.gemm(a, w, out2, bias=bias, block_n=block_n, cta_pair=cta_pair)       # no residual
     _close(out2, ref - resid, 2e-3, 1e-4, "fp32 store without residual")
+
+
+@pytest.mark.parametrize("m,n,k,act", [(16512, 3072, 768, 3), (3200, 3072, 768, 3),
+                                       (1000, 768, 256, 0), (130, 192, 64, 0)])
+def test_gemm_epilogue_column_sums(m, n, k, act):
+    """out_colsum accumulates the column sums of the stored bf16 output (the FFN-up bias gradient
+    comes out of the x gelu' dgrad this way instead of a second pass over its output)."""
+    from hero_b200 import ops
+    a, w = _rand((m, k), 1.0, seed=70), _rand((k, n), 0.05, seed=71)
+    aux = _rand((m, n), 1.0, seed=72) if act == 3 else None
+    out = torch.empty(m, n, dtype=BF16, device=_dev())
+    cs = torch.full((n,), 0.25, device=_dev())
+    ops.gemm(a, w, out, b_mn=True, act=act, aux_in=aux, out_colsum=cs)
+    ref = torch.empty_like(out)
+    ops.gemm(a, w, ref, b_mn=True, act=act, aux_in=aux)
+    assert torch.equal(out, ref)
+    want = 0.25 + out.double().sum(0)
+    tol = 1e-5 * out.double().abs().sum(0).max().item() + 1e-3
+    assert (cs.double() - want).abs().max().item() <= tol
 
 
 def test_gemm_fp32_residual_with_dropout_matches_bf16_path_mask():

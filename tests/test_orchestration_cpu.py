@@ -119,6 +119,32 @@ def test_plan_can_be_attached_at_collate_time(tmp_path, monkeypatch):
     assert torch.equal(qa, qb_out)
 
 
+def test_host_gathered_ids_equal_the_device_gathers(tmp_path, monkeypatch):
+    """Plans built from host id tensors carry the per-token vocabulary / position ids
+    (FPlan.gather_ids); plans built without them (ids already on the device) leave the gathers
+    to the forward. Both must give the same outputs, separately and in the fused joint pass."""
+    fake_ops.install(monkeypatch)
+    from hero_b200 import plan as hp
+    fx = gu.load("hier_tiny.npz")
+    model = _model(tmp_path, fx)
+    vb, qb = gu.stored_batches(fx)
+    with torch.no_grad():
+        vb1, qb1 = hp.attach_plan(dict(vb)), hp.attach_plan(dict(qb), kind="txt")
+        assert vb1[hp.PLAN_KEY].f.txt_ids is not None and qb1[hp.PLAN_KEY].f.txt_ids is not None
+        a, qa = model(vb1, "repr"), model.f_encoder(qb1, "txt")[0]
+        ja, jqa = model.forward_repr_txt(dict(vb), dict(qb))
+
+        def no_ids(self, *a, **k):
+            self.txt_ids = self.txt_pos = self.img_kpos = None
+        monkeypatch.setattr(hp.FPlan, "gather_ids", no_ids)
+        vb2, qb2 = hp.attach_plan(dict(vb)), hp.attach_plan(dict(qb), kind="txt")
+        assert vb2[hp.PLAN_KEY].f.txt_ids is None
+        b, qb_out = model(vb2, "repr"), model.f_encoder(qb2, "txt")[0]
+        jb, jqb = model.forward_repr_txt(dict(vb), dict(qb))
+    assert torch.equal(a, b) and torch.equal(qa, qb_out)
+    assert torch.equal(ja, jb) and torch.equal(jqa, jqb)
+
+
 def test_in_place_gradient_sinks_match_autograd_accumulation(tmp_path, monkeypatch):
     """With FlatParams.ensure_flat_grads the backward accumulates straight into the flat gradient
     buffer (no zero-fill / add pass); the result must equal the plain autograd path, and a second
