@@ -45,11 +45,12 @@ constexpr float AT_MASK_BIG = 16384.0f;
 
 // Column i of the membership operand (MN-major: one 128-byte row per ordinal, tokens contiguous,
 // two 64-token chunks of 2 KB): thread i owns its token's 16 entries.
+template <int K0 = 0, int K1 = AT_MAX_SEQS>
 __device__ __forceinline__ void write_membership(uint8_t* sE, int i, int ord) {
   uint8_t* base = sE + (i >> 6) * (AT_MAX_SEQS * 128) + ((i & 7) << 1);
   const int u = (i & 63) >> 3;
 #pragma unroll
-  for (int k = 0; k < AT_MAX_SEQS; ++k)
+  for (int k = K0; k < K1; ++k)
     *reinterpret_cast<uint16_t*>(base + k * 128 + ((u ^ (k & 7)) << 4)) =
         (k == ord) ? static_cast<uint16_t>(0x4300) : static_cast<uint16_t>(0);   // bf16 128.0
 }
@@ -59,11 +60,12 @@ __device__ __forceinline__ void write_membership(uint8_t* sE, int i, int ord) {
 // caller synchronises the CTA between the two halves.
 __device__ __forceinline__ uint32_t seq_starts_ballot(bool valid, int lo, int i, int* warp_starts) {
   const uint32_t bal = __ballot_sync(0xffffffffu, valid && lo == i);
-  if ((threadIdx.x & 31) == 0) warp_starts[threadIdx.x >> 5] = __popc(bal);
+  // (a 256-thread CTA has two warps per row quadrant: both write the same count)
+  if ((threadIdx.x & 31) == 0) warp_starts[(threadIdx.x >> 5) & 3] = __popc(bal);
   return bal;
 }
 __device__ __forceinline__ int seq_ordinal(bool valid, uint32_t bal, const int* warp_starts) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 3;
   int ord = __popc(bal & (0xffffffffu >> (31 - lane))) - 1;
   for (int w = 0; w < warp; ++w) ord += warp_starts[w];
   return valid ? ord : -1;
@@ -105,6 +107,20 @@ __device__ __forceinline__ void stage_row(uint8_t* tile, int row, const uint32_t
     v.z = pack_bf16x2(__uint_as_float(r[b + 4]) * scale, __uint_as_float(r[b + 5]) * scale);
     v.w = pack_bf16x2(__uint_as_float(r[b + 6]) * scale, __uint_as_float(r[b + 7]) * scale);
     *reinterpret_cast<uint4*>(tile + row * 128 + ((g ^ (row & 7)) << 4)) = v;
+  }
+}
+// 32 of the row's 64 features (one TMEM fragment): units 4 * half .. 4 * half + 3
+__device__ __forceinline__ void stage_half_row(uint8_t* tile, int row, int half,
+                                               const uint32_t (&r)[32], float scale) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int b = g * 8;
+    uint4 v;
+    v.x = pack_bf16x2(__uint_as_float(r[b]) * scale, __uint_as_float(r[b + 1]) * scale);
+    v.y = pack_bf16x2(__uint_as_float(r[b + 2]) * scale, __uint_as_float(r[b + 3]) * scale);
+    v.z = pack_bf16x2(__uint_as_float(r[b + 4]) * scale, __uint_as_float(r[b + 5]) * scale);
+    v.w = pack_bf16x2(__uint_as_float(r[b + 6]) * scale, __uint_as_float(r[b + 7]) * scale);
+    *reinterpret_cast<uint4*>(tile + row * 128 + (((half * 4 + g) ^ (row & 7)) << 4)) = v;
   }
 }
 // ... and the CTA then writes the tile(s) out with every warp covering 4 full 128-byte rows per
@@ -306,7 +322,12 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnTcArg
 // P's first 64-column chunk is written over V (dead after dP = dO V^T), so two CTAs fit per SM and
 // overlap each other's TMA / MMA / softmax phases. Probabilities are rebuilt from the forward's
 // log-sum-exp in ONE pass over S.
-__global__ void __launch_bounds__(128)
+// 256 threads: TWO threads per tile row (warps w and w + 4 share TMEM lane quadrant w), each owning
+// 64 of the row's 128 score columns and 32 of the 64 features of every output row. With only two
+// CTAs per SM (TMEM: 2 x 256 columns) the 128-thread version left the SM with 8 warps to hide the
+// TMEM / MUFU / smem latencies of its longest phase.
+constexpr int AT_BWD_THREADS = 256;
+__global__ void __launch_bounds__(AT_BWD_THREADS)
 attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                    const __grid_constant__ CUtensorMap tmap_do,
                    const __grid_constant__ CUtensorMap tmap_o, const AttnTcArgs a,
@@ -333,7 +354,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   const int warp = threadIdx.x >> 5;
   const int tok0 = a.tile_tok0[tile];
   const int ntok = a.tile_ntok[tile];
-  const int i = threadIdx.x;
+  const int i = threadIdx.x & 127;        // tile row
+  const int half = threadIdx.x >> 7;      // which 64 score columns / 32 output features
   const bool valid = i < ntok;
   int lo = 0, hi = 0;
   if (valid) {
@@ -375,7 +397,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   {
     const int ord = seq_ordinal(valid, starts, warp_starts);
     if (ord >= AT_MAX_SEQS) __trap();
-    write_membership(sE, i, ord);
+    if (half == 0) write_membership<0, AT_MAX_SEQS / 2>(sE, i, ord);
+    else write_membership<AT_MAX_SEQS / 2, AT_MAX_SEQS>(sE, i, ord);
     fence_proxy_async();
   }
   __syncthreads();
@@ -398,6 +421,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     }
   }
 
+  // both threads of a row have read its O row: its smem is P's second chunk from here on
+  __syncthreads();
   if (threadIdx.x == 0) {
     tc_fence_after_sync();
     constexpr uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
@@ -428,7 +453,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     wlo = min(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
     whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, o));
   }
-  const uint32_t t_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t t_row = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
   // exponent offset of this row: its log-sum-exp plus the membership shift; rows past the tile's
   // end get +inf so that their P and dS rows (which the transposed products sum over) are 0
   const float row_c = valid ? fmaf(AT_MASK_BIG, a.scale_log2,
@@ -440,7 +465,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   const uint32_t k2 = attn_drop_k2(a.drop_thr);
   // Stored tiles: P = bf16(p) on kept lanes (dV = keep_scale * P^T dO, scaled when dV is staged),
   // dS = p * (dP * keep - D) (dQ, dK scaled by 1 / sqrt(d) when staged; a power of two).
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 2 * half; c < 2 * half + 2; ++c) {
     uint32_t pk[16], dk[16];
     const bool touch = !(c * 32 >= whi || c * 32 + 32 <= wlo);
     if (touch) {
@@ -524,11 +549,10 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   // (now dead) Q / K / V tiles, then written with coalesced row stores
 #pragma unroll 1
   for (int part = 0; part < 3; ++part) {
-    uint32_t r0[32], r1[32];
-    tmem_ld_32x32(t_row + part * 64, r0);
-    tmem_ld_32x32(t_row + part * 64 + 32, r1);
+    uint32_t r0[32];
+    tmem_ld_32x32(t_row + part * 64 + half * 32, r0);
     tmem_ld_wait();
-    stage_row(smem + part * AT_TILE_BYTES, i, r0, r1, part == 2 ? keep_scale : a.scale);
+    stage_half_row(smem + part * AT_TILE_BYTES, i, half, r0, part == 2 ? keep_scale : a.scale);
   }
   // Bias gradient of the QKV projection = column sums of dqkv over the tile's tokens: one more
   // MMA over the staged tiles. A = [dQ | dK] (then [dV | -]) read MN-major (m = feature,
@@ -537,9 +561,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   // separate pass over dqkv (hero_colsum_bf16: 76 MB per layer).
   uint8_t* sB = sdS;
   if (dbias != nullptr) {
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int idx = threadIdx.x + t * 128;               // unit (n, chunk, u)
+    {
+      const int idx = threadIdx.x;                          // unit (n, chunk, u)
       const int n = idx >> 4, ch = (idx >> 3) & 1, u = idx & 7;
       const int k0 = ch * 64 + u * 8;
       uint32_t w[4];
@@ -572,15 +595,14 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   if (dbias != nullptr) {
     mbar_wait(mma_bar, 0);       // third phase of this barrier
     tc_fence_after_sync();
-    const float qk = __uint_as_float(tmem_ld_32x1(t_row + 192));
-    const float vv = __uint_as_float(tmem_ld_32x1(t_row + 208));
+    const float cs = __uint_as_float(tmem_ld_32x1(t_row + 192 + half * 16));
     tmem_ld_wait();
     float* db = dbias + head * AT_D;
-    if (i < AT_D) {
-      atomicAdd(db + i, qk);                    // dQ feature i
-      atomicAdd(db + 2 * a.H + i, vv);          // dV feature i
-    } else {
-      atomicAdd(db + a.H + (i - AT_D), qk);     // dK feature i - 64
+    if (half == 0) {
+      if (i < AT_D) atomicAdd(db + i, cs);                 // dQ feature i
+      else atomicAdd(db + a.H + (i - AT_D), cs);           // dK feature i - 64
+    } else if (i < AT_D) {
+      atomicAdd(db + 2 * a.H + i, cs);                     // dV feature i
     }
   }
   tc_fence_before_sync();
@@ -954,7 +976,7 @@ extern "C" int hero_attn_bwd(const void* qkv, const int32_t* tile_tok0, const in
   }
   if (n_short > 0) {
     dim3 grid(n_short, heads);
-    HERO_CUDA_CHECK(launch_pdl(attn_tc_bwd_kernel, grid, dim3(128), smem,
+    HERO_CUDA_CHECK(launch_pdl(attn_tc_bwd_kernel, grid, dim3(AT_BWD_THREADS), smem,
                                reinterpret_cast<cudaStream_t>(stream), tq, td, to, a, lse,
                                reinterpret_cast<__nv_bfloat16*>(dqkv), dbias));
   }

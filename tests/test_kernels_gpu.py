@@ -296,7 +296,8 @@ def test_attention_tiles_hold_at_most_16_sequences_and_mask_out_their_neighbours
     ref.backward(dctx.float())
     dqkv = torch.empty_like(qkv)
     ops.attn_bwd(qkv, att, ctx, dctx, lse, dqkv, heads=heads)
-    _close(dqkv, qr.grad, 4e-2, 3e-2, "attention bwd, 16-sequence tiles")
+    # (operands 3-8x larger than in the other tests: tolerance relative to the gradient scale)
+    _close(dqkv, qr.grad, 6e-3 * qr.grad.abs().max().item(), 3e-2, "attention bwd, 16-sequence tiles")
 
 
 def test_attention_dropout_rate_and_pair_independence():
