@@ -176,15 +176,17 @@ class FlatGradExchange:
     def self_check(self):
         """Known-answer test of the exchange on this job's ranks and transport: rank r fills the
         buffer with (r + 1) * base, base a fixed pattern of multiples of 1/16 (exact in bf16);
-        afterwards every rank must hold base * (W + 1) / 2 (within bf16 rounding when the wire is
-        bf16) and all ranks must hold bit-identical buffers. Leaves the buffer zeroed."""
+        afterwards every rank must hold base * (W + 1) / 2 and all ranks must hold bit-identical
+        buffers. With the bf16 wire the partial sums of W > 4 ranks are no longer all exact in
+        bf16 (e.g. 21 * 13/16): the bound is one rounding (2^-9 relative) per addition plus the
+        final one. Leaves the buffer zeroed."""
         g = self.flat.ensure_flat_grads()
         W, r = size(), rank()
         base = ((torch.arange(g.numel(), device=g.device) % 31) - 15).float() / 16.0
         g.copy_(base * (r + 1))
         self.all_reduce()
         want = base * ((W + 1) / 2.0)
-        tol = (2.0 ** -7 if self.stage is not None else 2.0 ** -20)
+        tol = (max(2.0 ** -7, (W + 1) * 2.0 ** -9) if self.stage is not None else 2.0 ** -20)
         err = float(((g - want).abs() - tol * want.abs()).max().item())
         same = self.ranks_agree()
         g.zero_()
