@@ -430,21 +430,15 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
   return t;
 }
 
-__global__ void __launch_bounds__(LNW_THREADS)
+// (gamma / beta are re-read per row - 35 KB that stay in L1 - instead of living in 48 registers:
+// at 64 registers four CTAs fit per SM, and one row per CTA in flight needs that many to cover
+// the HBM latency: 36 -> see profiles/r02_ln_bench.txt)
+__global__ void __launch_bounds__(LNW_THREADS, 4)
 ln_fwd_wide_kernel(const hero_ln_args a) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ float red[LNW_THREADS / 32];
   const float inv_h = 1.0f / (float)a.h;
-  float g[LNW_C][8], b[LNW_C][8];
-#pragma unroll
-  for (int c = 0; c < LNW_C; ++c) {
-    const int e0 = (c * LNW_THREADS + threadIdx.x) * 8;
-    if (e0 < a.h) {
-      load_f32x8(a.gamma + e0, g[c]);
-      load_f32x8(a.beta + e0, b[c]);
-    }
-  }
   for (int i = blockIdx.x; i < a.n_rows; i += gridDim.x) {
     const long long xrow = a.x_rows ? a.x_rows[i] : i;
     const int add_row = a.add_tab ? a.add_idx[i] : 0;
@@ -483,9 +477,11 @@ ln_fwd_wide_kernel(const hero_ln_args a) {
     for (int c = 0; c < LNW_C; ++c) {
       const int e0 = (c * LNW_THREADS + threadIdx.x) * 8;
       if (e0 < a.h) {
-        float o[8];
+        float o[8], g[8], b[8];
+        load_f32x8(a.gamma + e0, g);
+        load_f32x8(a.beta + e0, b);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * g[c][j] + b[c][j];
+        for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * g[j] + b[j];
         if (a.drop_threshold != 0u)
           dropout_apply8(o, a.drop_key, (uint32_t)i * (uint32_t)a.h + (uint32_t)e0,
                          a.drop_threshold, a.drop_scale);
@@ -831,7 +827,7 @@ extern "C" int hero_ln_fwd(const hero_ln_args* a, void* stream) {
     HERO_CUDA_CHECK(launch_pdl(ln_fwd_kernel<3, 1>, dim3(ceil_div(a->n_rows, LN_WARPS)),
                                dim3(LN_WARPS * 32), 0, st, *a));
   } else if (a->h <= LNW_C * LNW_THREADS * 8 && a->n_rows >= 64) {
-    int grid = a->n_rows < sms * 4 ? a->n_rows : sms * 4;
+    int grid = a->n_rows < sms * 8 ? a->n_rows : sms * 8;
     HERO_CUDA_CHECK(launch_pdl(ln_fwd_wide_kernel, dim3(grid), dim3(LNW_THREADS), 0, st, *a));
   } else {
     int grid = ceil_div(a->n_rows, LN_WARPS);

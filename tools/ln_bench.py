@@ -61,3 +61,14 @@ for M in (16512, 3200):
                                       dbeta=db, dbias=dbias))
     print(f"M={M} fp32 rows: ln_fwd {t_f:.1f} us ({3 * by / t_f:.2f} TB/s)  +fp32 copy {t_f2:.1f} us "
           f"({5 * by / t_f2:.2f} TB/s)  ln_bwd rows+params {t_p:.1f} us ({5 * by / t_p:.2f} TB/s)")
+
+# 4352-wide rows: the video-feature LayerNorm of ImageEmbeddings (model/embed.py:108-116), fp32
+# features in, bf16 normalised rows out (+ the bf16 low halves for the split GEMM when asked)
+D, M = 4352, 3200
+R = 4
+xw = [torch.randn(M, D, device=dev) for _ in range(R)]
+yw = [torch.empty(M, D, dtype=torch.bfloat16, device=dev) for _ in range(R)]
+gw, bw = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+mean, rstd = torch.empty(M, device=dev), torch.empty(M, device=dev)
+t_w = timeit(lambda i: ops.ln_fwd(xw[i % R], gw, bw, 1e-12, yw[i % R], n_rows=M, mean=mean, rstd=rstd))
+print(f"wide rows {M} x {D} fp32 -> bf16: ln_fwd {t_w:.1f} us ({M * D * 6 / 1e6 / t_w:.2f} TB/s)")
