@@ -260,7 +260,7 @@ class _PtrTensor:
 
 
 # kernels launched per layer by the native runtime (for bench.py's gpu_launches)
-_STACK_FWD_LAUNCHES, _STACK_BWD_LAUNCHES = 7, 15   # bwd: 8 GEMM, 2x2 LN, attn, 2 colsum
+_STACK_FWD_LAUNCHES, _STACK_BWD_LAUNCHES = 7, 11   # bwd: 8 GEMM, 2 LN (one pass each), attention
 _ACT_FIELDS = ("qkv", "cx", "lse", "s1", "mean1", "rstd1", "a", "a_f32", "pre", "f", "s2", "mean2",
                "rstd2", "out", "out_f32")
 _GRAD_FIELDS = ("dwqkv", "dbqkv", "dwo", "dbo", "dln1_g", "dln1_b", "dw1", "db1", "dw2", "db2",
