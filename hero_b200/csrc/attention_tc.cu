@@ -407,26 +407,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   }
   __syncthreads();
   mbar_wait(tma_bar, 0);
-  // D_i = dO_i . O_i from the swizzled smem tiles (conflict-free 16-byte reads)
-  float Di = 0.f;
-  if (valid) {
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const uint32_t off = i * 128 + ((g ^ (i & 7)) << 4);
-      const uint4 o = *reinterpret_cast<const uint4*>(sP + P_CHUNK + off);
-      const uint4 d = *reinterpret_cast<const uint4*>(sdO + off);
-      const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, dw[4] = {d.x, d.y, d.z, d.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 x = unpack_bf16x2(ow[j]), y = unpack_bf16x2(dw[j]);
-        Di = fmaf(x.x, y.x, Di);
-        Di = fmaf(x.y, y.y, Di);
-      }
-    }
-  }
-
-  // both threads of a row have read its O row: its smem is P's second chunk from here on
-  __syncthreads();
+  // S, dP go first; D_i is computed while they run
   if (threadIdx.x == 0) {
     tc_fence_after_sync();
     constexpr uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
@@ -448,6 +429,26 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     }
     umma_commit(mma_bar);
   }
+  // D_i = dO_i . O_i from the swizzled smem tiles (conflict-free 16-byte reads)
+  float Di = 0.f;
+  if (valid) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint32_t off = i * 128 + ((g ^ (i & 7)) << 4);
+      const uint4 o = *reinterpret_cast<const uint4*>(sP + P_CHUNK + off);
+      const uint4 d = *reinterpret_cast<const uint4*>(sdO + off);
+      const uint32_t ow[4] = {o.x, o.y, o.z, o.w}, dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 x = unpack_bf16x2(ow[j]), y = unpack_bf16x2(dw[j]);
+        Di = fmaf(x.x, y.x, Di);
+        Di = fmaf(x.y, y.y, Di);
+      }
+    }
+  }
+
+  // both threads of a row have read its O row: its smem is P's second chunk from here on
+  __syncthreads();
   mbar_wait(mma_bar, 0);
   tc_fence_after_sync();
 
