@@ -537,15 +537,17 @@ def run_ours(args):
         stage_t["h2d_enqueue"] += time.perf_counter() - t2
         return vb_dev, qb_dev, ev, slot
 
-    result_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    RESULT_LAG = 2       # the scalar of step i is consumed after step i + 2 has been enqueued
+    result_host = torch.zeros(RESULT_LAG + 1, dtype=torch.float32).pin_memory()
 
     def e2e_loop(n):
         """Every step: wait for its prefetched inputs, enqueue fwd+bwd, start the (async) D2H
         read of a result scalar, then build the NEXT batch's plan on the host and start its H2D
         copy on the side stream while the GPU computes. The scalar of step i is consumed right
-        after step i+1 has been enqueued (one-step-lagged logging), so the host never idles the
-        GPU; all n results are read."""
-        out, pending = 0.0, None
+        after step i+2 has been enqueued (lagged logging: with eight ranks meeting in an all-reduce
+        every step, a one-step lag let any rank's host hiccup stall all of them), so the host
+        never idles the GPU; all n results are read inside the timed region."""
+        out, pending = 0.0, collections.deque()
         tt = collections.defaultdict(float)
         dones = []
         nxt = stage(0, n)
@@ -560,7 +562,7 @@ def run_ours(args):
             t_b = time.perf_counter()
             clip = fwd_bwd(vb_dev, qb_dev)
             t_c = time.perf_counter()
-            slot = result_host[i % 2:i % 2 + 1]
+            slot = result_host[i % (RESULT_LAG + 1):i % (RESULT_LAG + 1) + 1]
             # (detach: the pinned result buffer must not become part of — and keep alive — the
             # step's autograd graph and its ~3 GB of saved activations)
             slot.copy_(clip.detach()[0, 0, :8].float().sum().reshape(1), non_blocking=True)   # D2H
@@ -572,16 +574,19 @@ def run_ours(args):
             if i + 1 < n:
                 nxt = stage(i + 1, n)                   # plan upload + H2D overlap this step's compute
             t_e = time.perf_counter()
-            if pending is not None:
-                pending[0].synchronize()
-                out += float(pending[1][0])
-            pending = (done, slot)
+            pending.append((done, slot))
+            if len(pending) > RESULT_LAG:
+                ev_done, ev_slot = pending.popleft()
+                ev_done.synchronize()
+                out += float(ev_slot[0])
             t_f = time.perf_counter()
             for k, v in (("record", t_b - t_a), ("fwd_bwd", t_c - t_b), ("d2h", t_d - t_c),
                          ("stage", t_e - t_d), ("sync_prev", t_f - t_e)):
                 tt[k] += v
-        pending[0].synchronize()
-        out += float(pending[1][0])
+        while pending:
+            ev_done, ev_slot = pending.popleft()
+            ev_done.synchronize()
+            out += float(ev_slot[0])
         gaps = [round(a.elapsed_time(b), 2) for a, b in zip(dones[:-1], dones[1:])]
         diag = {"stage_totals_ms": {k: round(v * 1e3, 1) for k, v in stage_t.items()},
                 "device_ms_between_step_ends": gaps,
