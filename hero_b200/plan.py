@@ -484,7 +484,10 @@ def attach_plan(batch, kind="repr"):
     the batch dict; `move_to_cuda`-style helpers leave non-tensor values alone.
     kind: 'repr' (video batch), 'txt' (query batch), or 'vsm' — a VSM / VCMR training batch that
     carries its queries as `query_input_ids / query_pos_ids / query_attn_masks` (data/vcmr.py):
-    attaches the video plan, the query plan (QUERY_PLAN_KEY) and their joint plan."""
+    attaches the video plan, the query plan (QUERY_PLAN_KEY) and their joint plan.
+    The plan captures the batch's token / position ids per packed token (FPlan.gather_ids): attach
+    it AFTER any masking of `input_ids` (the reference masks in the dataset, before collate), and
+    attach again if the ids are edited afterwards."""
     if kind == "vsm":
         rplan = ReprPlan(batch)
         tplan = TxtPlan(batch["query_attn_masks"], pos_ids=batch.get("query_pos_ids"),
