@@ -242,3 +242,52 @@ def test_long_rows_become_trailing_tiles_and_joint_plans_keep_them_last():
     import pytest
     with pytest.raises(ValueError, match="row 1"):
         SeqPlan(mask_of([3, ATTN_LONG_MAX + 1]))
+
+
+def test_tiles_hold_at_most_16_sequences():
+    """The attention kernels apply the block-diagonal mask as a K = 16 membership MMA
+    (csrc/attention_tc.cu): a tile closes after 128 tokens OR 16 sequences, whichever comes first,
+    including across empty rows, long rows and the joint (video + query) concatenation."""
+    import numpy as np
+    from hero_b200.plan import ATTN_TILE_SEQS, SeqPlan
+
+    rng = np.random.RandomState(3)
+    for _ in range(20):
+        lens = rng.choice([0, 1, 2, 3, 5, 9, 40, 130], size=rng.randint(1, 120)).tolist()
+        if max(lens) == 0:
+            lens[0] = 1
+        m = np.zeros((len(lens), max(lens)), np.int64)
+        for r, n in enumerate(lens):
+            m[r, :n] = 1
+        sp = SeqPlan(m)
+        starts = np.asarray([c for c, n in zip(sp.cu[:-1], np.diff(sp.cu)) if n > 0])
+        len_at = {int(c): int(n) for c, n in zip(sp.cu[:-1], np.diff(sp.cu)) if n > 0}
+        n_short = sp.n_tiles - sp.n_long
+        assert int(sp.tile_ntok.sum()) == sp.n_tok
+        for a, n in zip(sp.tile_tok0[:n_short], sp.tile_ntok[:n_short]):
+            assert 0 < n <= 128
+            assert ((starts >= a) & (starts < a + n)).sum() <= ATTN_TILE_SEQS
+        # tiles are maximal: merging two neighbours would break one of the two limits
+        for (a, n), (b, k) in zip(zip(sp.short_tok0, sp.short_ntok),
+                                  zip(sp.short_tok0[1:], sp.short_ntok[1:])):
+            if a + n == b:      # adjacent in the token stream (no long row between them)
+                both = ((starts >= a) & (starts < b + k)).sum()
+                first_of_next = len_at[int(b)]
+                assert n + first_of_next > 128 or \
+                    ((starts >= a) & (starts < a + n)).sum() == ATTN_TILE_SEQS, (a, n, b, k, both)
+
+
+def test_zero_grads_async_on_cpu_is_a_plain_zero(monkeypatch):
+    import torch
+    from hero_b200.params import flat_of
+    from tests import fake_ops
+    fake_ops.install(monkeypatch)      # CPU process: the bf16 mirror cast has no CUDA library
+
+    lin = torch.nn.Linear(4, 3)
+    fp = flat_of(lin, torch.device("cpu"))
+    g = fp.ensure_flat_grads()
+    g.fill_(2.0)
+    fp.zero_grads_async()
+    fp.wait_grads_zeroed()
+    assert float(g.abs().sum()) == 0.0
+    assert float(lin.weight.grad.abs().sum()) == 0.0
